@@ -1,0 +1,400 @@
+// extern "C" boundary (include/b200gan.h) and the host-side geometry builders that turn a TF-style
+// SAME convolution into TMA tensor maps + tap tables for the tcgen05 kernels.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+
+#include "../../include/b200gan.h"
+#include "simt_kernels.cuh"
+#include "tc_gemm.cuh"
+
+using namespace b200;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return -1; }
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor, dims[0] contiguous; strides in ELEMENTS for dims 1..rank-1; 128-byte swizzle, zero OOB fill
+static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides,
+                     const int* box, const int* estride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail("tensor map base not 16-byte aligned");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    b[i] = (cuuint32_t)box[i];
+    es[i] = (cuuint32_t)estride[i];
+    if (box[i] < 1 || box[i] > 256) return fail("TMA box dim out of range");
+    if (i > 0) {
+      gstr[i - 1] = (cuuint64_t)strides[i] * 2;
+      if (gstr[i - 1] & 15) return fail("TMA stride not a multiple of 16 bytes (channels must be a multiple of 8)");
+    }
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, b, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return fail(buf);
+  }
+  return 0;
+}
+
+static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+static void pick_pixel_tile(int Wo, int Ho, int total, int* bw, int* bh, int* bn) {
+  *bw = std::min(pow2ceil(Wo), total);
+  *bh = std::min(pow2ceil(Ho), total / *bw);
+  *bn = total / (*bw * *bh);
+}
+static int pick_bn_tile(int cols) {
+  const int nt = cdiv(cols, 256);
+  return std::max(16, cdiv(cdiv(cols, nt), 16) * 16);
+}
+static int pick_stages(int stage_bytes) {
+  int s = (227 * 1024 - 2048) / stage_bytes;
+  return std::max(2, std::min(s, 8));
+}
+
+static bool is_small(int c) { return c <= 4; }
+
+extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
+  const int kk = g->k * g->k;
+  if (is_small(g->Cin)) {
+    if (kk * g->Cin <= 80 && g->Cout <= 1024) return 2;
+    return fail("small-channel conv: k*k*Cin > 80 or Cout > 1024");
+  }
+  if (g->Cin % 8) return fail("tensor-core conv needs Cin % 8 == 0");
+  if (op != 0 && g->Cout % 8) return fail("tensor-core dgrad/wgrad need Cout % 8 == 0");
+  if (kk > kMaxTaps) return fail("filter larger than 5x5");
+  if (op == 1 && g->stride * g->stride > kMaxPhases) return fail("dgrad stride > 2");
+  return 1;
+}
+
+static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
+  p.bias = e ? e->bias : nullptr;
+  p.act = e ? e->act : 0;
+  p.leak = e ? e->leak : 0.f;
+  p.mask_src = e ? (const __nv_bfloat16*)e->mask_src : nullptr;
+  p.mask_kind = e ? e->mask_kind : 0;
+  p.out_f32 = e ? e->out_f32 : 0;
+  p.accumulate = e ? e->accumulate : 0;
+  p.alpha = 1.f;
+}
+
+extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, void* y, const b200_conv_geom* g,
+                                 const b200_epilogue* e, b200_stream s) {
+  cudaStream_t st = (cudaStream_t)s;
+  const int route = b200_conv2d_route(g, 0);
+  if (route < 0) return route;
+  if (route == 2) {
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
+                    e ? e->mask_kind : 0, y, e ? e->out_f32 : 0};
+    if (e && e->accumulate) return fail("small-channel fprop: accumulate unsupported");
+    if (smallc_fprop(x, w, a, st)) return fail("smallc_fprop: unsupported shape");
+    return check_launch("smallc_fprop");
+  }
+  if (!w_t) return fail("conv2d_fprop: tensor-core path needs w_t");
+  TapGemmParams p;
+  memset(&p, 0, sizeof p);
+  fill_epilogue(p, e);
+  pick_pixel_tile(g->Wo, g->Ho, kTileM, &p.bw, &p.bh, &p.bn);
+  const int st_ = g->stride;
+  if (p.bw * st_ > 256 || p.bh * st_ > 256) return fail("conv2d_fprop: tile exceeds TMA box limit");
+  {
+    long long dims[4] = {g->Cin, g->W, g->H, g->N};
+    long long str[4] = {1, g->Cin, (long long)g->W * g->Cin, (long long)g->H * g->W * g->Cin};
+    int box[4] = {kBlockK, p.bw * st_, p.bh * st_, p.bn};
+    int es[4] = {1, st_, st_, 1};
+    if (make_tmap(&p.tmA, x, 4, dims, str, box, es)) return -1;
+  }
+  p.a_rank = 4;
+  p.ncols = g->Cout;
+  p.bn_tile = pick_bn_tile(g->Cout);
+  {
+    long long dims[2] = {g->Cin, (long long)g->k * g->k * g->Cout};
+    long long str[2] = {1, g->Cin};
+    int box[2] = {kBlockK, p.bn_tile};
+    int es[2] = {1, 1};
+    if (make_tmap(&p.tmB, w_t, 2, dims, str, box, es)) return -1;
+  }
+  p.kchunks = cdiv(g->Cin, kBlockK);
+  p.nphases = 1;
+  p.phase_tap_begin[0] = 0;
+  p.phase_tap_begin[1] = g->k * g->k;
+  for (int r = 0; r < g->k; ++r)
+    for (int c = 0; c < g->k; ++c) {
+      const int t = r * g->k + c;
+      p.tap_a_off[t][0] = c - g->pad_l;
+      p.tap_a_off[t][1] = r - g->pad_t;
+      p.tap_a_off[t][2] = 0;
+      p.tap_b_row[t] = t * g->Cout;
+    }
+  p.a_mul[0][0] = st_; p.a_mul[1][1] = st_; p.a_mul[2][2] = 1;
+  p.tiles_w = cdiv(g->Wo, p.bw); p.tiles_h = cdiv(g->Ho, p.bh); p.tiles_n = cdiv(g->N, p.bn);
+  p.phase_ext_w[0] = g->Wo; p.phase_ext_h[0] = g->Ho; p.ext_n = g->N;
+  p.phase_o_off[0] = 0;
+  p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
+  p.stages = pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.out = y;
+  launch_tapgemm(p, st);
+  return check_launch("conv2d_fprop");
+}
+
+extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const b200_conv_geom* g,
+                                 const b200_epilogue* e, b200_stream s) {
+  cudaStream_t st = (cudaStream_t)s;
+  const int route = b200_conv2d_route(g, 1);
+  if (route < 0) return route;
+  if (route == 2) {
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
+                    e ? e->mask_kind : 0, dx, e ? e->out_f32 : 0};
+    if (e && e->accumulate) return fail("small-channel dgrad: accumulate unsupported");
+    if (smallc_dgrad(dy, w, a, st)) return fail("smallc_dgrad: unsupported shape");
+    return check_launch("smallc_dgrad");
+  }
+  TapGemmParams p;
+  memset(&p, 0, sizeof p);
+  fill_epilogue(p, e);
+  const int st_ = g->stride;
+  const int ext_w0 = cdiv(g->W, st_), ext_h0 = cdiv(g->H, st_);
+  pick_pixel_tile(ext_w0, ext_h0, kTileM, &p.bw, &p.bh, &p.bn);
+  {
+    long long dims[4] = {g->Cout, g->Wo, g->Ho, g->N};
+    long long str[4] = {1, g->Cout, (long long)g->Wo * g->Cout, (long long)g->Ho * g->Wo * g->Cout};
+    int box[4] = {kBlockK, p.bw, p.bh, p.bn};
+    int es[4] = {1, 1, 1, 1};
+    if (make_tmap(&p.tmA, dy, 4, dims, str, box, es)) return -1;
+  }
+  p.a_rank = 4;
+  p.ncols = g->Cin;
+  p.bn_tile = pick_bn_tile(g->Cin);
+  {
+    long long dims[2] = {g->Cout, (long long)g->k * g->k * g->Cin};
+    long long str[2] = {1, g->Cout};
+    int box[2] = {kBlockK, p.bn_tile};
+    int es[2] = {1, 1};
+    if (make_tmap(&p.tmB, w, 2, dims, str, box, es)) return -1;
+  }
+  p.kchunks = cdiv(g->Cout, kBlockK);
+  // output parities, heaviest first so the tail of the grid is made of the cheap phases
+  struct Ph { int ph, pw, nt; } phs[kMaxPhases];
+  int np = 0;
+  for (int ph = 0; ph < st_; ++ph)
+    for (int pw = 0; pw < st_; ++pw) {
+      int nr = 0, nc = 0;
+      for (int r = 0; r < g->k; ++r) nr += ((ph + g->pad_t - r) % st_ == 0);
+      for (int c = 0; c < g->k; ++c) nc += ((pw + g->pad_l - c) % st_ == 0);
+      if (nr * nc == 0) return fail("conv2d_dgrad: output phase without taps (k < stride) unsupported");
+      phs[np++] = {ph, pw, nr * nc};
+    }
+  std::stable_sort(phs, phs + np, [](const Ph& a, const Ph& b) { return a.nt > b.nt; });
+  int t = 0;
+  for (int i = 0; i < np; ++i) {
+    const int ph = phs[i].ph, pw = phs[i].pw;
+    p.phase_tap_begin[i] = t;
+    for (int r = 0; r < g->k; ++r) {
+      if ((ph + g->pad_t - r) % st_) continue;
+      for (int c = 0; c < g->k; ++c) {
+        if ((pw + g->pad_l - c) % st_) continue;
+        p.tap_a_off[t][0] = (pw + g->pad_l - c) / st_;
+        p.tap_a_off[t][1] = (ph + g->pad_t - r) / st_;
+        p.tap_a_off[t][2] = 0;
+        p.tap_b_row[t] = (r * g->k + c) * g->Cin;
+        ++t;
+      }
+    }
+    p.phase_ext_w[i] = cdiv(g->W - pw, st_);
+    p.phase_ext_h[i] = cdiv(g->H - ph, st_);
+    p.phase_o_off[i] = ((long long)ph * g->W + pw) * g->Cin;
+  }
+  p.phase_tap_begin[np] = t;
+  p.nphases = np;
+  p.a_mul[0][0] = 1; p.a_mul[1][1] = 1; p.a_mul[2][2] = 1;
+  p.tiles_w = cdiv(ext_w0, p.bw); p.tiles_h = cdiv(ext_h0, p.bh); p.tiles_n = cdiv(g->N, p.bn);
+  p.ext_n = g->N;
+  p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
+  p.stages = pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.out = dx;
+  launch_tapgemm(p, st);
+  return check_launch("conv2d_dgrad");
+}
+
+extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha,
+                                 b200_stream s) {
+  cudaStream_t st = (cudaStream_t)s;
+  const int route = b200_conv2d_route(g, 2);
+  if (route < 0) return route;
+  if (route == 2) {
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
+    if (smallc_wgrad(x, dy, dw, a, alpha, st)) return fail("smallc_wgrad: unsupported shape");
+    return check_launch("smallc_wgrad");
+  }
+  WgradParams p;
+  memset(&p, 0, sizeof p);
+  const int st_ = g->stride;
+  pick_pixel_tile(g->Wo, g->Ho, 64, &p.bw, &p.bh, &p.bn);
+  if (p.bw * st_ > 256 || p.bh * st_ > 256) return fail("conv2d_wgrad: tile exceeds TMA box limit");
+  {
+    long long dims[4] = {g->Cin, g->W, g->H, g->N};
+    long long str[4] = {1, g->Cin, (long long)g->W * g->Cin, (long long)g->H * g->W * g->Cin};
+    int box[4] = {64, p.bw * st_, p.bh * st_, p.bn};
+    int es[4] = {1, st_, st_, 1};
+    if (make_tmap(&p.tmA, x, 4, dims, str, box, es)) return -1;
+  }
+  {
+    long long dims[4] = {g->Cout, g->Wo, g->Ho, g->N};
+    long long str[4] = {1, g->Cout, (long long)g->Wo * g->Cout, (long long)g->Ho * g->Wo * g->Cout};
+    int box[4] = {64, p.bw, p.bh, p.bn};
+    int es[4] = {1, 1, 1, 1};
+    if (make_tmap(&p.tmB, dy, 4, dims, str, box, es)) return -1;
+  }
+  p.a_rank = 4; p.b_rank = 4;
+  p.ntaps = g->k * g->k;
+  for (int r = 0; r < g->k; ++r)
+    for (int c = 0; c < g->k; ++c) {
+      const int t = r * g->k + c;
+      p.tap_a_off[t][0] = c - g->pad_l;
+      p.tap_a_off[t][1] = r - g->pad_t;
+      p.tap_a_off[t][2] = 0;
+    }
+  p.a_mul[0][0] = st_; p.a_mul[1][1] = st_; p.a_mul[2][2] = 1;
+  p.chunks_w = cdiv(g->Wo, p.bw); p.chunks_h = cdiv(g->Ho, p.bh); p.chunks_n = cdiv(g->N, p.bn);
+  p.total_chunks = p.chunks_w * p.chunks_h * p.chunks_n;
+  p.Ca = g->Cin; p.Cb = g->Cout;
+  p.m_tiles = cdiv(g->Cin, kTileM);
+  p.bn_tile = pick_bn_tile(g->Cout);
+  p.n_tiles = cdiv(g->Cout, p.bn_tile);
+  p.nb_boxes = cdiv(p.bn_tile, 64);
+  p.stages = pick_stages((2 + p.nb_boxes) * 64 * 64 * 2);
+  p.out = dw;
+  p.out_tap_stride = (long long)g->Cin * g->Cout;
+  p.ldo = g->Cout;
+  p.alpha = alpha;
+  const int base = p.m_tiles * p.n_tiles * p.ntaps;
+  int splits = cdiv(148 * 3, base);
+  splits = std::min(splits, std::max(1, p.total_chunks / 4));
+  splits = std::max(1, splits);
+  p.chunks_per_split = cdiv(p.total_chunks, splits);
+  splits = cdiv(p.total_chunks, p.chunks_per_split);
+  launch_wgrad(p, splits, st);
+  return check_launch("conv2d_wgrad");
+}
+
+// ------------------------------------------------------------------------------------------------
+// thin wrappers
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_device_check(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device"); }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail("device is not compute capability 10.x (B200, sm_100a)");
+  return 0;
+}
+
+#define WRAP(call, name) do { if ((call) != 0) return fail(name ": unsupported arguments"); return check_launch(name); } while (0)
+
+extern "C" int b200_gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act,
+                              float leak, b200_stream s) {
+  WRAP(gemv_rows(a, w, bias, out, M, K, act, leak, (cudaStream_t)s), "gemv_rows");
+}
+extern "C" int b200_outer_mask(const float* g, const void* w, const void* mask, void* out, int M, int K, int kind,
+                               float leak, b200_stream s) {
+  WRAP(outer_mask(g, w, mask, out, M, K, kind, leak, (cudaStream_t)s), "outer_mask");
+}
+extern "C" int b200_bn_sums(const void* z, float* stats, long long R, int C, b200_stream s) {
+  WRAP(bn_sums(z, stats, R, C, (cudaStream_t)s), "bn_sums");
+}
+extern "C" int b200_bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C,
+                             float eps, int act, float leak, b200_stream s) {
+  WRAP(bn_apply(z, stats, beta, out, R, C, eps, act, leak, (cudaStream_t)s), "bn_apply");
+}
+extern "C" int b200_bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* dz, long long R, int C,
+                           float eps, b200_stream s) {
+  WRAP(bn_bwd(g, z, stats, bsum, dz, R, C, eps, (cudaStream_t)s), "bn_bwd");
+}
+extern "C" int b200_maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, b200_stream s) {
+  WRAP(maskmul(g, a, out, n, kind, leak, (cudaStream_t)s), "maskmul");
+}
+extern "C" int b200_affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add,
+                               int act, float leak, b200_stream s) {
+  WRAP(affine_act(in, in_f32, out, out_f32, n, mul, add, act, leak, (cudaStream_t)s), "affine_act");
+}
+extern "C" int b200_axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb,
+                          void* out, int out_f32, long long n, b200_stream s) {
+  WRAP(axpby(a, a_f32, sa, dev_sa, b, b_f32, sb, out, out_f32, n, (cudaStream_t)s), "axpby");
+}
+extern "C" int b200_fill_f32(float* out, long long n, float v, b200_stream s) {
+  WRAP(fill_f32(out, n, v, (cudaStream_t)s), "fill_f32");
+}
+extern "C" int b200_interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, b200_stream s) {
+  WRAP(interp(x, g, alpha, out, B, D, (cudaStream_t)s), "interp");
+}
+extern "C" int b200_rowscale(const void* in, const float* s_row, float mul, float add, void* out, int B, int D,
+                             b200_stream s) {
+  WRAP(rowscale(in, s_row, mul, add, out, B, D, (cudaStream_t)s), "rowscale");
+}
+extern "C" int b200_transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, b200_stream s) {
+  WRAP(transpose_to_bf16(in, in_f32, out, T, A, B, (cudaStream_t)s), "transpose_to_bf16");
+}
+extern "C" int b200_colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha,
+                           b200_stream s) {
+  WRAP(colsum(x, wrow, out, R, C, alpha, (cudaStream_t)s), "colsum");
+}
+extern "C" int b200_reduce_sum(const void* x, int x_f32, long long n, float* out, float alpha, int squared,
+                               b200_stream s) {
+  WRAP(reduce_sum(x, x_f32, n, out, alpha, squared, (cudaStream_t)s), "reduce_sum");
+}
+extern "C" int b200_wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out4, b200_stream s) {
+  WRAP(wgan_loss(sums, B, use_gp, lambda, out4, (cudaStream_t)s), "wgan_loss");
+}
+extern "C" int b200_eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float label, float scale,
+                            float gscale, float* out_sum, void* grad, int grad_f32, b200_stream s) {
+  WRAP(eltloss(a, a_f32, b, n, kind, label, scale, gscale, out_sum, grad, grad_f32, (cudaStream_t)s), "eltloss");
+}
+extern "C" int b200_philox(void* out, int out_f32, long long n, unsigned long long seed,
+                           unsigned long long* dev_draw_counter, unsigned int stream_id, int normal, b200_stream s) {
+  WRAP(philox_fill(out, out_f32, n, seed, dev_draw_counter, stream_id, normal, (cudaStream_t)s), "philox");
+}
+extern "C" int b200_optim_step(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, int kind,
+                               float lr, float b1, float b2, float eps, float grad_scale, float clip, int* dev_step,
+                               b200_stream s) {
+  WRAP(optim_step(p, m, v, g, p_bf16, n, kind, lr, b1, b2, eps, grad_scale, clip, dev_step, (cudaStream_t)s),
+       "optim_step");
+}

@@ -1,0 +1,114 @@
+// Fused epilogue shared by the tensor-core and the small-channel kernels:
+//   v = alpha*acc (+ bias[col]);  v = act(v);  v *= act'(mask_src[off+col]);  store bf16|fp32.
+// Order follows the reference's layer definition conv -> +bias -> activation
+// (ops/layers.py:101-105); the mask multiply is the activation-gradient of the consumer layer
+// (derivatives are expressed through the stored post-activation value).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "tc_gemm.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ float act_fwd(float v, int act, float leak) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_LRELU: return fmaxf(leak * v, v);
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+// derivative of act at the point whose OUTPUT is a (A.5: lrelu slope = leak for x <= 0)
+__device__ __forceinline__ float act_grad_from_out(float a, int act, float leak) {
+  switch (act) {
+    case ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case ACT_LRELU: return a > 0.f ? 1.f : leak;
+    case ACT_TANH: return 1.f - a * a;
+    case ACT_SIGMOID: return a * (1.f - a);
+    default: return 1.f;
+  }
+}
+
+struct EpilogueArgs {
+  const float* bias;
+  int act;
+  float leak;
+  const __nv_bfloat16* mask_src;
+  int mask_kind;
+  float alpha;
+  void* out;
+  int out_f32;
+  int accumulate;
+  int ncols;
+};
+
+// 16 consecutive columns [col, col+16) of one output row starting at element offset `off`.
+__device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const uint32_t* acc, long long off,
+                                                 int col) {
+  float v[16];
+  const int nvalid = min(16, e.ncols - col);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) v[j] += __ldg(e.bias + col + j);
+  }
+  if (e.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act, e.leak);
+  }
+  const long long o = off + col;
+  if (e.mask_src) {
+    const __nv_bfloat16* m = e.mask_src + o;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(m) & 15) == 0)) {
+      uint4 raw[2];
+      raw[0] = __ldg(reinterpret_cast<const uint4*>(m));
+      raw[1] = __ldg(reinterpret_cast<const uint4*>(m) + 1);
+      const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(raw);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= act_grad_from_out(__bfloat162float(mv[j]), e.mask_kind, e.leak);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) v[j] *= act_grad_from_out(__bfloat162float(m[j]), e.mask_kind, e.leak);
+    }
+  }
+  if (e.out_f32) {
+    float* dst = reinterpret_cast<float*>(e.out) + o;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (e.accumulate) {
+          float4 old = *reinterpret_cast<float4*>(dst + j);
+          f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
+        }
+        *reinterpret_cast<float4*>(dst + j) = f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) dst[j] = e.accumulate ? dst[j] + v[j] : v[j];
+    }
+  } else {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *(reinterpret_cast<uint4*>(dst) + 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+}  // namespace b200

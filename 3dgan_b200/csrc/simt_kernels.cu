@@ -1,0 +1,745 @@
+// HBM-bound kernels of the training step: small-channel convolutions (image <-> first feature map),
+// batch-norm, activation gradients, GEMV for the critic's 1-unit dense layer, gradient-penalty
+// helpers, loss reductions, Philox noise and the fused Adam/RMSProp update.  All coalesced /
+// vectorised; grids are sized as multiples of the SM count where the kernel is a grid-stride loop.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "epilogue.cuh"
+#include "simt_kernels.cuh"
+
+namespace b200 {
+
+typedef __nv_bfloat16 bf16;
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+static int stride_grid(long long n, int threads, int per_thread = 1) {
+  long long need = (n + (long long)threads * per_thread - 1) / ((long long)threads * per_thread);
+  long long cap = (long long)num_sms() * 8;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// =============================================================================================
+// Small-channel convolutions.  "small" side has Cs channels with k*k*Cs <= kSmallK taps
+// (image side: 3, 1 or 4 channels); "big" side has Cb channels, contiguous, one thread per channel.
+// Weight layout [k,k,Cs,Cb] == TF's [kh,kw,in,out] for a conv whose input is the small side, and
+// TF's conv2d_transpose layout [kh,kw,out,in] for a deconv whose output is the small side.
+// =============================================================================================
+constexpr int kSmallK = 80;
+
+struct ConvGeom {
+  int N, H, W, Cs;      // small-channel tensor  [N,H,W,Cs]   (the strided conv's INPUT)
+  int Ho, Wo, Cb;       // big-channel tensor    [N,Ho,Wo,Cb] (the strided conv's OUTPUT)
+  int k, stride, pad_t, pad_l;
+};
+
+// big[n,oh,ow,cb] = epi( sum_{r,s,cs} small[n, oh*st+r-pt, ow*st+s-pl, cs] * w[r,s,cs,cb] )
+// block = one thread per cb (rounded up to a warp multiple); each block walks pixels.
+__global__ void smallc_fprop_kernel(const bf16* __restrict__ xs, const bf16* __restrict__ w, ConvGeom g,
+                                    EpilogueArgs e, long long npix, int pix_per_block) {
+  __shared__ float patch[kSmallK];
+  const int kk = g.k * g.k * g.Cs;
+  const int cb = threadIdx.x;
+  float wreg[kSmallK];
+#pragma unroll
+  for (int j = 0; j < kSmallK; ++j)
+    wreg[j] = (j < kk && cb < g.Cb) ? __bfloat162float(w[(long long)j * g.Cb + cb]) : 0.f;
+  const float bias = (e.bias && cb < g.Cb) ? e.bias[cb] : 0.f;
+  long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  for (long long p = p0; p < p1; ++p) {
+    const int ow = (int)(p % g.Wo);
+    const int oh = (int)((p / g.Wo) % g.Ho);
+    const int n = (int)(p / ((long long)g.Wo * g.Ho));
+    __syncthreads();
+    for (int j = threadIdx.x; j < kk; j += blockDim.x) {
+      const int cs = j % g.Cs;
+      const int s = (j / g.Cs) % g.k;
+      const int r = j / (g.Cs * g.k);
+      const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
+      float v = 0.f;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+        v = __bfloat162float(xs[(((long long)n * g.H + ih) * g.W + iw) * g.Cs + cs]);
+      patch[j] = v;
+    }
+    __syncthreads();
+    if (cb < g.Cb) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < kSmallK; ++j)
+        if (j < kk) acc = fmaf(patch[j], wreg[j], acc);
+      float v = acc * e.alpha + bias;
+      v = act_fwd(v, e.act, e.leak);
+      const long long o = p * g.Cb + cb;
+      if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[o]), e.mask_kind, e.leak);
+      if (e.out_f32) reinterpret_cast<float*>(e.out)[o] = v;
+      else reinterpret_cast<bf16*>(e.out)[o] = __float2bfloat16(v);
+    }
+  }
+}
+
+// small[n,h,w,cs] = epi( sum_{r,s valid} sum_cb big[n,(h+pt-r)/st,(w+pl-s)/st,cb] * w[r,s,cs,cb] )
+// one warp per small-side pixel; lanes stride over cb (coalesced), Cs (<=4) accumulators each.
+__global__ void smallc_dgrad_kernel(const bf16* __restrict__ big, const bf16* __restrict__ w, ConvGeom g,
+                                    EpilogueArgs e, long long npix) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long p = warp0; p < npix; p += nwarps) {
+    const int x = (int)(p % g.W);
+    const int y = (int)((p / g.W) % g.H);
+    const int n = (int)(p / ((long long)g.W * g.H));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < g.k; ++r) {
+      const int th = y + g.pad_t - r;
+      if (th < 0 || th % g.stride) continue;
+      const int oh = th / g.stride;
+      if (oh >= g.Ho) continue;
+      for (int s = 0; s < g.k; ++s) {
+        const int tw = x + g.pad_l - s;
+        if (tw < 0 || tw % g.stride) continue;
+        const int ow = tw / g.stride;
+        if (ow >= g.Wo) continue;
+        const bf16* brow = big + (((long long)n * g.Ho + oh) * g.Wo + ow) * g.Cb;
+        const bf16* wrow = w + (long long)((r * g.k + s) * g.Cs) * g.Cb;
+        for (int c = lane; c < g.Cb; c += 32) {
+          const float b = __bfloat162float(brow[c]);
+#pragma unroll
+          for (int cs = 0; cs < 4; ++cs)
+            if (cs < g.Cs) acc[cs] = fmaf(b, __bfloat162float(wrow[(long long)cs * g.Cb + c]), acc[cs]);
+        }
+      }
+    }
+#pragma unroll
+    for (int cs = 0; cs < 4; ++cs) acc[cs] = warp_sum(acc[cs]);
+    if (lane < g.Cs) {
+      float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) * e.alpha;
+      if (e.bias) v += e.bias[lane];
+      v = act_fwd(v, e.act, e.leak);
+      const long long o = p * g.Cs + lane;
+      if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[o]), e.mask_kind, e.leak);
+      if (e.out_f32) reinterpret_cast<float*>(e.out)[o] = v;
+      else reinterpret_cast<bf16*>(e.out)[o] = __float2bfloat16(v);
+    }
+  }
+}
+
+// dw[r,s,cs,cb] += alpha * sum_pixels small[n, oh*st+r-pt, ow*st+s-pl, cs] * big[n,oh,ow,cb]
+// thread per cb keeps all k*k*Cs accumulators in registers; the small-side patch is broadcast from
+// shared memory; one atomicAdd per (tap, cb) per block.
+__global__ void smallc_wgrad_kernel(const bf16* __restrict__ xs, const bf16* __restrict__ big, float* dw,
+                                    ConvGeom g, float alpha, long long npix, int pix_per_block) {
+  __shared__ float patch[kSmallK];
+  const int kk = g.k * g.k * g.Cs;
+  const int cb = threadIdx.x;
+  float acc[kSmallK];
+#pragma unroll
+  for (int j = 0; j < kSmallK; ++j) acc[j] = 0.f;
+  long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  for (long long p = p0; p < p1; ++p) {
+    const int ow = (int)(p % g.Wo);
+    const int oh = (int)((p / g.Wo) % g.Ho);
+    const int n = (int)(p / ((long long)g.Wo * g.Ho));
+    __syncthreads();
+    for (int j = threadIdx.x; j < kk; j += blockDim.x) {
+      const int cs = j % g.Cs;
+      const int s = (j / g.Cs) % g.k;
+      const int r = j / (g.Cs * g.k);
+      const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
+      float v = 0.f;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+        v = __bfloat162float(xs[(((long long)n * g.H + ih) * g.W + iw) * g.Cs + cs]);
+      patch[j] = v;
+    }
+    __syncthreads();
+    if (cb < g.Cb) {
+      const float b = __bfloat162float(big[p * g.Cb + cb]);
+#pragma unroll
+      for (int j = 0; j < kSmallK; ++j)
+        if (j < kk) acc[j] = fmaf(patch[j], b, acc[j]);
+    }
+  }
+  if (cb < g.Cb) {
+#pragma unroll
+    for (int j = 0; j < kSmallK; ++j)
+      if (j < kk) atomicAdd(dw + (long long)j * g.Cb + cb, acc[j] * alpha);
+  }
+}
+
+static int round_up32(int v) { return (v + 31) / 32 * 32; }
+
+int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStream_t st) {
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  if (a.k * a.k * a.Cs > kSmallK || a.Cb > 1024) return -1;
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cb};
+  const long long npix = (long long)a.N * a.Ho * a.Wo;
+  const int threads = round_up32(a.Cb);
+  long long blocks = (long long)num_sms() * (threads <= 256 ? 8 : 4);
+  int ppb = (int)((npix + blocks - 1) / blocks);
+  if (ppb < 1) ppb = 1;
+  blocks = (npix + ppb - 1) / ppb;
+  smallc_fprop_kernel<<<(int)blocks, threads, 0, st>>>((const bf16*)xs, (const bf16*)w, g, e, npix, ppb);
+  return 0;
+}
+
+int smallc_dgrad(const void* big, const void* w, const SmallConvArgs& a, cudaStream_t st) {
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  if (a.Cs > 4) return -1;
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs};
+  const long long npix = (long long)a.N * a.H * a.W;
+  const int threads = 256;
+  long long blocks = (npix * 32 + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  smallc_dgrad_kernel<<<(int)blocks, threads, 0, st>>>((const bf16*)big, (const bf16*)w, g, e, npix);
+  return 0;
+}
+
+int smallc_wgrad(const void* xs, const void* big, float* dw, const SmallConvArgs& a, float alpha,
+                 cudaStream_t st) {
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  if (a.k * a.k * a.Cs > kSmallK || a.Cb > 1024) return -1;
+  const long long npix = (long long)a.N * a.Ho * a.Wo;
+  const int threads = round_up32(a.Cb);
+  long long blocks = (long long)num_sms() * 4;
+  int ppb = (int)((npix + blocks - 1) / blocks);
+  if (ppb < 1) ppb = 1;
+  blocks = (npix + ppb - 1) / ppb;
+  smallc_wgrad_kernel<<<(int)blocks, threads, 0, st>>>((const bf16*)xs, (const bf16*)big, dw, g, alpha, npix, ppb);
+  return 0;
+}
+
+// =============================================================================================
+// Elementwise
+// =============================================================================================
+__global__ void maskmul_kernel(const bf16* __restrict__ gsrc, const bf16* __restrict__ a, bf16* out,
+                               long long n, int kind, float leak) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      uint4 gv = *reinterpret_cast<const uint4*>(gsrc + i);
+      uint4 av = *reinterpret_cast<const uint4*>(a + i);
+      const bf16* gp = reinterpret_cast<const bf16*>(&gv);
+      const bf16* ap = reinterpret_cast<const bf16*>(&av);
+      uint4 ov;
+      bf16* op = reinterpret_cast<bf16*>(&ov);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        op[j] = __float2bfloat16(__bfloat162float(gp[j]) * act_grad_from_out(__bfloat162float(ap[j]), kind, leak));
+      *reinterpret_cast<uint4*>(out + i) = ov;
+    } else {
+      for (long long j = i; j < n; ++j)
+        out[j] = __float2bfloat16(__bfloat162float(gsrc[j]) * act_grad_from_out(__bfloat162float(a[j]), kind, leak));
+    }
+  }
+}
+int maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, cudaStream_t st) {
+  maskmul_kernel<<<stride_grid(n, 256, 8), 256, 0, st>>>((const bf16*)g, (const bf16*)a, (bf16*)out, n, kind, leak);
+  return 0;
+}
+
+// out = act(in * mul + add) elementwise; fp32 or bf16 in, bf16 or fp32 out
+template <typename TI, typename TO>
+__global__ void affine_act_kernel(const TI* __restrict__ in, TO* out, long long n, float mul, float add, int act,
+                                  float leak) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = (float)in[i] * mul + add;
+    out[i] = (TO)act_fwd(v, act, leak);
+  }
+}
+int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
+               float leak, cudaStream_t st) {
+  const int grid = stride_grid(n, 256, 4);
+  if (in_f32 && out_f32) affine_act_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, n, mul, add, act, leak);
+  else if (in_f32) affine_act_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)in, (bf16*)out, n, mul, add, act, leak);
+  else if (out_f32) affine_act_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)in, (float*)out, n, mul, add, act, leak);
+  else affine_act_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)in, (bf16*)out, n, mul, add, act, leak);
+  return 0;
+}
+
+// out[i] (+)= a[i]*sa*(*dev_a or 1) + b[i]*sb   (fp32/bf16 mixes through float conversion)
+template <typename TA, typename TB, typename TO>
+__global__ void axpby_kernel(const TA* __restrict__ a, float sa, const float* dev_sa, const TB* __restrict__ b,
+                             float sb, TO* out, long long n) {
+  const float s = dev_sa ? sa * (*dev_sa) : sa;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = (float)a[i] * s;
+    if (b) v += (float)b[i] * sb;
+    out[i] = (TO)v;
+  }
+}
+int axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
+          int out_f32, long long n, cudaStream_t st) {
+  const int grid = stride_grid(n, 256, 4);
+#define AXPBY_CASE(TA, TB, TO) axpby_kernel<TA, TB, TO><<<grid, 256, 0, st>>>((const TA*)a, sa, dev_sa, (const TB*)b, sb, (TO*)out, n)
+  const int key = (a_f32 ? 4 : 0) | (b_f32 ? 2 : 0) | (out_f32 ? 1 : 0);
+  switch (key) {
+    case 0: AXPBY_CASE(bf16, bf16, bf16); break;
+    case 1: AXPBY_CASE(bf16, bf16, float); break;
+    case 2: AXPBY_CASE(bf16, float, bf16); break;
+    case 3: AXPBY_CASE(bf16, float, float); break;
+    case 4: AXPBY_CASE(float, bf16, bf16); break;
+    case 5: AXPBY_CASE(float, bf16, float); break;
+    case 6: AXPBY_CASE(float, float, bf16); break;
+    default: AXPBY_CASE(float, float, float); break;
+  }
+#undef AXPBY_CASE
+  return 0;
+}
+
+__global__ void fill_kernel(float* out, long long n, float v) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
+}
+int fill_f32(float* out, long long n, float v, cudaStream_t st) {
+  fill_kernel<<<stride_grid(n, 256, 4), 256, 0, st>>>(out, n, v);
+  return 0;
+}
+
+// x_hat[b,:] = x[b,:] + alpha[b]*(g[b,:]-x[b,:])      (models/gan.py:224-226)
+__global__ void interp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ g, const float* __restrict__ alpha,
+                              bf16* out, int B, int D) {
+  const long long n = (long long)B * D;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float a = alpha[i / D];
+    const float xv = __bfloat162float(x[i]);
+    out[i] = __float2bfloat16(xv + a * (__bfloat162float(g[i]) - xv));
+  }
+}
+int interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, cudaStream_t st) {
+  interp_kernel<<<stride_grid((long long)B * D, 256, 4), 256, 0, st>>>((const bf16*)x, (const bf16*)g, alpha, (bf16*)out, B, D);
+  return 0;
+}
+// rowscale: out[b,:] = in[b,:] * s[b] * mul   (backward of interp w.r.t. g and x)
+__global__ void rowscale_kernel(const bf16* __restrict__ in, const float* __restrict__ s, float mul, float add,
+                                bf16* out, int B, int D) {
+  const long long n = (long long)B * D;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16(__bfloat162float(in[i]) * (s[i / D] * mul + add));
+}
+int rowscale(const void* in, const float* s, float mul, float add, void* out, int B, int D, cudaStream_t st) {
+  rowscale_kernel<<<stride_grid((long long)B * D, 256, 4), 256, 0, st>>>((const bf16*)in, s, mul, add, (bf16*)out, B, D);
+  return 0;
+}
+
+// [T][A][B] -> [T][B][A], fp32 or bf16 in, bf16 out (weight re-layout for the K-major GEMM operand)
+template <typename TI>
+__global__ void transpose_kernel(const TI* __restrict__ in, bf16* out, int A, int B) {
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * A * B;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int a = a0 + i, b = b0 + threadIdx.x;
+    if (a < A && b < B) tile[i][threadIdx.x] = (float)in[base + (long long)a * B + b];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int b = b0 + i, a = a0 + threadIdx.x;
+    if (a < A && b < B) out[base + (long long)b * A + a] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, cudaStream_t st) {
+  dim3 grid((B + 31) / 32, (A + 31) / 32, T), block(32, 8);
+  if (in_f32) transpose_kernel<float><<<grid, block, 0, st>>>((const float*)in, (bf16*)out, A, B);
+  else transpose_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)in, (bf16*)out, A, B);
+  return 0;
+}
+
+// =============================================================================================
+// Column reductions over a row-major [R, C] bf16 matrix (C contiguous)
+// =============================================================================================
+// out[c] += alpha * sum_r x[r,c] * (wrow ? wrow[r] : 1);   out2[c] += alpha * sum_r x[r,c]^2 (optional)
+__global__ void colsum_kernel(const bf16* __restrict__ x, const float* __restrict__ wrow, float* out, float* out2,
+                              long long R, int C, float alpha, int rows_per_block) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (c >= C) return;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const bool pair = (c + 1 < C) && ((C & 1) == 0);
+  for (long long r = r0; r < r1; ++r) {
+    const float wr = wrow ? wrow[r] : 1.f;
+    float v0, v1 = 0.f;
+    if (pair) {
+      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(x + r * C + c);
+      v0 = __low2float(h); v1 = __high2float(h);
+    } else {
+      v0 = __bfloat162float(x[r * C + c]);
+      if (c + 1 < C) v1 = __bfloat162float(x[r * C + c + 1]);
+    }
+    s0 = fmaf(v0, wr, s0); s1 = fmaf(v1, wr, s1);
+    q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
+  }
+  atomicAdd(out + c, s0 * alpha);
+  if (c + 1 < C) atomicAdd(out + c + 1, s1 * alpha);
+  if (out2) {
+    atomicAdd(out2 + c, q0 * alpha);
+    if (c + 1 < C) atomicAdd(out2 + c + 1, q1 * alpha);
+  }
+}
+static void colsum_launch(const bf16* x, const float* wrow, float* out, float* out2, long long R, int C, float alpha,
+                          cudaStream_t st) {
+  const int threads = 128;
+  const int gx = ((C + 1) / 2 + threads - 1) / threads;
+  long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
+  if (want > R) want = R;
+  if (want < 1) want = 1;
+  const int rpb = (int)((R + want - 1) / want);
+  const int gy = (int)((R + rpb - 1) / rpb);
+  colsum_kernel<<<dim3(gx, gy), threads, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
+}
+int colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, cudaStream_t st) {
+  colsum_launch((const bf16*)x, wrow, out, nullptr, R, C, alpha, st);
+  return 0;
+}
+
+// ---- batch norm (tf.contrib.layers.batch_norm defaults: no gamma, eps 1e-3, batch statistics)
+// stats[0:C] = sum, stats[C:2C] = sum of squares (zeroed by the caller)
+int bn_sums(const void* z, float* stats, long long R, int C, cudaStream_t st) {
+  colsum_launch((const bf16*)z, nullptr, stats, stats + C, R, C, 1.f, st);
+  return 0;
+}
+// a = act((z-mean)*rstd + beta)
+__global__ void bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ beta,
+                                bf16* out, long long R, int C, float eps, int act, float leak) {
+  const long long n = R * C;
+  const float invR = 1.f / (float)R;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = (int)(i % C);
+    const float mean = stats[c] * invR;
+    const float var = fmaxf(stats[C + c] * invR - mean * mean, 0.f);
+    const float v = (__bfloat162float(z[i]) - mean) * rsqrtf(var + eps) + beta[c];
+    out[i] = __float2bfloat16(act_fwd(v, act, leak));
+  }
+}
+int bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps, int act,
+             float leak, cudaStream_t st) {
+  bn_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
+  return 0;
+}
+// backward sums: bsum[0:C] += sum_r g ; bsum[C:2C] += sum_r g * xhat      (g already holds act')
+__global__ void bn_bwd_sums_kernel(const bf16* __restrict__ g, const bf16* __restrict__ z, const float* __restrict__ stats,
+                                   float* bsum, long long R, int C, float eps, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invR = 1.f / (float)R;
+  const float mean = stats[c] * invR;
+  const float rstd = rsqrtf(fmaxf(stats[C + c] * invR - mean * mean, 0.f) + eps);
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float gv = __bfloat162float(g[r * C + c]);
+    const float xh = (__bfloat162float(z[r * C + c]) - mean) * rstd;
+    s1 += gv;
+    s2 = fmaf(gv, xh, s2);
+  }
+  atomicAdd(bsum + c, s1);
+  atomicAdd(bsum + C + c, s2);
+}
+// dz = rstd * (g - s1/R - xhat*s2/R)
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ z, const float* __restrict__ stats,
+                                    const float* __restrict__ bsum, bf16* dz, long long R, int C, float eps) {
+  const long long n = R * C;
+  const float invR = 1.f / (float)R;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = (int)(i % C);
+    const float mean = stats[c] * invR;
+    const float rstd = rsqrtf(fmaxf(stats[C + c] * invR - mean * mean, 0.f) + eps);
+    const float xh = (__bfloat162float(z[i]) - mean) * rstd;
+    const float v = rstd * (__bfloat162float(g[i]) - bsum[c] * invR - xh * bsum[C + c] * invR);
+    dz[i] = __float2bfloat16(v);
+  }
+}
+int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* dz, long long R, int C, float eps,
+           cudaStream_t st) {
+  const int threads = 128;
+  const int gx = (C + threads - 1) / threads;
+  long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
+  if (want > R) want = R;
+  if (want < 1) want = 1;
+  const int rpb = (int)((R + want - 1) / want);
+  const int gy = (int)((R + rpb - 1) / rpb);
+  bn_bwd_sums_kernel<<<dim3(gx, gy), threads, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, R, C, eps, rpb);
+  bn_bwd_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, (bf16*)dz, R, C, eps);
+  return 0;
+}
+
+// =============================================================================================
+// GEMV family for 1-unit dense layers (critic fc2, models/gan.py:285)
+// =============================================================================================
+// out[m] = act( sum_k a[m,k]*w[k] + bias[0] )    one warp per row
+__global__ void gemv_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ w, const float* bias, float* out,
+                                 int M, int K, int act, float leak) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= M) return;
+  const bf16* ar = a + (long long)row * K;
+  float s = 0.f;
+  if ((K & 7) == 0) {
+    for (int k = lane * 8; k < K; k += 256) {
+      uint4 av = *reinterpret_cast<const uint4*>(ar + k);
+      uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + k));
+      const bf16* ap = reinterpret_cast<const bf16*>(&av);
+      const bf16* wp = reinterpret_cast<const bf16*>(&wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(__bfloat162float(ap[j]), __bfloat162float(wp[j]), s);
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(ar[k]), __bfloat162float(w[k]), s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = act_fwd(s + (bias ? bias[0] : 0.f), act, leak);
+}
+int gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act, float leak,
+              cudaStream_t st) {
+  const int threads = 256;
+  gemv_rows_kernel<<<(M * 32 + threads - 1) / threads, threads, 0, st>>>((const bf16*)a, (const bf16*)w, bias, out, M, K, act, leak);
+  return 0;
+}
+// out[m,k] = g[m] * w[k] * act'(mask[m,k])
+__global__ void outer_mask_kernel(const float* __restrict__ g, const bf16* __restrict__ w, const bf16* __restrict__ mask,
+                                  bf16* out, int M, int K, int kind, float leak) {
+  const long long n = (long long)M * K;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = g[i / K] * __bfloat162float(w[i % K]);
+    if (mask) v *= act_grad_from_out(__bfloat162float(mask[i]), kind, leak);
+    out[i] = __float2bfloat16(v);
+  }
+}
+int outer_mask(const float* g, const void* w, const void* mask, void* out, int M, int K, int kind, float leak,
+               cudaStream_t st) {
+  outer_mask_kernel<<<stride_grid((long long)M * K, 256, 4), 256, 0, st>>>(g, (const bf16*)w, (const bf16*)mask, (bf16*)out, M, K, kind, leak);
+  return 0;
+}
+
+// =============================================================================================
+// Reductions to a device scalar
+// =============================================================================================
+// out[0] += alpha * sum x^2  (sq=1) or alpha * sum x (sq=0)
+template <typename TI>
+__global__ void reduce_kernel(const TI* __restrict__ x, long long n, float* out, float alpha, int sq) {
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = (float)x[i];
+    s += sq ? v * v : v;
+  }
+  __shared__ float ws[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s * alpha);
+  }
+}
+int reduce_sum(const void* x, int x_f32, long long n, float* out, float alpha, int sq, cudaStream_t st) {
+  int grid = stride_grid(n, 256, 8);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  if (x_f32) reduce_kernel<float><<<grid, 256, 0, st>>>((const float*)x, n, out, alpha, sq);
+  else reduce_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, n, out, alpha, sq);
+  return 0;
+}
+
+// WGAN / IWGAN scalar losses (models/gan.py:194-205,229-230).  sums = {sum d_real, sum d_fake, sumsq grad}
+// out = {g_loss, d_loss, slopes, dloss/d(sumsq)}
+__global__ void wgan_loss_kernel(const float* sums, float inv_b, int use_gp, float lambda, float* out) {
+  const float mr = sums[0] * inv_b, mf = sums[1] * inv_b;
+  float d = mf - mr, slopes = 0.f, dss = 0.f;
+  if (use_gp) {
+    slopes = sqrtf(sums[2]);
+    d += lambda * (slopes - 1.f) * (slopes - 1.f);
+    dss = slopes > 0.f ? lambda * (slopes - 1.f) / slopes : 0.f;   // d/d(sumsq) of lambda*(sqrt(ss)-1)^2
+  }
+  out[0] = -mf; out[1] = d; out[2] = slopes; out[3] = dss;
+}
+int wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out, cudaStream_t st) {
+  wgan_loss_kernel<<<1, 1, 0, st>>>(sums, 1.f / (float)B, use_gp, lambda, out);
+  return 0;
+}
+
+// Elementwise losses with fused gradient: kind 0: GAN d-loss/g-loss pieces etc. are assembled on the host
+// side of the tape from these primitives:
+//   kind 0  L1:            l = |a-b|                          dl/da = sign(a-b)
+//   kind 1  -log(a+eps)                                       dl/da = -1/(a+eps)
+//   kind 2  -log(1-a+eps)                                     dl/da =  1/(1-a+eps)
+//   kind 3  Bernoulli recon: -(b*log(eps+a)+(1-b)*log(eps+1-a))   dl/da = -(b/(eps+a) - (1-b)/(eps+1-a))
+//   kind 4  sigmoid-CE(logits a, label scalar `lab`)          dl/da = sigmoid(a)-lab
+//   kind 5  squared error (a-b)^2                             dl/da = 2(a-b)
+// out_sum[0] += scale * sum l ;  grad[i] = gscale * dl/da  (bf16 or fp32), optional
+template <typename TA, typename TG>
+__global__ void eltloss_kernel(const TA* __restrict__ a, const bf16* __restrict__ b, long long n, int kind, float lab,
+                               float scale, float gscale, float* out_sum, TG* grad) {
+  float s = 0.f;
+  const float eps = 1e-8f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float av = (float)a[i];
+    const float bv = b ? __bfloat162float(b[i]) : 0.f;
+    float l, d;
+    switch (kind) {
+      case 0: l = fabsf(av - bv); d = av > bv ? 1.f : (av < bv ? -1.f : 0.f); break;
+      case 1: l = -logf(av + eps); d = -1.f / (av + eps); break;
+      case 2: l = -logf(1.f - av + eps); d = 1.f / (1.f - av + eps); break;
+      case 3: l = -(bv * logf(eps + av) + (1.f - bv) * logf(eps + 1.f - av));
+              d = -(bv / (eps + av) - (1.f - bv) / (eps + 1.f - av)); break;
+      case 4: l = fmaxf(av, 0.f) - av * lab + log1pf(__expf(-fabsf(av))); d = 1.f / (1.f + __expf(-av)) - lab; break;
+      default: l = (av - bv) * (av - bv); d = 2.f * (av - bv); break;
+    }
+    s += l;
+    if (grad) grad[i] = (TG)(d * gscale);
+  }
+  __shared__ float ws[32];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0 && out_sum) atomicAdd(out_sum, s * scale);
+  }
+}
+int eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float lab, float scale, float gscale,
+            float* out_sum, void* grad, int grad_f32, cudaStream_t st) {
+  int grid = stride_grid(n, 256, 8);
+  if (grid > num_sms() * 2) grid = num_sms() * 2;
+  if (a_f32 && grad_f32) eltloss_kernel<float, float><<<grid, 256, 0, st>>>((const float*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (float*)grad);
+  else if (a_f32) eltloss_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (bf16*)grad);
+  else if (grad_f32) eltloss_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (float*)grad);
+  else eltloss_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (bf16*)grad);
+  return 0;
+}
+
+// =============================================================================================
+// Philox4x32-10 noise (stands in for tf.random_normal / tf.random_uniform, models/gan.py:224,246)
+// counter = (element/4, draw counter read from device memory), key = (seed lo, seed hi)
+// =============================================================================================
+__device__ __forceinline__ void philox_round(uint32_t* c, uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t* c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// normal=1: N(0,1) via Box-Muller; normal=0: U[0,1).  `draw` is advanced by the kernel (one block does it last
+// is unnecessary: a separate 1-thread bump kernel follows) so CUDA-graph replays see fresh noise.
+template <typename TO>
+__global__ void philox_kernel(TO* out, long long n, unsigned long long seed, const unsigned long long* draw,
+                              unsigned int stream_id, int normal) {
+  const unsigned long long d = draw ? *draw : 0ull;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), (uint32_t)d, (uint32_t)(d >> 32) ^ stream_id};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float v[4];
+    if (normal) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)c[2 * h] + 1.f) * 2.3283064365386963e-10f;   // (0,1]
+        const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;
+        const float rad = sqrtf(-2.f * __logf(u1));
+        float sn, cs;
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
+        v[2 * h] = rad * cs; v[2 * h + 1] = rad * sn;
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) v[h] = (float)(c[h] >> 8) * 5.9604644775390625e-08f;   // [0,1)
+    }
+    for (int h = 0; h < 4 && q * 4 + h < n; ++h) out[q * 4 + h] = (TO)v[h];
+  }
+}
+__global__ void bump_kernel(unsigned long long* draw) { *draw += 1ull; }
+int philox_fill(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* draw,
+                unsigned int stream_id, int normal, cudaStream_t st) {
+  const int grid = stride_grid((n + 3) / 4, 256, 1);
+  if (out_f32) philox_kernel<float><<<grid, 256, 0, st>>>((float*)out, n, seed, draw, stream_id, normal);
+  else philox_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)out, n, seed, draw, stream_id, normal);
+  if (draw) bump_kernel<<<1, 1, 0, st>>>(draw);
+  return 0;
+}
+
+// =============================================================================================
+// Fused optimizer update over a flat fp32 parameter bucket (util.py:150-183 -> tf.train.*Optimizer)
+// 28 B/param: read g,p,m,v; write p,m,v; + 2 B for the bf16 compute copy.
+// =============================================================================================
+// kind 0 Adam (TF epsilon-hat form, A.4), 1 RMSProp (ms init 1.0, A.4), 2 SGD, 3 Momentum
+__global__ void optim_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                             const float* __restrict__ g, bf16* __restrict__ p16, long long n, int kind, float lr,
+                             float b1, float b2, float eps, float gscale, float clip, int* step) {
+  float lr_t = lr;
+  if (kind == 0) {
+    const float t = (float)(*step + 1);
+    lr_t = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+  }
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * gscale;
+    float pi = p[i];
+    if (clip > 0.f) pi = fminf(fmaxf(pi, -clip), clip);     // WGAN: clip BEFORE the update (models/gan.py:142-148)
+    if (kind == 0) {
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi; v[i] = vi;
+      pi -= lr_t * mi / (sqrtf(vi) + eps);
+    } else if (kind == 1) {                                  // b1 = decay, b2 = momentum
+      const float ms = b1 * v[i] + (1.f - b1) * gi * gi;
+      const float mom = b2 * m[i] + lr * gi * rsqrtf(ms + eps);
+      v[i] = ms; m[i] = mom;
+      pi -= mom;
+    } else if (kind == 2) {
+      pi -= lr * gi;
+    } else {                                                 // b1 = momentum
+      const float acc = b1 * m[i] + gi;
+      m[i] = acc;
+      pi -= lr * acc;
+    }
+    p[i] = pi;
+    if (p16) p16[i] = __float2bfloat16(pi);
+  }
+}
+__global__ void step_bump_kernel(int* step) { *step += 1; }
+int optim_step(float* p, float* m, float* v, const float* g, void* p16, long long n, int kind, float lr, float b1,
+               float b2, float eps, float gscale, float clip, int* step, cudaStream_t st) {
+  optim_kernel<<<stride_grid(n, 256, 4), 256, 0, st>>>(p, m, v, g, (bf16*)p16, n, kind, lr, b1, b2, eps, gscale, clip, step);
+  step_bump_kernel<<<1, 1, 0, st>>>(step);
+  return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,52 @@
+// Host-callable launchers of the HBM-bound kernels (simt_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+struct SmallConvArgs {
+  int N, H, W, Cs;          // small-channel tensor [N,H,W,Cs]
+  int Ho, Wo, Cb;           // big-channel tensor   [N,Ho,Wo,Cb]
+  int k, stride, pad_t, pad_l;
+  const float* bias;
+  int act;
+  float leak;
+  const void* mask_src;
+  int mask_kind;
+  void* out;
+  int out_f32;
+};
+
+int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStream_t st);
+int smallc_dgrad(const void* big, const void* w, const SmallConvArgs& a, cudaStream_t st);
+int smallc_wgrad(const void* xs, const void* big, float* dw, const SmallConvArgs& a, float alpha, cudaStream_t st);
+
+int maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, cudaStream_t st);
+int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
+               float leak, cudaStream_t st);
+int axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
+          int out_f32, long long n, cudaStream_t st);
+int fill_f32(float* out, long long n, float v, cudaStream_t st);
+int interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, cudaStream_t st);
+int rowscale(const void* in, const float* s, float mul, float add, void* out, int B, int D, cudaStream_t st);
+int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, cudaStream_t st);
+int colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, cudaStream_t st);
+int bn_sums(const void* z, float* stats, long long R, int C, cudaStream_t st);
+int bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps, int act,
+             float leak, cudaStream_t st);
+int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* dz, long long R, int C, float eps,
+           cudaStream_t st);
+int gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act, float leak,
+              cudaStream_t st);
+int outer_mask(const float* g, const void* w, const void* mask, void* out, int M, int K, int kind, float leak,
+               cudaStream_t st);
+int reduce_sum(const void* x, int x_f32, long long n, float* out, float alpha, int sq, cudaStream_t st);
+int wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out, cudaStream_t st);
+int eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float lab, float scale, float gscale,
+            float* out_sum, void* grad, int grad_f32, cudaStream_t st);
+int philox_fill(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* draw,
+                unsigned int stream_id, int normal, cudaStream_t st);
+int optim_step(float* p, float* m, float* v, const float* g, void* p16, long long n, int kind, float lr, float b1,
+               float b2, float eps, float gscale, float clip, int* step, cudaStream_t st);
+
+}  // namespace b200

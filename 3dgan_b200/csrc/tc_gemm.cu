@@ -1,0 +1,314 @@
+// Hand-written sm_100a implicit-GEMM kernels: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) fed by TMA
+// through a multi-stage mbarrier pipeline, warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue
+// warps).  Replaces the cuDNN/cuBLAS calls TensorFlow made for the reference's
+// tf.nn.conv2d / conv2d_transpose / matmul call sites (ops/layers.py:57,101,142;
+// hem/ops/layers.py:61,118,189) and their autodiff gradients.
+#include "tc_gemm.cuh"
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+namespace b200 {
+
+namespace {
+
+constexpr int kThreads = 192;         // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KiB: 128 rows x 128 B
+
+struct PipeSmem {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  return reinterpret_cast<uint8_t*>((a + 1023) & ~uintptr_t(1023));
+}
+
+}  // namespace
+
+// =============================================================================================
+// Tap GEMM (conv fprop / dgrad phases / transposed-conv forward / dense)
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int b_bytes = p.bn_tile * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
+
+  // tile -> first pixel of the tile, phase, N offset
+  const int phase = blockIdx.z;
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int tn = t;
+  const int pw0 = tw * p.bw, ph0 = th * p.bh, pn0 = tn * p.bn;
+  const int n0 = blockIdx.y * p.bn_tile;
+  const int ext_w = p.phase_ext_w[phase], ext_h = p.phase_ext_h[phase];
+  // a tile wholly outside this phase's extent has nothing to do (phases can differ by one row)
+  if (pw0 >= ext_w || ph0 >= ext_h) return;
+
+  const int tap_begin = p.phase_tap_begin[phase];
+  const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
+  const int iters = ntaps * p.kchunks;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ps->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ TMA producer
+      int base[5];
+      base[0] = 0;
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        base[d + 1] = pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
+      int it = 0;
+      for (int tp = 0; tp < ntaps; ++tp) {
+        const int tap = tap_begin + tp;
+        int c[5];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) c[d + 1] = base[d + 1] + p.tap_a_off[tap][d];
+        const int brow = p.tap_b_row[tap] + n0;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          const uint32_t par = (it / p.stages) & 1;
+          mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
+          const uint32_t full = smem_u32(&ps->full[s]);
+          mbar_arrive_expect_tx(full, stage_bytes);
+          const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+          c[0] = kc * kBlockK;
+          tma_load_nd(p.a_rank, a_dst, &p.tmA, full, c);
+          tma_load_2d(a_dst + kABytes, &p.tmB, full, kc * kBlockK, brow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.bn_tile, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t par = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&ps->full[s]), par);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4)
+          umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+        }
+        umma_commit(smem_u32(&ps->empty[s]));
+      }
+      umma_commit(smem_u32(&ps->tmem_full));
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue (4 warps)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // tile row == TMEM lane
+    const int iw = r % p.bw;
+    const int ih = (r / p.bw) % p.bh;
+    const int in = r / (p.bw * p.bh);
+    const int pw = pw0 + iw, ph = ph0 + ih, pn = pn0 + in;
+    const bool row_ok = pw < ext_w && ph < ext_h && pn < p.ext_n;
+    const long long off = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh +
+                          (long long)pw * p.o_sw;
+    EpilogueArgs ea;
+    ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
+    ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
+    ea.accumulate = p.accumulate; ea.ncols = p.ncols;
+
+    mbar_wait(smem_u32(&ps->tmem_full), 0);
+    tc_fence_after();
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+      if (n0 + c0 >= p.ncols) break;        // warp-uniform
+      uint32_t v[16];
+      tmem_ld16(trow + c0, v);
+      tmem_ld_wait();
+      if (row_ok) epilogue_store16(ea, v, off, n0 + c0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem);
+}
+
+void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+  const int stage_bytes = kABytes + p.bn_tile * kBlockK * 2;
+  const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = 227 * 1024;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, (p.ncols + p.bn_tile - 1) / p.bn_tile, p.nphases);
+  tapgemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+}
+
+// =============================================================================================
+// Weight gradient (MN-major operands, split-K, fp32 atomics)
+// =============================================================================================
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  constexpr int kBox = 64 * 64 * 2;                     // 8 KiB: 64 pixels x 64 channels
+  const int a_bytes = 2 * kBox;                         // 128 "M" channels
+  const int stage_bytes = a_bytes + p.nb_boxes * kBox;
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
+
+  int t = blockIdx.x;
+  const int nt = t % p.n_tiles; t /= p.n_tiles;
+  const int mt = t % p.m_tiles; t /= p.m_tiles;
+  const int tap = t;
+  const int m0 = mt * kTileM, n0 = nt * p.bn_tile;
+  const int chunk_begin = blockIdx.y * p.chunks_per_split;
+  const int chunk_end = min(chunk_begin + p.chunks_per_split, p.total_chunks);
+  const int iters = chunk_end - chunk_begin;
+  if (iters <= 0) return;
+
+  // number of 64-channel boxes that actually hold data (the rest of the tile is never loaded
+  // nor stored; stale smem feeds accumulator rows/columns that the epilogue masks off)
+  const int a_boxes = min(2, (p.Ca - m0 + 63) / 64);
+  const int b_boxes = min(p.nb_boxes, (p.Cb - n0 + 63) / 64);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ps->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        int ch = chunk_begin + it;
+        const int jw = ch % p.chunks_w; ch /= p.chunks_w;
+        const int jh = ch % p.chunks_h; ch /= p.chunks_h;
+        const int jn = ch;
+        const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
+        const int s = it % p.stages;
+        const uint32_t par = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
+        const uint32_t full = smem_u32(&ps->full[s]);
+        mbar_arrive_expect_tx(full, (a_boxes + b_boxes) * kBox);
+        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+        int c[5];
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+          c[d + 1] = p.tap_a_off[tap][d] + pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
+        for (int b = 0; b < a_boxes; ++b) {
+          c[0] = m0 + b * 64;
+          tma_load_nd(p.a_rank, a_dst + b * kBox, &p.tmA, full, c);
+        }
+        int cb[5] = {0, pw0, ph0, pn0, 0};
+        for (int b = 0; b < b_boxes; ++b) {
+          cb[0] = n0 + b * 64;
+          tma_load_nd(p.b_rank, a_dst + a_bytes + b * kBox, &p.tmB, full, cb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.bn_tile, 1, 1);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t par = (it / p.stages) & 1;
+        mbar_wait(smem_u32(&ps->full[s]), par);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        // MN-major SW128: 64-channel blocks kBox apart (LBO), 8-pixel groups 1024 B apart (SBO)
+        const uint64_t adesc = make_smem_desc_sw128(a_addr, kBox, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(a_addr + a_bytes, kBox, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 pixels per MMA = two 8-pixel groups = 2048 bytes (addr field is >>4)
+          umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
+        }
+        umma_commit(smem_u32(&ps->empty[s]));
+      }
+      umma_commit(smem_u32(&ps->tmem_full));
+    }
+  } else {
+    const int q = warp & 3;
+    const int ca = m0 + q * 32 + lane;
+    const bool row_ok = ca < p.Ca;
+    float* orow = p.out + (long long)tap * p.out_tap_stride + (long long)ca * p.ldo;
+    mbar_wait(smem_u32(&ps->tmem_full), 0);
+    tc_fence_after();
+    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+    const bool vec_ok = (p.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        ((p.out_tap_stride & 3) == 0);
+    for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+      const int col = n0 + c0;
+      if (col >= p.Cb) break;
+      uint32_t v[16];
+      tmem_ld16(trow + c0, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      if (vec_ok && col + 16 <= p.Cb) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 f = make_float4(__uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
+                                 __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j), "f"(f.x),
+                       "f"(f.y), "f"(f.z), "f"(f.w)
+                       : "memory");
+        }
+      } else {
+        for (int j = 0; j < 16 && col + j < p.Cb; ++j) atomicAdd(orow + col + j, __uint_as_float(v[j]) * p.alpha);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem);
+}
+
+void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream) {
+  const int stage_bytes = (2 + p.nb_boxes) * 64 * 64 * 2;
+  const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  dim3 grid(p.m_tiles * p.n_tiles * p.ntaps, splits, 1);
+  wgrad_kernel<<<grid, kThreads, smem, stream>>>(p);
+}
+
+}  // namespace b200

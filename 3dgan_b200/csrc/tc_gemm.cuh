@@ -1,0 +1,77 @@
+// Parameter blocks shared by the tcgen05 implicit-GEMM kernels (tc_gemm.cu) and their host-side
+// geometry builders (capi.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kMaxTaps = 25;      // 5x5 filters
+constexpr int kMaxPhases = 4;     // stride-2 dgrad output parities
+constexpr int kTileM = 128;       // UMMA M (TMEM lanes)
+constexpr int kBlockK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kTmemCols = 256;
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+
+// "Tap GEMM": out[pixel, n] = epilogue( sum_taps sum_k A_tap[pixel, k] * B_tap[n, k] ).
+// A tiles are TMA boxes of 128 pixels x 64 channels out of an NHWC activation tensor (rank-2..5
+// tensor map, per-tap start offsets, zero fill = conv padding); B tiles are rows of a K-major
+// weight matrix.  Covers conv fprop, strided dgrad / transposed-conv forward (one phase per
+// blockIdx.z) and dense layers (one tap).
+struct TapGemmParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int a_rank;
+  int kchunks;                        // ceil(K / 64) per tap
+  int nphases;
+  int phase_tap_begin[kMaxPhases + 1];
+  int tap_a_off[kMaxTaps][4];         // start coordinate of A dims 1..4 for this tap
+  int tap_b_row[kMaxTaps];            // first B row of this tap
+  int a_mul[3][4];                    // [w|h|n] pixel index -> A dims 1..4 coordinate step
+  int bw, bh, bn;                     // pixels per tile along w, h, n (product 128)
+  int tiles_w, tiles_h, tiles_n;
+  int phase_ext_w[kMaxPhases], phase_ext_h[kMaxPhases];
+  int ext_n;
+  long long phase_o_off[kMaxPhases];  // output element offset of the phase
+  long long o_sw, o_sh, o_sn;         // output element strides per pixel index
+  int ncols, bn_tile;                 // valid output columns, N tile (multiple of 16, <= 256)
+  int stages;
+  void* out;
+  int out_f32;                        // 0: bf16, 1: fp32
+  int accumulate;                     // fp32 only: out += result
+  const float* bias;                  // [ncols] or null
+  int act;
+  float leak;
+  const __nv_bfloat16* mask_src;      // same geometry as out; result *= act'(mask_src)
+  int mask_kind;
+  float alpha;
+};
+
+// Weight gradient: out[tap][ca][cb] += alpha * sum_pixels A_tap[pixel, ca] * B[pixel, cb], both
+// operands MN-major (channels contiguous), reduction over pixels, split-K over blockIdx.y with
+// fp32 atomics.
+struct WgradParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int a_rank, b_rank;
+  int ntaps;
+  int tap_a_off[kMaxTaps][4];
+  int a_mul[3][4];
+  int bw, bh, bn;                     // pixels per K-chunk along w, h, n (product 64)
+  int chunks_w, chunks_h, chunks_n;
+  int total_chunks, chunks_per_split;
+  int Ca, Cb;
+  int m_tiles, n_tiles, bn_tile, nb_boxes;
+  int stages;
+  float* out;
+  long long out_tap_stride;
+  int ldo;
+  float alpha;
+};
+
+void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
+void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,564 @@
+"""Define-by-run tape over device buffers: the host side of the hot path.
+
+The reference builds a symbolic TF graph from `ops/layers.py` calls and lets TF autodiff derive
+the backward (models/gan.py:65-68, 224-231).  Here the same layer calls launch the CUDA kernels
+immediately (through the C ABI in `_capi`) and record a tape node whose backward is written in
+terms of the same ops, so second-order gradients (the IWGAN gradient penalty) come from running
+the backward with recording on.  torch is used for buffers and streams only.
+
+Mask convention: a tensor `t` may carry `t.mask = (src, kind, leak)` meaning
+t = act(raw) with src = t, or t = raw * act'(src).  Whoever delivers a gradient to `t` multiplies
+it by act'(src) (fused into the producing kernel's epilogue wherever possible), so every node's
+backward receives the gradient w.r.t. its raw (pre-activation) output.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _capi as K
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class _State:
+    recording = False          # tape on/off
+    accumulate = True          # backward sweeps add parameter gradients into the buckets
+    dry = False                # build pass: shapes and variables only, no launches (meta tensors)
+    active = frozenset()       # ids of Param objects whose gradients are being computed
+    seq = 0
+    stream = None              # ctypes stream handle for the current step
+    device = None
+    launches = 0               # kernels launched through the C ABI (bench.py reports it)
+
+
+S = _State()
+
+
+def _p(t):
+    return None if (t is None or S.dry) else C.c_void_p(t.data_ptr())
+
+
+def begin(device=None):
+    """Bind the engine to torch's current device/stream for the calls that follow."""
+    S.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    S.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch(name, *args, n=1):
+    if S.dry:
+        return 0
+    S.launches += n
+    return K.call(name, *args, S.stream)
+
+
+def empty(shape, dtype=BF16):
+    return torch.empty(shape, dtype=dtype, device="meta" if S.dry else S.device)
+
+
+class recording:
+    def __init__(self, on=True, active=None):
+        self.on, self.active = on, active
+
+    def __enter__(self):
+        self.prev = (S.recording, S.active)
+        S.recording = self.on
+        if self.active is not None:
+            S.active = frozenset(id(p) for p in self.active)
+        return self
+
+    def __exit__(self, *a):
+        S.recording, S.active = self.prev
+
+
+# ------------------------------------------------------------------------------------------ tensors
+class Tensor:
+    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "__weakref__")
+
+    def __init__(self, buf, shape=None, requires_grad=False, mask=None):
+        self.buf = buf
+        self.shape = tuple(buf.shape if shape is None else shape)
+        self.requires_grad = requires_grad
+        self.mask = mask
+        self.node = None
+        self.grad_f32 = False      # leaf whose gradient is wanted in fp32 (the GP interpolates)
+
+    @property
+    def f32(self):
+        return self.buf.dtype == F32
+
+    @property
+    def numel(self):
+        return self.buf.numel()
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return reshape(self, shape)
+
+    def torch(self):
+        return self.buf.view(self.shape)
+
+
+class Node:
+    __slots__ = ("seq", "inputs", "outputs", "bw")
+
+
+def _record(inputs, outputs, bw, uses_active_param=False):
+    if not S.recording:
+        return
+    if not (uses_active_param or any(t.requires_grad for t in inputs)):
+        return
+    n = Node()
+    S.seq += 1
+    n.seq, n.inputs, n.outputs, n.bw = S.seq, list(inputs), list(outputs), bw
+    for o in outputs:
+        o.requires_grad = True
+        o.node = n
+
+
+class Param:
+    """One trainable variable: fp32 master / gradient views into the group's flat buckets, a bf16
+    compute copy, and (lazily) a per-tap transposed bf16 copy for the K-major fprop operand."""
+
+    def __init__(self, name, shape):
+        self.name, self.shape = name, tuple(shape)
+        self.numel = int(math.prod(shape))
+        self.p32 = self.g32 = self.p16 = self.p16_t = None
+        self.group = None
+        self.need_t = False
+
+    @property
+    def active(self):
+        return id(self) in S.active
+
+    @property
+    def accum(self):
+        """True when the running backward sweep should add this variable's gradient to its bucket."""
+        if not S.accumulate or id(self) not in S.active:
+            return False
+        return S.accumulate is True or id(self) in S.accumulate
+
+    def transposed(self):
+        """bf16 [T, B, A] copy of a [T, A, B] weight (T = k*k taps)."""
+        self.need_t = True
+        if S.dry:
+            return None
+        if self.p16_t is None:
+            self.p16_t = empty((self.numel,), BF16)
+            self.refresh_transposed()
+        return self.p16_t
+
+    def refresh_transposed(self):
+        if self.p16_t is None:
+            return
+        a, b = self.shape[-2], self.shape[-1]
+        t = self.numel // (a * b)
+        launch("b200_transpose_to_bf16", _p(self.p32), 1, _p(self.p16_t), t, a, b)
+
+
+def _act_code(act):
+    return {None: K.ACT_NONE, "none": K.ACT_NONE, "relu": K.ACT_RELU, "lrelu": K.ACT_LRELU, "tanh": K.ACT_TANH,
+            "sigmoid": K.ACT_SIGMOID}[act] if not isinstance(act, int) else act
+
+
+def _epilogue(bias=None, act=K.ACT_NONE, leak=0.0, mask=None, out_f32=False, accumulate=False):
+    e = K.Epilogue()
+    e.bias = None if (bias is None or S.dry) else bias.data_ptr()
+    e.act, e.leak = act, leak
+    if mask is not None:
+        e.mask_src, e.mask_kind = (None if S.dry else mask[0].buf.data_ptr()), mask[1]
+        if act == K.ACT_NONE:
+            e.leak = mask[2]
+        elif mask[1] == K.ACT_LRELU and act == K.ACT_LRELU and mask[2] != leak:
+            raise K.B200Error("epilogue cannot fuse two different lrelu leaks")
+    e.out_f32, e.accumulate = int(out_f32), int(accumulate)
+    return e
+
+
+def same_pad(size, k, s):
+    out = -(-size // s)
+    total = max((out - 1) * s + k - size, 0)
+    return out, total // 2
+
+
+def conv_geom(N, H, W, Cin, Cout, k, stride):
+    """TF SAME geometry of conv [N,H,W,Cin] -> [N,ceil(H/s),ceil(W/s),Cout]."""
+    g = K.ConvGeom()
+    g.N, g.H, g.W, g.Cin, g.Cout, g.k, g.stride = N, H, W, Cin, Cout, k, stride
+    g.Ho, g.pad_t = same_pad(H, k, stride)
+    g.Wo, g.pad_l = same_pad(W, k, stride)
+    return g
+
+
+# ------------------------------------------------------------------------------------------ conv family
+def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_mask=None, out_f32=False):
+    """direction 'fprop': x [N,H,W,Cin] -> [N,Ho,Wo,Cout];  'dgrad': x [N,Ho,Wo,Cout] -> [N,H,W,Cin]
+    (the adjoint: TF's conv2d_transpose / input gradient).  W is a Param laid out [k,k,Cin,Cout].
+    out = act(op(x,W) + bias) * act'(out_mask.src)."""
+    g = geom
+    if x.f32:
+        raise K.B200Error("conv_like needs a bf16 input")
+    if direction == "fprop":
+        out_shape = (g.N, g.Ho, g.Wo, g.Cout)
+    else:
+        out_shape = (g.N, g.H, g.W, g.Cin)
+    out = Tensor(empty(out_shape, F32 if out_f32 else BF16))
+    e = _epilogue(None if bias is None else bias.p32, act, leak, out_mask, out_f32)
+    if direction == "fprop":
+        wt = W.transposed() if K.route(g, 0) == 1 else None
+        launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e))
+    else:
+        launch("b200_conv2d_dgrad", _p(x.buf), _p(W.p16), _p(out.buf), C.byref(g), C.byref(e))
+    if act != K.ACT_NONE:
+        if out_mask is not None:
+            raise K.B200Error("conv_like: activation and out_mask are mutually exclusive")
+        out.mask = (out, act, leak)
+    else:
+        out.mask = out_mask
+
+    def bw(gouts):
+        (go,) = gouts
+        go = _as_bf16(go)
+        gx = None
+        if x.requires_grad:
+            gx = conv_like("dgrad" if direction == "fprop" else "fprop", go, W, g, out_mask=x.mask,
+                           out_f32=x.grad_f32)
+        if W.accum:
+            if direction == "fprop":
+                launch("b200_conv2d_wgrad", _p(x.buf), _p(go.buf), _p(W.g32), C.byref(g), 1.0)
+            else:
+                launch("b200_conv2d_wgrad", _p(go.buf), _p(x.buf), _p(W.g32), C.byref(g), 1.0)
+        if bias is not None and bias.accum:
+            c = out_shape[-1]
+            launch("b200_colsum", _p(go.buf), None, _p(bias.g32), go.numel // c, c, 1.0)
+        return [gx]
+
+    _record([x], [out], bw, W.active or (bias is not None and bias.active))
+    return out
+
+
+def _as_bf16(t):
+    if not t.f32:
+        return t
+    o = Tensor(empty(t.shape, BF16))
+    launch("b200_affine_act", _p(t.buf), 1, _p(o.buf), 0, t.numel, 1.0, 0.0, 0, 0.0)
+    return o
+
+
+# ------------------------------------------------------------------------------------------ dense, one unit
+def dense_n1(x, W, bias, act=K.ACT_NONE, leak=0.0):
+    """x [M,K] bf16, W Param [K,1] -> fp32 [M]  (critic fc2, models/gan.py:285)."""
+    M, Kd = x.shape
+    out = Tensor(empty((M,), F32))
+    launch("b200_gemv_rows", _p(x.buf), _p(W.p16), _p(bias.p32), _p(out.buf), M, Kd, act, leak)
+    if act != K.ACT_NONE:
+        out.mask = (out, act, leak)
+
+    def bw(gouts):
+        (go,) = gouts           # fp32 [M]; if act != none the deliverer already applied act'
+        gx = outer_mask(go, W, x) if x.requires_grad else None
+        if W.accum:
+            launch("b200_colsum", _p(x.buf), _p(go.buf), _p(W.g32), M, Kd, 1.0)
+        if bias.accum:
+            launch("b200_reduce_sum", _p(go.buf), 1, M, _p(bias.g32), 1.0, 0)
+        return [gx]
+
+    _record([x], [out], bw, W.active or bias.active)
+    return out
+
+
+def outer_mask(g, W, like):
+    """out[m,k] = g[m] * W[k] * act'(like.mask) — gradient of dense_n1 w.r.t. its input."""
+    M, Kd = like.shape
+    out = Tensor(empty((M, Kd), BF16), mask=like.mask)
+    m = like.mask
+    launch("b200_outer_mask", _p(g.buf), _p(W.p16), None if m is None else _p(m[0].buf), _p(out.buf), M, Kd,
+           0 if m is None else m[1], 0.0 if m is None else m[2])
+
+    def bw(gouts):
+        (c,) = gouts            # bf16 [M,K], already multiplied by act'(mask)
+        if W.accum:
+            launch("b200_colsum", _p(c.buf), _p(g.buf), _p(W.g32), M, Kd, 1.0)
+        gg = None
+        if g.requires_grad:
+            gg = Tensor(empty((M,), F32))
+            launch("b200_gemv_rows", _p(c.buf), _p(W.p16), None, _p(gg.buf), M, Kd, 0, 0.0)
+        return [gg]
+
+    _record([g], [out], bw, W.active)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ batch norm
+def batch_norm_act(z, beta, act=K.ACT_NONE, leak=0.0, eps=1e-3):
+    """tf.contrib.layers.batch_norm(h) with defaults, then the layer activation
+    (ops/layers.py:58-59,103-104,144-145): beta only, biased batch statistics, eps 1e-3."""
+    Cc = z.shape[-1]
+    R = z.numel // Cc
+    stats = empty((2 * Cc,), F32)
+    launch("b200_fill_f32", _p(stats), 2 * Cc, 0.0)
+    launch("b200_bn_sums", _p(z.buf), _p(stats), R, Cc)
+    out = Tensor(empty(z.shape, BF16))
+    launch("b200_bn_apply", _p(z.buf), _p(stats), _p(beta.p32), _p(out.buf), R, Cc, eps, act, leak)
+    if act != K.ACT_NONE:
+        out.mask = (out, act, leak)
+
+    def bw(gouts):
+        (go,) = gouts
+        go = _as_bf16(go)
+        bsum = empty((2 * Cc,), F32)
+        launch("b200_fill_f32", _p(bsum), 2 * Cc, 0.0)
+        dz = Tensor(empty(z.shape, BF16))
+        launch("b200_bn_bwd", _p(go.buf), _p(z.buf), _p(stats), _p(bsum), _p(dz.buf), R, Cc, eps, n=2)
+        if beta.accum:
+            launch("b200_axpby", _p(bsum), 1, 1.0, None, _p(beta.g32), 1, 1.0, _p(beta.g32), 1, Cc)
+        if z.mask is not None:
+            dz = maskmul(dz, z.mask)
+        return [dz]
+
+    _record([z], [out], bw, beta.active)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ elementwise
+def maskmul(g, mask):
+    out = Tensor(empty(g.shape, BF16), mask=mask)
+    g = _as_bf16(g)
+    launch("b200_maskmul", _p(g.buf), _p(mask[0].buf), _p(out.buf), g.numel, mask[1], mask[2])
+
+    def bw(gouts):
+        return [gouts[0]]       # deliverer already applied the mask (out.mask == mask)
+
+    _record([g], [out], bw)
+    return out
+
+
+def activation(x, act, leak=0.0):
+    """Stand-alone activation (used when a layer's activation cannot be fused)."""
+    out = Tensor(empty(x.shape, BF16))
+    launch("b200_affine_act", _p(x.buf), int(x.f32), _p(out.buf), 0, x.numel, 1.0, 0.0, act, leak)
+    out.mask = (out, act, leak)
+
+    def bw(gouts):
+        go = gouts[0]
+        return [maskmul(go, x.mask) if x.mask is not None else go]
+
+    _record([x], [out], bw)
+    return out
+
+
+def affine(x, mul, add, out_f32=False):
+    """out = x*mul + add (e.g. the [0,1] -> [-1,1] rescale, models/gan.py:50)."""
+    out = Tensor(empty(x.shape, F32 if out_f32 else BF16))
+    launch("b200_affine_act", _p(x.buf), int(x.f32), _p(out.buf), int(out_f32), x.numel, mul, add, 0, 0.0)
+
+    def bw(gouts):
+        go = gouts[0]
+        o = Tensor(empty(x.shape, BF16))
+        launch("b200_affine_act", _p(go.buf), int(go.f32), _p(o.buf), 0, go.numel, mul, 0.0, 0, 0.0)
+        return [maskmul(o, x.mask) if x.mask is not None else o]
+
+    _record([x], [out], bw)
+    return out
+
+
+def reshape(x, shape):
+    shape = tuple(shape)
+    if -1 in shape:
+        known = -int(math.prod(shape))
+        shape = tuple(x.numel // known if d == -1 else d for d in shape)
+    assert int(math.prod(shape)) == x.numel, (shape, x.shape)
+    out = Tensor(x.buf, shape, mask=x.mask)
+
+    def bw(gouts):
+        go = gouts[0]
+        return [Tensor(go.buf, x.shape, mask=go.mask)]
+
+    _record([x], [out], bw)
+    return out
+
+
+def add_grads(a, b):
+    out = Tensor(empty(a.shape, F32 if (a.f32 and b.f32) else BF16))
+    launch("b200_axpby", _p(a.buf), int(a.f32), 1.0, None, _p(b.buf), int(b.f32), 1.0, _p(out.buf), int(out.f32),
+           a.numel)
+    return out
+
+
+def concat_channels(xs):
+    """NHWC channel concat (pix2pix skip connections).  Copy through torch (plumbing, not math)."""
+    out = Tensor(torch.cat([t.torch() for t in xs], dim=-1).contiguous())
+    sizes = [t.shape[-1] for t in xs]
+
+    def bw(gouts):
+        go = gouts[0].torch()
+        outs, o = [], 0
+        for t, c in zip(xs, sizes):
+            piece = Tensor(go[..., o:o + c].contiguous())
+            outs.append(maskmul(piece, t.mask) if t.mask is not None else piece)
+            o += c
+        return outs
+
+    _record(xs, [out], bw)
+    return out
+
+
+def interpolate(x, g, alpha):
+    """x_hat = x + alpha*(g - x), alpha [B] fp32 (models/gan.py:224-226).  A leaf for the tape:
+    in the critic step G is a constant and in the generator step d_loss is only evaluated."""
+    B = x.shape[0]
+    out = Tensor(empty(x.shape, BF16))
+    launch("b200_interp", _p(x.buf), _p(g.buf), _p(alpha.buf), _p(out.buf), B, x.numel // B)
+    return out
+
+
+def sumsq(x):
+    """sum(x^2) -> fp32 [1] (tf.reduce_sum(tf.square(gradients)), models/gan.py:229)."""
+    out = Tensor(empty((1,), F32))
+    launch("b200_fill_f32", _p(out.buf), 1, 0.0)
+    launch("b200_reduce_sum", _p(x.buf), int(x.f32), x.numel, _p(out.buf), 1.0, 1)
+
+    def bw(gouts):
+        go = gouts[0]           # fp32 [1] device scalar
+        o = Tensor(empty(x.shape, BF16))
+        launch("b200_axpby", _p(x.buf), int(x.f32), 2.0, _p(go.buf), None, 0, 0.0, _p(o.buf), 0, x.numel)
+        return [maskmul(o, x.mask) if x.mask is not None else o]
+
+    _record([x], [out], bw)
+    return out
+
+
+def wgan_losses(d_real, d_fake, ss=None, lam=10.0):
+    """g_loss = -mean(d_fake); d_loss = mean(d_fake) - mean(d_real) [+ lam*(sqrt(ss)-1)^2]
+    (models/gan.py:194-205).  Returns (g_loss, d_loss) fp32 [1] tensors sharing one node."""
+    B = d_real.shape[0]
+    sums = empty((3,), F32)
+    launch("b200_fill_f32", _p(sums), 3, 0.0)
+    launch("b200_reduce_sum", _p(d_real.buf), 1, B, _p(sums[0:1]), 1.0, 0)
+    launch("b200_reduce_sum", _p(d_fake.buf), 1, d_fake.shape[0], _p(sums[1:2]), 1.0, 0)
+    if ss is not None:
+        launch("b200_axpby", _p(ss.buf), 1, 1.0, None, None, 0, 0.0, _p(sums[2:3]), 1, 1)
+    out4 = empty((4,), F32)
+    launch("b200_wgan_loss", _p(sums), B, int(ss is not None), lam, _p(out4))
+    g_loss, d_loss = Tensor(out4[0:1]), Tensor(out4[1:2])
+    inputs = [d_real, d_fake] + ([ss] if ss is not None else [])
+
+    def bw(gouts):
+        gg, gd = gouts
+        cr = cf = None
+        if gd is not None:       # seed 1.0 on d_loss
+            cr = Tensor(empty((B,), F32)); cf = Tensor(empty((B,), F32))
+            launch("b200_fill_f32", _p(cr.buf), B, -1.0 / B)
+            launch("b200_fill_f32", _p(cf.buf), B, 1.0 / B)
+        if gg is not None:       # seed 1.0 on g_loss
+            t = Tensor(empty((B,), F32))
+            launch("b200_fill_f32", _p(t.buf), B, -1.0 / B)
+            cf = t if cf is None else add_grads(cf, t)
+        res = [cr if d_real.requires_grad else None, cf if d_fake.requires_grad else None]
+        if ss is not None:
+            res.append(Tensor(out4[3:4]) if gd is not None else None)
+        return res
+
+    _record(inputs, [g_loss, d_loss], bw)
+    return g_loss, d_loss
+
+
+def add_scalars(a, b):
+    """a + b for fp32 [1] loss pieces."""
+    out = Tensor(empty((1,), F32))
+    launch("b200_axpby", _p(a.buf), 1, 1.0, None, _p(b.buf), 1, 1.0, _p(out.buf), 1, 1)
+
+    def bw(gouts):
+        return [gouts[0], gouts[0]]
+
+    _record([a, b], [out], bw)
+    return out
+
+
+def eltloss(a, b, kind, label=0.0, scale=1.0):
+    """sum_i l(a_i, b_i) * scale -> fp32 [1]; backward fuses dl/da (kinds: see simt_kernels.cu)."""
+    out = Tensor(empty((1,), F32))
+    launch("b200_fill_f32", _p(out.buf), 1, 0.0)
+    launch("b200_eltloss", _p(a.buf), int(a.f32), None if b is None else _p(b.buf), a.numel, kind, label, scale, 0.0,
+           _p(out.buf), None, 0)
+
+    def bw(gouts):
+        g = Tensor(empty(a.shape, F32 if a.f32 else BF16))
+        launch("b200_eltloss", _p(a.buf), int(a.f32), None if b is None else _p(b.buf), a.numel, kind, label, 0.0,
+               scale, None, _p(g.buf), int(a.f32))
+        if a.mask is not None:
+            g = maskmul_any(g, a.mask)
+        return [g]
+
+    _record([a], [out], bw)
+    return out
+
+
+def maskmul_any(g, mask):
+    """maskmul that also accepts fp32 gradients/sources (tiny tensors only: goes through bf16)."""
+    src = mask[0]
+    if src.f32:
+        src16 = _as_bf16(src)
+        mask = (src16, mask[1], mask[2])
+    o = maskmul(g, mask)
+    if g.f32:
+        f = Tensor(empty(g.shape, F32))
+        launch("b200_affine_act", _p(o.buf), 0, _p(f.buf), 1, o.numel, 1.0, 0.0, 0, 0.0)
+        return f
+    return o
+
+
+def random_fill(shape, normal, seed, counter, stream_id, f32=True):
+    """tf.random_normal / tf.random_uniform stand-in (Philox4x32-10, device-side draw counter)."""
+    out = Tensor(empty(shape, F32 if f32 else BF16))
+    launch("b200_philox", _p(out.buf), int(f32), out.numel, seed, _p(counter), stream_id, int(normal), n=2)
+    return out
+
+
+# ------------------------------------------------------------------------------------------ backward pass
+def backward(seeds, wrt=(), create_graph=False, accumulate=True):
+    """Reverse sweep.  seeds: list of (tensor, grad Tensor | None); None = seed 1.0 on a scalar loss.
+    With accumulate=True (or a list of Params) parameter gradients are added into those Params' g32 views;
+    tf.gradients(ys, xs)-style calls (models/gan.py:228) pass accumulate=False and read `wrt`."""
+    grads = {}
+    nodes = {}
+    if accumulate not in (True, False):
+        accumulate = frozenset(id(p) for p in accumulate)
+    prev_acc, S.accumulate = S.accumulate, accumulate
+
+    def push(t, g):
+        if t.node is None and not any(t is w for w in wrt):
+            return
+        key = id(t)
+        if key in grads:
+            grads[key] = (t, add_grads(grads[key][1], g) if g is not True and grads[key][1] is not True else g)
+        else:
+            grads[key] = (t, g)
+        if t.node is not None:
+            nodes[t.node.seq] = t.node
+
+    for t, g in seeds:
+        push(t, True if g is None else g)
+    with recording(create_graph):
+        while nodes:
+            seq = max(nodes)
+            node = nodes.pop(seq)
+            gouts = []
+            for o in node.outputs:
+                ent = grads.pop(id(o), None) if not any(o is w for w in wrt) else grads.get(id(o))
+                gouts.append(None if ent is None else ent[1])
+            if all(g is None for g in gouts):
+                continue
+            gins = node.bw(gouts)
+            for inp, gi in zip(node.inputs, gins):
+                if gi is not None and inp.requires_grad:
+                    push(inp, gi)
+    S.accumulate = prev_acc
+    return [grads[id(w)][1] if id(w) in grads else None for w in wrt]
+
+
+def leaf(buf, shape=None, requires_grad=True):
+    t = Tensor(buf, shape)
+    t.requires_grad = requires_grad
+    return t

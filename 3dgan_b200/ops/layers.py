@@ -1,0 +1,144 @@
+"""The reference's layer API (ops/layers.py:27-166) with identical signatures, NHWC.
+
+conv2d / deconv2d / dense create `<scope>/vars/<name>/weights|bias` on first use and look them up
+again when `reuse=True` (ops/layers.py:50-53); op order is conv -> +bias -> batch_norm -> activation
+(ops/layers.py:101-105).  Underneath: tcgen05 implicit-GEMM kernels through the C ABI.
+"""
+import contextlib
+
+from .. import _capi as K
+from .. import engine as E
+from ..variables import xavier_initializer, zeros_initializer
+from .arg_scope import add_arg_scope
+
+_store = None
+
+
+def set_store(store):
+    global _store
+    _store = store
+
+
+def get_store():
+    if _store is None:
+        raise K.B200Error("no VariableStore bound (models bind one with ops.layers.set_store)")
+    return _store
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    """tf.variable_scope(name) as the models use it (models/gan.py:57-59,201)."""
+    st = get_store()
+    st.scope.append(name)
+    try:
+        yield
+    finally:
+        st.scope.pop()
+
+
+def weight_name(name):
+    return name if name is None else name + '/weights'
+
+
+def bias_name(name):
+    return name if name is None else name + '/bias'
+
+
+def _variables(name, w_shape, b_shape, init):
+    st = get_store()
+    st.scope.append('vars')
+    try:
+        W = st.get_variable(weight_name(name), w_shape, init())
+        b = st.get_variable(bias_name(name), b_shape, init())
+    finally:
+        st.scope.pop()
+    return W, b
+
+
+def _fusable(activation):
+    if activation is None:
+        return K.ACT_NONE, 0.0, True
+    code = getattr(activation, 'b200_act', None)
+    if code is None:
+        return K.ACT_NONE, 0.0, False
+    return code[0], code[1], True
+
+
+def batch_norm(h, activation=None):
+    """tf.contrib.layers.batch_norm(h) with defaults (ops/layers.py:10,58): creates
+    `<scope>/BatchNorm[_k]/beta`; never shares it through `reuse`."""
+    st = get_store()
+    st.scope.append(st.unique_bn_scope())
+    try:
+        beta = st.get_variable('beta', (h.shape[-1],), zeros_initializer())
+    finally:
+        st.scope.pop()
+    act, leak, ok = _fusable(activation)
+    out = E.batch_norm_act(h, beta, act, leak)
+    return out if ok else activation(out)
+
+
+def _finish(h, use_batch_norm, activation, fused):
+    if use_batch_norm:
+        return batch_norm(h, activation)
+    if activation is not None and not fused:
+        return activation(h)
+    return h
+
+
+@add_arg_scope
+def dense(x, input_size, output_size, init=xavier_initializer, use_batch_norm=False, activation=None,
+          reuse=False, name=None):
+    """ops/layers.py:27-62 — act(BN(x W + b)), W [input_size, output_size]."""
+    W, b = _variables(name, (input_size, output_size), (output_size,), init)
+    act, leak, ok = _fusable(activation)
+    fuse = ok and not use_batch_norm
+    M = x.shape[0]
+    if output_size == 1:
+        h = E.dense_n1(x, W, b, act if fuse else K.ACT_NONE, leak)
+        h = E.reshape(h, (M, 1))
+    else:
+        g = E.conv_geom(M, 1, 1, input_size, output_size, 1, 1)
+        h = E.conv_like('fprop', E.reshape(x, (M, 1, 1, input_size)), W, g, bias=b,
+                        act=act if fuse else K.ACT_NONE, leak=leak)
+        h = E.reshape(h, (M, output_size))
+    return _finish(h, use_batch_norm, activation, fuse)
+
+
+@add_arg_scope
+def conv2d(x, input_size, output_size, filter_size=3, stride=1, init=xavier_initializer, use_batch_norm=False,
+           activation=None, reuse=False, name=None):
+    """ops/layers.py:66-107 — act(BN(conv_SAME(x, K) + b)), K [k,k,input_size,output_size]."""
+    W, b = _variables(name, (filter_size, filter_size, input_size, output_size), (output_size,), init)
+    act, leak, ok = _fusable(activation)
+    fuse = ok and not use_batch_norm
+    N, H, Wd, C = x.shape
+    assert C == input_size, "conv2d %s: input has %d channels, input_size=%d" % (name, C, input_size)
+    g = E.conv_geom(N, H, Wd, input_size, output_size, filter_size, stride)
+    h = E.conv_like('fprop', x, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak)
+    return _finish(h, use_batch_norm, activation, fuse)
+
+
+@add_arg_scope
+def deconv2d(x, input_size, output_size, filter_size=3, stride=2, init=xavier_initializer, use_batch_norm=False,
+             activation=None, reuse=False, name=None, output_shape=None):
+    """ops/layers.py:111-148 — act(BN(conv2d_transpose_SAME(x, K) + b)), K [k,k,output_size,input_size];
+    output is 2x the input (ops/layers.py:141) unless output_shape=(H,W) is given (the Gen-2 kwarg,
+    hem/ops/layers.py:185-187, used by the shape-generalised autoencoders)."""
+    W, b = _variables(name, (filter_size, filter_size, output_size, input_size), (output_size,), init)
+    act, leak, ok = _fusable(activation)
+    fuse = ok and not use_batch_norm
+    N, h_in, w_in, C = x.shape
+    assert C == input_size, "deconv2d %s: input has %d channels, input_size=%d" % (name, C, input_size)
+    Ho, Wo = (h_in * 2, w_in * 2) if output_shape is None else output_shape
+    # the forward conv whose adjoint this is: [N,Ho,Wo,output_size] -> [N,h_in,w_in,input_size]
+    g = E.conv_geom(N, Ho, Wo, output_size, input_size, filter_size, stride)
+    assert (g.Ho, g.Wo) == (h_in, w_in), "deconv2d %s: output_shape incompatible with stride" % name
+    h = E.conv_like('dgrad', x, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak)
+    return _finish(h, use_batch_norm, activation, fuse)
+
+
+@add_arg_scope
+def flatten(x, name=None):
+    """ops/layers.py:152-166 — [B, -1]."""
+    return E.reshape(x, (x.shape[0], -1))

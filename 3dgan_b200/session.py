@@ -1,0 +1,151 @@
+"""Session: what `tf.Session` + `tf.train.Supervisor` meant to the hot path (train.py:254-308) —
+device binding, the variable store, noise streams, the input feed, CUDA-graph capture of a step and
+the data-parallel exchange (one process per GPU; NCCL all-reduce of the flat gradient bucket in
+place of util.py:118-147's CPU averaging).
+"""
+import contextlib
+import os
+
+import torch
+
+from . import engine as E
+from .ops import layers as L
+from .variables import VariableStore
+
+_current = None
+
+
+def current():
+    if _current is None:
+        raise RuntimeError("no b200gan Session is active")
+    return _current
+
+
+class Input:
+    """The `x` tensor the reference's input pipeline hands to a model (data.py:34-60): yields one
+    [B,H,W,C] float32 batch in [0,1] per `next()`.  Batches are fed by the caller (`feed`) into a
+    static device ring so that a captured CUDA graph always reads the same addresses."""
+
+    def __init__(self, batch_size, shape, slots=1, device=None):
+        self.batch_size, self.shape, self.slots = batch_size, tuple(shape), slots
+        self.device = device
+        self.ring = None
+        self.cursor = 0
+
+    def materialize(self, device):
+        self.device = device
+        self.ring = torch.zeros((self.slots, self.batch_size) + self.shape, dtype=torch.float32, device=device)
+
+    def feed(self, slot, host_or_device_batch, non_blocking=True):
+        self.ring[slot].copy_(host_or_device_batch, non_blocking=non_blocking)
+
+    def reset(self):
+        self.cursor = 0
+
+    def next(self):
+        if E.S.dry:
+            return E.Tensor(torch.empty((self.batch_size,) + self.shape, dtype=torch.float32, device="meta"))
+        t = E.Tensor(self.ring[self.cursor % self.slots])
+        self.cursor += 1
+        return t
+
+
+class Session:
+    def __init__(self, seed=0, noise_seed=1234, device=None):
+        global _current
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.cuda = torch.cuda.is_available()
+        if device is None:
+            device = torch.device("cuda", self.local_rank) if self.cuda else torch.device("meta")
+        self.device = device
+        if self.cuda:
+            torch.cuda.set_device(device)
+        self.store = VariableStore(seed)
+        L.set_store(self.store)
+        self.noise_seed = noise_seed + self.rank        # per-tower noise
+        self.counter = None
+        self.noise_queue = []                           # parity tests inject noise here
+        self.graphs = {}
+        self.use_graphs = os.environ.get("B200GAN_CUDA_GRAPHS", "1") != "0"
+        self.dist = None
+        _current = self
+
+    # ---------------------------------------------------------------- build / run modes
+    @contextlib.contextmanager
+    def building(self):
+        """Graph-construction pass: shapes + variable creation only (works without a GPU)."""
+        prev = E.S.dry
+        E.S.dry = True
+        self.store.begin_pass()
+        try:
+            yield
+        finally:
+            E.S.dry = prev
+
+    def begin_step(self):
+        if not self.cuda:
+            raise RuntimeError("b200gan needs a CUDA device: there is no CPU fallback for the training step")
+        E.begin(self.device)
+        self.store.begin_pass()
+        if self.counter is None:
+            self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    # ---------------------------------------------------------------- noise
+    def _noise(self, shape, normal, stream_id, f32):
+        if self.noise_queue and not E.S.dry:
+            v = self.noise_queue.pop(0)
+            assert tuple(v.shape) == tuple(shape), (tuple(v.shape), tuple(shape))
+            return E.Tensor(v.to(self.device, torch.float32 if f32 else torch.bfloat16).contiguous())
+        return E.random_fill(shape, normal, self.noise_seed, self.counter, stream_id, f32)
+
+    def random_normal(self, shape, stream_id=0, f32=False):
+        return self._noise(shape, True, stream_id, f32)
+
+    def random_uniform(self, shape, stream_id=1, f32=True):
+        return self._noise(shape, False, stream_id, f32)
+
+    # ---------------------------------------------------------------- data parallel
+    def init_distributed(self, backend="nccl"):
+        import torch.distributed as dist
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world,
+                                    device_id=self.device if backend == "nccl" else None)
+        self.dist = dist if self.world > 1 else None
+
+    def all_reduce_grads(self, group):
+        """average_gradients (util.py:118-147): sum over ranks here, the 1/n is folded into the
+        optimizer kernel's grad_scale."""
+        if self.dist is not None:
+            self.dist.all_reduce(group.g32)
+        return 1.0 / self.world
+
+    # ---------------------------------------------------------------- CUDA graphs
+    def run(self, key, fn):
+        """Run `fn()` (a whole step: forward, backward, exchange, update).  First call: eager
+        (warm-up, lazy allocations).  Second call: captured into a CUDA graph.  Later: replay.
+        fn returns a dict of fp32 [1] device tensors (losses)."""
+        if not self.use_graphs or self.noise_queue:
+            self.begin_step()
+            return fn()
+        ent = self.graphs.get(key)
+        if ent is None:
+            self.begin_step()
+            out = fn()
+            self.graphs[key] = {"state": "warm"}
+            return out
+        if ent["state"] == "warm":
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            launches0 = E.S.launches
+            with torch.cuda.graph(g):
+                self.begin_step()
+                out = fn()
+            ent.update(state="graph", graph=g, out=out, launches=E.S.launches - launches0)
+            # capture does not execute: replay once so this call has the step's effect
+            g.replay()
+            return out
+        ent["graph"].replay()
+        E.S.launches += ent["launches"]
+        return ent["out"]

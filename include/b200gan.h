@@ -1,0 +1,105 @@
+/* b200gan C ABI — the drop-in boundary for the 3dgan training-step hot path on B200 (sm_100a).
+ *
+ * Each entry point replaces what TensorFlow executed for one call site of the reference layer API
+ * (citations are into algoterranean/3dgan).  Conventions: every pointer is a DEVICE pointer owned by
+ * the caller (the Python host keeps them in torch tensors used purely as buffers); activations are
+ * NHWC bf16 unless a flag says fp32; parameters/gradients/optimizer state are fp32 with a bf16
+ * compute copy; every call is asynchronous on the given CUDA stream and allocates nothing; return
+ * value 0 = success, negative = error (b200_last_error() has the text).  Thread-compatible, not
+ * thread-safe.  There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200GAN_H_
+#define B200GAN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b200_stream;   /* cudaStream_t */
+
+enum { B200_ACT_NONE = 0, B200_ACT_RELU = 1, B200_ACT_LRELU = 2, B200_ACT_TANH = 3, B200_ACT_SIGMOID = 4 };
+enum { B200_OPT_ADAM = 0, B200_OPT_RMSPROP = 1, B200_OPT_SGD = 2, B200_OPT_MOMENTUM = 3 };
+
+/* Geometry of one strided SAME convolution (TF semantics, ops/layers.py:101):
+ * input [N,H,W,Cin] -> output [N,Ho,Wo,Cout], filter k x k, pad_t/pad_l = TF's pad_before. */
+typedef struct {
+  int N, H, W, Cin;
+  int Ho, Wo, Cout;
+  int k, stride, pad_t, pad_l;
+} b200_conv_geom;
+
+/* Fused epilogue: v = acc (+bias[c]); v = act(v); v *= act'(mask_src) ; store bf16 | fp32 (+=). */
+typedef struct {
+  const float* bias;      /* [channels] or NULL                       (tf.nn.bias_add, ops/layers.py:102,143) */
+  int act;                /* B200_ACT_*                               (activation(h), ops/layers.py:104,145)   */
+  float leak;             /* lrelu leak                               (ops/activations.py:11-29)               */
+  const void* mask_src;   /* bf16, same shape as out, or NULL: multiply by the derivative of mask_kind at the
+                             stored post-activation value (gradient of the consumer's activation)            */
+  int mask_kind;
+  int out_f32;            /* 0: bf16 output, 1: fp32 output */
+  int accumulate;         /* fp32 only: out += result */
+} b200_epilogue;
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* 0 if the current CUDA device can run the library (compute capability 10.x), negative otherwise. */
+int b200_device_check(void);
+
+/* ---- convolution family (tcgen05 implicit GEMM; small-channel image-side layers use coalesced SIMT kernels)
+ * fprop : y  = epi(conv_SAME(x, W))            replaces tf.nn.conv2d            ops/layers.py:101, hem/ops/layers.py:118
+ * dgrad : dx = epi(conv_SAME^T(dy, W))         replaces tf.nn.conv2d_transpose  ops/layers.py:142, hem/ops/layers.py:189
+ *                                              and the input-gradient TF autodiff emits (models/gan.py:67-68,228)
+ * wgrad : dW += alpha * d(conv)/dW             replaces the filter-gradient TF autodiff emits
+ * w  : bf16 [k,k,Cin,Cout] (TF filter layout; for a deconv layer TF's [k,k,out,in] is the same thing)
+ * w_t: bf16 [k,k,Cout,Cin] (per-tap transpose; only fprop on the tensor-core path reads it) */
+int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, void* y, const b200_conv_geom* g,
+                      const b200_epilogue* e, b200_stream s);
+int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const b200_conv_geom* g, const b200_epilogue* e,
+                      b200_stream s);
+int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha, b200_stream s);
+/* which kernel family a geometry maps to: 1 tensor core, 2 small-channel SIMT, negative = unsupported */
+int b200_conv2d_route(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
+
+/* ---- dense with one output unit (critic fc2, models/gan.py:285; replaces tf.matmul ops/layers.py:57) */
+int b200_gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act, float leak,
+                   b200_stream s);                                   /* out[m] = act(a[m,:].w + bias[0])      */
+int b200_outer_mask(const float* g, const void* w, const void* mask, void* out, int M, int K, int mask_kind,
+                    float leak, b200_stream s);                      /* out[m,k] = g[m] w[k] act'(mask[m,k])  */
+
+/* ---- batch norm, tf.contrib.layers.batch_norm defaults (ops/layers.py:58,103,144): beta only, eps, batch stats */
+int b200_bn_sums(const void* z, float* stats /*[2C], zeroed*/, long long R, int C, b200_stream s);
+int b200_bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps,
+                  int act, float leak, b200_stream s);
+int b200_bn_bwd(const void* g, const void* z, const float* stats, float* bsum /*[2C], zeroed; bsum[0:C] = dbeta*/,
+                void* dz, long long R, int C, float eps, b200_stream s);
+
+/* ---- elementwise / reductions */
+int b200_maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, b200_stream s);
+int b200_affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
+                    float leak, b200_stream s);                      /* out = act(in*mul+add); x -> 2(x-0.5), models/gan.py:50 */
+int b200_axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
+               int out_f32, long long n, b200_stream s);             /* out = a*sa*(*dev_sa) + b*sb */
+int b200_fill_f32(float* out, long long n, float v, b200_stream s);
+int b200_interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, b200_stream s);
+                                                                     /* x + alpha (g - x), models/gan.py:224-226 */
+int b200_rowscale(const void* in, const float* s_row, float mul, float add, void* out, int B, int D, b200_stream s);
+int b200_transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, b200_stream s);
+int b200_colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, b200_stream s);
+                                                                     /* out[c] += alpha sum_r wrow[r] x[r,c]: bias / fc2 weight grads */
+int b200_reduce_sum(const void* x, int x_f32, long long n, float* out, float alpha, int squared, b200_stream s);
+int b200_wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out4, b200_stream s);
+                                                                     /* models/gan.py:194-205,229-230 */
+int b200_eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float label, float scale,
+                 float gscale, float* out_sum, void* grad, int grad_f32, b200_stream s);
+                                                                     /* models/cnn.py:77, vae.py:76-83, gan.py:193-194, pix2pix.py:283-299 */
+/* ---- noise (tf.random_normal / tf.random_uniform, models/gan.py:224,246; models/vae.py:127) */
+int b200_philox(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* dev_draw_counter,
+                unsigned int stream_id, int normal, b200_stream s);
+/* ---- optimizer (util.py:150-183; tf.train.AdamOptimizer / RMSProp / SGD / Momentum), WGAN clip fused (gan.py:142) */
+int b200_optim_step(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, int kind, float lr,
+                    float b1, float b2, float eps, float grad_scale, float clip, int* dev_step, b200_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GAN_H_ */

@@ -1,0 +1,152 @@
+"""Shared parity helpers: run the CUDA path through the engine / C ABI and compare with the CPU oracle
+on identical (bf16-rounded) inputs.  Used by tests/test_*_gpu.py and __graft_entry__.smoke()."""
+import argparse
+from collections import OrderedDict
+
+import torch
+
+import b200gan  # noqa: F401  (import shim)
+from b200gan import _capi as K
+from b200gan import engine as E
+from b200gan import session as S
+from oracle import models as OM
+from oracle import tf_ops as OT
+
+ACT_NAMES = {K.ACT_NONE: None, K.ACT_RELU: "relu", K.ACT_LRELU: "lrelu", K.ACT_TANH: "tanh", K.ACT_SIGMOID: "sigmoid"}
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def make_param(t, name="p"):
+    """A stand-alone Param (own buffers) from a CPU fp32 tensor."""
+    p = E.Param(name, tuple(t.shape))
+    p.p32 = t.reshape(-1).to("cuda", torch.float32).contiguous()
+    p.g32 = torch.zeros_like(p.p32)
+    p.p16 = p.p32.to(torch.bfloat16)
+    return p
+
+
+def dev(t, dtype=torch.bfloat16):
+    return E.Tensor(t.to("cuda", dtype).contiguous())
+
+
+def act_grad_from_out(a, kind, leak=0.2):
+    if kind == K.ACT_RELU:
+        return (a > 0).float()
+    if kind == K.ACT_LRELU:
+        return torch.where(a > 0, torch.ones_like(a), torch.full_like(a, leak))
+    if kind == K.ACT_TANH:
+        return 1 - a * a
+    if kind == K.ACT_SIGMOID:
+        return a * (1 - a)
+    return torch.ones_like(a)
+
+
+def conv_case(N, H, W, Cin, Cout, k, stride, seed=0, act=K.ACT_LRELU, with_mask=False, scale=1.0):
+    """fprop, dgrad and wgrad of one SAME conv geometry vs torch-CPU autograd over the oracle's conv.
+    Returns dict of relative errors."""
+    E.begin()
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(N, H, W, Cin, generator=g) * scale)
+    Wt = bf16_round(torch.randn(k, k, Cin, Cout, generator=g) / (k * (Cin ** 0.5)))
+    b = torch.randn(Cout, generator=g) * 0.1
+    geom = E.conv_geom(N, H, W, Cin, Cout, k, stride)
+    dy = bf16_round(torch.randn(N, geom.Ho, geom.Wo, Cout, generator=g))
+    Wp, bp = make_param(Wt, "w"), make_param(b, "b")
+    out = {}
+    # ---- fprop (+bias +act)
+    y_ref = OT.conv2d(x, Wt, b, stride, None, ACT_NAMES[act])
+    y = E.conv_like("fprop", dev(x), Wp, geom, bias=bp, act=act, leak=0.2)
+    torch.cuda.synchronize()
+    out["fprop"] = rel_err(y.torch().float(), y_ref)
+    # ---- dgrad (optionally with a fused activation-gradient mask)
+    xr = x.clone().requires_grad_(True)
+    Wr = Wt.clone().requires_grad_(True)
+    yy = OT.conv2d_same(xr, Wr, stride)
+    gx_ref, gw_ref = torch.autograd.grad(yy, [xr, Wr], dy)
+    mask = None
+    if with_mask:
+        a_prev = bf16_round(torch.randn(N, H, W, Cin, generator=g))
+        gx_ref = gx_ref * act_grad_from_out(a_prev, K.ACT_LRELU)
+        mask = (dev(a_prev), K.ACT_LRELU, 0.2)
+    gx = E.conv_like("dgrad", dev(dy), Wp, geom, out_mask=mask)
+    torch.cuda.synchronize()
+    out["dgrad"] = rel_err(gx.torch().float(), gx_ref)
+    # ---- wgrad (accumulates into g32)
+    E.launch("b200_conv2d_wgrad", E._p(dev(x).buf), E._p(dev(dy).buf), E._p(Wp.g32), E.C.byref(geom), 1.0)
+    torch.cuda.synchronize()
+    out["wgrad"] = rel_err(Wp.g32.reshape(Wt.shape), gw_ref)
+    return out
+
+
+def load_oracle_params(sess, p):
+    sess.store.load({k: v for k, v in p.items()})
+
+
+def iwgan_step_parity(H=32, C=3, L=16, B=8, model="iwgan", seed=0, verbose=False):
+    """One critic run and one generator run of the GAN family vs the oracle, identical bf16-rounded
+    weights, batch and noise.  Tolerances (bf16 operands, fp32 accumulation; north_star / SURVEY 7.2):
+    losses rtol 2e-2 (abs 2e-3), gradients relative-L2 <= 3e-2 per variable (variables whose reference
+    gradient is ~0, i.e. biases under batch-norm, are compared absolutely)."""
+    from b200gan.models import gan as gan_model
+    args = argparse.Namespace(model=model, batch_size=B, latent_size=L, n_disc_train=1, optimizer="adam", lr=1e-4,
+                              beta1=0.5, beta2=0.9)
+    sess = S.Session(seed=seed)
+    sess.use_graphs = False
+    x_in = S.Input(B, (H, H, C), slots=2)
+    train = gan_model.gan(x_in, args)
+    store = sess.store
+    gs, ds = OM.gan_param_specs(model, H, C, L)
+    p = OM.init_params(OrderedDict(list(gs.items()) + list(ds.items())), seed)
+    for k_ in p:
+        p[k_] = bf16_round(p[k_])
+    load_oracle_params(sess, p)
+    gen = torch.Generator().manual_seed(seed + 1)
+    x01 = bf16_round(torch.rand(B, H, H, C, generator=gen))
+    z = bf16_round(torch.randn(B, L, generator=gen))
+    alpha = torch.rand(B, 1, generator=gen)
+    ref = OM.gan_grads(p, x01, z, alpha, model, H, C, L)
+    x_in.feed(0, x01.cuda()); x_in.feed(1, x01.cuda())
+    report = {"ok": True}
+    worst = 0.0
+    for mode, group_prefix in (("d", "discriminator"), ("g", "generator")):
+        sess.begin_step()
+        x_in.reset()
+        sess.noise_queue = [z.clone(), alpha.clone()] if model == "iwgan" else [z.clone()]
+        for gsrc in store.groups:
+            gsrc.zero_grad()
+        gl, dl = train.tower(x_in.next(), mode)
+        E.backward([(dl if mode == "d" else gl, None)])
+        torch.cuda.synchronize()
+        gl, dl = float(gl.buf.item()), float(dl.buf.item())
+        for name, got, want in (("g_loss", gl, float(ref["g_loss"])), ("d_loss", dl, float(ref["d_loss"]))):
+            err = abs(got - want)
+            report["%s/%s" % (mode, name)] = (got, want)
+            if err > 2e-3 + 2e-2 * abs(want):
+                report["ok"] = False
+        for name, prm in store.params.items():
+            if not name.startswith(group_prefix):
+                continue
+            want = ref["grads"][name]
+            got = prm.g32.reshape(prm.shape).float().cpu()
+            wn = float(want.norm())
+            if wn < 1e-6:
+                e = float((got - want).abs().max())
+                bad = e > 1e-3
+            else:
+                e = rel_err(got, want)
+                bad = e > 3e-2
+            worst = max(worst, e)
+            if verbose or bad:
+                print("  [%s] %-40s err %.3e (ref norm %.3e)%s" % (mode, name, e, wn, "  <-- FAIL" if bad else ""))
+            if bad:
+                report["ok"] = False
+    report["worst_grad_err"] = worst
+    return report

@@ -1,0 +1,158 @@
+"""GPU parity: each CUDA kernel family through the C ABI vs the CPU oracle (bit-for-bit inputs:
+operands are bf16-rounded on both sides; accumulation is fp32 on the GPU, fp32 on the CPU)."""
+import math
+
+import pytest
+import torch
+
+from tests import parity as P
+from b200gan import _capi as K
+from b200gan import engine as E
+
+pytestmark = pytest.mark.gpu
+
+# bf16 output rounding is 2^-9 relative per element; fp32 outputs (wgrad) are much tighter
+TOL = {"fprop": 6e-3, "dgrad": 6e-3, "wgrad": 2e-3}
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, stride          what it exercises
+    (4, 16, 16, 64, 64, 5, 2),               # aligned tensor-core case
+    (4, 16, 16, 200, 400, 5, 2),             # IWGAN c2 shape (ragged K chunk, N tile 208)
+    (16, 8, 8, 400, 800, 5, 2),              # IWGAN c3 shape
+    (3, 8, 8, 72, 40, 5, 2),                 # ragged everything, partial M tile
+    (2, 7, 7, 64, 32, 5, 2),                 # odd spatial size: pad (2,2), deconv 4 -> 7
+    (6, 4, 4, 256, 96, 1, 1),                # 1x1 conv (autoencoder c5)
+    (64, 1, 1, 200, 512, 1, 1),              # dense as a 1x1 conv on 1x1 images
+    (2, 32, 32, 64, 128, 4, 2),              # pix2pix k4 s2, pad (1,1)
+    (2, 64, 64, 24, 16, 5, 2),               # wide rows: tile = part of one image
+    (8, 32, 32, 3, 200, 5, 2),               # small-channel path (IWGAN c1 / dc-last)
+    (4, 28, 28, 1, 64, 5, 2),                # MNIST-shaped first conv
+    (2, 16, 16, 4, 64, 4, 2),                # pix2pix PatchGAN first conv (rgb+depth)
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_family(case):
+    res = P.conv_case(*case)
+    for op, err in res.items():
+        assert err < TOL[op], (case, res)
+
+
+def test_conv_dgrad_fused_mask():
+    res = P.conv_case(4, 16, 16, 200, 400, 5, 2, with_mask=True)
+    assert res["dgrad"] < TOL["dgrad"], res
+    res = P.conv_case(4, 32, 32, 3, 200, 5, 2, with_mask=True)
+    assert res["dgrad"] < TOL["dgrad"], res
+
+
+def test_gemv_outer_colsum():
+    E.begin()
+    g = torch.Generator().manual_seed(3)
+    M, Kd = 48, 12800
+    a = P.bf16_round(torch.randn(M, Kd, generator=g))
+    w = P.bf16_round(torch.randn(Kd, 1, generator=g) / math.sqrt(Kd))
+    b = torch.randn(1, generator=g)
+    Wp, bp = P.make_param(w), P.make_param(b)
+    out = E.dense_n1(P.dev(a), Wp, bp)
+    torch.cuda.synchronize()
+    assert P.rel_err(out.torch(), (a @ w + b).reshape(-1)) < 1e-5
+    gvec = torch.randn(M, generator=g)
+    gt = E.Tensor(gvec.cuda())
+    like = P.dev(a); like.mask = (like, K.ACT_LRELU, 0.2)
+    om = E.outer_mask(gt, Wp, like)
+    want = gvec[:, None] * w.reshape(1, -1) * P.act_grad_from_out(a, K.ACT_LRELU)
+    torch.cuda.synchronize()
+    assert P.rel_err(om.torch().float(), want) < 6e-3
+    E.launch("b200_colsum", E._p(like.buf), E._p(gt.buf), E._p(Wp.g32), M, Kd, 1.0)
+    torch.cuda.synchronize()
+    assert P.rel_err(Wp.g32, (gvec[:, None] * a).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("R,C", [(512, 12800), (8 * 8 * 8, 400), (37, 72), (1024, 3)])
+def test_batch_norm_fwd_bwd(R, C):
+    from oracle import tf_ops as OT
+    E.begin()
+    g = torch.Generator().manual_seed(5)
+    z = P.bf16_round(torch.randn(R, C, generator=g) * 1.5 + 0.3)
+    beta = torch.randn(C, generator=g) * 0.1
+    bp = P.make_param(beta)
+    with E.recording(True, active=[bp]):
+        zt = P.dev(z); zt.requires_grad = True
+        out = E.batch_norm_act(zt, bp, K.ACT_RELU, 0.0)
+        zr = z.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+        ref = torch.relu(OT.batch_norm_train(zr, br))
+        torch.cuda.synchronize()
+        assert P.rel_err(out.torch().float(), ref) < 6e-3
+        go = P.bf16_round(torch.randn(R, C, generator=g))
+        gz_ref, gb_ref = torch.autograd.grad(ref, [zr, br], go)
+        # deliverer applies relu' (mask convention)
+        gdel = P.bf16_round(go * (ref > 0).float())
+        (gz,) = E.backward([(out, P.dev(gdel))], wrt=[zt])
+    torch.cuda.synchronize()
+    assert P.rel_err(gz.torch().float(), gz_ref) < 1.5e-2
+    assert P.rel_err(bp.g32, gb_ref) < 1e-3
+
+
+def test_optimizers_match_tf_formulas():
+    from oracle import tf_ops as OT
+    E.begin()
+    g = torch.Generator().manual_seed(7)
+    n = 1000
+    for kind, name in ((K.OPT_ADAM, "adam"), (K.OPT_RMSPROP, "rmsprop"), (K.OPT_SGD, "sgd"), (K.OPT_MOMENTUM, "momentum")):
+        p = torch.randn(n, generator=g); m = torch.zeros(n); v = torch.ones(n) if name == "rmsprop" else torch.zeros(n)
+        dp, dm, dv = p.cuda(), m.cuda(), v.cuda()
+        p16 = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+        step = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for t in range(1, 4):
+            gr = torch.randn(n, generator=g)
+            if name == "adam":
+                OT.adam_step(p, gr, m, v, t, 1e-3, 0.5, 0.9)
+                args = (1e-3, 0.5, 0.9, 1e-8)
+            elif name == "rmsprop":
+                OT.rmsprop_step(p, gr, v, m, 1e-3, 0.9, 0.01)
+                args = (1e-3, 0.9, 0.01, 1e-10)
+            elif name == "sgd":
+                OT.sgd_step(p, gr, 1e-2)
+                args = (1e-2, 0.0, 0.0, 0.0)
+            else:
+                OT.momentum_step(p, gr, m, 1e-2, 0.9)
+                args = (1e-2, 0.9, 0.0, 0.0)
+            E.launch("b200_optim_step", E._p(dp), E._p(dm), E._p(dv), E._p(gr.cuda()), E._p(p16), n, kind, *args,
+                     1.0, 0.0, E._p(step))
+        torch.cuda.synchronize()
+        assert torch.allclose(dp.cpu(), p, rtol=2e-5, atol=1e-6), name
+        assert int(step.item()) == 3
+        assert torch.equal(p16.cpu(), dp.cpu().to(torch.bfloat16))
+
+
+def test_philox_moments_and_counter():
+    E.begin()
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    a = E.random_fill((1 << 20,), True, 1234, cnt, 0)
+    b = E.random_fill((1 << 20,), True, 1234, cnt, 0)
+    u = E.random_fill((1 << 20,), False, 1234, cnt, 1)
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 3
+    assert abs(float(a.torch().mean())) < 5e-3 and abs(float(a.torch().std()) - 1) < 5e-3
+    assert not torch.equal(a.torch(), b.torch())
+    assert 0.0 <= float(u.torch().min()) and float(u.torch().max()) < 1.0 and abs(float(u.torch().mean()) - 0.5) < 3e-3
+
+
+def test_interp_sumsq_wgan_loss():
+    E.begin()
+    g = torch.Generator().manual_seed(9)
+    B, D = 16, 3072
+    x = P.bf16_round(torch.rand(B, D, generator=g) * 2 - 1); f = P.bf16_round(torch.rand(B, D, generator=g) * 2 - 1)
+    al = torch.rand(B, 1, generator=g)
+    it = E.interpolate(P.dev(x), P.dev(f), E.Tensor(al.cuda()))
+    torch.cuda.synchronize()
+    assert P.rel_err(it.torch().float(), x + al * (f - x)) < 4e-3
+    gr = torch.randn(B, D, generator=g)
+    ss = E.sumsq(E.Tensor(gr.cuda()))
+    dr, df = torch.randn(B, generator=g), torch.randn(B, generator=g)
+    gl, dl = E.wgan_losses(E.Tensor(dr.cuda()), E.Tensor(df.cuda()), ss, 10.0)
+    torch.cuda.synchronize()
+    s = float((gr.double() ** 2).sum().sqrt())
+    assert abs(float(gl.buf.item()) + float(df.mean())) < 1e-5
+    want = float(df.mean() - dr.mean()) + 10.0 * (s - 1) ** 2
+    assert abs(float(dl.buf.item()) - want) < 1e-3 * abs(want)
