@@ -30,6 +30,7 @@ class _State:
     stream = None              # ctypes stream handle for the current step
     device = None
     launches = 0               # kernels launched through the C ABI (bench.py reports it)
+    profile = None             # list -> per-launch CUDA-event records of the conv-family launches
 
 
 S = _State()
@@ -45,11 +46,26 @@ def begin(device=None):
     S.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def launch(name, *args, n=1):
+def launch(name, *args, n=1, flops=0, tag=None):
     if S.dry:
         return 0
     S.launches += n
+    if S.profile is not None and tag is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = K.call(name, *args, S.stream)
+        e1.record()
+        S.profile.append((name, flops, e0, e1, tag))
+        return rc
     return K.call(name, *args, S.stream)
+
+
+def _conv_tag(op, g):
+    """(tag, algorithmic FLOPs) of one conv-family launch: 2*N*Ho*Wo*k^2*Cin*Cout, logical channels
+    (SURVEY 8d); tc: tensor-core route, simt: small-channel route."""
+    fam = "tc" if K.route(g, {"fprop": 0, "dgrad": 1, "wgrad": 2}[op]) == 1 else "simt"
+    tag = "%s:%s N%d %dx%dx%d->%dx%dx%d k%ds%d" % (fam, op, g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.k, g.stride)
+    return tag, 2.0 * g.N * g.Ho * g.Wo * g.k * g.k * g.Cin * g.Cout
 
 
 def empty(shape, dtype=BF16):
@@ -101,7 +117,7 @@ class Tensor:
 
 
 class Node:
-    __slots__ = ("seq", "inputs", "outputs", "bw")
+    __slots__ = ("seq", "inputs", "outputs", "bw", "active")
 
 
 def _record(inputs, outputs, bw, uses_active_param=False):
@@ -111,7 +127,7 @@ def _record(inputs, outputs, bw, uses_active_param=False):
         return
     n = Node()
     S.seq += 1
-    n.seq, n.inputs, n.outputs, n.bw = S.seq, list(inputs), list(outputs), bw
+    n.seq, n.inputs, n.outputs, n.bw, n.active = S.seq, list(inputs), list(outputs), bw, S.active
     for o in outputs:
         o.requires_grad = True
         o.node = n
@@ -207,9 +223,12 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
     e = _epilogue(None if bias is None else bias.p32, act, leak, out_mask, out_f32)
     if direction == "fprop":
         wt = W.transposed() if K.route(g, 0) == 1 else None
-        launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e))
+        tag, fl = _conv_tag("fprop", g) if S.profile is not None else (None, 0)
+        launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e), flops=fl,
+               tag=tag)
     else:
-        launch("b200_conv2d_dgrad", _p(x.buf), _p(W.p16), _p(out.buf), C.byref(g), C.byref(e))
+        tag, fl = _conv_tag("dgrad", g) if S.profile is not None else (None, 0)
+        launch("b200_conv2d_dgrad", _p(x.buf), _p(W.p16), _p(out.buf), C.byref(g), C.byref(e), flops=fl, tag=tag)
     if act != K.ACT_NONE:
         if out_mask is not None:
             raise K.B200Error("conv_like: activation and out_mask are mutually exclusive")
@@ -225,10 +244,11 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
             gx = conv_like("dgrad" if direction == "fprop" else "fprop", go, W, g, out_mask=x.mask,
                            out_f32=x.grad_f32)
         if W.accum:
+            tag, fl = _conv_tag("wgrad", g) if S.profile is not None else (None, 0)
             if direction == "fprop":
-                launch("b200_conv2d_wgrad", _p(x.buf), _p(go.buf), _p(W.g32), C.byref(g), 1.0)
+                launch("b200_conv2d_wgrad", _p(x.buf), _p(go.buf), _p(W.g32), C.byref(g), 1.0, flops=fl, tag=tag)
             else:
-                launch("b200_conv2d_wgrad", _p(go.buf), _p(x.buf), _p(W.g32), C.byref(g), 1.0)
+                launch("b200_conv2d_wgrad", _p(go.buf), _p(x.buf), _p(W.g32), C.byref(g), 1.0, flops=fl, tag=tag)
         if bias is not None and bias.accum:
             c = out_shape[-1]
             launch("b200_colsum", _p(go.buf), None, _p(bias.g32), go.numel // c, c, 1.0)
@@ -372,8 +392,7 @@ def reshape(x, shape):
     out = Tensor(x.buf, shape, mask=x.mask)
 
     def bw(gouts):
-        go = gouts[0]
-        return [Tensor(go.buf, x.shape, mask=go.mask)]
+        return [reshape(gouts[0], x.shape)]     # through the op so second-order tapes stay connected
 
     _record([x], [out], bw)
     return out
@@ -526,6 +545,7 @@ def backward(seeds, wrt=(), create_graph=False, accumulate=True):
     if accumulate not in (True, False):
         accumulate = frozenset(id(p) for p in accumulate)
     prev_acc, S.accumulate = S.accumulate, accumulate
+    prev_active = S.active
 
     def push(t, g):
         if t.node is None and not any(t is w for w in wrt):
@@ -550,11 +570,12 @@ def backward(seeds, wrt=(), create_graph=False, accumulate=True):
                 gouts.append(None if ent is None else ent[1])
             if all(g is None for g in gouts):
                 continue
+            S.active = node.active      # the variables that were trainable when the node was recorded
             gins = node.bw(gouts)
             for inp, gi in zip(node.inputs, gins):
                 if gi is not None and inp.requires_grad:
                     push(inp, gi)
-    S.accumulate = prev_acc
+    S.accumulate, S.active = prev_acc, prev_active
     return [grads[id(w)][1] if id(w) in grads else None for w in wrt]
 
 

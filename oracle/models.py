@@ -154,7 +154,7 @@ def discriminator(p, x, H, C, L, model, bn_base=0):
 def gan_losses(p, x01, z, alpha, model, H, C, L):
     """models/gan.py:49-50 (rescale), 55-63, 178-231.  x01: [B,H,W,C] in [0,1].
     Returns (g_loss, d_loss, g)."""
-    x = 2 * (x01.reshape(x01.shape[0], -1) - 0.5)
+    x = T.stored(2 * (x01.reshape(x01.shape[0], -1) - 0.5))
     g = generator(p, z, H, C, L)
     d_real = discriminator(p, x, H, C, L, model, 0)
     d_fake = discriminator(p, g, H, C, L, model, 2)
@@ -166,13 +166,35 @@ def gan_losses(p, x01, z, alpha, model, H, C, L):
         d_loss = d_fake.mean() - d_real.mean()
     else:
         g_loss = -d_fake.mean()
-        interp = x + alpha * (g - x)
+        interp = T.stored(x + alpha * (g - x))
+        if not interp.requires_grad:                     # pure evaluation (no trainable inputs)
+            interp = interp.detach().requires_grad_(True)
         d_int = discriminator(p, interp, H, C, L, model)
         grads = torch.autograd.grad(d_int.sum(), interp, create_graph=True)[0]
         slopes = torch.sqrt(torch.sum(grads ** 2))        # ONE norm over the tower batch (App. C #3)
         gp = (slopes - 1.0) ** 2
         d_loss = d_fake.mean() - d_real.mean() + 10.0 * gp
     return g_loss, d_loss, g
+
+
+def iwgan_critic_grad_terms(p, x01, z, alpha, H, C, L):
+    """The three additive pieces of the IWGAN critic gradient (fake, real, penalty) separately:
+    parity tests scale their tolerance by the sum of the pieces' norms because the pieces cancel."""
+    names_d = [k for k in p if k.startswith("discriminator/")]
+    q = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in p.items())
+    x = T.stored(2 * (x01.reshape(x01.shape[0], -1) - 0.5))
+    g = generator(q, z, H, C, L).detach()
+    d_real = discriminator(q, x, H, C, L, "iwgan")
+    d_fake = discriminator(q, g, H, C, L, "iwgan")
+    interp = T.stored(x + alpha * (g - x)).detach().requires_grad_(True)
+    d_int = discriminator(q, interp, H, C, L, "iwgan")
+    grads = torch.autograd.grad(d_int.sum(), interp, create_graph=True)[0]
+    gp = 10.0 * (torch.sqrt(torch.sum(grads ** 2)) - 1.0) ** 2
+    terms = []
+    for loss in (d_fake.mean(), -d_real.mean(), gp):
+        gs = torch.autograd.grad(loss, [q[k] for k in names_d], retain_graph=True, allow_unused=True)
+        terms.append(OrderedDict((k, torch.zeros_like(q[k]) if v is None else v) for k, v in zip(names_d, gs)))
+    return terms
 
 
 def gan_grads(p, x01, z, alpha, model, H, C, L):

@@ -11,6 +11,44 @@ import torch
 import torch.nn.functional as F
 
 
+# --------------------------------------------------------------------------- storage-precision emulation
+class _RoundBF16(torch.autograd.Function):
+    """Round to bf16 in the forward, identity in the backward (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+_STORE_BF16 = False
+
+
+class store_bf16:
+    """Context: emulate the CUDA path's storage precision — every tensor it writes to HBM as bf16
+    (conv/dense outputs before batch-norm, layer outputs after the activation, the rescaled input, the
+    GP interpolates) is rounded to bf16 here too.  Arithmetic stays fp32.  With it on, ReLU/LReLU masks
+    agree with the GPU's, which removes the mask-flip noise that dominates fp32-oracle comparisons."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _STORE_BF16
+        self.prev, _STORE_BF16 = _STORE_BF16, self.on
+
+    def __exit__(self, *a):
+        global _STORE_BF16
+        _STORE_BF16 = self.prev
+
+
+def stored(t):
+    return _RoundBF16.apply(t) if _STORE_BF16 else t
+
+
 # --------------------------------------------------------------------------- padding
 def same_pad(in_size, k, s):
     """TF 'SAME' padding (A.1): out = ceil(in/s); pad_total = max((out-1)s+k-in, 0);
@@ -114,16 +152,17 @@ def dense(x, W, b, beta=None, activation=None):
     """ops/layers.py:27-62: act(BN(xW + b))."""
     h = x @ W + b
     if beta is not None:
-        h = batch_norm_train(h, beta)
-    return ACTIVATIONS[activation](h)
+        h = batch_norm_train(stored(h), beta)
+    out = ACTIVATIONS[activation](h)
+    return out if (W.shape[1] == 1) else stored(out)       # 1-unit dense keeps fp32 (GEMV kernel)
 
 
 def conv2d(x, K, b, stride, beta=None, activation=None):
     """ops/layers.py:66-107: act(BN(conv_SAME(x,K) + b))."""
     h = conv2d_same(x, K, stride) + b
     if beta is not None:
-        h = batch_norm_train(h, beta)
-    return ACTIVATIONS[activation](h)
+        h = batch_norm_train(stored(h), beta)
+    return stored(ACTIVATIONS[activation](h))
 
 
 def deconv2d(x, K, b, stride=2, beta=None, activation=None, out_hw=None):
@@ -133,8 +172,8 @@ def deconv2d(x, K, b, stride=2, beta=None, activation=None, out_hw=None):
         out_hw = (x.shape[1] * 2, x.shape[2] * 2)
     h = conv2d_transpose_same(x, K, out_hw, stride) + b
     if beta is not None:
-        h = batch_norm_train(h, beta)
-    return ACTIVATIONS[activation](h)
+        h = batch_norm_train(stored(h), beta)
+    return stored(ACTIVATIONS[activation](h))
 
 
 # --------------------------------------------------------------------------- initialisers
