@@ -31,9 +31,10 @@ _GP, _EP = C.POINTER(ConvGeom), C.POINTER(Epilogue)
 
 # name -> argtypes; mirrors include/b200gan.h one to one (tests/test_abi.py checks the export list)
 SIGNATURES = {
-    "b200_conv2d_fprop": [_P, _P, _P, _P, _GP, _EP, _P],
-    "b200_conv2d_dgrad": [_P, _P, _P, _GP, _EP, _P],
-    "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P],
+    "b200_conv2d_fprop": [_P, _P, _P, _P, _GP, _EP, _P, _LL, _P],
+    "b200_conv2d_dgrad": [_P, _P, _P, _GP, _EP, _P, _LL, _P],
+    "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P, _LL, _P],
+    "b200_conv2d_workspace_bytes": [_GP, _I],
     "b200_conv2d_route": [_GP, _I],
     "b200_gemv_rows": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "b200_outer_mask": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
@@ -71,6 +72,7 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = C.c_int
+        L.b200_conv2d_workspace_bytes.restype = C.c_longlong
         L.b200_last_error.restype = C.c_char_p
         L.b200_last_error.argtypes = []
         _lib = L
@@ -83,6 +85,10 @@ def call(name, *args):
     if rc != 0:
         raise B200Error("%s failed (%d): %s" % (name, rc, L.b200_last_error().decode()))
     return rc
+
+
+def workspace_bytes(geom, op):
+    return int(lib().b200_conv2d_workspace_bytes(C.byref(geom), op))
 
 
 def route(geom, op):

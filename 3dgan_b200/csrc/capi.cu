@@ -90,8 +90,8 @@ static bool is_small(int c) { return c <= 4; }
 extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
   const int kk = g->k * g->k;
   if (is_small(g->Cin)) {
-    if (kk * g->Cin <= 80 && g->Cout <= 1024) return 2;
-    return fail("small-channel conv: k*k*Cin > 80 or Cout > 1024");
+    if (g->Cout % 8 == 0 || (kk * g->Cin <= 80 && g->Cout <= 1024)) return 2;
+    return fail("small-channel conv: needs Cout % 8 == 0, or k*k*Cin <= 80 and Cout <= 1024");
   }
   if (g->Cin % 8) return fail("tensor-core conv needs Cin % 8 == 0");
   if (op != 0 && g->Cout % 8) return fail("tensor-core dgrad/wgrad need Cout % 8 == 0");
@@ -111,11 +111,126 @@ static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
   p.alpha = 1.f;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Plain GEMMs on the same kernels (rank-2 tensor maps): used by the small-channel im2col route.
+// ------------------------------------------------------------------------------------------------
+// out[m, n] = epi( sum_k A[m,k] * B[n,k] ),  A [M,K] row stride lda, B [Nrows,K] row stride ldb
+static int dense_gemm(const void* A, long long M, int K, int lda, const void* B, int Nrows, int ldb, void* out,
+                      long long ldo, int ncols, const b200_epilogue* e, cudaStream_t st) {
+  TapGemmParams p;
+  memset(&p, 0, sizeof p);
+  fill_epilogue(p, e);
+  p.bw = kTileM; p.bh = 1; p.bn = 1;
+  {
+    long long dims[2] = {K, M};
+    long long str[2] = {1, lda};
+    int box[2] = {kBlockK, kTileM};
+    int es[2] = {1, 1};
+    if (make_tmap(&p.tmA, A, 2, dims, str, box, es)) return -1;
+  }
+  p.a_rank = 2;
+  p.ncols = ncols;
+  p.bn_tile = pick_bn_tile(ncols);
+  {
+    long long dims[2] = {K, Nrows};
+    long long str[2] = {1, ldb};
+    int box[2] = {kBlockK, p.bn_tile};
+    int es[2] = {1, 1};
+    if (make_tmap(&p.tmB, B, 2, dims, str, box, es)) return -1;
+  }
+  p.kchunks = cdiv(K, kBlockK);
+  p.k_total = K;
+  p.nphases = 1;
+  p.phase_tap_begin[0] = 0; p.phase_tap_begin[1] = 1;
+  p.a_mul[0][0] = 1;
+  p.tiles_w = (int)((M + kTileM - 1) / kTileM); p.tiles_h = 1; p.tiles_n = 1;
+  p.phase_ext_w[0] = (int)M; p.phase_ext_h[0] = 1; p.ext_n = 1;
+  p.o_sw = ldo;
+  p.stages = pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.out = out;
+  launch_tapgemm(p, st);
+  return 0;
+}
+
+// out[ca, cb] += alpha * sum_m A[m,ca] * B[m,cb];  A [M, Ka] (Ka physical width, Ca logical), B [M, Cb]
+static int dense_wgrad(const void* A, int Ca, int Ka, const void* B, int Cb, long long M, float* out, int ldo,
+                       float alpha, cudaStream_t st) {
+  WgradParams p;
+  memset(&p, 0, sizeof p);
+  p.bw = 64; p.bh = 1; p.bn = 1;
+  {
+    long long dims[2] = {Ka, M};
+    long long str[2] = {1, Ka};
+    int box[2] = {64, 64};
+    int es[2] = {1, 1};
+    if (make_tmap(&p.tmA, A, 2, dims, str, box, es)) return -1;
+  }
+  {
+    long long dims[2] = {Cb, M};
+    long long str[2] = {1, Cb};
+    int box[2] = {64, 64};
+    int es[2] = {1, 1};
+    if (make_tmap(&p.tmB, B, 2, dims, str, box, es)) return -1;
+  }
+  p.a_rank = 2; p.b_rank = 2;
+  p.ntaps = 1;
+  p.a_mul[0][0] = 1;
+  p.chunks_w = (int)((M + 63) / 64); p.chunks_h = 1; p.chunks_n = 1;
+  p.total_chunks = p.chunks_w;
+  p.Ca = Ca; p.Cb = Cb;
+  p.m_tiles = cdiv(Ca, kTileM);
+  p.bn_tile = pick_bn_tile(Cb);
+  p.n_tiles = cdiv(Cb, p.bn_tile);
+  p.nb_boxes = cdiv(p.bn_tile, 64);
+  p.stages = pick_stages((2 + p.nb_boxes) * 64 * 64 * 2);
+  p.out = out;
+  p.out_tap_stride = 0;
+  p.ldo = ldo;
+  p.alpha = alpha;
+  const int base = p.m_tiles * p.n_tiles;
+  int splits = cdiv(148 * 3, base);
+  splits = std::min(splits, std::max(1, p.total_chunks / 4));
+  splits = std::max(1, splits);
+  p.chunks_per_split = cdiv(p.total_chunks, splits);
+  splits = cdiv(p.total_chunks, p.chunks_per_split);
+  launch_wgrad(p, splits, st);
+  return 0;
+}
+
+static long long align256(long long v) { return (v + 255) / 256 * 256; }
+static int small_kp(const b200_conv_geom* g) { return cdiv(g->k * g->k * g->Cin, 8) * 8; }
+// the small-channel layers can run as im2col/col2im + tensor-core GEMM when the big side is TMA-aligned
+static bool small_gemm_ok(const b200_conv_geom* g) { return g->Cout % 8 == 0; }
+
+extern "C" long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op) {
+  if (!is_small(g->Cin) || !small_gemm_ok(g)) return 0;
+  const long long M = (long long)g->N * g->Ho * g->Wo;
+  const int Kp = small_kp(g);
+  if (op == 0) return align256(M * Kp * 2) + align256((long long)g->Cout * Kp * 2);
+  if (op == 1) return align256(M * Kp * 4);
+  return align256(M * Kp * 2);
+}
+
 extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, void* y, const b200_conv_geom* g,
-                                 const b200_epilogue* e, b200_stream s) {
+                                 const b200_epilogue* e, void* workspace, long long workspace_bytes, b200_stream s) {
   cudaStream_t st = (cudaStream_t)s;
   const int route = b200_conv2d_route(g, 0);
   if (route < 0) return route;
+  if (route == 2 && workspace && small_gemm_ok(g)) {
+    // im2col (bf16 [M,Kp]) + padded transposed filter [Cout,Kp] -> tcgen05 GEMM with the fused epilogue
+    if (workspace_bytes < b200_conv2d_workspace_bytes(g, 0)) return fail("conv2d_fprop: workspace too small");
+    const long long M = (long long)g->N * g->Ho * g->Wo;
+    const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
+    char* A = (char*)workspace;
+    char* Wt = A + align256(M * Kp * 2);
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
+    im2col_small(x, A, a, Kp, st);
+    wpad_transpose(w, Wt, kk, g->Cout, Kp, st);
+    if (dense_gemm(A, M, Kp, Kp, Wt, g->Cout, Kp, y, g->Cout, g->Cout, e, st)) return -1;
+    return check_launch("conv2d_fprop(im2col)");
+  }
   if (route == 2) {
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
@@ -149,6 +264,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     if (make_tmap(&p.tmB, w_t, 2, dims, str, box, es)) return -1;
   }
   p.kchunks = cdiv(g->Cin, kBlockK);
+  p.k_total = g->Cin;
   p.nphases = 1;
   p.phase_tap_begin[0] = 0;
   p.phase_tap_begin[1] = g->k * g->k;
@@ -172,10 +288,26 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
 }
 
 extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const b200_conv_geom* g,
-                                 const b200_epilogue* e, b200_stream s) {
+                                 const b200_epilogue* e, void* workspace, long long workspace_bytes, b200_stream s) {
   cudaStream_t st = (cudaStream_t)s;
   const int route = b200_conv2d_route(g, 1);
   if (route < 0) return route;
+  if (route == 2 && workspace && small_gemm_ok(g)) {
+    // T[M, k*k*Cin] = dy[M, Cout] . W[k*k*Cin, Cout]^T on tensor cores (fp32), then col2im + epilogue
+    if (workspace_bytes < b200_conv2d_workspace_bytes(g, 1)) return fail("conv2d_dgrad: workspace too small");
+    if (e && e->accumulate) return fail("small-channel dgrad: accumulate unsupported");
+    const long long M = (long long)g->N * g->Ho * g->Wo;
+    const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
+    b200_epilogue te;
+    memset(&te, 0, sizeof te);
+    te.out_f32 = 1;
+    if (dense_gemm(dy, M, g->Cout, g->Cout, w, kk, g->Cout, workspace, Kp, kk, &te, st)) return -1;
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
+                    e ? e->mask_kind : 0, dx, e ? e->out_f32 : 0};
+    col2im_small((const float*)workspace, a, Kp, st);
+    return check_launch("conv2d_dgrad(col2im)");
+  }
   if (route == 2) {
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
@@ -208,6 +340,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
     if (make_tmap(&p.tmB, w, 2, dims, str, box, es)) return -1;
   }
   p.kchunks = cdiv(g->Cout, kBlockK);
+  p.k_total = g->Cout;
   // output parities, heaviest first so the tail of the grid is made of the cheap phases
   struct Ph { int ph, pw, nt; } phs[kMaxPhases];
   int np = 0;
@@ -252,10 +385,20 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
 }
 
 extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha,
-                                 b200_stream s) {
+                                 void* workspace, long long workspace_bytes, b200_stream s) {
   cudaStream_t st = (cudaStream_t)s;
   const int route = b200_conv2d_route(g, 2);
   if (route < 0) return route;
+  if (route == 2 && workspace && small_gemm_ok(g)) {
+    if (workspace_bytes < b200_conv2d_workspace_bytes(g, 2)) return fail("conv2d_wgrad: workspace too small");
+    const long long M = (long long)g->N * g->Ho * g->Wo;
+    const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
+    im2col_small(x, workspace, a, Kp, st);
+    if (dense_wgrad(workspace, kk, Kp, dy, g->Cout, M, dw, g->Cout, alpha, st)) return -1;
+    return check_launch("conv2d_wgrad(im2col)");
+  }
   if (route == 2) {
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     nullptr, 0, 0.f, nullptr, 0, nullptr, 0};

@@ -185,6 +185,90 @@ __global__ void smallc_wgrad_kernel(const bf16* __restrict__ xs, const bf16* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// im2col / col2im for the small-channel layers: they turn the image-side conv into a plain GEMM
+// that the tcgen05 kernels run (K = k*k*Cs padded to Kp, a multiple of 8 for TMA alignment).
+// ---------------------------------------------------------------------------------------------
+// A[m][j] = small[n, oh*st+r-pt, ow*st+s-pl, cs]  (j = (r*k+s)*Cs+cs; zero for padding and j >= k*k*Cs)
+__global__ void im2col_small_kernel(const bf16* __restrict__ xs, bf16* __restrict__ A, ConvGeom g, int Kp,
+                                    long long total) {
+  const int kk = g.k * g.k * g.Cs;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int j = (int)(i % Kp);
+    const long long m = i / Kp;
+    float v = 0.f;
+    if (j < kk) {
+      const int ow = (int)(m % g.Wo);
+      const int oh = (int)((m / g.Wo) % g.Ho);
+      const int n = (int)(m / ((long long)g.Wo * g.Ho));
+      const int cs = j % g.Cs;
+      const int s = (j / g.Cs) % g.k;
+      const int r = j / (g.Cs * g.k);
+      const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+        v = __bfloat162float(xs[(((long long)n * g.H + ih) * g.W + iw) * g.Cs + cs]);
+    }
+    A[i] = __float2bfloat16(v);
+  }
+}
+int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaStream_t st) {
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  const long long total = (long long)a.N * a.Ho * a.Wo * Kp;
+  im2col_small_kernel<<<stride_grid(total, 256, 4), 256, 0, st>>>((const bf16*)xs, (bf16*)A, g, Kp, total);
+  return 0;
+}
+// Wt[cb][j] = w[j][cb] for j < kk, 0 for kk <= j < Kp   (K-major B operand of the fprop GEMM)
+__global__ void wpad_transpose_kernel(const bf16* __restrict__ w, bf16* __restrict__ wt, int kk, int Cb, int Kp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cb * Kp) return;
+  const int j = i % Kp, cb = i / Kp;
+  wt[i] = j < kk ? w[(long long)j * Cb + cb] : __float2bfloat16(0.f);
+}
+int wpad_transpose(const void* w, void* wt, int kk, int Cb, int Kp, cudaStream_t st) {
+  wpad_transpose_kernel<<<(Cb * Kp + 255) / 256, 256, 0, st>>>((const bf16*)w, (bf16*)wt, kk, Cb, Kp);
+  return 0;
+}
+// small[n,h,w,cs] = epi( sum_{r,s valid} T[(n,oh,ow)][(r*k+s)*Cs+cs] ),  T fp32 with row stride Kp
+__global__ void col2im_small_kernel(const float* __restrict__ T, ConvGeom g, int Kp, EpilogueArgs e, long long total) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cs = (int)(i % g.Cs);
+    const long long p = i / g.Cs;
+    const int x = (int)(p % g.W);
+    const int y = (int)((p / g.W) % g.H);
+    const int n = (int)(p / ((long long)g.W * g.H));
+    float acc = 0.f;
+    for (int r = 0; r < g.k; ++r) {
+      const int th = y + g.pad_t - r;
+      if (th < 0 || th % g.stride) continue;
+      const int oh = th / g.stride;
+      if (oh >= g.Ho) continue;
+      for (int s = 0; s < g.k; ++s) {
+        const int tw = x + g.pad_l - s;
+        if (tw < 0 || tw % g.stride) continue;
+        const int ow = tw / g.stride;
+        if (ow >= g.Wo) continue;
+        acc += T[(((long long)n * g.Ho + oh) * g.Wo + ow) * Kp + (r * g.k + s) * g.Cs + cs];
+      }
+    }
+    float v = acc * e.alpha;
+    if (e.bias) v += e.bias[cs];
+    v = act_fwd(v, e.act, e.leak);
+    if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[i]), e.mask_kind, e.leak);
+    if (e.out_f32) reinterpret_cast<float*>(e.out)[i] = v;
+    else reinterpret_cast<bf16*>(e.out)[i] = __float2bfloat16(v);
+  }
+}
+int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st) {
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs};
+  const long long total = (long long)a.N * a.H * a.W * a.Cs;
+  col2im_small_kernel<<<stride_grid(total, 256, 1), 256, 0, st>>>(T, g, Kp, e, total);
+  return 0;
+}
+
 static int round_up32(int v) { return (v + 31) / 32 * 32; }
 
 int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStream_t st) {

@@ -21,6 +21,10 @@ int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStre
 int smallc_dgrad(const void* big, const void* w, const SmallConvArgs& a, cudaStream_t st);
 int smallc_wgrad(const void* xs, const void* big, float* dw, const SmallConvArgs& a, float alpha, cudaStream_t st);
 
+int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaStream_t st);
+int wpad_transpose(const void* w, void* wt, int kk, int Cb, int Kp, cudaStream_t st);
+int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st);
+
 int maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, cudaStream_t st);
 int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
                float leak, cudaStream_t st);

@@ -105,6 +105,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc = make_idesc_bf16(kTileM, p.bn_tile, 0, 0);
+      // the last K chunk of a tap is zero-filled beyond K: issue only the 16-wide steps that hold data
+      const int tail_steps = (p.k_total - (p.kchunks - 1) * kBlockK + 15) / 16;
+      int kc = 0;
       for (int it = 0; it < iters; ++it) {
         const int s = it % p.stages;
         const uint32_t par = (it / p.stages) & 1;
@@ -113,12 +116,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
+        const int nsteps = (kc == p.kchunks - 1) ? tail_steps : kBlockK / 16;
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4)
-          umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          if (k < nsteps) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
         }
         umma_commit(smem_u32(&ps->empty[s]));
+        if (++kc == p.kchunks) kc = 0;
       }
       umma_commit(smem_u32(&ps->tmem_full));
     }

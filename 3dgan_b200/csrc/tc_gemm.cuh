@@ -25,6 +25,7 @@ struct TapGemmParams {
   CUtensorMap tmB;
   int a_rank;
   int kchunks;                        // ceil(K / 64) per tap
+  int k_total;                        // K per tap (channels)
   int nphases;
   int phase_tap_begin[kMaxPhases + 1];
   int tap_a_off[kMaxTaps][4];         // start coordinate of A dims 1..4 for this tap

@@ -60,10 +60,22 @@ def launch(name, *args, n=1, flops=0, tag=None):
     return K.call(name, *args, S.stream)
 
 
+SMALL_CHANNEL_GEMM = True      # False: image-side layers use the SIMT kernels (no workspace)
+
+
+def _workspace(g, op):
+    """Scratch for the small-channel im2col/col2im route (torch tensor as a byte buffer)."""
+    n = K.workspace_bytes(g, op) if SMALL_CHANNEL_GEMM else 0
+    if n == 0:
+        return None, 0
+    return empty((n,), torch.uint8), n
+
+
 def _conv_tag(op, g):
     """(tag, algorithmic FLOPs) of one conv-family launch: 2*N*Ho*Wo*k^2*Cin*Cout, logical channels
     (SURVEY 8d); tc: tensor-core route, simt: small-channel route."""
-    fam = "tc" if K.route(g, {"fprop": 0, "dgrad": 1, "wgrad": 2}[op]) == 1 else "simt"
+    opi = {"fprop": 0, "dgrad": 1, "wgrad": 2}[op]
+    fam = "tc" if K.route(g, opi) == 1 else ("smallc-gemm" if SMALL_CHANNEL_GEMM and K.workspace_bytes(g, opi) else "simt")
     tag = "%s:%s N%d %dx%dx%d->%dx%dx%d k%ds%d" % (fam, op, g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.k, g.stride)
     return tag, 2.0 * g.N * g.Ho * g.Wo * g.k * g.k * g.Cin * g.Cout
 
@@ -224,11 +236,14 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
     if direction == "fprop":
         wt = W.transposed() if K.route(g, 0) == 1 else None
         tag, fl = _conv_tag("fprop", g) if S.profile is not None else (None, 0)
-        launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e), flops=fl,
-               tag=tag)
+        ws, wsb = _workspace(g, 0)
+        launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e), _p(ws), wsb,
+               flops=fl, tag=tag)
     else:
         tag, fl = _conv_tag("dgrad", g) if S.profile is not None else (None, 0)
-        launch("b200_conv2d_dgrad", _p(x.buf), _p(W.p16), _p(out.buf), C.byref(g), C.byref(e), flops=fl, tag=tag)
+        ws, wsb = _workspace(g, 1)
+        launch("b200_conv2d_dgrad", _p(x.buf), _p(W.p16), _p(out.buf), C.byref(g), C.byref(e), _p(ws), wsb, flops=fl,
+               tag=tag)
     if act != K.ACT_NONE:
         if out_mask is not None:
             raise K.B200Error("conv_like: activation and out_mask are mutually exclusive")
@@ -245,10 +260,10 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
                            out_f32=x.grad_f32)
         if W.accum:
             tag, fl = _conv_tag("wgrad", g) if S.profile is not None else (None, 0)
-            if direction == "fprop":
-                launch("b200_conv2d_wgrad", _p(x.buf), _p(go.buf), _p(W.g32), C.byref(g), 1.0, flops=fl, tag=tag)
-            else:
-                launch("b200_conv2d_wgrad", _p(go.buf), _p(x.buf), _p(W.g32), C.byref(g), 1.0, flops=fl, tag=tag)
+            ws, wsb = _workspace(g, 2)
+            a_, b_ = (x, go) if direction == "fprop" else (go, x)
+            launch("b200_conv2d_wgrad", _p(a_.buf), _p(b_.buf), _p(W.g32), C.byref(g), 1.0, _p(ws), wsb, flops=fl,
+                   tag=tag)
         if bias is not None and bias.accum:
             c = out_shape[-1]
             launch("b200_colsum", _p(go.buf), None, _p(bias.g32), go.numel // c, c, 1.0)

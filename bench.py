@@ -174,7 +174,9 @@ def run_b200(a):
         return {k: float(v.item()) for k, v in out.items()}
 
     for i in range(max(a.warmup, 3)):
-        step_resident(i)
+        out = step_resident(i)
+        if os.environ.get("B200GAN_BENCH_VERBOSE"):
+            print("warmup step", i, {k: float(v.item()) for k, v in out.items()}, file=sys.stderr, flush=True)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = E.S.launches
@@ -199,6 +201,8 @@ def run_b200(a):
     last = None
     for i in range(a.steps):
         last = step_e2e(i)
+        if os.environ.get("B200GAN_BENCH_VERBOSE"):
+            print("e2e step", i, last, file=sys.stderr, flush=True)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

@@ -53,10 +53,15 @@ int b200_device_check(void);
  * w  : bf16 [k,k,Cin,Cout] (TF filter layout; for a deconv layer TF's [k,k,out,in] is the same thing)
  * w_t: bf16 [k,k,Cout,Cin] (per-tap transpose; only fprop on the tensor-core path reads it) */
 int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, void* y, const b200_conv_geom* g,
-                      const b200_epilogue* e, b200_stream s);
+                      const b200_epilogue* e, void* workspace, long long workspace_bytes, b200_stream s);
 int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const b200_conv_geom* g, const b200_epilogue* e,
-                      b200_stream s);
-int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha, b200_stream s);
+                      void* workspace, long long workspace_bytes, b200_stream s);
+int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha,
+                      void* workspace, long long workspace_bytes, b200_stream s);
+/* scratch the call needs (0 for the direct tensor-core route).  Small-channel (image-side, Cin <= 4) layers
+ * run as im2col / col2im + the same tcgen05 GEMM when a workspace of this size is passed; with
+ * workspace == NULL they fall back to the coalesced SIMT kernels. */
+long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
 /* which kernel family a geometry maps to: 1 tensor core, 2 small-channel SIMT, negative = unsupported */
 int b200_conv2d_route(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
 

@@ -81,7 +81,8 @@ def conv_case(N, H, W, Cin, Cout, k, stride, seed=0, act=K.ACT_LRELU, with_mask=
     out["dgrad"] = rel_err(gx.torch().float(), gx_ref)
     # ---- wgrad (accumulates into g32)
     xd, dyd = dev(x), dev(dy)           # keep both alive: the allocator may otherwise alias them
-    E.launch("b200_conv2d_wgrad", E._p(xd.buf), E._p(dyd.buf), E._p(Wp.g32), E.C.byref(geom), 1.0)
+    ws, wsb = E._workspace(geom, 2)
+    E.launch("b200_conv2d_wgrad", E._p(xd.buf), E._p(dyd.buf), E._p(Wp.g32), E.C.byref(geom), 1.0, E._p(ws), wsb)
     torch.cuda.synchronize()
     out["wgrad"] = rel_err(Wp.g32.reshape(Wt.shape), gw_ref)
     return out
@@ -165,4 +166,66 @@ def iwgan_step_parity(H=32, C=3, L=16, B=8, model="iwgan", seed=0, verbose=False
             if bad:
                 report["ok"] = False
     report["worst_grad_err"] = worst
+    return report
+
+
+def iwgan_trajectory_parity(H=32, C=3, L=16, B=16, iters=3, n_disc=2, model="iwgan", seed=0, verbose=False):
+    """`iters` full train_func calls (n_disc critic updates + 1 generator update each, Adam) on both
+    sides with identical weights, batches and noise; compares the reported losses of every iteration
+    and the total parameter displacement."""
+    from b200gan.models import gan as gan_model
+    args = argparse.Namespace(model=model, batch_size=B, latent_size=L, n_disc_train=n_disc, optimizer="adam",
+                              lr=1e-4, beta1=0.5, beta2=0.9)
+    sess = S.Session(seed=seed)
+    sess.use_graphs = False
+    runs = n_disc + 1 if model != "gan" else 1
+    x_in = S.Input(B, (H, H, C), slots=runs)
+    train = gan_model.gan(x_in, args)
+    tr = OM.GanTrainer(model, H, C, L, B, lr=1e-4, beta1=0.5, beta2=0.9, n_disc=n_disc, seed=seed)
+    for k_ in tr.p:
+        tr.p[k_].copy_(bf16_round(tr.p[k_]))
+    p0 = OrderedDict((k_, v.clone()) for k_, v in tr.p.items())
+    load_oracle_params(sess, tr.p)
+    gen = torch.Generator().manual_seed(seed + 7)
+    report = {"ok": True, "losses": []}
+    for it in range(iters):
+        batches = [bf16_round(torch.rand(B, H, H, C, generator=gen)) for _ in range(runs)]
+        noises = [(bf16_round(torch.randn(B, L, generator=gen)), torch.rand(B, 1, generator=gen)) for _ in range(runs)]
+        bi, ni = iter(batches), iter(noises)
+        with OT.store_bf16(True):
+            ref = tr.iteration(lambda: next(bi), lambda: next(ni))
+        for s_, b_ in enumerate(batches):
+            x_in.feed(s_, b_.cuda())
+        q = []
+        for z_, a_ in noises:
+            q += [z_.clone(), a_.clone()] if model == "iwgan" else [z_.clone()]
+        sess.noise_queue = q
+        sess.begin_step()
+        out = train.iteration()
+        torch.cuda.synchronize()
+        got = {k_: float(v.item()) for k_, v in out.items()}
+        report["losses"].append((got, ref))
+        for k_ in ("g_loss", "d_loss"):
+            # d_loss = mean(D(g)) - mean(D(x)) + 10 gp is a difference of O(1) terms: tolerance is on that scale
+            if abs(got[k_] - ref[k_]) > 6e-2:
+                report["ok"] = False
+        if verbose:
+            print("  iter %d ours %s oracle %s" % (it, got, ref))
+    worst = 0.0
+    for name, prm in sess.store.params.items():
+        d_ref = tr.p[name] - p0[name]
+        d_got = prm.p32.reshape(prm.shape).float().cpu() - p0[name]
+        under_bn = name.startswith("generator/vars/") and name.endswith("/bias") and \
+            ("generator/vars/dc%d/bias" % OM.n_up_stages(H)) != name
+        if float(d_ref.norm()) < 1e-9 or under_bn:
+            # a bias feeding batch-norm has an analytically zero gradient: Adam random-walks it on
+            # rounding noise in TF as well (SURVEY App. C #6), so it is not comparable
+            continue
+        e = float((d_got - d_ref).norm() / d_ref.norm())
+        worst = max(worst, e)
+        if verbose:
+            print("  displacement %-40s err %.3e (|d| %.3e)" % (name, e, float(d_ref.norm())))
+    report["worst_displacement_err"] = worst
+    if worst > 0.25:
+        report["ok"] = False
     return report

@@ -38,6 +38,18 @@ def test_conv_family(case):
         assert err < TOL[op], (case, res)
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] <= 4], ids=lambda c: "x".join(map(str, c)))
+def test_small_channel_simt_fallback(case):
+    """The image-side layers without a workspace: coalesced SIMT kernels instead of im2col + GEMM."""
+    E.SMALL_CHANNEL_GEMM = False
+    try:
+        res = P.conv_case(*case)
+    finally:
+        E.SMALL_CHANNEL_GEMM = True
+    for op, err in res.items():
+        assert err < TOL[op], (case, res)
+
+
 def test_conv_dgrad_fused_mask():
     res = P.conv_case(4, 16, 16, 200, 400, 5, 2, with_mask=True)
     assert res["dgrad"] < TOL["dgrad"], res
