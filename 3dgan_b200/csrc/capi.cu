@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <string>
 
 #include "../../include/b200gan.h"
@@ -112,6 +113,23 @@ static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
 }
 
 
+// split-K factor from a small cost model: GEMM time / wave fill + fp32-atomic epilogue traffic per split
+// (each CTA reduces a 128 x bn_tile fp32 tile into the gradient bucket with red.global.add)
+static int pick_splits(int base, int total_chunks, int bn_tile) {
+  const int max_splits = std::max(1, std::min(total_chunks / 4, 148));
+  const double t_gemm = 2.0 * 128 * bn_tile * 64 * (double)total_chunks * base / 8e14;
+  const double t_atomic = (double)base * 128 * bn_tile * 4 / 2e12;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= max_splits; ++s) {
+    const double waves = (double)base * s / 148.0;
+    const double eff = waves / std::ceil(waves);
+    const double cost = t_gemm / eff + s * t_atomic;
+    if (cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Plain GEMMs on the same kernels (rank-2 tensor maps): used by the small-channel im2col route.
 // ------------------------------------------------------------------------------------------------
@@ -189,9 +207,7 @@ static int dense_wgrad(const void* A, int Ca, int Ka, const void* B, int Cb, lon
   p.ldo = ldo;
   p.alpha = alpha;
   const int base = p.m_tiles * p.n_tiles;
-  int splits = cdiv(148 * 3, base);
-  splits = std::min(splits, std::max(1, p.total_chunks / 4));
-  splits = std::max(1, splits);
+  int splits = pick_splits(base, p.total_chunks, p.bn_tile);
   p.chunks_per_split = cdiv(p.total_chunks, splits);
   splits = cdiv(p.total_chunks, p.chunks_per_split);
   launch_wgrad(p, splits, st);
@@ -447,9 +463,7 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
   p.ldo = g->Cout;
   p.alpha = alpha;
   const int base = p.m_tiles * p.n_tiles * p.ntaps;
-  int splits = cdiv(148 * 3, base);
-  splits = std::min(splits, std::max(1, p.total_chunks / 4));
-  splits = std::max(1, splits);
+  int splits = pick_splits(base, p.total_chunks, p.bn_tile);
   p.chunks_per_split = cdiv(p.total_chunks, splits);
   splits = cdiv(p.total_chunks, p.chunks_per_split);
   launch_wgrad(p, splits, st);

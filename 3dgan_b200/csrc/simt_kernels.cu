@@ -191,32 +191,40 @@ __global__ void smallc_wgrad_kernel(const bf16* __restrict__ xs, const bf16* __r
 // that the tcgen05 kernels run (K = k*k*Cs padded to Kp, a multiple of 8 for TMA alignment).
 // ---------------------------------------------------------------------------------------------
 // A[m][j] = small[n, oh*st+r-pt, ow*st+s-pl, cs]  (j = (r*k+s)*Cs+cs; zero for padding and j >= k*k*Cs)
+// one thread per (output pixel m, filter row r): the k*Cs values of a filter row are contiguous in the
+// image, so the thread copies one short run; index arithmetic is per run, not per element.
 __global__ void im2col_small_kernel(const bf16* __restrict__ xs, bf16* __restrict__ A, ConvGeom g, int Kp,
                                     long long total) {
   const int kk = g.k * g.k * g.Cs;
+  const int run = g.k * g.Cs;
+  const bf16 zero = __float2bfloat16(0.f);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int j = (int)(i % Kp);
-    const long long m = i / Kp;
-    float v = 0.f;
-    if (j < kk) {
-      const int ow = (int)(m % g.Wo);
-      const int oh = (int)((m / g.Wo) % g.Ho);
-      const int n = (int)(m / ((long long)g.Wo * g.Ho));
-      const int cs = j % g.Cs;
-      const int s = (j / g.Cs) % g.k;
-      const int r = j / (g.Cs * g.k);
-      const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
-      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
-        v = __bfloat162float(xs[(((long long)n * g.H + ih) * g.W + iw) * g.Cs + cs]);
+    const int r = (int)(i % g.k);
+    const long long m = i / g.k;
+    const int ow = (int)(m % g.Wo);
+    const int oh = (int)((m / g.Wo) % g.Ho);
+    const int n = (int)(m / ((long long)g.Wo * g.Ho));
+    bf16* dst = A + m * Kp + r * run;
+    const int ih = oh * g.stride + r - g.pad_t;
+    const int iw0 = ow * g.stride - g.pad_l;
+    if (ih < 0 || ih >= g.H) {
+      for (int j = 0; j < run; ++j) dst[j] = zero;
+    } else {
+      const bf16* src = xs + (((long long)n * g.H + ih) * g.W + iw0) * g.Cs;
+      for (int s = 0; s < g.k; ++s) {
+        const bool ok = (iw0 + s) >= 0 && (iw0 + s) < g.W;
+        for (int c = 0; c < g.Cs; ++c) dst[s * g.Cs + c] = ok ? src[s * g.Cs + c] : zero;
+      }
     }
-    A[i] = __float2bfloat16(v);
+    if (r == g.k - 1)
+      for (int j = kk; j < Kp; ++j) A[m * Kp + j] = zero;
   }
 }
 int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
-  const long long total = (long long)a.N * a.Ho * a.Wo * Kp;
-  im2col_small_kernel<<<stride_grid(total, 256, 4), 256, 0, st>>>((const bf16*)xs, (bf16*)A, g, Kp, total);
+  const long long total = (long long)a.N * a.Ho * a.Wo * a.k;
+  im2col_small_kernel<<<stride_grid(total, 256, 1), 256, 0, st>>>((const bf16*)xs, (bf16*)A, g, Kp, total);
   return 0;
 }
 // Wt[cb][j] = w[j][cb] for j < kk, 0 for kk <= j < Kp   (K-major B operand of the fprop GEMM)
@@ -231,15 +239,14 @@ int wpad_transpose(const void* w, void* wt, int kk, int Cb, int Kp, cudaStream_t
   return 0;
 }
 // small[n,h,w,cs] = epi( sum_{r,s valid} T[(n,oh,ow)][(r*k+s)*Cs+cs] ),  T fp32 with row stride Kp
-__global__ void col2im_small_kernel(const float* __restrict__ T, ConvGeom g, int Kp, EpilogueArgs e, long long total) {
+// one thread per small-side pixel: the valid taps are resolved once, the Cs channels are adjacent in T.
+__global__ void col2im_small_kernel(const float* __restrict__ T, ConvGeom g, int Kp, EpilogueArgs e, long long npix) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int cs = (int)(i % g.Cs);
-    const long long p = i / g.Cs;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
     const int x = (int)(p % g.W);
     const int y = (int)((p / g.W) % g.H);
     const int n = (int)(p / ((long long)g.W * g.H));
-    float acc = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int r = 0; r < g.k; ++r) {
       const int th = y + g.pad_t - r;
       if (th < 0 || th % g.stride) continue;
@@ -250,22 +257,30 @@ __global__ void col2im_small_kernel(const float* __restrict__ T, ConvGeom g, int
         if (tw < 0 || tw % g.stride) continue;
         const int ow = tw / g.stride;
         if (ow >= g.Wo) continue;
-        acc += T[(((long long)n * g.Ho + oh) * g.Wo + ow) * Kp + (r * g.k + s) * g.Cs + cs];
+        const float* t = T + (((long long)n * g.Ho + oh) * g.Wo + ow) * Kp + (r * g.k + s) * g.Cs;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < g.Cs) acc[c] += t[c];
       }
     }
-    float v = acc * e.alpha;
-    if (e.bias) v += e.bias[cs];
-    v = act_fwd(v, e.act, e.leak);
-    if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[i]), e.mask_kind, e.leak);
-    if (e.out_f32) reinterpret_cast<float*>(e.out)[i] = v;
-    else reinterpret_cast<bf16*>(e.out)[i] = __float2bfloat16(v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= g.Cs) break;
+      const long long i = p * g.Cs + c;
+      float v = acc[c] * e.alpha;
+      if (e.bias) v += e.bias[c];
+      v = act_fwd(v, e.act, e.leak);
+      if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[i]), e.mask_kind, e.leak);
+      if (e.out_f32) reinterpret_cast<float*>(e.out)[i] = v;
+      else reinterpret_cast<bf16*>(e.out)[i] = __float2bfloat16(v);
+    }
   }
 }
 int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
   EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs};
-  const long long total = (long long)a.N * a.H * a.W * a.Cs;
-  col2im_small_kernel<<<stride_grid(total, 256, 1), 256, 0, st>>>(T, g, Kp, e, total);
+  const long long npix = (long long)a.N * a.H * a.W;
+  col2im_small_kernel<<<stride_grid(npix, 128, 1), 128, 0, st>>>(T, g, Kp, e, npix);
   return 0;
 }
 
