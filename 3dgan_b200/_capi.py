@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200_maskmul": [_P, _P, _P, _LL, _I, _F, _P],
     "b200_affine_act": [_P, _I, _P, _I, _LL, _F, _F, _I, _F, _P],
     "b200_axpby": [_P, _I, _F, _P, _P, _I, _F, _P, _I, _LL, _P],
+    "b200_mul_add": [_P, _P, _P, _P, _LL, _P],
     "b200_fill_f32": [_P, _LL, _F, _P],
     "b200_interp": [_P, _P, _P, _P, _I, _I, _P],
     "b200_rowscale": [_P, _P, _F, _F, _P, _I, _I, _P],

@@ -517,6 +517,9 @@ extern "C" int b200_axpby(const void* a, int a_f32, float sa, const float* dev_s
                           void* out, int out_f32, long long n, b200_stream s) {
   WRAP(axpby(a, a_f32, sa, dev_sa, b, b_f32, sb, out, out_f32, n, (cudaStream_t)s), "axpby");
 }
+extern "C" int b200_mul_add(const void* a, const void* b, const void* c, void* out, long long n, b200_stream s) {
+  WRAP(mul_add(a, b, c, out, n, (cudaStream_t)s), "mul_add");
+}
 extern "C" int b200_fill_f32(float* out, long long n, float v, b200_stream s) {
   WRAP(fill_f32(out, n, v, (cudaStream_t)s), "fill_f32");
 }

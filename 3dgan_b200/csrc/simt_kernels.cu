@@ -407,6 +407,21 @@ int axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b
   return 0;
 }
 
+// out = a + b*c (a optional): VAE reparameterisation z = mu + sigma*eps and its gradient g*eps (models/vae.py:127-128)
+__global__ void mul_add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ c,
+                               bf16* out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = __bfloat162float(b[i]) * __bfloat162float(c[i]);
+    if (a) v += __bfloat162float(a[i]);
+    out[i] = __float2bfloat16(v);
+  }
+}
+int mul_add(const void* a, const void* b, const void* c, void* out, long long n, cudaStream_t st) {
+  mul_add_kernel<<<stride_grid(n, 256, 4), 256, 0, st>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n);
+  return 0;
+}
+
 __global__ void fill_kernel(float* out, long long n, float v) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = v;
@@ -695,6 +710,7 @@ int wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out, cu
 //   kind 3  Bernoulli recon: -(b*log(eps+a)+(1-b)*log(eps+1-a))   dl/da = -(b/(eps+a) - (1-b)/(eps+1-a))
 //   kind 4  sigmoid-CE(logits a, label scalar `lab`)          dl/da = sigmoid(a)-lab
 //   kind 5  squared error (a-b)^2                             dl/da = 2(a-b)
+//   kind 6  0.5 a^2 ; kind 7  0.5 (a^2 - log(eps+a^2) - 1)    VAE latent loss pieces (models/vae.py:80-81)
 // out_sum[0] += scale * sum l ;  grad[i] = gscale * dl/da  (bf16 or fp32), optional
 template <typename TA, typename TG>
 __global__ void eltloss_kernel(const TA* __restrict__ a, const bf16* __restrict__ b, long long n, int kind, float lab,
@@ -713,6 +729,8 @@ __global__ void eltloss_kernel(const TA* __restrict__ a, const bf16* __restrict_
       case 3: l = -(bv * logf(eps + av) + (1.f - bv) * logf(eps + 1.f - av));
               d = -(bv / (eps + av) - (1.f - bv) / (eps + 1.f - av)); break;
       case 4: l = fmaxf(av, 0.f) - av * lab + log1pf(__expf(-fabsf(av))); d = 1.f / (1.f + __expf(-av)) - lab; break;
+      case 6: l = 0.5f * av * av; d = av; break;                                   // KL piece of the mean
+      case 7: l = 0.5f * (av * av - logf(eps + av * av) - 1.f); d = av - av / (eps + av * av); break;  // KL piece of sigma
       default: l = (av - bv) * (av - bv); d = 2.f * (av - bv); break;
     }
     s += l;

@@ -30,6 +30,7 @@ int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, 
                float leak, cudaStream_t st);
 int axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
           int out_f32, long long n, cudaStream_t st);
+int mul_add(const void* a, const void* b, const void* c, void* out, long long n, cudaStream_t st);
 int fill_f32(float* out, long long n, float v, cudaStream_t st);
 int interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, cudaStream_t st);
 int rowscale(const void* in, const float* s, float mul, float add, void* out, int B, int D, cudaStream_t st);

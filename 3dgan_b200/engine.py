@@ -84,6 +84,16 @@ def empty(shape, dtype=BF16):
     return torch.empty(shape, dtype=dtype, device="meta" if S.dry else S.device)
 
 
+class _All(frozenset):
+    """Sentinel active-set: every variable is trainable (single-optimizer models)."""
+
+    def __contains__(self, item):
+        return True
+
+
+ALL = _All()
+
+
 class recording:
     def __init__(self, on=True, active=None):
         self.on, self.active = on, active
@@ -92,7 +102,7 @@ class recording:
         self.prev = (S.recording, S.active)
         S.recording = self.on
         if self.active is not None:
-            S.active = frozenset(id(p) for p in self.active)
+            S.active = ALL if self.active == 'all' else frozenset(id(p) for p in self.active)
         return self
 
     def __exit__(self, *a):
@@ -496,6 +506,24 @@ def wgan_losses(d_real, d_fake, ss=None, lam=10.0):
 
     _record(inputs, [g_loss, d_loss], bw)
     return g_loss, d_loss
+
+
+def reparameterize(mu, sd, eps):
+    """z = mu + sd*eps (models/vae.py:127-128); eps is noise (no gradient)."""
+    out = Tensor(empty(mu.shape, BF16))
+    launch("b200_mul_add", _p(mu.buf), _p(sd.buf), _p(eps.buf), _p(out.buf), mu.numel)
+
+    def bw(gouts):
+        go = _as_bf16(gouts[0])
+        gsd = Tensor(empty(sd.shape, BF16))
+        launch("b200_mul_add", None, _p(go.buf), _p(eps.buf), _p(gsd.buf), sd.numel)
+        gmu = maskmul(go, mu.mask) if mu.mask is not None else go
+        if sd.mask is not None:
+            gsd = maskmul(gsd, sd.mask)
+        return [gmu, gsd]
+
+    _record([mu, sd], [out], bw)
+    return out
 
 
 def add_scalars(a, b):

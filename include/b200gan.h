@@ -84,6 +84,8 @@ int b200_affine_act(const void* in, int in_f32, void* out, int out_f32, long lon
                     float leak, b200_stream s);                      /* out = act(in*mul+add); x -> 2(x-0.5), models/gan.py:50 */
 int b200_axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
                int out_f32, long long n, b200_stream s);             /* out = a*sa*(*dev_sa) + b*sb */
+int b200_mul_add(const void* a, const void* b, const void* c, void* out, long long n, b200_stream s);
+                                                                     /* out = a + b*c (bf16): z = mu + sigma*eps, models/vae.py:127-128 */
 int b200_fill_f32(float* out, long long n, float v, b200_stream s);
 int b200_interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, b200_stream s);
                                                                      /* x + alpha (g - x), models/gan.py:224-226 */

@@ -240,7 +240,7 @@ def ae_decoder(p, z, sizes, final_act):
 
 def cnn_losses(p, x01, sizes):
     """models/cnn.py:20-79: x -> 2(x-0.5); loss = mean|x - d|."""
-    x = 2 * (x01 - 0.5)
+    x = T.stored(2 * (x01 - 0.5))
     e = ae_encoder(p, x, "cnn")
     z = T.dense(e.reshape(e.shape[0], -1), p["latent/vars/d1/weights"], p["latent/vars/d1/bias"])
     d = ae_decoder(p, z, sizes, "tanh")
@@ -254,7 +254,7 @@ def vae_losses(p, x01, eps, sizes):
     flat = e.reshape(e.shape[0], -1)
     mu = T.dense(flat, p["latent/vars/d1/weights"], p["latent/vars/d1/bias"])
     sd = T.dense(flat, p["latent/vars/d2/weights"], p["latent/vars/d2/bias"])
-    z = mu + sd * eps
+    z = T.stored(mu + sd * eps)
     d = ae_decoder(p, z, sizes, "sigmoid")
     rec = -torch.sum(x01 * torch.log(1e-8 + d) + (1 - x01) * torch.log(1e-8 + (1 - d)))
     kl = 0.5 * torch.sum(mu ** 2 + sd ** 2 - torch.log(1e-8 + sd ** 2) - 1)

@@ -1,0 +1,189 @@
+"""CPU: host-side logic of the hot path — graph-construction (dry) pass, variable naming, kernel
+schedule of the critic step, arg_scope, tower slicing and the data-parallel exchange (gloo, world 2)."""
+import argparse
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+
+import b200gan  # noqa: F401
+from b200gan import engine as E
+from b200gan import session as S
+from b200gan.models import gan as gan_model
+from b200gan.ops import layers as L
+from b200gan.ops.activations import lrelu
+from b200gan.ops.arg_scope import arg_scope
+from oracle import models as OM
+from oracle import tf_ops as OT
+
+
+def _args(model="iwgan", B=8, Lz=16):
+    return argparse.Namespace(model=model, batch_size=B, latent_size=Lz, n_disc_train=5, optimizer="adam", lr=1e-4,
+                              beta1=0.5, beta2=0.9)
+
+
+@pytest.mark.parametrize("model,H", [("iwgan", 32), ("iwgan", 64), ("gan", 32), ("wgan", 64)])
+def test_build_pass_creates_reference_variables(model, H):
+    """The dry graph-construction pass creates exactly the TF variables (names, shapes, order) the
+    reference would (oracle.gan_param_specs restates models/gan.py + ops/layers.py naming)."""
+    sess = S.Session()
+    x = S.Input(8, (H, H, 3), slots=6)
+    gan_model.gan(x, _args(model))
+    gs, ds = OM.gan_param_specs(model, H, 3, 16)
+    want = OrderedDict(list(gs.items()) + list(ds.items()))
+    got = OrderedDict((n, p.shape) for n, p in sess.store.params.items())
+    assert set(got) == set(want)
+    for n in want:
+        assert tuple(want[n]) == got[n], n
+    # creation order inside each scope follows the reference's layer order
+    assert [n for n in got if n.startswith("generator")][:3] == list(gs)[:3]
+
+
+def _trace_launches(fn):
+    calls = []
+    orig = E.launch
+
+    def rec(name, *a, **k):
+        calls.append(name)
+        return 0
+    E.launch = rec
+    try:
+        fn()
+    finally:
+        E.launch = orig
+    return calls
+
+
+def test_critic_step_kernel_schedule():
+    """One IWGAN critic run = 3 critic forwards + first-order GP backward + second-order sweep + real/fake
+    backward; count the conv-family launches of each kind (~10 D_fwd-equivalents)."""
+    sess = S.Session()
+    x = S.Input(8, (32, 32, 3), slots=6)
+    train = gan_model.gan(x, _args())
+    E.S.dry = True
+    try:
+        sess.store.begin_pass()
+
+        def run():
+            gl, dl = train.tower(x.next(), "d")
+            E.backward([(dl, None)])
+        calls = _trace_launches(run)
+    finally:
+        E.S.dry = False
+    n_f = calls.count("b200_conv2d_fprop")
+    n_d = calls.count("b200_conv2d_dgrad")
+    n_w = calls.count("b200_conv2d_wgrad")
+    # fprop: G (fc1) + 3 critic passes x 3 convs + second-order 3  = 1 + 9 + 3
+    assert n_f == 13, calls
+    # dgrad: G's 3 deconvs + first-order GP chain (3) + real and fake paths (c3, c2 each)
+    assert n_d == 3 + 3 + 4, calls
+    # wgrad: 3 convs x (real, fake, second-order)
+    assert n_w == 9, calls
+    assert calls.count("b200_gemv_rows") == 3 and calls.count("b200_wgan_loss") == 1
+
+
+def test_generator_step_does_not_touch_critic_gradients():
+    sess = S.Session()
+    x = S.Input(8, (32, 32, 3), slots=6)
+    train = gan_model.gan(x, _args())
+    E.S.dry = True
+    try:
+        sess.store.begin_pass()
+        touched = []
+        orig = E.launch
+
+        def rec(name, *a, **k):
+            touched.append(name)
+            return 0
+        E.launch = rec
+        gl, dl = train.tower(x.next(), "g")
+        E.backward([(gl, None)])
+        E.launch = orig
+    finally:
+        E.S.dry = False
+    # generator run: wgrad only for fc1 + 3 deconvs; the GP path is evaluated (first order) but not differentiated
+    assert touched.count("b200_conv2d_wgrad") == 4
+    assert touched.count("b200_bn_bwd") == 3
+
+
+def test_arg_scope_overrides_defaults_and_nests():
+    seen = {}
+
+    @L.add_arg_scope
+    def layer(x, a=1, b=2):
+        seen["v"] = (a, b)
+    with arg_scope([layer], a=10):
+        layer(0)
+        assert seen["v"] == (10, 2)
+        with arg_scope([layer], b=20):
+            layer(0, a=11)
+            assert seen["v"] == (11, 20)
+        layer(0)
+        assert seen["v"] == (10, 2)
+    layer(0)
+    assert seen["v"] == (1, 2)
+
+
+def test_activation_tags_and_same_padding():
+    assert lrelu.b200_act[0] == b200gan._capi.ACT_LRELU and abs(lrelu.b200_act[1] - 0.2) < 1e-9
+    for size, k, s in [(64, 5, 2), (28, 5, 2), (7, 5, 2), (256, 4, 2), (8, 1, 1)]:
+        out, before, _ = OT.same_pad(size, k, s)
+        assert E.same_pad(size, k, s) == (out, before)
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    sess = S.Session()
+    x = S.Input(8, (32, 32, 3), slots=6)
+    train = gan_model.gan(x, _args())
+    with pytest.raises(RuntimeError):
+        train(sess, _args())
+
+
+# --------------------------------------------------------------------------------------------- gloo, world 2
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    sess = S.Session()
+    sess.cuda = False
+    sess.init_distributed("gloo")
+
+    class G:       # stands in for variables.Group: the exchange only needs the flat gradient bucket
+        g32 = torch.arange(8, dtype=torch.float32) * (rank + 1)
+    scale = sess.all_reduce_grads(G)
+    avg = G.g32 * scale
+    # ops.input.batch_slice: tower r takes rows [r*B, (r+1)*B)
+    from b200gan.ops.input import batch_slice
+    glob = E.Tensor(torch.arange(4 * world, dtype=torch.float32).reshape(4 * world, 1))
+    sl = batch_slice(glob, 4, rank).torch().flatten().tolist()
+    if rank == 0:
+        out.put((avg.tolist(), scale, sl))
+    else:
+        out.put((None, scale, sl))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_exchange_is_tower_mean_gloo_world2():
+    """average_gradients (util.py:118-147) == sum all-reduce x 1/n; batch_slice == tower rows."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    avg = [r[0] for r in res if r[0] is not None][0]
+    towers = [[torch.arange(8, dtype=torch.float32) * (r + 1)] for r in range(2)]
+    want = OT.average_gradients(towers)[0].tolist()
+    assert avg == pytest.approx(want)
+    assert all(abs(r[1] - 0.5) < 1e-9 for r in res)
+    slices = sorted(r[2] for r in res)
+    assert slices == [[0.0, 1.0, 2.0, 3.0], [4.0, 5.0, 6.0, 7.0]]

@@ -50,3 +50,25 @@ def test_cuda_graph_replay_equals_eager():
             assert abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (l0, l1)
     for k in p0:
         assert torch.allclose(p0[k], p1[k], rtol=0, atol=2e-3), k
+
+
+@pytest.mark.parametrize("model,H,C,L,B", [("cnn", 28, 1, 16, 8), ("cnn", 28, 1, 200, 64), ("cnn", 64, 3, 32, 4),
+                                           ("vae", 32, 3, 16, 64), ("vae", 32, 3, 200, 32)])
+def test_autoencoder_step_matches_oracle(model, H, C, L, B):
+    """cnn AE (BASELINE configs[0] shape 28x28x1 B64) and VAE (configs[3] shape 32x32x3)."""
+    res = P.ae_step_parity(model=model, H=H, C=C, L=L, B=B, verbose=True)
+    assert res["ok"], res
+
+
+@pytest.mark.parametrize("model", ["wgan", "gan"])
+def test_gan_wgan_step_matches_oracle(model):
+    """Batch-norm critic with unshared betas for D(real)/D(fake) (SURVEY App. C #5), sigmoid + log losses."""
+    res = P.iwgan_step_parity(H=32, C=3, L=16, B=32, model=model, verbose=True, grad_tol=5e-2)
+    assert res["ok"], res
+
+
+def test_smooth_activation_chain_gradients_are_tight():
+    """conv/dense/deconv forward+backward composition through the public layer API, tanh/sigmoid only
+    (no mask flips): every gradient within 1.5e-2 of the oracle."""
+    res = P.smooth_chain_parity(verbose=True)
+    assert res["ok"], res

@@ -1,0 +1,131 @@
+"""CPU: pins the oracle — against the reference's own known-answer vectors (hem.rmse, the only ones it
+has for this path), against independent derivations (adjointness, float64 finite differences) and
+against its own committed outputs."""
+import json
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import models as OM
+from oracle import tf_ops as OT
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_rmse_reference_known_answers():
+    fx = json.load(open(os.path.join(GOLD, "rmse_known_answers.json")))
+    for c in fx["cases"]:
+        x = torch.full(fx["shape"], c["x"])
+        xh = torch.full(fx["shape"], c["x_hat"])
+        assert abs(float(OT.rmse(x, xh)) - c["rmse"]) < 1e-6
+
+
+@pytest.mark.parametrize("size,k,s,want", [(64, 5, 2, (32, 1, 2)), (32, 5, 2, (16, 1, 2)), (28, 5, 2, (14, 1, 2)),
+                                           (14, 5, 2, (7, 1, 2)), (4, 5, 2, (2, 1, 2)), (7, 5, 2, (4, 2, 2)),
+                                           (256, 4, 2, (128, 1, 1)), (2, 4, 2, (1, 1, 1)), (8, 1, 1, (8, 0, 0))])
+def test_same_padding_table(size, k, s, want):
+    """SURVEY A.1 table (TF SAME: the smaller half of the padding goes first)."""
+    assert OT.same_pad(size, k, s) == want
+
+
+@pytest.mark.parametrize("h,k,hout", [(4, 5, 8), (16, 5, 32), (4, 5, 7), (2, 5, 4), (7, 5, 14), (8, 4, 16), (1, 4, 2)])
+def test_conv_transpose_is_exact_adjoint(h, k, hout):
+    """<conv(x), y> == <x, conv_transpose(y)> for every geometry the models use."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, hout, hout, 3, generator=g, dtype=torch.float64)
+    K = torch.randn(k, k, 3, 4, generator=g, dtype=torch.float64)
+    y = OT.conv2d_same(x, K, 2)
+    assert y.shape[1] == h
+    gy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    lhs = float((y * gy).sum())
+    rhs = float((x * OT.conv2d_transpose_same(gy, K, (hout, hout), 2)).sum())
+    assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs))
+
+
+def test_lrelu_gradient_at_zero_is_leak():
+    x = torch.tensor([-1.0, 0.0, 2.0], requires_grad=True)
+    OT.lrelu(x, 0.2).sum().backward()
+    assert x.grad.tolist() == pytest.approx([0.2, 0.2, 1.0])
+
+
+def test_batch_norm_defaults():
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(6, 4, 4, 5, generator=g) * 3 + 1
+    out = OT.batch_norm_train(h, torch.zeros(5))
+    assert torch.allclose(out.mean(dim=(0, 1, 2)), torch.zeros(5), atol=1e-5)
+    var = out.var(dim=(0, 1, 2), unbiased=False)
+    want = h.var(dim=(0, 1, 2), unbiased=False) / (h.var(dim=(0, 1, 2), unbiased=False) + 1e-3)
+    assert torch.allclose(var, want, atol=1e-4)
+
+
+def test_adam_is_tf_epsilon_hat_form():
+    p, g, m, v = torch.tensor([1.0]), torch.tensor([0.5]), torch.zeros(1), torch.zeros(1)
+    OT.adam_step(p, g, m, v, 1, 0.1, 0.9, 0.999)
+    lr_t = 0.1 * (1 - 0.999) ** 0.5 / (1 - 0.9)
+    want = 1.0 - lr_t * (0.1 * 0.5) / ((0.001 * 0.25) ** 0.5 + 1e-8)
+    assert abs(float(p) - want) < 1e-7
+
+
+def test_iwgan_gradients_match_finite_differences():
+    """The double backward of the gradient penalty, checked in float64 on a tiny critic/generator."""
+    H, C, L, B = 32, 3, 4, 2
+    gs, ds = OM.gan_param_specs("iwgan", H, C, L)
+    p = OM.init_params(OrderedDict(list(gs.items()) + list(ds.items())), 0, torch.float64)
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(B, H, H, C, generator=g, dtype=torch.float64)
+    z = torch.randn(B, L, generator=g, dtype=torch.float64)
+    a = torch.rand(B, 1, generator=g, dtype=torch.float64)
+    r = OM.gan_grads(p, x, z, a, "iwgan", H, C, L)
+    for name, which in (("discriminator/vars/c2/weights", 1), ("discriminator/vars/fc2/weights", 1),
+                        ("generator/vars/dc1/weights", 0), ("generator/BatchNorm_1/beta", 0)):
+        grad = r["grads"][name]
+        idx = tuple(int(torch.randint(0, s, (1,), generator=g)) for s in grad.shape)
+        eps = 1e-6
+        q = OrderedDict((k, v.clone()) for k, v in p.items())
+        q[name][idx] += eps
+        lp = OM.gan_losses(q, x, z, a, "iwgan", H, C, L)[which]
+        q[name][idx] -= 2 * eps
+        lm = OM.gan_losses(q, x, z, a, "iwgan", H, C, L)[which]
+        fd = float(lp - lm) / (2 * eps)
+        assert abs(fd - float(grad[idx])) < 1e-6 * max(1.0, abs(fd)), (name, idx, fd, float(grad[idx]))
+
+
+def test_oracle_matches_committed_outputs():
+    fx = json.load(open(os.path.join(GOLD, "oracle_iwgan_tiny.json")))
+    c = fx["config"]
+    gs, ds = OM.gan_param_specs("iwgan", c["H"], c["C"], c["L"])
+    p = OM.init_params(OrderedDict(list(gs.items()) + list(ds.items())), c["seed"], torch.float64)
+    g = torch.Generator().manual_seed(c["noise_seed"])
+    x = torch.rand(c["B"], c["H"], c["H"], c["C"], generator=g, dtype=torch.float64)
+    z = torch.randn(c["B"], c["L"], generator=g, dtype=torch.float64)
+    a = torch.rand(c["B"], 1, generator=g, dtype=torch.float64)
+    r = OM.gan_grads(p, x, z, a, "iwgan", c["H"], c["C"], c["L"])
+    assert abs(float(r["g_loss"]) - fx["g_loss"]) < 1e-9
+    assert abs(float(r["d_loss"]) - fx["d_loss"]) < 1e-9
+    for k, v in fx["grad_norms"].items():
+        assert abs(float(r["grads"][k].norm()) - v) < 1e-8 * max(1.0, v), k
+
+
+def test_models_run_at_reference_native_and_baseline_shapes():
+    g = torch.Generator().manual_seed(0)
+    for model, H in (("iwgan", 64), ("gan", 32), ("wgan", 32)):
+        gs, ds = OM.gan_param_specs(model, H, 3, 4)
+        p = OM.init_params(OrderedDict(list(gs.items()) + list(ds.items())))
+        r = OM.gan_grads(p, torch.rand(2, H, H, 3, generator=g), torch.randn(2, 4, generator=g),
+                         torch.rand(2, 1, generator=g), model, H, 3, 4)
+        assert torch.isfinite(r["d_loss"]) and torch.isfinite(r["g_loss"])
+        if H == 64:      # 4 critic scores per image at 64x64
+            d = OM.discriminator(p, torch.rand(2, H * H * 3, generator=g), H, 3, 4, model)
+            assert d.shape[0] == 8
+    sp, sizes = OM.ae_param_specs("cnn", 28, 1, 8)
+    assert sizes == [28, 14, 7, 4, 2]
+    r = OM.ae_grads(OM.init_params(sp), torch.rand(2, 28, 28, 1, generator=g), None, "cnn", sizes)
+    assert torch.isfinite(r["losses"]["loss"])
+    sp, sizes = OM.ae_param_specs("vae", 32, 3, 8)
+    r = OM.ae_grads(OM.init_params(sp), torch.rand(2, 32, 32, 3, generator=g), torch.randn(2, 8, generator=g), "vae", sizes)
+    assert all(torch.isfinite(v) for v in r["losses"].values())
+    # VAE differentiates the reconstruction term only (models/vae.py:41): the KL head d2 still gets a
+    # gradient through z = mu + sigma*eps, but nothing flows from the KL term itself
+    assert float(r["grads"]["latent/vars/d2/weights"].abs().sum()) > 0
