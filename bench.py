@@ -144,6 +144,11 @@ def run_b200(a):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU fallback")
+    verbose = bool(os.environ.get("B200GAN_BENCH_VERBOSE"))
+
+    def mark(msg):
+        if verbose:
+            print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
     sess = S.Session(seed=0, noise_seed=1234)
     world, rank = sess.world, sess.rank
     if world > 1:
@@ -153,6 +158,7 @@ def run_b200(a):
     runs = a.n_disc_train + 1
     x = S.Input(a.batch, (a.size, a.size, 3), slots=runs)
     train = gan_model.gan(x, args)
+    mark("model built")
 
     # synthetic data: two sets of `runs` device-resident batches (fresh batch per sess.run-equivalent)
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
@@ -175,9 +181,10 @@ def run_b200(a):
 
     for i in range(max(a.warmup, 3)):
         out = step_resident(i)
-        if os.environ.get("B200GAN_BENCH_VERBOSE"):
-            print("warmup step", i, {k: float(v.item()) for k, v in out.items()}, file=sys.stderr, flush=True)
+        if verbose:
+            mark("warmup step %d %s" % (i, {k: float(v.item()) for k, v in out.items()}))
     barrier()
+    mark("warm-up done")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = E.S.launches
     with ClockSampler(sess.local_rank) as clk:
@@ -229,10 +236,16 @@ def run_b200(a):
                                 "sample": "2 timed iterations (after 1 warm-up) at batch 32 instead of %d, "
                                           "torch-CPU restatement of the reference graph" % a.batch}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # captured graphs hold NCCL work: drop them before tearing the communicator down, and do not
+        # linger in interpreter shutdown (destroy_process_group can wait forever on captured collectives)
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        sess.graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def roofline(sess, train, x, pool, a):
@@ -246,14 +259,14 @@ def roofline(sess, train, x, pool, a):
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
         peak, src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "measured (sustained: timed inside a long step)"
-    prev = sess.use_graphs
-    sess.use_graphs = False
+    prev, prev_dist = sess.use_graphs, sess.dist
+    sess.use_graphs, sess.dist = False, None        # rank-0-only pass: no collective inside
     E.S.profile = []
     x.ring.copy_(pool[0])
     sess.run("profile", train.iteration)
     torch.cuda.synchronize()
     recs, E.S.profile = E.S.profile, None
-    sess.use_graphs = prev
+    sess.use_graphs, sess.dist = prev, prev_dist
     rows = {}
     tot_f = tot_ms = 0.0
     for name, flops, e0, e1, tag in recs:
