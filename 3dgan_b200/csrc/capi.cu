@@ -150,10 +150,11 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
   p.a_rank = 2;
   p.ncols = ncols;
   p.bn_tile = pick_bn_tile(ncols);
+  p.cluster = tapgemm_cluster_size(p);
   {
     long long dims[2] = {K, Nrows};
     long long str[2] = {1, ldb};
-    int box[2] = {kBlockK, p.bn_tile};
+    int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, B, 2, dims, str, box, es)) return -1;
   }
@@ -165,7 +166,7 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
   p.tiles_w = (int)((M + kTileM - 1) / kTileM); p.tiles_h = 1; p.tiles_n = 1;
   p.phase_ext_w[0] = (int)M; p.phase_ext_h[0] = 1; p.ext_n = 1;
   p.o_sw = ldo;
-  p.stages = pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.stages = std::min(pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks));
   p.out = out;
   launch_tapgemm(p, st);
   return 0;
@@ -272,10 +273,11 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.a_rank = 4;
   p.ncols = g->Cout;
   p.bn_tile = pick_bn_tile(g->Cout);
+  p.cluster = tapgemm_cluster_size(p);
   {
     long long dims[2] = {g->Cin, (long long)g->k * g->k * g->Cout};
     long long str[2] = {1, g->Cin};
-    int box[2] = {kBlockK, p.bn_tile};
+    int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, w_t, 2, dims, str, box, es)) return -1;
   }
@@ -297,7 +299,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.phase_ext_w[0] = g->Wo; p.phase_ext_h[0] = g->Ho; p.ext_n = g->N;
   p.phase_o_off[0] = 0;
   p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
-  p.stages = pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.stages = std::min(pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks * g->k * g->k));
   p.out = y;
   launch_tapgemm(p, st);
   return check_launch("conv2d_fprop");
@@ -348,10 +350,11 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.a_rank = 4;
   p.ncols = g->Cin;
   p.bn_tile = pick_bn_tile(g->Cin);
+  p.cluster = tapgemm_cluster_size(p);
   {
     long long dims[2] = {g->Cout, (long long)g->k * g->k * g->Cin};
     long long str[2] = {1, g->Cout};
-    int box[2] = {kBlockK, p.bn_tile};
+    int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, w, 2, dims, str, box, es)) return -1;
   }

@@ -42,6 +42,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Bounded wait: a protocol bug becomes a trap (launch error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
@@ -90,6 +91,34 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// multicast variants: the box lands at the same smem offset in every CTA of `mask` and completes bytes on
+// the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                               int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // rank-dispatched load; c[0] is the innermost (contiguous) coordinate
 __device__ __forceinline__ void tma_load_nd(int rank, uint32_t dst, const void* tmap, uint32_t bar,
                                             const int* c) {
@@ -134,6 +163,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
+}
+// same, arriving on the mbarrier at this offset in every CTA of `mask` (stage release seen by both producers)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask)
+      : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns: thread i gets TMEM lane (base_lane + i)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {

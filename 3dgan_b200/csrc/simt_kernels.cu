@@ -486,45 +486,57 @@ int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B
 // Column reductions over a row-major [R, C] bf16 matrix (C contiguous)
 // =============================================================================================
 // out[c] += alpha * sum_r x[r,c] * (wrow ? wrow[r] : 1);   out2[c] += alpha * sum_r x[r,c]^2 (optional)
+// block = 32 column-pairs x 8 row lanes: each warp reads 128 contiguous bytes of a row, 8 rows in flight per
+// block iteration, 4-way unrolled; row lanes are combined through shared memory, one atomic per column.
 __global__ void colsum_kernel(const bf16* __restrict__ x, const float* __restrict__ wrow, float* out, float* out2,
                               long long R, int C, float alpha, int rows_per_block) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (c >= C) return;
+  __shared__ float red[4][8][64];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 2;
   long long r0 = (long long)blockIdx.y * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > R) r1 = R;
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  const bool pair = (c + 1 < C) && ((C & 1) == 0);
-  for (long long r = r0; r < r1; ++r) {
-    const float wr = wrow ? wrow[r] : 1.f;
-    float v0, v1 = 0.f;
-    if (pair) {
-      __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(x + r * C + c);
-      v0 = __low2float(h); v1 = __high2float(h);
-    } else {
-      v0 = __bfloat162float(x[r * C + c]);
-      if (c + 1 < C) v1 = __bfloat162float(x[r * C + c + 1]);
+  const bool even = (C & 1) == 0;
+  if (c < C) {
+#pragma unroll 4
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const float wr = wrow ? wrow[r] : 1.f;
+      float v0, v1 = 0.f;
+      if (even) {
+        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(x + r * C + c);
+        v0 = __low2float(h); v1 = __high2float(h);
+      } else {
+        v0 = __bfloat162float(x[r * C + c]);
+        if (c + 1 < C) v1 = __bfloat162float(x[r * C + c + 1]);
+      }
+      s0 = fmaf(v0, wr, s0); s1 = fmaf(v1, wr, s1);
+      q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
     }
-    s0 = fmaf(v0, wr, s0); s1 = fmaf(v1, wr, s1);
-    q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
   }
-  atomicAdd(out + c, s0 * alpha);
-  if (c + 1 < C) atomicAdd(out + c + 1, s1 * alpha);
-  if (out2) {
-    atomicAdd(out2 + c, q0 * alpha);
-    if (c + 1 < C) atomicAdd(out2 + c + 1, q1 * alpha);
+  red[0][ty][2 * tx] = s0; red[0][ty][2 * tx + 1] = s1;
+  red[1][ty][2 * tx] = q0; red[1][ty][2 * tx + 1] = q1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < C) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a += red[0][j][threadIdx.x]; b += red[1][j][threadIdx.x]; }
+      atomicAdd(out + cc, a * alpha);
+      if (out2) atomicAdd(out2 + cc, b * alpha);
+    }
   }
 }
 static void colsum_launch(const bf16* x, const float* wrow, float* out, float* out2, long long R, int C, float alpha,
                           cudaStream_t st) {
-  const int threads = 128;
-  const int gx = ((C + 1) / 2 + threads - 1) / threads;
+  const int gx = (C + 63) / 64;
   long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
-  if (want > R) want = R;
+  if (want > (R + 31) / 32) want = (R + 31) / 32;
   if (want < 1) want = 1;
   const int rpb = (int)((R + want - 1) / want);
   const int gy = (int)((R + rpb - 1) / rpb);
-  colsum_kernel<<<dim3(gx, gy), threads, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
+  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
 }
 int colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, cudaStream_t st) {
   colsum_launch((const bf16*)x, wrow, out, nullptr, R, C, alpha, st);

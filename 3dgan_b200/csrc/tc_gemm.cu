@@ -6,6 +6,8 @@
 #include "tc_gemm.cuh"
 #include "ptx.cuh"
 #include "epilogue.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace b200 {
 
@@ -31,11 +33,17 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // =============================================================================================
 // Tap GEMM (conv fprop / dgrad phases / transposed-conv forward / dense)
 // =============================================================================================
+// kCluster == 2: the two CTAs of a cluster own adjacent pixel tiles (same N tile, same phase); each loads
+// its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, so the L2->SM
+// traffic per K chunk drops from A+B to A+B/2.  Stage release (tcgen05.commit) is multicast to both CTAs'
+// empty barriers because either producer writes into both CTAs.
+template <int kCluster>
 __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0;
 
   const int b_bytes = p.bn_tile * kBlockK * 2;
   const int stage_bytes = kABytes + b_bytes;
@@ -50,8 +58,9 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   const int pw0 = tw * p.bw, ph0 = th * p.bh, pn0 = tn * p.bn;
   const int n0 = blockIdx.y * p.bn_tile;
   const int ext_w = p.phase_ext_w[phase], ext_h = p.phase_ext_h[phase];
-  // a tile wholly outside this phase's extent has nothing to do (phases can differ by one row)
-  if (pw0 >= ext_w || ph0 >= ext_h) return;
+  // a tile wholly outside this phase's extent has nothing to do (phases can differ by one row); in a
+  // cluster both CTAs must keep feeding each other, so such a tile only skips its stores
+  if (kCluster == 1 && (pw0 >= ext_w || ph0 >= ext_h)) return;
 
   const int tap_begin = p.phase_tap_begin[phase];
   const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
@@ -62,7 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&ps->full[s]), 1);
-      mbar_init(smem_u32(&ps->empty[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), kCluster);
     }
     mbar_init(smem_u32(&ps->tmem_full), 1);
     fence_mbar_init();
@@ -70,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();       // peer barriers are initialised before anything lands on them
   tc_fence_after();
   const uint32_t tmem = ps->tmem_base;
 
@@ -81,52 +91,79 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 #pragma unroll
       for (int d = 0; d < 4; ++d)
         base[d + 1] = pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
-      int it = 0;
+      int s = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const uint32_t smem0 = smem_u32(smem);
       for (int tp = 0; tp < ntaps; ++tp) {
         const int tap = tap_begin + tp;
         int c[5];
 #pragma unroll
         for (int d = 0; d < 4; ++d) c[d + 1] = base[d + 1] + p.tap_a_off[tap][d];
         const int brow = p.tap_b_row[tap] + n0;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-          const int s = it % p.stages;
-          const uint32_t par = (it / p.stages) & 1;
-          mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
-          const uint32_t full = smem_u32(&ps->full[s]);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(empty0 + 8 * s, par ^ 1);
+          const uint32_t full = full0 + 8 * s;
           mbar_arrive_expect_tx(full, stage_bytes);
-          const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t a_dst = smem0 + s * stage_bytes;
           c[0] = kc * kBlockK;
           tma_load_nd(p.a_rank, a_dst, &p.tmA, full, c);
-          tma_load_2d(a_dst + kABytes, &p.tmB, full, kc * kBlockK, brow);
+          if (kCluster == 1) {
+            tma_load_2d(a_dst + kABytes, &p.tmB, full, kc * kBlockK, brow);
+          } else {
+            const int half_rows = p.bn_tile / 2;
+            tma_load_2d_mc(a_dst + kABytes + crank * half_rows * (kBlockK * 2), &p.tmB, full, kc * kBlockK,
+                           brow + crank * half_rows, (uint16_t)0x3);
+          }
+          if (++s == p.stages) { s = 0; par ^= 1; }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
       const uint32_t idesc = make_idesc_bf16(kTileM, p.bn_tile, 0, 0);
       // the last K chunk of a tap is zero-filled beyond K: issue only the 16-wide steps that hold data
       const int tail_steps = (p.k_total - (p.kchunks - 1) * kBlockK + 15) / 16;
-      int kc = 0;
+      // this loop is the critical path of the kernel (one thread feeds the tensor pipe): no divisions,
+      // descriptors advanced by adds, barrier addresses by a stage counter
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem0, 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + kABytes, 16, 1024);
+      const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      int s = 0, kc = 0;
+      uint32_t par = 0, acc = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t par = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&ps->full[s]), par);
+        mbar_wait(full0 + 8 * s, par);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(a_addr + kABytes, 16, 1024);
-        const int nsteps = (kc == p.kchunks - 1) ? tail_steps : kBlockK / 16;
+        const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
+        const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
+        if (kc != p.kchunks - 1) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4)
-          if (k < nsteps) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4)
+            umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            acc = 1;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (k < tail_steps) {
+              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+              acc = 1;
+            }
+          }
         }
-        umma_commit(smem_u32(&ps->empty[s]));
+        if (kCluster == 1) umma_commit(empty0 + 8 * s);
+        else umma_commit_mc(empty0 + 8 * s, (uint16_t)0x3);
         if (++kc == p.kchunks) kc = 0;
+        if (++s == p.stages) { s = 0; par ^= 1; }
       }
       umma_commit(smem_u32(&ps->tmem_full));
     }
+    __syncwarp();
   } else {
     // -------------------------------------------------------------------- epilogue (4 warps)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
@@ -157,19 +194,62 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();       // the peer may still be signalling our barriers
   if (warp == 1) tmem_dealloc<kTmemCols>(tmem);
+}
+
+static int env_cluster() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200GAN_CLUSTER");
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2) v = 2;
+  }
+  return v;
+}
+
+template <typename Params>
+static void launch_clustered(void (*kern)(Params), const Params& p, dim3 grid, size_t smem, int cluster,
+                             cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+int tapgemm_cluster_size(const TapGemmParams& p) {
+  // the B half each CTA loads must be whole 8-row swizzle atoms: bn_tile % 16 == 0 always holds
+  return env_cluster();
 }
 
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   const int stage_bytes = kABytes + p.bn_tile * kBlockK * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = 227 * 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(tapgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, (p.ncols + p.bn_tile - 1) / p.bn_tile, p.nphases);
-  tapgemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int ntile_y = (p.ncols + p.bn_tile - 1) / p.bn_tile;
+  if (p.cluster == 2) {
+    dim3 grid((tiles + 1) / 2 * 2, ntile_y, p.nphases);
+    launch_clustered(tapgemm_kernel<2>, p, grid, smem, 2, stream);
+  } else {
+    dim3 grid(tiles, ntile_y, p.nphases);
+    tapgemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+  }
 }
 
 // =============================================================================================
@@ -219,18 +299,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 
   if (warp == 0) {
     if (elect_one()) {
+      // running (w,h,n) chunk coordinates: one division at the start, increments afterwards
+      int jw, jh, jn;
+      {
+        int ch = chunk_begin;
+        jw = ch % p.chunks_w; ch /= p.chunks_w;
+        jh = ch % p.chunks_h; ch /= p.chunks_h;
+        jn = ch;
+      }
+      int s = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const uint32_t smem0 = smem_u32(smem);
       for (int it = 0; it < iters; ++it) {
-        int ch = chunk_begin + it;
-        const int jw = ch % p.chunks_w; ch /= p.chunks_w;
-        const int jh = ch % p.chunks_h; ch /= p.chunks_h;
-        const int jn = ch;
         const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
-        const int s = it % p.stages;
-        const uint32_t par = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
-        const uint32_t full = smem_u32(&ps->full[s]);
+        mbar_wait(empty0 + 8 * s, par ^ 1);
+        const uint32_t full = full0 + 8 * s;
         mbar_arrive_expect_tx(full, (a_boxes + b_boxes) * kBox);
-        const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t a_dst = smem0 + s * stage_bytes;
         int c[5];
 #pragma unroll
         for (int d = 0; d < 4; ++d)
@@ -244,29 +330,39 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
           cb[0] = n0 + b * 64;
           tma_load_nd(p.b_rank, a_dst + a_bytes + b * kBox, &p.tmB, full, cb);
         }
+        if (++s == p.stages) { s = 0; par ^= 1; }
+        if (++jw == p.chunks_w) { jw = 0; if (++jh == p.chunks_h) { jh = 0; ++jn; } }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kTileM, p.bn_tile, 1, 1);
+      const uint32_t smem0 = smem_u32(smem);
+      // MN-major SW128: 64-channel blocks kBox apart (LBO), 8-pixel groups 1024 B apart (SBO)
+      const uint64_t adesc0 = make_smem_desc_sw128(smem0, kBox, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, kBox, 1024);
+      const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      int s = 0;
+      uint32_t par = 0, acc = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t par = (it / p.stages) & 1;
-        mbar_wait(smem_u32(&ps->full[s]), par);
+        mbar_wait(full0 + 8 * s, par);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        // MN-major SW128: 64-channel blocks kBox apart (LBO), 8-pixel groups 1024 B apart (SBO)
-        const uint64_t adesc = make_smem_desc_sw128(a_addr, kBox, 1024);
-        const uint64_t bdesc = make_smem_desc_sw128(a_addr + a_bytes, kBox, 1024);
+        const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
+        const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // 16 pixels per MMA = two 8-pixel groups = 2048 bytes (addr field is >>4)
-          umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, (it | k) != 0);
+          umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, acc);
+          acc = 1;
         }
-        umma_commit(smem_u32(&ps->empty[s]));
+        umma_commit(empty0 + 8 * s);
+        if (++s == p.stages) { s = 0; par ^= 1; }
       }
       umma_commit(smem_u32(&ps->tmem_full));
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int ca = m0 + q * 32 + lane;

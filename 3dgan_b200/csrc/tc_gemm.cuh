@@ -39,6 +39,7 @@ struct TapGemmParams {
   long long o_sw, o_sh, o_sn;         // output element strides per pixel index
   int ncols, bn_tile;                 // valid output columns, N tile (multiple of 16, <= 256)
   int stages;
+  int cluster;                        // 1, or 2: CTA pairs share B through TMA multicast (B box = bn_tile/2 rows)
   void* out;
   int out_f32;                        // 0: bf16, 1: fp32
   int accumulate;                     // fp32 only: out += result
@@ -72,6 +73,7 @@ struct WgradParams {
   float alpha;
 };
 
+int tapgemm_cluster_size(const TapGemmParams& p);
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
 void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream);
 
