@@ -115,10 +115,10 @@ static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
 
 // split-K factor from a small cost model: GEMM time / wave fill + fp32-atomic epilogue traffic per split
 // (each CTA reduces a 128 x bn_tile fp32 tile into the gradient bucket with red.global.add)
-static int pick_splits(int base, int total_chunks, int bn_tile) {
+static int pick_splits(int base, int total_chunks, int bn_tile, int dual = 1) {
   const int max_splits = std::max(1, std::min(total_chunks / 4, 148));
-  const double t_gemm = 2.0 * 128 * bn_tile * 64 * (double)total_chunks * base / 8e14;
-  const double t_atomic = (double)base * 128 * bn_tile * 4 / 2e12;
+  const double t_gemm = 2.0 * 128 * dual * bn_tile * 64 * (double)total_chunks * base / 8e14;
+  const double t_atomic = (double)base * 128 * dual * bn_tile * 4 / 2e12;
   int best = 1;
   double best_cost = 1e30;
   for (int s = 1; s <= max_splits; ++s) {
@@ -166,7 +166,8 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
   p.tiles_w = (int)((M + kTileM - 1) / kTileM); p.tiles_h = 1; p.tiles_n = 1;
   p.phase_ext_w[0] = (int)M; p.phase_ext_h[0] = 1; p.ext_n = 1;
   p.o_sw = ldo;
-  p.stages = std::min(pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks));
+  p.dual = tapgemm_dual(p.tiles_w, p.kchunks);
+  p.stages = std::min(pick_stages(p.dual * kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks));
   p.out = out;
   launch_tapgemm(p, st);
   return 0;
@@ -202,13 +203,14 @@ static int dense_wgrad(const void* A, int Ca, int Ka, const void* B, int Cb, lon
   p.bn_tile = pick_bn_tile(Cb);
   p.n_tiles = cdiv(Cb, p.bn_tile);
   p.nb_boxes = cdiv(p.bn_tile, 64);
-  p.stages = pick_stages((2 + p.nb_boxes) * 64 * 64 * 2);
+  p.dual = wgrad_dual(p.m_tiles);
+  p.stages = pick_stages((2 * p.dual + p.nb_boxes) * 64 * 64 * 2);
   p.out = out;
   p.out_tap_stride = 0;
   p.ldo = ldo;
   p.alpha = alpha;
-  const int base = p.m_tiles * p.n_tiles;
-  int splits = pick_splits(base, p.total_chunks, p.bn_tile);
+  const int base = cdiv(p.m_tiles, p.dual) * p.n_tiles;
+  int splits = pick_splits(base, p.total_chunks, p.bn_tile, p.dual);
   p.chunks_per_split = cdiv(p.total_chunks, splits);
   splits = cdiv(p.total_chunks, p.chunks_per_split);
   launch_wgrad(p, splits, st);
@@ -299,7 +301,8 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.phase_ext_w[0] = g->Wo; p.phase_ext_h[0] = g->Ho; p.ext_n = g->N;
   p.phase_o_off[0] = 0;
   p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
-  p.stages = std::min(pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks * g->k * g->k));
+  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks * g->k * g->k);
+  p.stages = std::min(pick_stages(p.dual * kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks * g->k * g->k));
   p.out = y;
   launch_tapgemm(p, st);
   return check_launch("conv2d_fprop");
@@ -397,7 +400,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.tiles_w = cdiv(ext_w0, p.bw); p.tiles_h = cdiv(ext_h0, p.bh); p.tiles_n = cdiv(g->N, p.bn);
   p.ext_n = g->N;
   p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
-  p.stages = pick_stages(kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks);
+  p.stages = pick_stages(p.dual * kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
   p.out = dx;
   launch_tapgemm(p, st);
   return check_launch("conv2d_dgrad");
@@ -460,13 +464,14 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
   p.bn_tile = pick_bn_tile(g->Cout);
   p.n_tiles = cdiv(g->Cout, p.bn_tile);
   p.nb_boxes = cdiv(p.bn_tile, 64);
-  p.stages = pick_stages((2 + p.nb_boxes) * 64 * 64 * 2);
+  p.dual = wgrad_dual(p.m_tiles);
+  p.stages = pick_stages((2 * p.dual + p.nb_boxes) * 64 * 64 * 2);
   p.out = dw;
   p.out_tap_stride = (long long)g->Cin * g->Cout;
   p.ldo = g->Cout;
   p.alpha = alpha;
-  const int base = p.m_tiles * p.n_tiles * p.ntaps;
-  int splits = pick_splits(base, p.total_chunks, p.bn_tile);
+  const int base = cdiv(p.m_tiles, p.dual) * p.n_tiles * p.ntaps;
+  int splits = pick_splits(base, p.total_chunks, p.bn_tile, p.dual);
   p.chunks_per_split = cdiv(p.total_chunks, splits);
   splits = cdiv(p.total_chunks, p.chunks_per_split);
   launch_wgrad(p, splits, st);

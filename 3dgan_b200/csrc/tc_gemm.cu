@@ -46,21 +46,23 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0;
 
   const int b_bytes = p.bn_tile * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
+  const int a_bytes = p.dual * kABytes;         // p.dual (1|2) pixel tiles per CTA share one B tile
+  const int stage_bytes = a_bytes + b_bytes;
   PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
 
-  // tile -> first pixel of the tile, phase, N offset
+  // CTA -> p.dual consecutive pixel tiles (first pixel of each), phase, N offset
   const int phase = blockIdx.z;
-  int t = blockIdx.x;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int tn = t;
-  const int pw0 = tw * p.bw, ph0 = th * p.bh, pn0 = tn * p.bn;
+  int pw0[2], ph0[2], pn0[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int t = blockIdx.x * p.dual + (i < p.dual ? i : 0);
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    pw0[i] = tw * p.bw; ph0[i] = th * p.bh; pn0[i] = t * p.bn;
+  }
   const int n0 = blockIdx.y * p.bn_tile;
   const int ext_w = p.phase_ext_w[phase], ext_h = p.phase_ext_h[phase];
-  // a tile wholly outside this phase's extent has nothing to do (phases can differ by one row); in a
-  // cluster both CTAs must keep feeding each other, so such a tile only skips its stores
-  if (kCluster == 1 && (pw0 >= ext_w || ph0 >= ext_h)) return;
+  // tiles outside this phase's extent / past the last tile load zeros (TMA OOB) and skip their stores
 
   const int tap_begin = p.phase_tap_begin[phase];
   const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
@@ -76,7 +78,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     mbar_init(smem_u32(&ps->tmem_full), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  if (warp == 1) {
+    if (p.dual == 2) tmem_alloc<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+    else tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  }
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();       // peer barriers are initialised before anything lands on them
@@ -86,33 +91,43 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   if (warp == 0) {
     if (elect_one()) {
       // ------------------------------------------------------------------ TMA producer
-      int base[5];
-      base[0] = 0;
+      int base[2][5];
 #pragma unroll
-      for (int d = 0; d < 4; ++d)
-        base[d + 1] = pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
+      for (int i = 0; i < 2; ++i) {
+        base[i][0] = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+          base[i][d + 1] = pw0[i] * p.a_mul[0][d] + ph0[i] * p.a_mul[1][d] + pn0[i] * p.a_mul[2][d];
+      }
       int s = 0;
       uint32_t par = 0;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       const uint32_t smem0 = smem_u32(smem);
       for (int tp = 0; tp < ntaps; ++tp) {
         const int tap = tap_begin + tp;
-        int c[5];
+        int c0[5], c1[5];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) c[d + 1] = base[d + 1] + p.tap_a_off[tap][d];
+        for (int d = 0; d < 4; ++d) {
+          c0[d + 1] = base[0][d + 1] + p.tap_a_off[tap][d];
+          c1[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
+        }
         const int brow = p.tap_b_row[tap] + n0;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(empty0 + 8 * s, par ^ 1);
           const uint32_t full = full0 + 8 * s;
           mbar_arrive_expect_tx(full, stage_bytes);
           const uint32_t a_dst = smem0 + s * stage_bytes;
-          c[0] = kc * kBlockK;
-          tma_load_nd(p.a_rank, a_dst, &p.tmA, full, c);
+          c0[0] = kc * kBlockK;
+          tma_load_nd(p.a_rank, a_dst, &p.tmA, full, c0);
+          if (p.dual == 2) {
+            c1[0] = kc * kBlockK;
+            tma_load_nd(p.a_rank, a_dst + kABytes, &p.tmA, full, c1);
+          }
           if (kCluster == 1) {
-            tma_load_2d(a_dst + kABytes, &p.tmB, full, kc * kBlockK, brow);
+            tma_load_2d(a_dst + a_bytes, &p.tmB, full, kc * kBlockK, brow);
           } else {
             const int half_rows = p.bn_tile / 2;
-            tma_load_2d_mc(a_dst + kABytes + crank * half_rows * (kBlockK * 2), &p.tmB, full, kc * kBlockK,
+            tma_load_2d_mc(a_dst + a_bytes + crank * half_rows * (kBlockK * 2), &p.tmB, full, kc * kBlockK,
                            brow + crank * half_rows, (uint16_t)0x3);
           }
           if (++s == p.stages) { s = 0; par ^= 1; }
@@ -130,9 +145,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       // descriptors advanced by adds, barrier addresses by a stage counter
       const uint32_t smem0 = smem_u32(smem);
       const uint64_t adesc0 = make_smem_desc_sw128(smem0, 16, 1024);
-      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + kABytes, 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, 16, 1024);
       const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const bool dual = p.dual == 2;
       int s = 0, kc = 0;
       uint32_t par = 0, acc = 0;
       for (int it = 0; it < iters; ++it) {
@@ -140,20 +156,15 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         tc_fence_after();
         const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
         const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
-        if (kc != p.kchunks - 1) {
+        const int nsteps = (kc != p.kchunks - 1) ? kBlockK / 16 : tail_steps;
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4)
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          if (k < nsteps) {
+            // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4);
+            // the second pixel tile (A + 16 KiB) accumulates into TMEM columns [256, 256 + N)
             umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            if (dual) umma_bf16(tmem + kTmemCols, adesc + (kABytes >> 4) + 2 * k, bdesc + 2 * k, idesc, acc);
             acc = 1;
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if (k < tail_steps) {
-              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-              acc = 1;
-            }
           }
         }
         if (kCluster == 1) umma_commit(empty0 + 8 * s);
@@ -171,10 +182,6 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     const int iw = r % p.bw;
     const int ih = (r / p.bw) % p.bh;
     const int in = r / (p.bw * p.bh);
-    const int pw = pw0 + iw, ph = ph0 + ih, pn = pn0 + in;
-    const bool row_ok = pw < ext_w && ph < ext_h && pn < p.ext_n;
-    const long long off = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh +
-                          (long long)pw * p.o_sw;
     EpilogueArgs ea;
     ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
     ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
@@ -182,20 +189,44 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
-      if (n0 + c0 >= p.ncols) break;        // warp-uniform
-      uint32_t v[16];
-      tmem_ld16(trow + c0, v);
-      tmem_ld_wait();
-      if (row_ok) epilogue_store16(ea, v, off, n0 + c0);
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    for (int i = 0; i < p.dual; ++i) {
+      const int pw = pw0[i] + iw, ph = ph0[i] + ih, pn = pn0[i] + in;
+      const bool tile_ok = (int)(blockIdx.x * p.dual + i) < total_tiles;
+      const bool row_ok = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
+      const long long off = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh +
+                            (long long)pw * p.o_sw;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+      for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+        if (n0 + c0 >= p.ncols) break;        // warp-uniform
+        uint32_t v[16];
+        tmem_ld16(trow + c0, v);
+        tmem_ld_wait();
+        if (row_ok) epilogue_store16(ea, v, off, n0 + c0);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if (kCluster > 1) cluster_sync_all();       // the peer may still be signalling our barriers
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 1) {
+    if (p.dual == 2) tmem_dealloc<2 * kTmemCols>(tmem);
+    else tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int tapgemm_dual(int m_tiles, int iters) {
+  // two pixel tiles per CTA when there is enough work to still fill the machine
+  static int v = -1;
+  if (v < 0) v = env_int("B200GAN_DUAL", 2);
+  // short K loops (image-side GEMMs) gain more from two co-resident CTAs per SM than from sharing B
+  return (v == 2 && m_tiles >= 2 && iters > 4) ? 2 : 1;
 }
 
 static int env_cluster() {
@@ -233,7 +264,7 @@ int tapgemm_cluster_size(const TapGemmParams& p) {
 }
 
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
-  const int stage_bytes = kABytes + p.bn_tile * kBlockK * 2;
+  const int stage_bytes = p.dual * kABytes + p.bn_tile * kBlockK * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -241,7 +272,7 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int tiles = (p.tiles_w * p.tiles_h * p.tiles_n + p.dual - 1) / p.dual;
   const int ntile_y = (p.ncols + p.bn_tile - 1) / p.bn_tile;
   if (p.cluster == 2) {
     dim3 grid((tiles + 1) / 2 * 2, ntile_y, p.nphases);
@@ -262,15 +293,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int lane = threadIdx.x & 31;
 
   constexpr int kBox = 64 * 64 * 2;                     // 8 KiB: 64 pixels x 64 channels
-  const int a_bytes = 2 * kBox;                         // 128 "M" channels
+  const int a_bytes = p.dual * 2 * kBox;                // p.dual x 128 "M" channels share one B tile
   const int stage_bytes = a_bytes + p.nb_boxes * kBox;
   PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
 
   int t = blockIdx.x;
   const int nt = t % p.n_tiles; t /= p.n_tiles;
-  const int mt = t % p.m_tiles; t /= p.m_tiles;
+  const int md_tiles = (p.m_tiles + p.dual - 1) / p.dual;
+  const int mt = t % md_tiles; t /= md_tiles;
   const int tap = t;
-  const int m0 = mt * kTileM, n0 = nt * p.bn_tile;
+  const int m0 = mt * p.dual * kTileM, n0 = nt * p.bn_tile;
   const int chunk_begin = blockIdx.y * p.chunks_per_split;
   const int chunk_end = min(chunk_begin + p.chunks_per_split, p.total_chunks);
   const int iters = chunk_end - chunk_begin;
@@ -278,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 
   // number of 64-channel boxes that actually hold data (the rest of the tile is never loaded
   // nor stored; stale smem feeds accumulator rows/columns that the epilogue masks off)
-  const int a_boxes = min(2, (p.Ca - m0 + 63) / 64);
+  const int a_boxes = min(2 * p.dual, (p.Ca - m0 + 63) / 64);
   const int b_boxes = min(p.nb_boxes, (p.Cb - n0 + 63) / 64);
 
   if (warp == 0 && elect_one()) {
@@ -291,7 +323,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     mbar_init(smem_u32(&ps->tmem_full), 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  if (warp == 1) {
+    if (p.dual == 2) tmem_alloc<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+    else tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -344,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, kBox, 1024);
       const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const bool second = a_boxes > 2;       // the second 128-channel tile exists
       int s = 0;
       uint32_t par = 0, acc = 0;
       for (int it = 0; it < iters; ++it) {
@@ -353,8 +389,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          // 16 pixels per MMA = two 8-pixel groups = 2048 bytes (addr field is >>4)
+          // 16 pixels per MMA = two 8-pixel groups = 2048 bytes (addr field is >>4); the second channel
+          // tile (A + 16 KiB) accumulates into TMEM columns [256, 256 + N)
           umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, acc);
+          if (second) umma_bf16(tmem + kTmemCols, adesc + ((2 * kBox) >> 4) + 128 * k, bdesc + 128 * k, idesc, acc);
           acc = 1;
         }
         umma_commit(empty0 + 8 * s);
@@ -365,50 +403,62 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     __syncwarp();
   } else {
     const int q = warp & 3;
-    const int ca = m0 + q * 32 + lane;
-    const bool row_ok = ca < p.Ca;
-    float* orow = p.out + (long long)tap * p.out_tap_stride + (long long)ca * p.ldo;
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
-    const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const bool vec_ok = (p.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                         ((p.out_tap_stride & 3) == 0);
-    for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
-      const int col = n0 + c0;
-      if (col >= p.Cb) break;
-      uint32_t v[16];
-      tmem_ld16(trow + c0, v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      if (vec_ok && col + 16 <= p.Cb) {
+    for (int i = 0; i < p.dual; ++i) {
+      if (m0 + i * kTileM >= p.Ca) break;
+      const int ca = m0 + i * kTileM + q * 32 + lane;
+      const bool row_ok = ca < p.Ca;
+      float* orow = p.out + (long long)tap * p.out_tap_stride + (long long)ca * p.ldo;
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+      for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+        const int col = n0 + c0;
+        if (col >= p.Cb) break;
+        uint32_t v[16];
+        tmem_ld16(trow + c0, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        if (vec_ok && col + 16 <= p.Cb) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 f = make_float4(__uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
-                                 __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha);
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j), "f"(f.x),
-                       "f"(f.y), "f"(f.z), "f"(f.w)
-                       : "memory");
+          for (int j = 0; j < 16; j += 4) {
+            float4 f = make_float4(__uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
+                                   __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j), "f"(f.x),
+                         "f"(f.y), "f"(f.z), "f"(f.w)
+                         : "memory");
+          }
+        } else {
+          for (int j = 0; j < 16 && col + j < p.Cb; ++j) atomicAdd(orow + col + j, __uint_as_float(v[j]) * p.alpha);
         }
-      } else {
-        for (int j = 0; j < 16 && col + j < p.Cb; ++j) atomicAdd(orow + col + j, __uint_as_float(v[j]) * p.alpha);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 1) {
+    if (p.dual == 2) tmem_dealloc<2 * kTmemCols>(tmem);
+    else tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+int wgrad_dual(int m_tiles) {
+  static int v = -1;
+  if (v < 0) v = env_int("B200GAN_DUAL", 2);
+  return (v == 2 && m_tiles >= 2) ? 2 : 1;
 }
 
 void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream) {
-  const int stage_bytes = (2 + p.nb_boxes) * 64 * 64 * 2;
+  const int stage_bytes = (2 * p.dual + p.nb_boxes) * 64 * 64 * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
-  dim3 grid(p.m_tiles * p.n_tiles * p.ntaps, splits, 1);
+  dim3 grid(((p.m_tiles + p.dual - 1) / p.dual) * p.n_tiles * p.ntaps, splits, 1);
   wgrad_kernel<<<grid, kThreads, smem, stream>>>(p);
 }
 

@@ -39,6 +39,7 @@ struct TapGemmParams {
   long long o_sw, o_sh, o_sn;         // output element strides per pixel index
   int ncols, bn_tile;                 // valid output columns, N tile (multiple of 16, <= 256)
   int stages;
+  int dual;                           // pixel tiles per CTA (1|2) sharing one B tile; 2 -> two TMEM accumulators
   int cluster;                        // 1, or 2: CTA pairs share B through TMA multicast (B box = bn_tile/2 rows)
   void* out;
   int out_f32;                        // 0: bf16, 1: fp32
@@ -66,6 +67,7 @@ struct WgradParams {
   int total_chunks, chunks_per_split;
   int Ca, Cb;
   int m_tiles, n_tiles, bn_tile, nb_boxes;
+  int dual;                           // 128-channel M tiles per CTA (1|2) sharing one B tile
   int stages;
   float* out;
   long long out_tap_stride;
@@ -74,7 +76,9 @@ struct WgradParams {
 };
 
 int tapgemm_cluster_size(const TapGemmParams& p);
+int tapgemm_dual(int m_tiles, int iters);
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
+int wgrad_dual(int m_tiles);
 void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream);
 
 }  // namespace b200
