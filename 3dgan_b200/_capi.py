@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200gan.so")
+LIB_PATH = os.environ.get("B200GAN_LIB") or os.path.join(_HERE, "lib", "libb200gan.so")
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID = range(5)
 OPT_ADAM, OPT_RMSPROP, OPT_SGD, OPT_MOMENTUM = range(4)
@@ -33,7 +33,7 @@ _GP, _EP = C.POINTER(ConvGeom), C.POINTER(Epilogue)
 SIGNATURES = {
     "b200_conv2d_fprop": [_P, _P, _P, _P, _GP, _EP, _P, _LL, _P],
     "b200_conv2d_dgrad": [_P, _P, _P, _GP, _EP, _P, _LL, _P],
-    "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P, _LL, _P],
+    "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P, _LL, _I, _P],
     "b200_conv2d_workspace_bytes": [_GP, _I],
     "b200_conv2d_route": [_GP, _I],
     "b200_gemv_rows": [_P, _P, _P, _P, _I, _I, _I, _F, _P],

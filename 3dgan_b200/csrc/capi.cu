@@ -110,6 +110,7 @@ static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
   p.out_f32 = e ? e->out_f32 : 0;
   p.accumulate = e ? e->accumulate : 0;
   p.alpha = 1.f;
+  p.epi_pipe = epilogue_pipelined();
 }
 
 
@@ -136,6 +137,31 @@ static int pick_splits(int base, int total_chunks, int bn_tile, int dual = 1) {
 // out[m, n] = epi( sum_k A[m,k] * B[n,k] ),  A [M,K] row stride lda, B [Nrows,K] row stride ldb
 static int dense_gemm(const void* A, long long M, int K, int lda, const void* B, int Nrows, int ldb, void* out,
                       long long ldo, int ncols, const b200_epilogue* e, cudaStream_t st) {
+  {
+    // small K, one N tile, many M tiles: persistent kernel with resident B and double-buffered accumulators
+    int slots = 0;
+    const int kch = cdiv(K, kBlockK), bn = pick_bn_tile(ncols);
+    const long long tiles = (M + kTileM - 1) / kTileM;
+    if (ncols <= 256 && tiles >= 296 && smallk_fits(kch, bn, &slots)) {
+      SmallKParams q;
+      memset(&q, 0, sizeof q);
+      long long dimsA[2] = {K, M}, strA[2] = {1, lda};
+      int boxA[2] = {kBlockK, kTileM}, es[2] = {1, 1};
+      if (make_tmap(&q.tmA, A, 2, dimsA, strA, boxA, es)) return -1;
+      long long dimsB[2] = {K, Nrows}, strB[2] = {1, ldb};
+      int boxB[2] = {kBlockK, bn};
+      if (make_tmap(&q.tmB, B, 2, dimsB, strB, boxB, es)) return -1;
+      q.kchunks = kch; q.k_total = K; q.num_tiles = (int)tiles; q.M = M; q.ncols = ncols; q.bn_tile = bn;
+      q.slots = slots; q.ldo = ldo; q.out = out;
+      q.out_f32 = e ? e->out_f32 : 0; q.accumulate = e ? e->accumulate : 0; q.bias = e ? e->bias : nullptr;
+      q.act = e ? e->act : 0; q.leak = e ? e->leak : 0.f;
+      q.mask_src = e ? (const __nv_bfloat16*)e->mask_src : nullptr; q.mask_kind = e ? e->mask_kind : 0;
+      q.alpha = 1.f;
+      q.epi_pipe = epilogue_pipelined();
+      launch_smallk(q, st);
+      return 0;
+    }
+  }
   TapGemmParams p;
   memset(&p, 0, sizeof p);
   fill_epilogue(p, e);
@@ -245,7 +271,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     char* Wt = A + align256(M * Kp * 2);
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
-    im2col_small(x, A, a, Kp, st);
+    if (im2col_small(x, A, a, Kp, st)) return fail("im2col: k*k*Cin too large");
     wpad_transpose(w, Wt, kk, g->Cout, Kp, st);
     if (dense_gemm(A, M, Kp, Kp, Wt, g->Cout, Kp, y, g->Cout, g->Cout, e, st)) return -1;
     return check_launch("conv2d_fprop(im2col)");
@@ -408,7 +434,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
 }
 
 extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha,
-                                 void* workspace, long long workspace_bytes, b200_stream s) {
+                                 void* workspace, long long workspace_bytes, int workspace_holds_im2col,
+                                 b200_stream s) {
   cudaStream_t st = (cudaStream_t)s;
   const int route = b200_conv2d_route(g, 2);
   if (route < 0) return route;
@@ -418,7 +445,8 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
     const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
-    im2col_small(x, workspace, a, Kp, st);
+    // the fprop of the same input leaves im2col(x) at the start of its workspace: reuse it when told so
+    if (!workspace_holds_im2col && im2col_small(x, workspace, a, Kp, st)) return fail("im2col: k*k*Cin too large");
     if (dense_wgrad(workspace, kk, Kp, dy, g->Cout, M, dw, g->Cout, alpha, st)) return -1;
     return check_launch("conv2d_wgrad(im2col)");
   }

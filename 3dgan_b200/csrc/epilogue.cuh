@@ -41,11 +41,38 @@ struct EpilogueArgs {
   int out_f32;
   int accumulate;
   int ncols;
+  int pipelined;          // prefetch mask rows to L2 + load them one chunk ahead (B200GAN_EPI_PIPE, default 1)
 };
+
+// Epilogue warps are idle during the main loop: pull the mask rows they will need into L2 meanwhile.
+__device__ __forceinline__ void epilogue_prefetch_mask(const EpilogueArgs& e, long long off, int col0, int ncols_tile) {
+  if (!e.mask_src || !e.pipelined) return;
+  const char* p = reinterpret_cast<const char*>(e.mask_src + off + col0);
+  const int bytes = min(ncols_tile, e.ncols - col0) * 2;
+  for (int b = 0; b < bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b));
+}
+// raw 32 bytes (16 bf16) of the mask for one chunk, loaded ahead of use; valid only on the aligned fast path
+struct MaskChunk {
+  uint4 lo, hi;
+  bool loaded;
+};
+__device__ __forceinline__ MaskChunk epilogue_load_mask(const EpilogueArgs& e, long long off, int col) {
+  MaskChunk m;
+  m.loaded = false;
+  if (e.mask_src && e.pipelined && col + 16 <= e.ncols) {
+    const __nv_bfloat16* p = e.mask_src + off + col;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      m.lo = __ldg(reinterpret_cast<const uint4*>(p));
+      m.hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+      m.loaded = true;
+    }
+  }
+  return m;
+}
 
 // 16 consecutive columns [col, col+16) of one output row starting at element offset `off`.
 __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const uint32_t* acc, long long off,
-                                                 int col) {
+                                                 int col, const MaskChunk* pre = nullptr) {
   float v[16];
   const int nvalid = min(16, e.ncols - col);
 #pragma unroll
@@ -60,7 +87,12 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
     for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act, e.leak);
   }
   const long long o = off + col;
-  if (e.mask_src) {
+  if (e.mask_src && pre && pre->loaded) {
+    uint4 raw[2] = {pre->lo, pre->hi};
+    const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(raw);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] *= act_grad_from_out(__bfloat162float(mv[j]), e.mask_kind, e.leak);
+  } else if (e.mask_src) {
     const __nv_bfloat16* m = e.mask_src + o;
     if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(m) & 15) == 0)) {
       uint4 raw[2];

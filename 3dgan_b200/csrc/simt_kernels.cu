@@ -191,39 +191,46 @@ __global__ void smallc_wgrad_kernel(const bf16* __restrict__ xs, const bf16* __r
 // that the tcgen05 kernels run (K = k*k*Cs padded to Kp, a multiple of 8 for TMA alignment).
 // ---------------------------------------------------------------------------------------------
 // A[m][j] = small[n, oh*st+r-pt, ow*st+s-pl, cs]  (j = (r*k+s)*Cs+cs; zero for padding and j >= k*k*Cs)
-// one thread per (output pixel m, filter row r): the k*Cs values of a filter row are contiguous in the
-// image, so the thread copies one short run; index arithmetic is per run, not per element.
+// one thread per 16-byte chunk of an output row (8 consecutive j): the (r, s, offset) decomposition of j
+// comes from a shared-memory table built once per block, stores are 16-byte and fully coalesced.
 __global__ void im2col_small_kernel(const bf16* __restrict__ xs, bf16* __restrict__ A, ConvGeom g, int Kp,
-                                    long long total) {
+                                    long long total_chunks) {
+  __shared__ short tr[128], ts[128];
+  __shared__ int toff[128];
   const int kk = g.k * g.k * g.Cs;
-  const int run = g.k * g.Cs;
-  const bf16 zero = __float2bfloat16(0.f);
+  for (int j = threadIdx.x; j < Kp && j < 128; j += blockDim.x) {
+    const int cs = j % g.Cs, s = (j / g.Cs) % g.k, r = j / (g.Cs * g.k);
+    tr[j] = (short)(j < kk ? r : -1000);
+    ts[j] = (short)s;
+    toff[j] = (r * g.W + s) * g.Cs + cs;
+  }
+  __syncthreads();
+  const int cpr = Kp / 8;                                   // chunks per row
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int r = (int)(i % g.k);
-    const long long m = i / g.k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_chunks; i += stride) {
+    const int ch = (int)(i % cpr);
+    const long long m = i / cpr;
     const int ow = (int)(m % g.Wo);
     const int oh = (int)((m / g.Wo) % g.Ho);
     const int n = (int)(m / ((long long)g.Wo * g.Ho));
-    bf16* dst = A + m * Kp + r * run;
-    const int ih = oh * g.stride + r - g.pad_t;
-    const int iw0 = ow * g.stride - g.pad_l;
-    if (ih < 0 || ih >= g.H) {
-      for (int j = 0; j < run; ++j) dst[j] = zero;
-    } else {
-      const bf16* src = xs + (((long long)n * g.H + ih) * g.W + iw0) * g.Cs;
-      for (int s = 0; s < g.k; ++s) {
-        const bool ok = (iw0 + s) >= 0 && (iw0 + s) < g.W;
-        for (int c = 0; c < g.Cs; ++c) dst[s * g.Cs + c] = ok ? src[s * g.Cs + c] : zero;
-      }
+    const int ih0 = oh * g.stride - g.pad_t, iw0 = ow * g.stride - g.pad_l;
+    const bf16* src = xs + (((long long)n * g.H + ih0) * g.W + iw0) * g.Cs;
+    uint4 outv;
+    bf16* o = reinterpret_cast<bf16*>(&outv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = ch * 8 + e;
+      const int ih = ih0 + tr[j], iw = iw0 + ts[j];
+      const bool ok = ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+      o[e] = ok ? src[toff[j]] : __float2bfloat16(0.f);
     }
-    if (r == g.k - 1)
-      for (int j = kk; j < Kp; ++j) A[m * Kp + j] = zero;
+    *reinterpret_cast<uint4*>(A + m * Kp + ch * 8) = outv;
   }
 }
 int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
-  const long long total = (long long)a.N * a.Ho * a.Wo * a.k;
+  if (Kp > 128) return -1;
+  const long long total = (long long)a.N * a.Ho * a.Wo * (Kp / 8);
   im2col_small_kernel<<<stride_grid(total, 256, 1), 256, 0, st>>>((const bf16*)xs, (bf16*)A, g, Kp, total);
   return 0;
 }
@@ -278,7 +285,7 @@ __global__ void col2im_small_kernel(const float* __restrict__ T, ConvGeom g, int
 }
 int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
-  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs};
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs, 0};
   const long long npix = (long long)a.N * a.H * a.W;
   col2im_small_kernel<<<stride_grid(npix, 128, 1), 128, 0, st>>>(T, g, Kp, e, npix);
   return 0;
@@ -289,7 +296,7 @@ static int round_up32(int v) { return (v + 31) / 32 * 32; }
 int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
   if (a.k * a.k * a.Cs > kSmallK || a.Cb > 1024) return -1;
-  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cb};
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cb, 0};
   const long long npix = (long long)a.N * a.Ho * a.Wo;
   const int threads = round_up32(a.Cb);
   long long blocks = (long long)num_sms() * (threads <= 256 ? 8 : 4);
@@ -303,7 +310,7 @@ int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStre
 int smallc_dgrad(const void* big, const void* w, const SmallConvArgs& a, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
   if (a.Cs > 4) return -1;
-  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs};
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs, 0};
   const long long npix = (long long)a.N * a.H * a.W;
   const int threads = 256;
   long long blocks = (npix * 32 + threads - 1) / threads;
@@ -550,6 +557,29 @@ int bn_sums(const void* z, float* stats, long long R, int C, cudaStream_t st) {
   return 0;
 }
 // a = act((z-mean)*rstd + beta)
+__global__ void bn_apply_vec_kernel(const bf16* __restrict__ z, const float* __restrict__ stats,
+                                    const float* __restrict__ beta, bf16* out, long long R, int C, float eps, int act,
+                                    float leak) {
+  const long long n8 = R * C / 8;
+  const float invR = 1.f / (float)R;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const int c0 = (int)((i * 8) % C);
+    uint4 zv = *reinterpret_cast<const uint4*>(z + i * 8);
+    const bf16* zp = reinterpret_cast<const bf16*>(&zv);
+    uint4 ov;
+    bf16* op = reinterpret_cast<bf16*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      const float mean = stats[c] * invR;
+      const float var = fmaxf(stats[C + c] * invR - mean * mean, 0.f);
+      const float v = (__bfloat162float(zp[e]) - mean) * rsqrtf(var + eps) + beta[c];
+      op[e] = __float2bfloat16(act_fwd(v, act, leak));
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = ov;
+  }
+}
 __global__ void bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ beta,
                                 bf16* out, long long R, int C, float eps, int act, float leak) {
   const long long n = R * C;
@@ -565,7 +595,10 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ z, const float* __restr
 }
 int bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps, int act,
              float leak, cudaStream_t st) {
-  bn_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
+  if ((C & 7) == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    bn_apply_vec_kernel<<<stride_grid(R * C / 8, 256, 2), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
+  else
+    bn_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
   return 0;
 }
 // backward sums: bsum[0:C] += sum_r g ; bsum[C:2C] += sum_r g * xhat      (g already holds act')
@@ -651,6 +684,29 @@ int gemv_rows(const void* a, const void* w, const float* bias, float* out, int M
   return 0;
 }
 // out[m,k] = g[m] * w[k] * act'(mask[m,k])
+__global__ void outer_mask_vec_kernel(const float* __restrict__ g, const bf16* __restrict__ w,
+                                      const bf16* __restrict__ mask, bf16* out, int M, int K, int kind, float leak) {
+  const long long n8 = (long long)M * K / 8;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const long long e0 = i * 8;
+    const float gv = g[e0 / K];
+    uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + (e0 % K)));
+    const bf16* wp = reinterpret_cast<const bf16*>(&wv);
+    uint4 mv = make_uint4(0, 0, 0, 0);
+    if (mask) mv = *reinterpret_cast<const uint4*>(mask + e0);
+    const bf16* mp = reinterpret_cast<const bf16*>(&mv);
+    uint4 ov;
+    bf16* op = reinterpret_cast<bf16*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float v = gv * __bfloat162float(wp[e]);
+      if (mask) v *= act_grad_from_out(__bfloat162float(mp[e]), kind, leak);
+      op[e] = __float2bfloat16(v);
+    }
+    *reinterpret_cast<uint4*>(out + e0) = ov;
+  }
+}
 __global__ void outer_mask_kernel(const float* __restrict__ g, const bf16* __restrict__ w, const bf16* __restrict__ mask,
                                   bf16* out, int M, int K, int kind, float leak) {
   const long long n = (long long)M * K;
@@ -663,7 +719,11 @@ __global__ void outer_mask_kernel(const float* __restrict__ g, const bf16* __res
 }
 int outer_mask(const float* g, const void* w, const void* mask, void* out, int M, int K, int kind, float leak,
                cudaStream_t st) {
-  outer_mask_kernel<<<stride_grid((long long)M * K, 256, 4), 256, 0, st>>>(g, (const bf16*)w, (const bf16*)mask, (bf16*)out, M, K, kind, leak);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if ((K & 7) == 0 && aligned)
+    outer_mask_vec_kernel<<<stride_grid((long long)M * K / 8, 256, 2), 256, 0, st>>>(g, (const bf16*)w, (const bf16*)mask, (bf16*)out, M, K, kind, leak);
+  else
+    outer_mask_kernel<<<stride_grid((long long)M * K, 256, 4), 256, 0, st>>>(g, (const bf16*)w, (const bf16*)mask, (bf16*)out, M, K, kind, leak);
   return 0;
 }
 

@@ -185,24 +185,38 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
     EpilogueArgs ea;
     ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
     ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
-    ea.accumulate = p.accumulate; ea.ncols = p.ncols;
+    ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
 
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    bool row_ok[2];
+    long long off[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int pw = pw0[i] + iw, ph = ph0[i] + ih, pn = pn0[i] + in;
+      const bool tile_ok = i < p.dual && (int)(blockIdx.x * p.dual + i) < total_tiles;
+      row_ok[i] = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
+      off[i] = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh + (long long)pw * p.o_sw;
+      if (row_ok[i]) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
+    }
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
-    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    for (int i = 0; i < p.dual; ++i) {
-      const int pw = pw0[i] + iw, ph = ph0[i] + ih, pn = pn0[i] + in;
-      const bool tile_ok = (int)(blockIdx.x * p.dual + i) < total_tiles;
-      const bool row_ok = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
-      const long long off = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh +
-                            (long long)pw * p.o_sw;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i >= p.dual) break;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+      MaskChunk cur;
+      cur.loaded = false;
+      if (row_ok[i]) cur = epilogue_load_mask(ea, off[i], n0);
       for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
         if (n0 + c0 >= p.ncols) break;        // warp-uniform
         uint32_t v[16];
         tmem_ld16(trow + c0, v);
+        MaskChunk nxt;
+        nxt.loaded = false;
+        if (row_ok[i] && c0 + 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off[i], n0 + c0 + 16);
         tmem_ld_wait();
-        if (row_ok) epilogue_store16(ea, v, off, n0 + c0);
+        if (row_ok[i]) epilogue_store16(ea, v, off[i], n0 + c0, &cur);
+        cur = nxt;
       }
     }
   }
@@ -219,6 +233,12 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
+}
+
+int epilogue_pipelined() {
+  static int v = -1;
+  if (v < 0) v = env_int("B200GAN_EPI_PIPE", 1);
+  return v;
 }
 
 int tapgemm_dual(int m_tiles, int iters) {
@@ -281,6 +301,174 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     dim3 grid(tiles, ntile_y, p.nphases);
     tapgemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
   }
+}
+
+// =============================================================================================
+// Persistent small-K GEMM (image-side layers after im2col / before col2im)
+// =============================================================================================
+struct SmallKSmem {
+  uint64_t b_full;
+  uint64_t a_full[8];
+  uint64_t a_empty[8];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) smallk_kernel(const __grid_constant__ SmallKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b_bytes = p.bn_tile * kBlockK * 2;            // one K chunk of B
+  const int slot_bytes = p.kchunks * kABytes;             // one A tile: 128 rows x full K
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem + (size_t)p.kchunks * b_bytes;
+  SmallKSmem* ps = reinterpret_cast<SmallKSmem*>(smem_a + (size_t)p.slots * slot_bytes);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    mbar_init(smem_u32(&ps->b_full), 1);
+    for (int s = 0; s < p.slots; ++s) {
+      mbar_init(smem_u32(&ps->a_full[s]), 1);
+      mbar_init(smem_u32(&ps->a_empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&ps->acc_full[a]), 1);
+      mbar_init(smem_u32(&ps->acc_empty[a]), 4);            // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t bfull = smem_u32(&ps->b_full);
+      mbar_arrive_expect_tx(bfull, p.kchunks * b_bytes);
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        tma_load_2d(smem_u32(smem_b + (size_t)kc * b_bytes), &p.tmB, bfull, kc * kBlockK, 0);
+      int s = 0;
+      uint32_t par = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&ps->a_empty[s]), par ^ 1);
+        const uint32_t full = smem_u32(&ps->a_full[s]);
+        mbar_arrive_expect_tx(full, slot_bytes);
+        const uint32_t dst = smem_u32(smem_a + (size_t)s * slot_bytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(dst + kc * kABytes, &p.tmA, full, kc * kBlockK, tile * kTileM);
+        if (++s == p.slots) { s = 0; par ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, p.bn_tile, 0, 0);
+      const int tail_steps = (p.k_total - (p.kchunks - 1) * kBlockK + 15) / 16;
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b), 16, 1024);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(smem_a), 16, 1024);
+      mbar_wait(smem_u32(&ps->b_full), 0);
+      int s = 0, acc = 0;
+      uint32_t par = 0, accpar = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&ps->acc_empty[acc]), accpar ^ 1);   // epilogue has drained this accumulator
+        mbar_wait(smem_u32(&ps->a_full[s]), par);
+        tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)(((uint32_t)slot_bytes >> 4) * s);
+        uint32_t accum = 0;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const int nsteps = (kc == p.kchunks - 1) ? tail_steps : kBlockK / 16;
+          const uint64_t ad = adesc + (uint64_t)((kABytes >> 4) * kc);
+          const uint64_t bd = bdesc0 + (uint64_t)(((uint32_t)b_bytes >> 4) * kc);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (k < nsteps) {
+              umma_bf16(tmem + acc * kTmemCols, ad + 2 * k, bd + 2 * k, idesc, accum);
+              accum = 1;
+            }
+          }
+        }
+        umma_commit(smem_u32(&ps->a_empty[s]));
+        umma_commit(smem_u32(&ps->acc_full[acc]));
+        if (++s == p.slots) { s = 0; par ^= 1; }
+        acc ^= 1;
+        if (acc == 0) accpar ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    EpilogueArgs ea;
+    ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
+    ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
+    ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
+    int acc = 0;
+    uint32_t accpar = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long row = (long long)tile * kTileM + r;
+      const bool row_ok = row < p.M;
+      const long long off = row * p.ldo;
+      if (row_ok) epilogue_prefetch_mask(ea, off, 0, p.bn_tile);
+      mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
+      tc_fence_after();
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols;
+      MaskChunk cur;
+      cur.loaded = false;
+      if (row_ok) cur = epilogue_load_mask(ea, off, 0);
+      for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+        if (c0 >= p.ncols) break;
+        uint32_t v[16];
+        tmem_ld16(trow + c0, v);
+        MaskChunk nxt;
+        nxt.loaded = false;
+        if (row_ok && c0 + 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off, c0 + 16);
+        tmem_ld_wait();
+        if (row_ok) epilogue_store16(ea, v, off, c0, &cur);
+        cur = nxt;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[acc]));
+      acc ^= 1;
+      if (acc == 0) accpar ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * kTmemCols>(tmem);
+}
+
+bool smallk_fits(int kchunks, int bn_tile, int* slots) {
+  if (getenv("B200GAN_NO_SMALLK")) return false;
+  if (kchunks < 1 || kchunks > 4 || bn_tile > 256) return false;
+  const int b_total = kchunks * bn_tile * kBlockK * 2;
+  const int slot = kchunks * kABytes;
+  int n = (227 * 1024 - 2048 - b_total) / slot;
+  if (n < 2) return false;
+  *slots = n > 8 ? 8 : n;
+  return true;
+}
+
+void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
+  const size_t smem = (size_t)p.kchunks * p.bn_tile * kBlockK * 2 + (size_t)p.slots * p.kchunks * kABytes +
+                      sizeof(SmallKSmem) + 1024;
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaFuncSetAttribute(smallk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  smallk_kernel<<<grid, kThreads, smem, stream>>>(p);
 }
 
 // =============================================================================================

@@ -39,6 +39,7 @@ struct TapGemmParams {
   long long o_sw, o_sh, o_sn;         // output element strides per pixel index
   int ncols, bn_tile;                 // valid output columns, N tile (multiple of 16, <= 256)
   int stages;
+  int epi_pipe;                       // epilogue: prefetch + pipelined mask loads
   int dual;                           // pixel tiles per CTA (1|2) sharing one B tile; 2 -> two TMEM accumulators
   int cluster;                        // 1, or 2: CTA pairs share B through TMA multicast (B box = bn_tile/2 rows)
   void* out;
@@ -77,7 +78,33 @@ struct WgradParams {
 
 int tapgemm_cluster_size(const TapGemmParams& p);
 int tapgemm_dual(int m_tiles, int iters);
+int epilogue_pipelined();
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
+
+// Persistent small-K GEMM: out[M, ncols] = epi(A[M,K] * B[ncols,K]^T) with K <= 256 (image-side im2col GEMMs).
+// The whole B stays resident in shared memory, A tiles (128 rows, full K) stream through a ring, and two TMEM
+// accumulators alternate so the epilogue of tile i overlaps the MMAs of tile i+1.  grid = #SMs.
+struct SmallKParams {
+  CUtensorMap tmA;                    // [M, K], box 64 x 128
+  CUtensorMap tmB;                    // [rows, K], box 64 x bn_tile
+  int kchunks, k_total;
+  int num_tiles;
+  long long M;
+  int ncols, bn_tile;
+  int slots;                          // A ring depth
+  int epi_pipe;
+  long long ldo;
+  void* out;
+  int out_f32, accumulate;
+  const float* bias;
+  int act;
+  float leak;
+  const __nv_bfloat16* mask_src;
+  int mask_kind;
+  float alpha;
+};
+bool smallk_fits(int kchunks, int bn_tile, int* slots);
+void launch_smallk(const SmallKParams& p, cudaStream_t stream);
 int wgrad_dual(int m_tiles);
 void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream);
 

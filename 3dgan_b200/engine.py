@@ -71,6 +71,10 @@ def _workspace(g, op):
     return empty((n,), torch.uint8), n
 
 
+def _geom_key(g):
+    return (g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.k, g.stride, g.pad_t, g.pad_l)
+
+
 def _conv_tag(op, g):
     """(tag, algorithmic FLOPs) of one conv-family launch: 2*N*Ho*Wo*k^2*Cin*Cout, logical channels
     (SURVEY 8d); tc: tensor-core route, simt: small-channel route."""
@@ -111,7 +115,7 @@ class recording:
 
 # ------------------------------------------------------------------------------------------ tensors
 class Tensor:
-    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "__weakref__")
+    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "im2col", "__weakref__")
 
     def __init__(self, buf, shape=None, requires_grad=False, mask=None):
         self.buf = buf
@@ -120,6 +124,7 @@ class Tensor:
         self.mask = mask
         self.node = None
         self.grad_f32 = False      # leaf whose gradient is wanted in fp32 (the GP interpolates)
+        self.im2col = None         # (geometry key, workspace) left by a small-channel fprop of this tensor
 
     @property
     def f32(self):
@@ -249,6 +254,8 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
         ws, wsb = _workspace(g, 0)
         launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e), _p(ws), wsb,
                flops=fl, tag=tag)
+        if ws is not None:
+            x.im2col = (_geom_key(g), ws)       # the filter gradient of this layer reads the same im2col
     else:
         tag, fl = _conv_tag("dgrad", g) if S.profile is not None else (None, 0)
         ws, wsb = _workspace(g, 1)
@@ -270,10 +277,14 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
                            out_f32=x.grad_f32)
         if W.accum:
             tag, fl = _conv_tag("wgrad", g) if S.profile is not None else (None, 0)
-            ws, wsb = _workspace(g, 2)
             a_, b_ = (x, go) if direction == "fprop" else (go, x)
-            launch("b200_conv2d_wgrad", _p(a_.buf), _p(b_.buf), _p(W.g32), C.byref(g), 1.0, _p(ws), wsb, flops=fl,
-                   tag=tag)
+            cached = a_.im2col if (a_.im2col is not None and a_.im2col[0] == _geom_key(g)) else None
+            if cached is not None:
+                ws, wsb, ready = cached[1], cached[1].numel(), 1
+            else:
+                (ws, wsb), ready = _workspace(g, 2), 0
+            launch("b200_conv2d_wgrad", _p(a_.buf), _p(b_.buf), _p(W.g32), C.byref(g), 1.0, _p(ws), wsb, ready,
+                   flops=fl, tag=tag)
         if bias is not None and bias.accum:
             c = out_shape[-1]
             launch("b200_colsum", _p(go.buf), None, _p(bias.g32), go.numel // c, c, 1.0)

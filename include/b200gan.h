@@ -57,7 +57,9 @@ int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, void* y, co
 int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const b200_conv_geom* g, const b200_epilogue* e,
                       void* workspace, long long workspace_bytes, b200_stream s);
 int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha,
-                      void* workspace, long long workspace_bytes, b200_stream s);
+                      void* workspace, long long workspace_bytes, int workspace_holds_im2col, b200_stream s);
+/* workspace_holds_im2col: pass 1 with the workspace a previous b200_conv2d_fprop of the SAME x and geometry
+ * used (its first bytes are im2col(x)); the small-channel wgrad then skips recomputing it. */
 /* scratch the call needs (0 for the direct tensor-core route).  Small-channel (image-side, Cin <= 4) layers
  * run as im2col / col2im + the same tcgen05 GEMM when a workspace of this size is passed; with
  * workspace == NULL they fall back to the coalesced SIMT kernels. */

@@ -82,7 +82,7 @@ def conv_case(N, H, W, Cin, Cout, k, stride, seed=0, act=K.ACT_LRELU, with_mask=
     # ---- wgrad (accumulates into g32)
     xd, dyd = dev(x), dev(dy)           # keep both alive: the allocator may otherwise alias them
     ws, wsb = E._workspace(geom, 2)
-    E.launch("b200_conv2d_wgrad", E._p(xd.buf), E._p(dyd.buf), E._p(Wp.g32), E.C.byref(geom), 1.0, E._p(ws), wsb)
+    E.launch("b200_conv2d_wgrad", E._p(xd.buf), E._p(dyd.buf), E._p(Wp.g32), E.C.byref(geom), 1.0, E._p(ws), wsb, 0)
     torch.cuda.synchronize()
     out["wgrad"] = rel_err(Wp.g32.reshape(Wt.shape), gw_ref)
     return out

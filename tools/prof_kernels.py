@@ -20,6 +20,6 @@ for (N, H, W, Cin, Cout, k, s) in CASES:
         y = E.conv_like("fprop", x, Wp, geom, bias=bp, act=K.ACT_LRELU, leak=0.2)
         gx = E.conv_like("dgrad", dy, Wp, geom)
         ws, wsb = E._workspace(geom, 2)
-        E.launch("b200_conv2d_wgrad", E._p(x.buf), E._p(dy.buf), E._p(Wp.g32), E.C.byref(geom), 1.0, E._p(ws), wsb)
+        E.launch("b200_conv2d_wgrad", E._p(x.buf), E._p(dy.buf), E._p(Wp.g32), E.C.byref(geom), 1.0, E._p(ws), wsb, 0)
     torch.cuda.synchronize()
 print("done")
