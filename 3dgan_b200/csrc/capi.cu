@@ -95,6 +95,7 @@ extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
     return fail("small-channel conv: needs Cout % 8 == 0, or k*k*Cin <= 80 and Cout <= 1024");
   }
   if (g->Cin % 8) return fail("tensor-core conv needs Cin % 8 == 0");
+  if (op != 0 && is_small(g->Cout)) return 3;     // <= 4 output channels: SIMT backward (PatchGAN head)
   if (op != 0 && g->Cout % 8) return fail("tensor-core dgrad/wgrad need Cout % 8 == 0");
   if (kk > kMaxTaps) return fail("filter larger than 5x5");
   if (op == 1 && g->stride * g->stride > kMaxPhases) return fail("dgrad stride > 2");
@@ -363,6 +364,14 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
     if (smallc_dgrad(dy, w, a, st)) return fail("smallc_dgrad: unsupported shape");
     return check_launch("smallc_dgrad");
   }
+  if (route == 3) {
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
+                    e ? e->mask_kind : 0, dx, e ? e->out_f32 : 0};
+    if (e && e->accumulate) return fail("small-output dgrad: accumulate unsupported");
+    smallout_dgrad(dy, w, a, st);
+    return check_launch("smallout_dgrad");
+  }
   TapGemmParams p;
   memset(&p, 0, sizeof p);
   fill_epilogue(p, e);
@@ -455,6 +464,12 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
                     nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
     if (smallc_wgrad(x, dy, dw, a, alpha, st)) return fail("smallc_wgrad: unsupported shape");
     return check_launch("smallc_wgrad");
+  }
+  if (route == 3) {
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
+    if (smallout_wgrad(x, dy, dw, a, alpha, st)) return fail("smallout_wgrad: unsupported shape");
+    return check_launch("smallout_wgrad");
   }
   WgradParams p;
   memset(&p, 0, sizeof p);

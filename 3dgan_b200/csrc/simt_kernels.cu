@@ -291,6 +291,95 @@ int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Convolutions whose OUTPUT has <= 4 channels (pix2pix PatchGAN head m5: 512 -> 1, hem/models/pix2pix.py:256).
+// The forward runs on the tensor cores (N tile 16); TMA cannot address a 1-channel gradient tensor, so the
+// two backward products are coalesced SIMT kernels (they are tiny: B*8*8 output pixels).
+// ---------------------------------------------------------------------------------------------
+// dx[n,h,w,ci] = epi( sum_{r,s valid} sum_co dy[n,(h+pt-r)/st,(w+pl-s)/st,co] * w[r,s,ci,co] )
+__global__ void smallout_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ w, ConvGeom g,
+                                      EpilogueArgs e, long long total) {
+  // here g.Cs = Cin (big), g.Cb = Cout (small): reuse of the struct with swapped meaning is avoided by
+  // passing Cin in g.Cs and Cout in g.Cb explicitly
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ci = (int)(i % g.Cs);
+    const long long p = i / g.Cs;
+    const int x = (int)(p % g.W);
+    const int y = (int)((p / g.W) % g.H);
+    const int n = (int)(p / ((long long)g.W * g.H));
+    float acc = 0.f;
+    for (int r = 0; r < g.k; ++r) {
+      const int th = y + g.pad_t - r;
+      if (th < 0 || th % g.stride) continue;
+      const int oh = th / g.stride;
+      if (oh >= g.Ho) continue;
+      for (int s = 0; s < g.k; ++s) {
+        const int tw = x + g.pad_l - s;
+        if (tw < 0 || tw % g.stride) continue;
+        const int ow = tw / g.stride;
+        if (ow >= g.Wo) continue;
+        const bf16* d = dy + (((long long)n * g.Ho + oh) * g.Wo + ow) * g.Cb;
+        const bf16* wr = w + ((long long)(r * g.k + s) * g.Cs + ci) * g.Cb;
+        for (int co = 0; co < g.Cb; ++co) acc = fmaf(__bfloat162float(d[co]), __bfloat162float(wr[co]), acc);
+      }
+    }
+    float v = acc * e.alpha;
+    if (e.bias) v += e.bias[ci];
+    v = act_fwd(v, e.act, e.leak);
+    if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[i]), e.mask_kind, e.leak);
+    if (e.out_f32) reinterpret_cast<float*>(e.out)[i] = v;
+    else reinterpret_cast<bf16*>(e.out)[i] = __float2bfloat16(v);
+  }
+}
+// dw[r,s,ci,co] += alpha * sum_{n,oh,ow} x[n,oh*st+r-pt,ow*st+s-pl,ci] * dy[n,oh,ow,co]
+// block (tap, pixel range); threads over ci (coalesced reads of x rows); one atomic per (tap,ci,co) per block
+__global__ void smallout_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* dw, ConvGeom g,
+                                      float alpha, long long npix, int pix_per_block) {
+  const int tap = blockIdx.y;
+  const int r = tap / g.k, s = tap % g.k;
+  long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  for (int ci = threadIdx.x; ci < g.Cs; ci += blockDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long p = p0; p < p1; ++p) {
+      const int ow = (int)(p % g.Wo);
+      const int oh = (int)((p / g.Wo) % g.Ho);
+      const int n = (int)(p / ((long long)g.Wo * g.Ho));
+      const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
+      if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
+      const float xv = __bfloat162float(x[(((long long)n * g.H + ih) * g.W + iw) * g.Cs + ci]);
+#pragma unroll
+      for (int co = 0; co < 4; ++co)
+        if (co < g.Cb) acc[co] = fmaf(xv, __bfloat162float(dy[p * g.Cb + co]), acc[co]);
+    }
+#pragma unroll
+    for (int co = 0; co < 4; ++co)
+      if (co < g.Cb) atomicAdd(dw + ((long long)tap * g.Cs + ci) * g.Cb + co, acc[co] * alpha);
+  }
+}
+int smallout_dgrad(const void* dy, const void* w, const SmallConvArgs& a, cudaStream_t st) {
+  // a.Cs = Cin (many channels, the conv input), a.Cb = Cout (<= 4)
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs, 0};
+  const long long total = (long long)a.N * a.H * a.W * a.Cs;
+  smallout_dgrad_kernel<<<stride_grid(total, 256, 2), 256, 0, st>>>((const bf16*)dy, (const bf16*)w, g, e, total);
+  return 0;
+}
+int smallout_wgrad(const void* x, const void* dy, float* dw, const SmallConvArgs& a, float alpha, cudaStream_t st) {
+  if (a.Cb > 4) return -1;
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  const long long npix = (long long)a.N * a.Ho * a.Wo;
+  int blocks = num_sms() * 2 / (a.k * a.k) + 1;
+  int ppb = (int)((npix + blocks - 1) / blocks);
+  if (ppb < 1) ppb = 1;
+  blocks = (int)((npix + ppb - 1) / ppb);
+  smallout_wgrad_kernel<<<dim3(blocks, a.k * a.k), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, g, alpha, npix, ppb);
+  return 0;
+}
+
 static int round_up32(int v) { return (v + 31) / 32 * 32; }
 
 int smallc_fprop(const void* xs, const void* w, const SmallConvArgs& a, cudaStream_t st) {

@@ -25,6 +25,9 @@ int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaSt
 int wpad_transpose(const void* w, void* wt, int kk, int Cb, int Kp, cudaStream_t st);
 int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st);
 
+int smallout_dgrad(const void* dy, const void* w, const SmallConvArgs& a, cudaStream_t st);
+int smallout_wgrad(const void* x, const void* dy, float* dw, const SmallConvArgs& a, float alpha, cudaStream_t st);
+
 int maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, cudaStream_t st);
 int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
                float leak, cudaStream_t st);

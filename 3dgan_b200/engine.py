@@ -549,6 +549,21 @@ def add_scalars(a, b):
     return out
 
 
+def scale_scalar(a, s):
+    """s * a for an fp32 [1] loss piece."""
+    out = Tensor(empty((1,), F32))
+    launch("b200_axpby", _p(a.buf), 1, float(s), None, None, 0, 0.0, _p(out.buf), 1, 1)
+
+    def bw(gouts):
+        go = gouts[0]
+        if go is True:
+            return [("scaled", float(s))]
+        raise K.B200Error("scale_scalar: only a seed gradient is supported")
+
+    _record([a], [out], bw)
+    return out
+
+
 def eltloss(a, b, kind, label=0.0, scale=1.0):
     """sum_i l(a_i, b_i) * scale -> fp32 [1]; backward fuses dl/da (kinds: see simt_kernels.cu)."""
     out = Tensor(empty((1,), F32))
@@ -557,9 +572,11 @@ def eltloss(a, b, kind, label=0.0, scale=1.0):
            _p(out.buf), None, 0)
 
     def bw(gouts):
+        seed = gouts[0]
+        mult = seed[1] if isinstance(seed, tuple) else 1.0      # True = seed 1.0; ("scaled", s) = seed s
         g = Tensor(empty(a.shape, F32 if a.f32 else BF16))
         launch("b200_eltloss", _p(a.buf), int(a.f32), None if b is None else _p(b.buf), a.numel, kind, label, 0.0,
-               scale, None, _p(g.buf), int(a.f32))
+               scale * mult, None, _p(g.buf), int(a.f32))
         if a.mask is not None:
             g = maskmul_any(g, a.mask)
         return [g]
@@ -606,7 +623,8 @@ def backward(seeds, wrt=(), create_graph=False, accumulate=True):
             return
         key = id(t)
         if key in grads:
-            grads[key] = (t, add_grads(grads[key][1], g) if g is not True and grads[key][1] is not True else g)
+            is_seed = lambda v: v is True or isinstance(v, tuple)
+            grads[key] = (t, add_grads(grads[key][1], g) if not is_seed(g) and not is_seed(grads[key][1]) else g)
         else:
             grads[key] = (t, g)
         if t.node is not None:

@@ -2,6 +2,7 @@
 from . import cnn as _cnn
 from . import gan as _gan
 from . import vae as _vae
+from .pix2pix import pix2pix  # noqa: F401  (Gen-2 plugin class: pix2pix(x_y, args).train(sess, args, feed))
 
 MODEL_FUNCS = {
     'gan': (_gan.gan, lambda a: 1),

@@ -64,7 +64,8 @@ int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_
  * run as im2col / col2im + the same tcgen05 GEMM when a workspace of this size is passed; with
  * workspace == NULL they fall back to the coalesced SIMT kernels. */
 long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
-/* which kernel family a geometry maps to: 1 tensor core, 2 small-channel SIMT, negative = unsupported */
+/* which kernel family a geometry maps to: 1 tensor core, 2 small-channel input (image side), 3 small-channel
+ * output backward (<= 4 output channels, SIMT), negative = unsupported */
 int b200_conv2d_route(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
 
 /* ---- dense with one output unit (critic fc2, models/gan.py:285; replaces tf.matmul ops/layers.py:57) */

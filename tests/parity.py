@@ -361,3 +361,68 @@ def smooth_chain_parity(B=16, seed=0, verbose=False):
             report["ok"] = False
     report["worst_grad_err"] = worst
     return report
+
+
+def pix2pix_step_parity(B=2, add_l1=True, seed=0, verbose=False, grad_tol=0.25, cos_tol=0.97):
+    """One discriminator run and one generator run of pix2pix (256x256, U-Net + PatchGAN) vs the oracle.
+    16 conv/deconv layers of ReLU/LReLU + batch-norm over tiny batches: tolerances follow ae_step_parity
+    (cosine >= cos_tol, relative L2 <= grad_tol per variable; losses 2e-2)."""
+    from b200gan.models import pix2pix
+    from oracle import pix2pix as OP
+    args = argparse.Namespace(batch_size=B, n_disc_train=1, optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.999,
+                              batch_norm_gen=False, batch_norm_disc=False, add_l1=add_l1, dropout=0, noise=[])
+    sess = S.Session(seed=seed)
+    sess.use_graphs = False
+    xi, yi = S.Input(B, (256, 256, 3), slots=2), S.Input(B, (256, 256, 1), slots=2)
+    model = pix2pix((xi, yi), args)
+    gs, ds = OP.param_specs()
+    p = OP.init_params(OrderedDict(list(gs.items()) + list(ds.items())), seed)
+    for k_ in p:
+        p[k_] = bf16_round(p[k_])
+    assert set(p) == set(sess.store.params), sorted(set(p) ^ set(sess.store.params))[:6]
+    load_oracle_params(sess, p)
+    gen = torch.Generator().manual_seed(seed + 5)
+    x01 = bf16_round(torch.rand(B, 256, 256, 3, generator=gen))
+    y01 = bf16_round(torch.rand(B, 256, 256, 1, generator=gen))
+    with OT.store_bf16(True):
+        ref = OP.grads(p, x01, y01, add_l1)
+    for s_ in range(2):
+        xi.feed(s_, x01.cuda()); yi.feed(s_, y01.cuda())
+    report = {"ok": True}
+    worst = 0.0
+    for mode, prefix in (("d", "discriminator"), ("g", "generator")):
+        sess.begin_step()
+        xi.reset(); yi.reset()
+        for grp in sess.store.groups:
+            grp.zero_grad()
+        ls = model.tower(xi.next(), yi.next(), mode)
+        E.backward([(ls["d_total"] if mode == "d" else ls["g_total"], None)])
+        torch.cuda.synchronize()
+        for nme, t in ls.items():
+            got = float(t.buf.item())
+            want = ref["losses"][nme] if nme != "rmse" else ref["losses"]["rmse"] ** 2
+            report["%s/%s" % (mode, nme)] = (got, want)
+            if abs(got - want) > 2e-3 + 2e-2 * abs(want):
+                report["ok"] = False
+        for name, prm in sess.store.params.items():
+            if not name.startswith(prefix):
+                continue
+            want = ref["grads"][name]
+            got = prm.g32.reshape(prm.shape).float().cpu()
+            wn = float(want.norm())
+            under_bn = name.startswith("generator/decoder/vars/") and name.endswith("/bias")
+            if wn < 1e-7 or under_bn:
+                e = float((got - want).abs().max())
+                bad = e > 1e-2
+                cos = 1.0
+            else:
+                e = float((got - want).norm()) / wn
+                cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
+                bad = e > grad_tol or cos < cos_tol
+                worst = max(worst, e)
+            if verbose or bad:
+                print("  [%s] %-40s err %.3e cos %.4f (norm %.3e)%s" % (mode, name, e, cos, wn, "  <-- FAIL" if bad else ""))
+            if bad:
+                report["ok"] = False
+    report["worst_grad_err"] = worst
+    return report

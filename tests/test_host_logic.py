@@ -187,3 +187,25 @@ def test_data_parallel_exchange_is_tower_mean_gloo_world2():
     assert all(abs(r[1] - 0.5) < 1e-9 for r in res)
     slices = sorted(r[2] for r in res)
     assert slices == [[0.0, 1.0, 2.0, 3.0], [4.0, 5.0, 6.0, 7.0]]
+
+
+def test_pix2pix_build_pass_matches_reference_variables():
+    """54.4 M generator + 2.77 M discriminator parameters, TF names incl. the 'enocder' typo (pix2pix.py:182)."""
+    from b200gan.models import pix2pix
+    from oracle import pix2pix as OP
+    a = argparse.Namespace(batch_size=2, n_disc_train=1, optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.999,
+                           batch_norm_gen=False, batch_norm_disc=False, add_l1=True, dropout=0, noise=[])
+    sess = S.Session()
+    pix2pix((S.Input(2, (256, 256, 3), slots=3), S.Input(2, (256, 256, 1), slots=3)), a)
+    gs, ds = OP.param_specs()
+    want = OrderedDict(list(gs.items()) + list(ds.items()))
+    got = OrderedDict((n, p.shape) for n, p in sess.store.params.items())
+    assert list(got) == list(want)
+    assert all(tuple(want[n]) == got[n] for n in want)
+    assert abs(sum(p.numel for n, p in sess.store.params.items() if n.startswith("generator")) - 54.408e6) < 1e3
+
+
+def test_small_output_conv_routes_to_simt_backward():
+    from b200gan import _capi
+    g = _capi.ConvGeom(N=2, H=16, W=16, Cin=512, Ho=8, Wo=8, Cout=1, k=4, stride=2, pad_t=1, pad_l=1)
+    assert _capi.route(g, 0) == 1 and _capi.route(g, 1) == 3 and _capi.route(g, 2) == 3

@@ -72,3 +72,52 @@ def test_smooth_activation_chain_gradients_are_tight():
     (no mask flips): every gradient within 1.5e-2 of the oracle."""
     res = P.smooth_chain_parity(verbose=True)
     assert res["ok"], res
+
+
+def test_pix2pix_step_matches_oracle():
+    """BASELINE configs[4] shape (256x256 rgb + depth) at batch 2, --add_l1: U-Net generator with skip
+    concatenations, PatchGAN discriminator (512 -> 1 head), sigmoid-CE + L1 losses."""
+    res = P.pix2pix_step_parity(B=4, verbose=True, grad_tol=0.3, cos_tol=0.95)
+    assert res["ok"], res
+
+
+def test_pix2pix_train_iterations_run_and_report_reference_losses():
+    """plugin.train(sess, args, feed) (hem/models/ModelPlugin.py:11-24): D update, G update, losses-only run."""
+    import argparse
+    import math
+    import torch
+    from b200gan import session as S
+    from b200gan.models import pix2pix
+    args = argparse.Namespace(batch_size=2, n_disc_train=1, optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.999,
+                              batch_norm_gen=False, batch_norm_disc=False, add_l1=True, dropout=0, noise=[])
+    sess = S.Session(seed=0)
+    xi, yi = S.Input(2, (256, 256, 3), slots=3), S.Input(2, (256, 256, 1), slots=3)
+    model = pix2pix((xi, yi), args)
+    gen = torch.Generator().manual_seed(0)
+    first = last = None
+    for it in range(4):
+        xi.ring.copy_(torch.rand(xi.ring.shape, generator=gen)); yi.ring.copy_(torch.rand(yi.ring.shape, generator=gen))
+        last = model.train(sess, args, None)
+        first = first or last
+        assert set(last) == {"l1", "g_fake", "g_total", "d_real", "d_fake", "d_total", "rmse"}
+        assert all(math.isfinite(v) for v in last.values()), last
+    assert abs(last["g_total"] - (last["g_fake"] + 10.0 * last["l1"])) < 1e-3
+    assert abs(last["d_total"] - (last["d_real"] + last["d_fake"])) < 1e-4
+
+
+def test_rmse_reference_known_answers_on_gpu():
+    """The reference's own golden vectors for this path (hem/ops/test_losses.py:7-27) through the CUDA op."""
+    import json
+    import math
+    import os
+    import torch
+    from b200gan import engine as E
+    from b200gan.hem_ops import layers as hem
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rmse_known_answers.json")))
+    E.begin()
+    for c in fx["cases"]:
+        x = E.Tensor(torch.full(fx["shape"], c["x"], dtype=torch.bfloat16, device="cuda"))
+        xh = E.Tensor(torch.full(fx["shape"], c["x_hat"], dtype=torch.bfloat16, device="cuda"))
+        ms = hem.rmse(x, xh)
+        torch.cuda.synchronize()
+        assert abs(math.sqrt(float(ms.buf.item())) - c["rmse"]) < 1e-5
