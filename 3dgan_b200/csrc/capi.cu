@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <cmath>
@@ -42,7 +43,7 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor, dims[0] contiguous; strides in ELEMENTS for dims 1..rank-1; 128-byte swizzle, zero OOB fill
 static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides,
-                     const int* box, const int* estride) {
+                     const int* box, const int* estride, int swizzle_bytes = 128) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail("tensor map base not 16-byte aligned");
@@ -59,7 +60,10 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long lon
     }
   }
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[64];
@@ -112,6 +116,7 @@ static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
   p.accumulate = e ? e->accumulate : 0;
   p.alpha = 1.f;
   p.epi_pipe = epilogue_pipelined();
+  p.l2_prefetch = l2_prefetch_distance();
 }
 
 
@@ -231,6 +236,7 @@ static int dense_wgrad(const void* A, int Ca, int Ka, const void* B, int Cb, lon
   p.n_tiles = cdiv(Cb, p.bn_tile);
   p.nb_boxes = cdiv(p.bn_tile, 64);
   p.dual = wgrad_dual(p.m_tiles);
+  p.l2_prefetch = l2_prefetch_distance();
   p.stages = pick_stages((2 * p.dual + p.nb_boxes) * 64 * 64 * 2);
   p.out = out;
   p.out_tap_stride = 0;
@@ -241,6 +247,15 @@ static int dense_wgrad(const void* A, int Ca, int Ka, const void* B, int Cb, lon
   p.chunks_per_split = cdiv(p.total_chunks, splits);
   splits = cdiv(p.total_chunks, p.chunks_per_split);
   launch_wgrad(p, splits, st);
+  return 0;
+}
+
+// narrow-box variant for the last K chunk of a tap: 1 -> 16 channels (SWIZZLE_32B), 2 -> 32 (SWIZZLE_64B), 0 -> none
+static int pick_tail_mode(int K) {
+  if (getenv("B200GAN_NO_TAIL")) return 0;
+  const int tail = K - (cdiv(K, kBlockK) - 1) * kBlockK;
+  if (tail <= 16) return 1;
+  if (tail <= 32) return 2;
   return 0;
 }
 
@@ -309,6 +324,17 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, w_t, 2, dims, str, box, es)) return -1;
+    p.tail_mode = pick_tail_mode(g->Cin);
+    if (p.tail_mode) {
+      const int tw = p.tail_mode == 1 ? 16 : 32;
+      box[0] = tw;
+      if (make_tmap(&p.tmB_tail, w_t, 2, dims, str, box, es, tw * 2)) return -1;
+      long long adims[4] = {g->Cin, g->W, g->H, g->N};
+      long long astr[4] = {1, g->Cin, (long long)g->W * g->Cin, (long long)g->H * g->W * g->Cin};
+      int abox[4] = {tw, p.bw * st_, p.bh * st_, p.bn};
+      int aes[4] = {1, st_, st_, 1};
+      if (make_tmap(&p.tmA_tail, x, 4, adims, astr, abox, aes, tw * 2)) return -1;
+    }
   }
   p.kchunks = cdiv(g->Cin, kBlockK);
   p.k_total = g->Cin;
@@ -329,7 +355,9 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.phase_o_off[0] = 0;
   p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
   p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks * g->k * g->k);
-  p.stages = std::min(pick_stages(p.dual * kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks * g->k * g->k));
+  p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
+  p.stages = std::min(pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)),
+                      std::max(2, (p.kchunks - p.merge_tail) * g->k * g->k));
   p.out = y;
   launch_tapgemm(p, st);
   return check_launch("conv2d_fprop");
@@ -395,6 +423,17 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
     int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, w, 2, dims, str, box, es)) return -1;
+    p.tail_mode = pick_tail_mode(g->Cout);
+    if (p.tail_mode) {
+      const int tw = p.tail_mode == 1 ? 16 : 32;
+      box[0] = tw;
+      if (make_tmap(&p.tmB_tail, w, 2, dims, str, box, es, tw * 2)) return -1;
+      long long adims[4] = {g->Cout, g->Wo, g->Ho, g->N};
+      long long astr[4] = {1, g->Cout, (long long)g->Wo * g->Cout, (long long)g->Ho * g->Wo * g->Cout};
+      int abox[4] = {tw, p.bw, p.bh, p.bn};
+      int aes[4] = {1, 1, 1, 1};
+      if (make_tmap(&p.tmA_tail, dy, 4, adims, astr, abox, aes, tw * 2)) return -1;
+    }
   }
   p.kchunks = cdiv(g->Cout, kBlockK);
   p.k_total = g->Cout;
@@ -436,7 +475,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.ext_n = g->N;
   p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
   p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks);
-  p.stages = pick_stages(p.dual * kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2);
+  p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
+  p.stages = pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail));
   p.out = dx;
   launch_tapgemm(p, st);
   return check_launch("conv2d_dgrad");
@@ -508,6 +548,7 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
   p.n_tiles = cdiv(g->Cout, p.bn_tile);
   p.nb_boxes = cdiv(p.bn_tile, 64);
   p.dual = wgrad_dual(p.m_tiles);
+  p.l2_prefetch = l2_prefetch_distance();
   p.stages = pick_stages((2 * p.dual + p.nb_boxes) * 64 * 64 * 2);
   p.out = dw;
   p.out_tap_stride = (long long)g->Cin * g->Cout;

@@ -91,6 +91,32 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+// L2 prefetch of a tile (no shared memory, no barrier): issued several K blocks ahead of the real load so
+// that the pipeline's TMA loads hit L2 instead of paying HBM latency
+__device__ __forceinline__ void tma_prefetch_nd(int rank, const void* tmap, const int* c) {
+  switch (rank) {
+    case 2:
+      asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c[0]), "r"(c[1])
+                   : "memory");
+      break;
+    case 3:
+      asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c[0]),
+                   "r"(c[1]), "r"(c[2])
+                   : "memory");
+      break;
+    case 4:
+      asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c[0]),
+                   "r"(c[1]), "r"(c[2]), "r"(c[3])
+                   : "memory");
+      break;
+    default:
+      asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(tmap), "r"(c[0]),
+                   "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+                   : "memory");
+      break;
+  }
+}
+
 // multicast variants: the box lands at the same smem offset in every CTA of `mask` and completes bytes on
 // the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
@@ -196,15 +222,20 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major
 }
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): [0,14) addr>>4 | [16,30) LBO>>4 |
 // [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
-                                                         uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (cute::UMMA::LayoutType)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= (uint64_t)layout << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes,
+                                                         uint32_t sbo_bytes) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes, 2);
 }
 
 }  // namespace b200

@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 
   const int b_bytes = p.bn_tile * kBlockK * 2;
   const int a_bytes = p.dual * kABytes;         // p.dual (1|2) pixel tiles per CTA share one B tile
-  const int stage_bytes = a_bytes + b_bytes;
+  // p.merge_tail: the narrow tail chunk of a tap rides in the stage of the tap's last full chunk
+  // (its own small area behind the full tiles), so it does not cost a pipeline slot of its own
+  const int tail_area = p.merge_tail ? (p.dual * kTileM + p.bn_tile) * 32 : 0;
+  const int stage_bytes = a_bytes + b_bytes + tail_area;
   PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
 
   // CTA -> p.dual consecutive pixel tiles (first pixel of each), phase, N offset
@@ -62,11 +65,13 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   }
   const int n0 = blockIdx.y * p.bn_tile;
   const int ext_w = p.phase_ext_w[phase], ext_h = p.phase_ext_h[phase];
+  const int tail_row_bytes = p.tail_mode == 1 ? 32 : 64;      // bytes per row of a narrow tail box
   // tiles outside this phase's extent / past the last tile load zeros (TMA OOB) and skip their stores
 
   const int tap_begin = p.phase_tap_begin[phase];
   const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
-  const int iters = ntaps * p.kchunks;
+  const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;     // pipeline iterations per tap
+  const int iters = ntaps * kloops;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmA);
@@ -103,6 +108,27 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       uint32_t par = 0;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       const uint32_t smem0 = smem_u32(smem);
+      // L2 prefetch iterator, p.l2_prefetch K blocks ahead of the loads
+      int ptp = 0, pkc = 0;
+      auto prefetch_next = [&]() {
+        if (ptp < ntaps) {
+          const int tap = tap_begin + ptp;
+          int c[5];
+          c[0] = pkc * kBlockK;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) c[d + 1] = base[0][d + 1] + p.tap_a_off[tap][d];
+          tma_prefetch_nd(p.a_rank, &p.tmA, c);
+          if (p.dual == 2) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) c[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
+            tma_prefetch_nd(p.a_rank, &p.tmA, c);
+          }
+          int cb[2] = {pkc * kBlockK, p.tap_b_row[tap] + n0 + (kCluster > 1 ? (int)crank * (p.bn_tile / 2) : 0)};
+          tma_prefetch_nd(2, &p.tmB, cb);
+          if (++pkc == p.kchunks) { pkc = 0; ++ptp; }
+        }
+      };
+      for (int i = 0; i < p.l2_prefetch; ++i) prefetch_next();
       for (int tp = 0; tp < ntaps; ++tp) {
         const int tap = tap_begin + tp;
         int c0[5], c1[5];
@@ -112,23 +138,45 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
           c1[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
         }
         const int brow = p.tap_b_row[tap] + n0;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+        for (int kc = 0; kc < kloops; ++kc) {
+          if (p.l2_prefetch) prefetch_next();
           mbar_wait(empty0 + 8 * s, par ^ 1);
           const uint32_t full = full0 + 8 * s;
-          mbar_arrive_expect_tx(full, stage_bytes);
           const uint32_t a_dst = smem0 + s * stage_bytes;
           c0[0] = kc * kBlockK;
-          tma_load_nd(p.a_rank, a_dst, &p.tmA, full, c0);
-          if (p.dual == 2) {
-            c1[0] = kc * kBlockK;
-            tma_load_nd(p.a_rank, a_dst + kABytes, &p.tmA, full, c1);
-          }
+          c1[0] = kc * kBlockK;
+          const bool tail = !p.merge_tail && p.tail_mode != 0 && kc == p.kchunks - 1;
+          const bool with_tail = p.merge_tail && kc == kloops - 1;
+          // the tail chunk of a tap moves only its 16 / 32 valid channels (narrow box, 32B / 64B swizzle)
+          const int row_bytes = tail ? tail_row_bytes : kBlockK * 2;
+          const int a_tile = kTileM * row_bytes;
+          const void* mA = tail ? (const void*)&p.tmA_tail : (const void*)&p.tmA;
+          const void* mB = tail ? (const void*)&p.tmB_tail : (const void*)&p.tmB;
+          mbar_arrive_expect_tx(full, p.dual * a_tile + p.bn_tile * row_bytes + (with_tail ? tail_area : 0));
+          tma_load_nd(p.a_rank, a_dst, mA, full, c0);
+          if (p.dual == 2) tma_load_nd(p.a_rank, a_dst + a_tile, mA, full, c1);
           if (kCluster == 1) {
-            tma_load_2d(a_dst + a_bytes, &p.tmB, full, kc * kBlockK, brow);
+            tma_load_2d(a_dst + p.dual * a_tile, mB, full, kc * kBlockK, brow);
           } else {
             const int half_rows = p.bn_tile / 2;
-            tma_load_2d_mc(a_dst + a_bytes + crank * half_rows * (kBlockK * 2), &p.tmB, full, kc * kBlockK,
+            tma_load_2d_mc(a_dst + p.dual * a_tile + crank * half_rows * row_bytes, mB, full, kc * kBlockK,
                            brow + crank * half_rows, (uint16_t)0x3);
+          }
+          if (with_tail) {
+            // 16-wide tail boxes (rows of 32 B) behind the full tiles of this stage
+            const uint32_t t_dst = a_dst + a_bytes + b_bytes;
+            const int t_tile = kTileM * 32;
+            c0[0] = (kc + 1) * kBlockK;
+            c1[0] = (kc + 1) * kBlockK;
+            tma_load_nd(p.a_rank, t_dst, &p.tmA_tail, full, c0);
+            if (p.dual == 2) tma_load_nd(p.a_rank, t_dst + t_tile, &p.tmA_tail, full, c1);
+            if (kCluster == 1) {
+              tma_load_2d(t_dst + p.dual * t_tile, &p.tmB_tail, full, (kc + 1) * kBlockK, brow);
+            } else {
+              const int half_rows = p.bn_tile / 2;
+              tma_load_2d_mc(t_dst + p.dual * t_tile + crank * half_rows * 32, &p.tmB_tail, full, (kc + 1) * kBlockK,
+                             brow + crank * half_rows, (uint16_t)0x3);
+            }
           }
           if (++s == p.stages) { s = 0; par ^= 1; }
         }
@@ -156,20 +204,55 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
         tc_fence_after();
         const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
         const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
-        const int nsteps = (kc != p.kchunks - 1) ? kBlockK / 16 : tail_steps;
+        if (p.merge_tail) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          if (k < nsteps) {
-            // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4);
-            // the second pixel tile (A + 16 KiB) accumulates into TMEM columns [256, 256 + N)
+          for (int k = 0; k < kBlockK / 16; ++k) {
             umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
             if (dual) umma_bf16(tmem + kTmemCols, adesc + (kABytes >> 4) + 2 * k, bdesc + 2 * k, idesc, acc);
             acc = 1;
           }
+          if (kc == kloops - 1) {
+            // the tap's 16-wide tail (SWIZZLE_32B tiles behind the full tiles of this stage): one K step
+            const uint32_t tb0 = smem0 + s * stage_bytes + a_bytes + b_bytes;
+            const uint32_t t_tile = kTileM * 32;
+            umma_bf16(tmem, make_smem_desc(tb0, 16, 256, 6), make_smem_desc(tb0 + p.dual * t_tile, 16, 256, 6), idesc, 1);
+            if (dual)
+              umma_bf16(tmem + kTmemCols, make_smem_desc(tb0 + t_tile, 16, 256, 6),
+                        make_smem_desc(tb0 + p.dual * t_tile, 16, 256, 6), idesc, 1);
+          }
+        } else if (kc != p.kchunks - 1 || p.tail_mode == 0) {
+          const int nsteps = (kc != p.kchunks - 1) ? kBlockK / 16 : tail_steps;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (k < nsteps) {
+              // +32 bytes per 16-element K step inside the 128-byte swizzle row (addr field is >>4);
+              // the second pixel tile (A + 16 KiB) accumulates into TMEM columns [256, 256 + N)
+              umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+              if (dual) umma_bf16(tmem + kTmemCols, adesc + (kABytes >> 4) + 2 * k, bdesc + 2 * k, idesc, acc);
+              acc = 1;
+            }
+          }
+        } else {
+          // narrow tail tile: rows of 32 B (SWIZZLE_32B, 8-row groups 256 B apart) or 64 B (SWIZZLE_64B, 512 B)
+          const uint32_t base = smem0 + s * stage_bytes;
+          const uint32_t a_tile = kTileM * tail_row_bytes;
+          const uint32_t layout = p.tail_mode == 1 ? 6u : 4u;
+          const uint32_t sbo = 8 * tail_row_bytes;
+          const uint64_t ta0 = make_smem_desc(base, 16, sbo, layout);
+          const uint64_t ta1 = make_smem_desc(base + a_tile, 16, sbo, layout);
+          const uint64_t tb = make_smem_desc(base + p.dual * a_tile, 16, sbo, layout);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (k < tail_steps) {
+              umma_bf16(tmem, ta0 + 2 * k, tb + 2 * k, idesc, acc);
+              if (dual) umma_bf16(tmem + kTmemCols, ta1 + 2 * k, tb + 2 * k, idesc, acc);
+              acc = 1;
+            }
+          }
         }
         if (kCluster == 1) umma_commit(empty0 + 8 * s);
         else umma_commit_mc(empty0 + 8 * s, (uint16_t)0x3);
-        if (++kc == p.kchunks) kc = 0;
+        if (++kc == kloops) kc = 0;
         if (++s == p.stages) { s = 0; par ^= 1; }
       }
       umma_commit(smem_u32(&ps->tmem_full));
@@ -241,6 +324,12 @@ int epilogue_pipelined() {
   return v;
 }
 
+int l2_prefetch_distance() {
+  static int v = -1;
+  if (v < 0) v = env_int("B200GAN_PREFETCH", 0);   // measured: prefetch requests compete with the loads (slower)
+  return v;
+}
+
 int tapgemm_dual(int m_tiles, int iters) {
   // two pixel tiles per CTA when there is enough work to still fill the machine
   static int v = -1;
@@ -283,8 +372,12 @@ int tapgemm_cluster_size(const TapGemmParams& p) {
   return env_cluster();
 }
 
+int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail) {
+  return dual * kABytes + bn_tile * kBlockK * 2 + (merge_tail ? (dual * kTileM + bn_tile) * 32 : 0);
+}
+
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
-  const int stage_bytes = p.dual * kABytes + p.bn_tile * kBlockK * 2;
+  const int stage_bytes = tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail);
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   static bool configured = false;
   if (!configured) {
@@ -534,7 +627,31 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       uint32_t par = 0;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       const uint32_t smem0 = smem_u32(smem);
+      // L2 prefetch iterator, p.l2_prefetch chunks ahead
+      int qw = jw, qh = jh, qn = jn, qit = 0;
+      auto prefetch_next = [&]() {
+        if (qit < iters) {
+          const int w0 = qw * p.bw, h0 = qh * p.bh, n0p = qn * p.bn;
+          int c[5];
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            c[d + 1] = p.tap_a_off[tap][d] + w0 * p.a_mul[0][d] + h0 * p.a_mul[1][d] + n0p * p.a_mul[2][d];
+          for (int b = 0; b < a_boxes; ++b) {
+            c[0] = m0 + b * 64;
+            tma_prefetch_nd(p.a_rank, &p.tmA, c);
+          }
+          int cb[5] = {0, w0, h0, n0p, 0};
+          for (int b = 0; b < b_boxes; ++b) {
+            cb[0] = n0 + b * 64;
+            tma_prefetch_nd(p.b_rank, &p.tmB, cb);
+          }
+          ++qit;
+          if (++qw == p.chunks_w) { qw = 0; if (++qh == p.chunks_h) { qh = 0; ++qn; } }
+        }
+      };
+      for (int i = 0; i < p.l2_prefetch; ++i) prefetch_next();
       for (int it = 0; it < iters; ++it) {
+        if (p.l2_prefetch) prefetch_next();
         const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
         mbar_wait(empty0 + 8 * s, par ^ 1);
         const uint32_t full = full0 + 8 * s;

@@ -23,6 +23,11 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_SIGMOID 
 struct TapGemmParams {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmA_tail;               // same tensors with a narrow inner box for the last K chunk of a tap
+  CUtensorMap tmB_tail;
+  int tail_mode;                      // 0: last chunk uses the 64-wide maps; 1: 16-wide box, SWIZZLE_32B;
+                                      // 2: 32-wide box, SWIZZLE_64B
+  int merge_tail;                     // tail_mode 1 only: the tail rides in the stage of the last full chunk
   int a_rank;
   int kchunks;                        // ceil(K / 64) per tap
   int k_total;                        // K per tap (channels)
@@ -40,6 +45,7 @@ struct TapGemmParams {
   int ncols, bn_tile;                 // valid output columns, N tile (multiple of 16, <= 256)
   int stages;
   int epi_pipe;                       // epilogue: prefetch + pipelined mask loads
+  int l2_prefetch;                    // K blocks the producer prefetches into L2 ahead of its loads (0 = off)
   int dual;                           // pixel tiles per CTA (1|2) sharing one B tile; 2 -> two TMEM accumulators
   int cluster;                        // 1, or 2: CTA pairs share B through TMA multicast (B box = bn_tile/2 rows)
   void* out;
@@ -68,6 +74,7 @@ struct WgradParams {
   int total_chunks, chunks_per_split;
   int Ca, Cb;
   int m_tiles, n_tiles, bn_tile, nb_boxes;
+  int l2_prefetch;                    // K chunks prefetched into L2 ahead of the loads
   int dual;                           // 128-channel M tiles per CTA (1|2) sharing one B tile
   int stages;
   float* out;
@@ -78,7 +85,9 @@ struct WgradParams {
 
 int tapgemm_cluster_size(const TapGemmParams& p);
 int tapgemm_dual(int m_tiles, int iters);
+int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail);
 int epilogue_pipelined();
+int l2_prefetch_distance();
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);
 
 // Persistent small-K GEMM: out[M, ncols] = epi(A[M,K] * B[ncols,K]^T) with K <= 256 (image-side im2col GEMMs).

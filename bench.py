@@ -69,7 +69,7 @@ class ClockSampler:
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def __enter__(self):
         self.th.start()
@@ -187,13 +187,14 @@ def run_b200(a):
     mark("warm-up done")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = E.S.launches
-    with ClockSampler(sess.local_rank) as clk:
-        barrier()
-        ev0.record()
-        for i in range(a.steps):
-            step_resident(i)
-        ev1.record()
-        barrier()
+    clk = ClockSampler(sess.local_rank)
+    clk.__enter__()
+    barrier()
+    ev0.record()
+    for i in range(a.steps):
+        step_resident(i)
+    ev1.record()
+    barrier()
     launches = E.S.launches - launches0
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -216,6 +217,7 @@ def run_b200(a):
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     e2e_value = a.batch * world * a.steps / float(t.item())
+    clk.__exit__(None, None, None)
     h2d = runs * a.batch * a.size * a.size * 3 * 4
     d2h = 8
 
@@ -263,8 +265,12 @@ def roofline(sess, train, x, pool, a):
     sess.use_graphs, sess.dist = False, None        # rank-0-only pass: no collective inside
     E.S.profile = []
     x.ring.copy_(pool[0])
+    it0, it1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    it0.record()
     sess.run("profile", train.iteration)
+    it1.record()
     torch.cuda.synchronize()
+    iter_ms = it0.elapsed_time(it1)
     recs, E.S.profile = E.S.profile, None
     sess.use_graphs, sess.dist = prev, prev_dist
     rows = {}
@@ -284,9 +290,30 @@ def roofline(sess, train, x, pool, a):
     n_tc = sum(r["launches"] for t_, r in rows.items() if t_.startswith("tc:"))
     achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": src, "kernel": "tapgemm_kernel+wgrad_kernel (tcgen05 implicit GEMM)",
+            "traffic": ncu_traffic_bytes(), "peak_source": src,
+            "kernel": "tapgemm_kernel+wgrad_kernel (tcgen05 implicit GEMM: conv fprop/dgrad/wgrad, dense)",
             "launches": n_tc, "flops_per_launch_avg": tot_f / max(n_tc, 1), "ms_per_launch_avg": tot_ms / max(n_tc, 1),
-            "step_share": None}
+            "step_share": tot_ms / iter_ms if iter_ms > 0 else None,
+            "note": "achieved = sum(2*N*Ho*Wo*k*k*Cin*Cout over the launches) / sum(CUDA-event durations), one eager "
+                    "iteration; traffic = mean dram read+write bytes per launch of the profiled c2/c3 launches "
+                    "(profiles/r1_ncu_kernels.csv)"}
+
+
+def ncu_traffic_bytes():
+    """Mean DRAM bytes (read+write) per launch of the tcgen05 kernels in the committed ncu --set full capture."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_ncu_kernels.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr = rows[1]
+    try:
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    vals = [(float(r[ri]) + float(r[wi])) * 1e6 for r in rows[3:] if r and ("tapgemm" in r[0] or "wgrad_kernel" in r[0])
+            and float(r[hdr.index("gpu__time_duration.sum")]) > 100.0]
+    return sum(vals) / len(vals) if vals else None
 
 
 if __name__ == "__main__":
