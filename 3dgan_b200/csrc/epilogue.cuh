@@ -78,9 +78,18 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
   if (e.bias) {
+    const float* bp = e.bias + col;
+    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < nvalid) v[j] += __ldg(e.bias + col + j);
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) v[j] += __ldg(bp + j);
+    }
   }
   if (e.act != ACT_NONE) {
 #pragma unroll

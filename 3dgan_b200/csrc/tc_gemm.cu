@@ -13,7 +13,7 @@ namespace b200 {
 
 namespace {
 
-constexpr int kThreads = 192;         // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int kMaxThreads = 64 + 32 * 16;   // warp0 TMA, warp1 MMA, then 4..16 epilogue warps (launch parameter)
 constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KiB: 128 rows x 128 B
 
 struct PipeSmem {
@@ -38,7 +38,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // traffic per K chunk drops from A+B to A+B/2.  Stage release (tcgen05.commit) is multicast to both CTAs'
 // empty barriers because either producer writes into both CTAs.
 template <int kCluster>
-__global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+__global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -261,6 +261,8 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
   } else {
     // -------------------------------------------------------------------- epilogue (4 warps)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int cg = (warp - 2) >> 2;         // column group: warps sharing a quarter split the column chunks
+    const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
     const int r = q * 32 + lane;            // tile row == TMEM lane
     const int iw = r % p.bw;
     const int ih = (r / p.bw) % p.bh;
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const bool tile_ok = i < p.dual && (int)(blockIdx.x * p.dual + i) < total_tiles;
       row_ok[i] = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
       off[i] = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh + (long long)pw * p.o_sw;
-      if (row_ok[i]) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
+      if (row_ok[i] && cg == 0) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
     }
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
@@ -289,14 +291,14 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
       MaskChunk cur;
       cur.loaded = false;
-      if (row_ok[i]) cur = epilogue_load_mask(ea, off[i], n0);
-      for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+      if (row_ok[i]) cur = epilogue_load_mask(ea, off[i], n0 + cg * 16);
+      for (int c0 = cg * 16; c0 < p.bn_tile; c0 += ncg * 16) {
         if (n0 + c0 >= p.ncols) break;        // warp-uniform
         uint32_t v[16];
         tmem_ld16(trow + c0, v);
         MaskChunk nxt;
         nxt.loaded = false;
-        if (row_ok[i] && c0 + 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off[i], n0 + c0 + 16);
+        if (row_ok[i] && c0 + ncg * 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off[i], n0 + c0 + ncg * 16);
         tmem_ld_wait();
         if (row_ok[i]) epilogue_store16(ea, v, off[i], n0 + c0, &cur);
         cur = nxt;
@@ -316,6 +318,18 @@ __global__ void __launch_bounds__(kThreads, 1) tapgemm_kernel(const __grid_const
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
+}
+
+int gemm_threads() {
+  static int v = -1;
+  if (v < 0) {
+    int w = env_int("B200GAN_EPI_WARPS", 12);
+    if (w < 4) w = 4;
+    if (w > 16) w = 16;
+    w = (w / 4) * 4;
+    v = 64 + 32 * w;
+  }
+  return v;
 }
 
 int epilogue_pipelined() {
@@ -354,7 +368,7 @@ static void launch_clustered(void (*kern)(Params), const Params& p, dim3 grid, s
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(gemm_threads());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -392,7 +406,7 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     launch_clustered(tapgemm_kernel<2>, p, grid, smem, 2, stream);
   } else {
     dim3 grid(tiles, ntile_y, p.nphases);
-    tapgemm_kernel<1><<<grid, kThreads, smem, stream>>>(p);
+    tapgemm_kernel<1><<<grid, gemm_threads(), smem, stream>>>(p);
   }
 }
 
@@ -408,7 +422,7 @@ struct SmallKSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) smallk_kernel(const __grid_constant__ SmallKParams p) {
+__global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_constant__ SmallKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -429,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) smallk_kernel(const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&ps->acc_full[a]), 1);
-      mbar_init(smem_u32(&ps->acc_empty[a]), 4);            // one arrival per epilogue warp
+      mbar_init(smem_u32(&ps->acc_empty[a]), (blockDim.x >> 5) - 2);   // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -495,6 +509,8 @@ __global__ void __launch_bounds__(kThreads, 1) smallk_kernel(const __grid_consta
     __syncwarp();
   } else {
     const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
     const int r = q * 32 + lane;
     EpilogueArgs ea;
     ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
@@ -506,20 +522,20 @@ __global__ void __launch_bounds__(kThreads, 1) smallk_kernel(const __grid_consta
       const long long row = (long long)tile * kTileM + r;
       const bool row_ok = row < p.M;
       const long long off = row * p.ldo;
-      if (row_ok) epilogue_prefetch_mask(ea, off, 0, p.bn_tile);
+      if (row_ok && cg == 0) epilogue_prefetch_mask(ea, off, 0, p.bn_tile);
       mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols;
       MaskChunk cur;
       cur.loaded = false;
-      if (row_ok) cur = epilogue_load_mask(ea, off, 0);
-      for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+      if (row_ok) cur = epilogue_load_mask(ea, off, cg * 16);
+      for (int c0 = cg * 16; c0 < p.bn_tile; c0 += ncg * 16) {
         if (c0 >= p.ncols) break;
         uint32_t v[16];
         tmem_ld16(trow + c0, v);
         MaskChunk nxt;
         nxt.loaded = false;
-        if (row_ok && c0 + 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off, c0 + 16);
+        if (row_ok && c0 + ncg * 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off, c0 + ncg * 16);
         tmem_ld_wait();
         if (row_ok) epilogue_store16(ea, v, off, c0, &cur);
         cur = nxt;
@@ -561,13 +577,13 @@ void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  smallk_kernel<<<grid, kThreads, smem, stream>>>(p);
+  smallk_kernel<<<grid, gemm_threads(), smem, stream>>>(p);
 }
 
 // =============================================================================================
 // Weight gradient (MN-major operands, split-K, fp32 atomics)
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -708,6 +724,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     __syncwarp();
   } else {
     const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
     const bool vec_ok = (p.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
@@ -718,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
       const bool row_ok = ca < p.Ca;
       float* orow = p.out + (long long)tap * p.out_tap_stride + (long long)ca * p.ldo;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
-      for (int c0 = 0; c0 < p.bn_tile; c0 += 16) {
+      for (int c0 = cg * 16; c0 < p.bn_tile; c0 += ncg * 16) {
         const int col = n0 + c0;
         if (col >= p.Cb) break;
         uint32_t v[16];
@@ -764,7 +782,7 @@ void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid(((p.m_tiles + p.dual - 1) / p.dual) * p.n_tiles * p.ntaps, splits, 1);
-  wgrad_kernel<<<grid, kThreads, smem, stream>>>(p);
+  wgrad_kernel<<<grid, gemm_threads(), smem, stream>>>(p);
 }
 
 }  // namespace b200

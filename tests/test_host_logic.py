@@ -209,3 +209,21 @@ def test_small_output_conv_routes_to_simt_backward():
     from b200gan import _capi
     g = _capi.ConvGeom(N=2, H=16, W=16, Cin=512, Ho=8, Wo=8, Cout=1, k=4, stride=2, pad_t=1, pad_l=1)
     assert _capi.route(g, 0) == 1 and _capi.route(g, 1) == 3 and _capi.route(g, 2) == 3
+
+
+def test_train_cli_flags_and_config_file(tmp_path):
+    """train.py keeps the reference's flags and `--config` file semantics (train.py:25-37: whitespace
+    `key value` tokens, `--` prepended, explicit CLI flags win)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b200_train", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "train.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    cfg = tmp_path / "iwgan.config"
+    cfg.write_text("model\t\tiwgan\nepochs\t\t20\nbatch_size \t256\nn_gpus \t\t2\noptimizer\tadam\nlr\t\t1e-4\nbeta1\t\t0.5\nbeta2\t\t0.9\n")
+    a = tr.build_parser().parse_args(["--config", str(cfg)])
+    assert (a.model, a.epochs, a.batch_size, a.n_gpus, a.optimizer, a.lr, a.beta1, a.beta2) == \
+        ("iwgan", "20", 256, 2, "adam", 1e-4, 0.5, 0.9)
+    d = tr.build_parser().parse_args([])
+    assert (d.optimizer, d.lr, d.momentum, d.decay, d.latent_size, d.n_disc_train, d.batch_size) == \
+        ("rmsprop", 0.001, 0.01, 0.9, 200, 5, 256)          # reference defaults, train.py:87-153
