@@ -86,8 +86,16 @@ static int pick_bn_tile(int cols) {
   return std::max(16, cdiv(cdiv(cols, nt), 16) * 16);
 }
 static int pick_stages(int stage_bytes) {
+  static int cap = -1;          // B200GAN_STAGES: cap the pipeline depth (2 leaves room for two CTAs per SM)
+  if (cap < 0) { const char* e = getenv("B200GAN_STAGES"); cap = e ? atoi(e) : 8; }
   int s = (227 * 1024 - 2048) / stage_bytes;
-  return std::max(2, std::min(s, 8));
+  return std::max(2, std::min(s, std::min(cap, 8)));
+}
+
+static int weight_prefetch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200GAN_PREFETCH_B"); v = e ? atoi(e) : 1; }
+  return v;
 }
 
 static bool is_small(int c) { return c <= 4; }
@@ -324,6 +332,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, w_t, 2, dims, str, box, es)) return -1;
+    p.b_base = w_t; p.b_pitch_bytes = g->Cin * 2; p.b_rows_total = g->k * g->k * g->Cout; p.b_prefetch = weight_prefetch();
     p.tail_mode = pick_tail_mode(g->Cin);
     if (p.tail_mode) {
       const int tw = p.tail_mode == 1 ? 16 : 32;
@@ -423,6 +432,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
     int box[2] = {kBlockK, p.bn_tile / p.cluster};
     int es[2] = {1, 1};
     if (make_tmap(&p.tmB, w, 2, dims, str, box, es)) return -1;
+    p.b_base = w; p.b_pitch_bytes = g->Cout * 2; p.b_rows_total = g->k * g->k * g->Cin; p.b_prefetch = weight_prefetch();
     p.tail_mode = pick_tail_mode(g->Cout);
     if (p.tail_mode) {
       const int tw = p.tail_mode == 1 ? 16 : 32;

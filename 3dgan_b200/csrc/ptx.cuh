@@ -135,6 +135,31 @@ __device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const void* tmap, u
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                               int c2, int c3, int c4, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_nd_mc(int rank, uint32_t dst, const void* tmap, uint32_t bar,
+                                               const int* c, uint16_t mask) {
+  switch (rank) {
+    case 2: tma_load_2d_mc(dst, tmap, bar, c[0], c[1], mask); break;
+    case 3: tma_load_3d_mc(dst, tmap, bar, c[0], c[1], c[2], mask); break;
+    case 4: tma_load_4d_mc(dst, tmap, bar, c[0], c[1], c[2], c[3], mask); break;
+    default: tma_load_5d_mc(dst, tmap, bar, c[0], c[1], c[2], c[3], c[4], mask); break;
+  }
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -37,6 +37,10 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // its own A tile and HALF of the shared B tile, multicast into both CTAs' shared memory, so the L2->SM
 // traffic per K chunk drops from A+B to A+B/2.  Stage release (tcgen05.commit) is multicast to both CTAs'
 // empty barriers because either producer writes into both CTAs.
+// p.cluster_y == 2 (with two pixel tiles per CTA): the cluster is 2 x 2 -- the CTAs of the two N tiles that
+// share the same pixel tiles each load ONE of the two A tiles and multicast it to the other, so a CTA
+// pulls A/2 + B/2 from L2 for an (256 x bn_tile) output block.  These GEMMs are bound by the L2->SM
+// fill rate (about 12 TB/s chip-wide), so halving the operand traffic is what raises tensor-pipe use.
 template <int kCluster>
 __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -44,6 +48,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0;
+  // cluster dims (2, cluster_y, 1): rank = x + 2*y.  cx pairs pixel tiles (shares B), cyi pairs N tiles (shares A)
+  const uint32_t cx = crank & 1, cyi = crank >> 1;
+  const bool share_a = kCluster > 1 && p.cluster_y == 2;
+  const uint16_t b_mask = (uint16_t)(0x3u << (2 * cyi));
+  const uint16_t a_mask = (uint16_t)((1u << cx) | (1u << (cx + 2)));
 
   const int b_bytes = p.bn_tile * kBlockK * 2;
   const int a_bytes = p.dual * kABytes;         // p.dual (1|2) pixel tiles per CTA share one B tile
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&ps->full[s]), 1);
-      mbar_init(smem_u32(&ps->empty[s]), kCluster);
+      mbar_init(smem_u32(&ps->empty[s]), kCluster + (share_a ? 1 : 0));   // every CTA a producer here writes into
     }
     mbar_init(smem_u32(&ps->tmem_full), 1);
     fence_mbar_init();
@@ -123,7 +132,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
             for (int d = 0; d < 4; ++d) c[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
             tma_prefetch_nd(p.a_rank, &p.tmA, c);
           }
-          int cb[2] = {pkc * kBlockK, p.tap_b_row[tap] + n0 + (kCluster > 1 ? (int)crank * (p.bn_tile / 2) : 0)};
+          int cb[2] = {pkc * kBlockK, p.tap_b_row[tap] + n0 + (kCluster > 1 ? (int)cx * (p.bn_tile / 2) : 0)};
           tma_prefetch_nd(2, &p.tmB, cb);
           if (++pkc == p.kchunks) { pkc = 0; ++ptp; }
         }
@@ -153,14 +162,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
           const void* mA = tail ? (const void*)&p.tmA_tail : (const void*)&p.tmA;
           const void* mB = tail ? (const void*)&p.tmB_tail : (const void*)&p.tmB;
           mbar_arrive_expect_tx(full, p.dual * a_tile + p.bn_tile * row_bytes + (with_tail ? tail_area : 0));
-          tma_load_nd(p.a_rank, a_dst, mA, full, c0);
-          if (p.dual == 2) tma_load_nd(p.a_rank, a_dst + a_tile, mA, full, c1);
+          if (share_a) {
+            tma_load_nd_mc(p.a_rank, a_dst + cyi * a_tile, mA, full, cyi ? c1 : c0, a_mask);
+          } else {
+            tma_load_nd(p.a_rank, a_dst, mA, full, c0);
+            if (p.dual == 2) tma_load_nd(p.a_rank, a_dst + a_tile, mA, full, c1);
+          }
           if (kCluster == 1) {
             tma_load_2d(a_dst + p.dual * a_tile, mB, full, kc * kBlockK, brow);
           } else {
             const int half_rows = p.bn_tile / 2;
-            tma_load_2d_mc(a_dst + p.dual * a_tile + crank * half_rows * row_bytes, mB, full, kc * kBlockK,
-                           brow + crank * half_rows, (uint16_t)0x3);
+            tma_load_2d_mc(a_dst + p.dual * a_tile + cx * half_rows * row_bytes, mB, full, kc * kBlockK,
+                           brow + cx * half_rows, b_mask);
           }
           if (with_tail) {
             // 16-wide tail boxes (rows of 32 B) behind the full tiles of this stage
@@ -168,14 +181,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
             const int t_tile = kTileM * 32;
             c0[0] = (kc + 1) * kBlockK;
             c1[0] = (kc + 1) * kBlockK;
-            tma_load_nd(p.a_rank, t_dst, &p.tmA_tail, full, c0);
-            if (p.dual == 2) tma_load_nd(p.a_rank, t_dst + t_tile, &p.tmA_tail, full, c1);
+            if (share_a) {
+              tma_load_nd_mc(p.a_rank, t_dst + cyi * t_tile, &p.tmA_tail, full, cyi ? c1 : c0, a_mask);
+            } else {
+              tma_load_nd(p.a_rank, t_dst, &p.tmA_tail, full, c0);
+              if (p.dual == 2) tma_load_nd(p.a_rank, t_dst + t_tile, &p.tmA_tail, full, c1);
+            }
             if (kCluster == 1) {
               tma_load_2d(t_dst + p.dual * t_tile, &p.tmB_tail, full, (kc + 1) * kBlockK, brow);
             } else {
               const int half_rows = p.bn_tile / 2;
-              tma_load_2d_mc(t_dst + p.dual * t_tile + crank * half_rows * 32, &p.tmB_tail, full, (kc + 1) * kBlockK,
-                             brow + crank * half_rows, (uint16_t)0x3);
+              tma_load_2d_mc(t_dst + p.dual * t_tile + cx * half_rows * 32, &p.tmB_tail, full, (kc + 1) * kBlockK,
+                             brow + cx * half_rows, b_mask);
             }
           }
           if (++s == p.stages) { s = 0; par ^= 1; }
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
           }
         }
         if (kCluster == 1) umma_commit(empty0 + 8 * s);
-        else umma_commit_mc(empty0 + 8 * s, (uint16_t)0x3);
+        else umma_commit_mc(empty0 + 8 * s, share_a ? (uint16_t)(b_mask | a_mask) : b_mask);
         if (++kc == kloops) kc = 0;
         if (++s == p.stages) { s = 0; par ^= 1; }
       }
@@ -282,6 +299,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
       row_ok[i] = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
       off[i] = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh + (long long)pw * p.o_sw;
       if (row_ok[i] && cg == 0) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
+    }
+    if (p.b_prefetch && blockIdx.x < kCluster) {
+      // weights are read by every pixel-tile CTA in lockstep; when they are not L2-resident each K chunk is
+      // a chip-wide HBM miss on the critical path.  The first cluster's idle epilogue threads pull this N
+      // tile's weight rows into L2 while the pipeline starts.
+      const int rows = p.bn_tile / kCluster;
+      const int row0 = n0 + (int)cx * rows;
+      const int lines = (p.k_total * 2 + 127) >> 7;
+      const int per_tap = rows * lines;
+      const int total = ntaps * per_tap;
+      const char* base = reinterpret_cast<const char*>(p.b_base);
+      for (int i = (int)threadIdx.x - 64; i < total; i += (int)blockDim.x - 64) {
+        const int tp = i / per_tap, rem = i - tp * per_tap;
+        const int rr = rem / lines, ln = rem - rr * lines;
+        const int row = p.tap_b_row[tap_begin + tp] + row0 + rr;
+        if (row < p.b_rows_total)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)row * p.b_pitch_bytes + ln * 128));
+      }
     }
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
@@ -323,7 +358,7 @@ static int env_int(const char* name, int dflt) {
 int gemm_threads() {
   static int v = -1;
   if (v < 0) {
-    int w = env_int("B200GAN_EPI_WARPS", 12);
+    int w = env_int("B200GAN_EPI_WARPS", 16);
     if (w < 4) w = 4;
     if (w > 16) w = 16;
     w = (w / 4) * 4;
@@ -364,7 +399,7 @@ static int env_cluster() {
 
 template <typename Params>
 static void launch_clustered(void (*kern)(Params), const Params& p, dim3 grid, size_t smem, int cluster,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, int cluster_y = 1) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid;
@@ -374,7 +409,7 @@ static void launch_clustered(void (*kern)(Params), const Params& p, dim3 grid, s
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.y = cluster_y;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
@@ -402,8 +437,12 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   const int tiles = (p.tiles_w * p.tiles_h * p.tiles_n + p.dual - 1) / p.dual;
   const int ntile_y = (p.ncols + p.bn_tile - 1) / p.bn_tile;
   if (p.cluster == 2) {
-    dim3 grid((tiles + 1) / 2 * 2, ntile_y, p.nphases);
-    launch_clustered(tapgemm_kernel<2>, p, grid, smem, 2, stream);
+    static int cy_env = -1;
+    if (cy_env < 0) cy_env = env_int("B200GAN_CLUSTER_Y", 1);
+    TapGemmParams q = p;
+    q.cluster_y = (cy_env == 2 && p.dual == 2 && ntile_y >= 2) ? 2 : 1;
+    dim3 grid((tiles + 1) / 2 * 2, (ntile_y + q.cluster_y - 1) / q.cluster_y * q.cluster_y, p.nphases);
+    launch_clustered(tapgemm_kernel<2>, q, grid, smem, 2, stream, q.cluster_y);
   } else {
     dim3 grid(tiles, ntile_y, p.nphases);
     tapgemm_kernel<1><<<grid, gemm_threads(), smem, stream>>>(p);

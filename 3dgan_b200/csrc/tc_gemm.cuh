@@ -48,6 +48,11 @@ struct TapGemmParams {
   int l2_prefetch;                    // K blocks the producer prefetches into L2 ahead of its loads (0 = off)
   int dual;                           // pixel tiles per CTA (1|2) sharing one B tile; 2 -> two TMEM accumulators
   int cluster;                        // 1, or 2: CTA pairs share B through TMA multicast (B box = bn_tile/2 rows)
+  const void* b_base;                 // B operand (weights) base / row pitch / rows: L2 prefetch by the idle epilogue warps
+  int b_pitch_bytes;
+  int b_rows_total;
+  int b_prefetch;                     // 1: CTAs of the first pixel tile pull their N tile's weight rows into L2 at kernel start
+  int cluster_y;                      // set by launch_tapgemm: 2 -> 2x2 clusters, the N-tile pair also shares A
   void* out;
   int out_f32;                        // 0: bf16, 1: fp32
   int accumulate;                     // fp32 only: out += result
