@@ -19,7 +19,8 @@ class ConvGeom(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int), ("leak", C.c_float), ("mask_src", C.c_void_p),
-                ("mask_kind", C.c_int), ("out_f32", C.c_int), ("accumulate", C.c_int)]
+                ("mask_kind", C.c_int), ("out_f32", C.c_int), ("accumulate", C.c_int),
+                ("mask_bits", C.c_void_p), ("bits_out", C.c_void_p), ("bits_pitch", C.c_int)]
 
 
 class B200Error(RuntimeError):
@@ -36,6 +37,7 @@ SIGNATURES = {
     "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P, _LL, _I, _P],
     "b200_conv2d_workspace_bytes": [_GP, _I],
     "b200_conv2d_route": [_GP, _I],
+    "b200_conv2d_epilogue_bits": [_GP, _I, _I],
     "b200_gemv_rows": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "b200_outer_mask": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "b200_bn_sums": [_P, _P, _LL, _I, _P],
@@ -90,6 +92,11 @@ def call(name, *args):
 
 def workspace_bytes(geom, op):
     return int(lib().b200_conv2d_workspace_bytes(C.byref(geom), op))
+
+
+def epilogue_bits(geom, op, has_workspace):
+    """True when that conv call reads / writes the sign bitmaps of b200_epilogue (tensor-core epilogues)."""
+    return lib().b200_conv2d_epilogue_bits(C.byref(geom), op, int(bool(has_workspace))) == 1
 
 
 def route(geom, op):

@@ -114,12 +114,24 @@ extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
   return 1;
 }
 
+// 1 when the epilogue of this call honours b200_epilogue.bits_out / mask_bits (the tcgen05 GEMM epilogues do;
+// the SIMT small-channel / small-output epilogues do not)
+extern "C" int b200_conv2d_epilogue_bits(const b200_conv_geom* g, int op, int has_workspace) {
+  const int r = b200_conv2d_route(g, op);
+  if (r == 1) return op == 0 || op == 1;
+  if (r == 2) return op == 0 && has_workspace && (g->Cout % 8 == 0);
+  return 0;
+}
+
 static void fill_epilogue(TapGemmParams& p, const b200_epilogue* e) {
   p.bias = e ? e->bias : nullptr;
   p.act = e ? e->act : 0;
   p.leak = e ? e->leak : 0.f;
   p.mask_src = e ? (const __nv_bfloat16*)e->mask_src : nullptr;
   p.mask_kind = e ? e->mask_kind : 0;
+  p.mask_bits = e ? (const uint16_t*)e->mask_bits : nullptr;
+  p.bits_out = e ? (uint16_t*)e->bits_out : nullptr;
+  p.bits_pitch = e ? e->bits_pitch : 0;
   p.out_f32 = e ? e->out_f32 : 0;
   p.accumulate = e ? e->accumulate : 0;
   p.alpha = 1.f;
@@ -170,6 +182,8 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
       q.out_f32 = e ? e->out_f32 : 0; q.accumulate = e ? e->accumulate : 0; q.bias = e ? e->bias : nullptr;
       q.act = e ? e->act : 0; q.leak = e ? e->leak : 0.f;
       q.mask_src = e ? (const __nv_bfloat16*)e->mask_src : nullptr; q.mask_kind = e ? e->mask_kind : 0;
+      q.mask_bits = e ? (const uint16_t*)e->mask_bits : nullptr; q.bits_out = e ? (uint16_t*)e->bits_out : nullptr;
+      q.bits_pitch = e ? e->bits_pitch : 0; q.row_elems = (int)ldo;
       q.alpha = 1.f;
       q.epi_pipe = epilogue_pipelined();
       launch_smallk(q, st);
@@ -179,6 +193,7 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
   TapGemmParams p;
   memset(&p, 0, sizeof p);
   fill_epilogue(p, e);
+  p.row_elems = (int)ldo;
   p.bw = kTileM; p.bh = 1; p.bn = 1;
   {
     long long dims[2] = {K, M};
@@ -312,6 +327,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   TapGemmParams p;
   memset(&p, 0, sizeof p);
   fill_epilogue(p, e);
+  p.row_elems = g->Cout;
   pick_pixel_tile(g->Wo, g->Ho, kTileM, &p.bw, &p.bh, &p.bn);
   const int st_ = g->stride;
   if (p.bw * st_ > 256 || p.bh * st_ > 256) return fail("conv2d_fprop: tile exceeds TMA box limit");
@@ -412,6 +428,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   TapGemmParams p;
   memset(&p, 0, sizeof p);
   fill_epilogue(p, e);
+  p.row_elems = g->Cin;
   const int st_ = g->stride;
   const int ext_w0 = cdiv(g->W, st_), ext_h0 = cdiv(g->H, st_);
   pick_pixel_tile(ext_w0, ext_h0, kTileM, &p.bw, &p.bh, &p.bn);
@@ -576,7 +593,7 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
 // thin wrappers
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
-extern "C" int b200_abi_version(void) { return 1; }
+extern "C" int b200_abi_version(void) { return 2; }
 extern "C" int b200_device_check(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device"); }

@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include "tc_gemm.cuh"
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -42,6 +43,12 @@ struct EpilogueArgs {
   int accumulate;
   int ncols;
   int pipelined;          // prefetch mask rows to L2 + load them one chunk ahead (B200GAN_EPI_PIPE, default 1)
+  // sign bitmaps (1 bit per element, 16-column words, `bits_pitch` words per output row): for relu / lrelu the
+  // activation gradient only needs sign(out), so a consumer reads 2 bytes per chunk instead of 32
+  const uint16_t* mask_bits;   // replaces mask_src when mask_kind is relu / lrelu
+  uint16_t* bits_out;          // written next to the output: bit j of word (row, col/16) = out[row, col+j] > 0
+  int bits_pitch;
+  int row_elems;               // elements per output row: row index = element offset / row_elems
 };
 
 // Epilogue warps are idle during the main loop: pull the mask rows they will need into L2 meanwhile.
@@ -70,85 +77,207 @@ __device__ __forceinline__ MaskChunk epilogue_load_mask(const EpilogueArgs& e, l
   return m;
 }
 
-// 16 consecutive columns [col, col+16) of one output row starting at element offset `off`.
-__device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const uint32_t* acc, long long off,
-                                                 int col, const MaskChunk* pre = nullptr) {
-  float v[16];
-  const int nvalid = min(16, e.ncols - col);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * e.alpha;
-  if (e.bias) {
+// fp32 bias for one chunk, loaded while the TMEM load of the chunk is in flight (aligned fast path only)
+struct BiasChunk {
+  float4 b[4];
+  bool loaded;
+};
+__device__ __forceinline__ BiasChunk epilogue_load_bias(const EpilogueArgs& e, int col) {
+  BiasChunk b;
+  b.loaded = false;
+  if (e.bias && col + 16 <= e.ncols) {
     const float* bp = e.bias + col;
-    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+    if ((reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      for (int j = 0; j < 4; ++j) b.b[j] = __ldg(reinterpret_cast<const float4*>(bp) + j);
+      b.loaded = true;
+    }
+  }
+  return b;
+}
+
+// everything a chunk needs besides its accumulators, fetched one chunk ahead
+struct ChunkSide {
+  MaskChunk m;
+  uint32_t bits;
+};
+__device__ __forceinline__ ChunkSide epilogue_load_side(const EpilogueArgs& e, long long off, int col, bool row_ok,
+                                                       long long bits_row) {
+  ChunkSide s;
+  s.m.loaded = false;
+  s.bits = 0;
+  if (row_ok) {
+    if (e.mask_bits) s.bits = __ldg(e.mask_bits + bits_row + (col >> 4));
+    else s.m = epilogue_load_mask(e, off, col);
+  }
+  return s;
+}
+
+// general (ragged / unaligned) path: per-element guards
+__device__ __forceinline__ void epilogue_store16_slow(const EpilogueArgs& e, const uint32_t* acc, long long off, int col,
+                                                      uint32_t mbits, long long bits_row) {
+  const int nvalid = min(16, e.ncols - col);
+  const long long o = off + col;
+  uint32_t obits = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (j < nvalid) {
+      float v = __uint_as_float(acc[j]) * e.alpha;
+      if (e.bias) v += __ldg(e.bias + col + j);
+      v = act_fwd(v, e.act, e.leak);
+      obits |= (v > 0.f ? 1u : 0u) << j;
+      if (e.mask_bits) v *= ((mbits >> j) & 1u) ? 1.f : (e.mask_kind == ACT_LRELU ? e.leak : 0.f);
+      else if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[o + j]), e.mask_kind, e.leak);
+      if (e.out_f32) {
+        float* dst = reinterpret_cast<float*>(e.out) + o + j;
+        *dst = e.accumulate ? *dst + v : v;
+      } else {
+        reinterpret_cast<__nv_bfloat16*>(e.out)[o + j] = __float2bfloat16(v);
+      }
+    }
+  }
+  if (e.bits_out) e.bits_out[bits_row + (col >> 4)] = (uint16_t)obits;
+}
+
+// 16 consecutive columns [col, col+16) of one output row starting at element offset `off`.
+// Fast path (full chunk, 16-byte aligned output, side data preloaded): straight-line code, the
+// activation / mask kind switches hoisted out of the element loops.
+__device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const uint32_t* acc, long long off,
+                                                 int col, const ChunkSide* side = nullptr, long long bits_row = 0) {
+  const long long o = off + col;
+  const bool full = col + 16 <= e.ncols;
+  const uintptr_t oaddr = reinterpret_cast<uintptr_t>(e.out) + (uintptr_t)o * (e.out_f32 ? 4 : 2);
+  const bool fast = full && (oaddr & 15) == 0 && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
+                    (e.mask_bits || !e.mask_src || (side && side->m.loaded));
+  if (!fast) {
+    epilogue_store16_slow(e, acc, off, col, side ? side->bits : 0u, bits_row);
+    return;
+  }
+  float v[16];
+  const float a = e.alpha;
+  if (e.bias) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = __ldg(bp + j);
+      v[4 * j + 0] = fmaf(__uint_as_float(acc[4 * j + 0]), a, b4.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), a, b4.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), a, b4.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(acc[4 * j + 3]), a, b4.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * a;
+  }
+  switch (e.act) {
+    case ACT_NONE: break;
+    case ACT_LRELU: {
+      const float leak = e.leak;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(leak * v[j], v[j]);
+      break;
+    }
+    case ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    default:
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act, e.leak);
+      break;
+  }
+  if (e.bits_out) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+    e.bits_out[bits_row + (col >> 4)] = (uint16_t)w;
+  }
+  if (e.mask_bits) {
+    const float neg = e.mask_kind == ACT_LRELU ? e.leak : 0.f;
+    const uint32_t w = side->bits;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = ((w >> j) & 1u) ? v[j] : v[j] * neg;
+  } else if (e.mask_src) {
+    const uint32_t mw[8] = {side->m.lo.x, side->m.lo.y, side->m.lo.z, side->m.lo.w,
+                            side->m.hi.x, side->m.hi.y, side->m.hi.z, side->m.hi.w};
+    if (e.mask_kind == ACT_LRELU || e.mask_kind == ACT_RELU) {
+      // derivative from the sign of the stored activation: bf16 > 0  <=>  its 16 bits as a signed int > 0
+      const float neg = e.mask_kind == ACT_LRELU ? e.leak : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool lo_pos = (short)(mw[j] & 0xffffu) > 0;
+        const bool hi_pos = (int)mw[j] >= 0x10000;
+        v[2 * j] = lo_pos ? v[2 * j] : v[2 * j] * neg;
+        v[2 * j + 1] = hi_pos ? v[2 * j + 1] : v[2 * j + 1] * neg;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) v[j] += __ldg(bp + j);
-    }
-  }
-  if (e.act != ACT_NONE) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act, e.leak);
-  }
-  const long long o = off + col;
-  if (e.mask_src && pre && pre->loaded) {
-    uint4 raw[2] = {pre->lo, pre->hi};
-    const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(raw);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] *= act_grad_from_out(__bfloat162float(mv[j]), e.mask_kind, e.leak);
-  } else if (e.mask_src) {
-    const __nv_bfloat16* m = e.mask_src + o;
-    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(m) & 15) == 0)) {
-      uint4 raw[2];
-      raw[0] = __ldg(reinterpret_cast<const uint4*>(m));
-      raw[1] = __ldg(reinterpret_cast<const uint4*>(m) + 1);
-      const __nv_bfloat16* mv = reinterpret_cast<const __nv_bfloat16*>(raw);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= act_grad_from_out(__bfloat162float(mv[j]), e.mask_kind, e.leak);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) v[j] *= act_grad_from_out(__bfloat162float(m[j]), e.mask_kind, e.leak);
+      for (int j = 0; j < 8; ++j) {
+        const float lo = __uint_as_float(mw[j] << 16), hi = __uint_as_float(mw[j] & 0xffff0000u);
+        v[2 * j] *= act_grad_from_out(lo, e.mask_kind, e.leak);
+        v[2 * j + 1] *= act_grad_from_out(hi, e.mask_kind, e.leak);
+      }
     }
   }
   if (e.out_f32) {
     float* dst = reinterpret_cast<float*>(e.out) + o;
-    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        if (e.accumulate) {
-          float4 old = *reinterpret_cast<float4*>(dst + j);
-          f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
-        }
-        *reinterpret_cast<float4*>(dst + j) = f;
+    for (int j = 0; j < 16; j += 4) {
+      float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      if (e.accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(dst + j);
+        f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) dst[j] = e.accumulate ? dst[j] + v[j] : v[j];
+      *reinterpret_cast<float4*>(dst + j) = f;
     }
   } else {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
-    if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-      uint32_t pk[8];
+    uint32_t pk[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-        pk[j] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *(reinterpret_cast<uint4*>(dst) + 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j < nvalid) dst[j] = __float2bfloat16(v[j]);
+    for (int j = 0; j < 8; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&h);
     }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *(reinterpret_cast<uint4*>(dst) + 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
+
+// One output row's chunks c0, c0+step, ... of an accumulator row in TMEM: the TMEM load and the mask /
+// bias loads of chunk i+1 are issued before chunk i is processed (two register buffers).
+__device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t trow, long long off, bool row_ok,
+                                             int n0, int c_first, int c_step, int c_end) {
+  // word offset of this output row in the sign bitmaps (the output is dense: row = element offset / row width)
+  const long long bits_row = (e.mask_bits || e.bits_out) ? (off / e.row_elems) * e.bits_pitch : 0;
+  // c_end: first column offset (relative to the tile) that must not be processed
+  int c = c_first;
+  if (c >= c_end) return;
+  uint32_t va[16], vb[16];
+  tmem_ld16(trow + c, va);
+  ChunkSide cur = epilogue_load_side(e, off, n0 + c, row_ok, bits_row);
+  while (true) {
+    const int c1 = c + c_step;
+    const bool more1 = c1 < c_end;
+    tmem_ld_wait16(va);
+    ChunkSide nxt;
+    nxt.m.loaded = false; nxt.bits = 0;
+    if (more1) {
+      tmem_ld16(trow + c1, vb);
+      nxt = epilogue_load_side(e, off, n0 + c1, row_ok, bits_row);
+    }
+    if (row_ok) epilogue_store16(e, va, off, n0 + c, &cur, bits_row);
+    if (!more1) break;
+    const int c2 = c1 + c_step;
+    const bool more2 = c2 < c_end;
+    tmem_ld_wait16(vb);
+    cur.m.loaded = false; cur.bits = 0;
+    if (more2) {
+      tmem_ld16(trow + c2, va);
+      cur = epilogue_load_side(e, off, n0 + c2, row_ok, bits_row);
+    }
+    if (row_ok) epilogue_store16(e, vb, off, n0 + c1, &nxt, bits_row);
+    if (!more2) break;
+    c = c2;
   }
 }
 

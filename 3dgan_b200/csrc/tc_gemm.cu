@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
     ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
     ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
+    ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
 
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     bool row_ok[2];
@@ -324,20 +325,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     for (int i = 0; i < 2; ++i) {
       if (i >= p.dual) break;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
-      MaskChunk cur;
-      cur.loaded = false;
-      if (row_ok[i]) cur = epilogue_load_mask(ea, off[i], n0 + cg * 16);
-      for (int c0 = cg * 16; c0 < p.bn_tile; c0 += ncg * 16) {
-        if (n0 + c0 >= p.ncols) break;        // warp-uniform
-        uint32_t v[16];
-        tmem_ld16(trow + c0, v);
-        MaskChunk nxt;
-        nxt.loaded = false;
-        if (row_ok[i] && c0 + ncg * 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off[i], n0 + c0 + ncg * 16);
-        tmem_ld_wait();
-        if (row_ok[i]) epilogue_store16(ea, v, off[i], n0 + c0, &cur);
-        cur = nxt;
-      }
+      epilogue_row(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols - n0));
     }
   }
 
@@ -555,6 +543,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
     ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
     ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
     ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
+    ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
     int acc = 0;
     uint32_t accpar = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -565,20 +554,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
       mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols;
-      MaskChunk cur;
-      cur.loaded = false;
-      if (row_ok) cur = epilogue_load_mask(ea, off, cg * 16);
-      for (int c0 = cg * 16; c0 < p.bn_tile; c0 += ncg * 16) {
-        if (c0 >= p.ncols) break;
-        uint32_t v[16];
-        tmem_ld16(trow + c0, v);
-        MaskChunk nxt;
-        nxt.loaded = false;
-        if (row_ok && c0 + ncg * 16 < p.bn_tile) nxt = epilogue_load_mask(ea, off, c0 + ncg * 16);
-        tmem_ld_wait();
-        if (row_ok) epilogue_store16(ea, v, off, c0, &cur);
-        cur = nxt;
-      }
+      epilogue_row(ea, trow, off, row_ok, 0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[acc]));
@@ -775,24 +751,38 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
       const bool row_ok = ca < p.Ca;
       float* orow = p.out + (long long)tap * p.out_tap_stride + (long long)ca * p.ldo;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
-      for (int c0 = cg * 16; c0 < p.bn_tile; c0 += ncg * 16) {
-        const int col = n0 + c0;
-        if (col >= p.Cb) break;
-        uint32_t v[16];
-        tmem_ld16(trow + c0, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
+      // chunks cg, cg+ncg, ...: the TMEM load of the next chunk is in flight while this one is reduced
+      auto reduce16 = [&](const uint32_t* v, int col) {
+        if (!row_ok) return;
         if (vec_ok && col + 16 <= p.Cb) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            float4 f = make_float4(__uint_as_float(v[j]) * p.alpha, __uint_as_float(v[j + 1]) * p.alpha,
-                                   __uint_as_float(v[j + 2]) * p.alpha, __uint_as_float(v[j + 3]) * p.alpha);
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j), "f"(f.x),
-                         "f"(f.y), "f"(f.z), "f"(f.w)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j),
+                         "f"(__uint_as_float(v[j]) * p.alpha), "f"(__uint_as_float(v[j + 1]) * p.alpha),
+                         "f"(__uint_as_float(v[j + 2]) * p.alpha), "f"(__uint_as_float(v[j + 3]) * p.alpha)
                          : "memory");
           }
         } else {
           for (int j = 0; j < 16 && col + j < p.Cb; ++j) atomicAdd(orow + col + j, __uint_as_float(v[j]) * p.alpha);
+        }
+      };
+      const int c_end = min(p.bn_tile, p.Cb - n0), step = ncg * 16;
+      int c = cg * 16;
+      if (c < c_end) {
+        uint32_t va[16], vb[16];
+        tmem_ld16(trow + c, va);
+        while (true) {
+          const int c1 = c + step;
+          tmem_ld_wait16(va);
+          if (c1 < c_end) tmem_ld16(trow + c1, vb);
+          reduce16(va, n0 + c);
+          if (c1 >= c_end) break;
+          const int c2 = c1 + step;
+          tmem_ld_wait16(vb);
+          if (c2 < c_end) tmem_ld16(trow + c2, va);
+          reduce16(vb, n0 + c1);
+          if (c2 >= c_end) break;
+          c = c2;
         }
       }
     }

@@ -61,6 +61,9 @@ struct TapGemmParams {
   float leak;
   const __nv_bfloat16* mask_src;      // same geometry as out; result *= act'(mask_src)
   int mask_kind;
+  const uint16_t* mask_bits;          // sign bitmaps (see epilogue.cuh): consumer side / producer side
+  uint16_t* bits_out;
+  int bits_pitch, row_elems;
   float alpha;
 };
 
@@ -115,6 +118,9 @@ struct SmallKParams {
   float leak;
   const __nv_bfloat16* mask_src;
   int mask_kind;
+  const uint16_t* mask_bits;          // sign bitmaps (see epilogue.cuh): consumer side / producer side
+  uint16_t* bits_out;
+  int bits_pitch, row_elems;
   float alpha;
 };
 bool smallk_fits(int kchunks, int bn_tile, int* slots);

@@ -13,6 +13,7 @@ backward receives the gradient w.r.t. its raw (pre-activation) output.
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -60,6 +61,8 @@ def launch(name, *args, n=1, flops=0, tag=None):
     return K.call(name, *args, S.stream)
 
 
+# relu/lrelu outputs also get a 1-bit/element sign map that the gradient epilogues read (B200GAN_SIGN_BITS=0: off)
+SIGN_BITMAPS = os.environ.get("B200GAN_SIGN_BITS", "1") != "0"
 SMALL_CHANNEL_GEMM = True      # False: image-side layers use the SIMT kernels (no workspace)
 
 
@@ -115,7 +118,7 @@ class recording:
 
 # ------------------------------------------------------------------------------------------ tensors
 class Tensor:
-    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "im2col", "__weakref__")
+    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "im2col", "bits", "__weakref__")
 
     def __init__(self, buf, shape=None, requires_grad=False, mask=None):
         self.buf = buf
@@ -125,6 +128,7 @@ class Tensor:
         self.node = None
         self.grad_f32 = False      # leaf whose gradient is wanted in fp32 (the GP interpolates)
         self.im2col = None         # (geometry key, workspace) left by a small-channel fprop of this tensor
+        self.bits = None           # int16 [rows, ceil(C/16)] sign bitmap written by the producing relu/lrelu epilogue
 
     @property
     def f32(self):
@@ -205,12 +209,14 @@ def _act_code(act):
             "sigmoid": K.ACT_SIGMOID}[act] if not isinstance(act, int) else act
 
 
-def _epilogue(bias=None, act=K.ACT_NONE, leak=0.0, mask=None, out_f32=False, accumulate=False):
+def _epilogue(bias=None, act=K.ACT_NONE, leak=0.0, mask=None, out_f32=False, accumulate=False, bits_ok=False):
     e = K.Epilogue()
     e.bias = None if (bias is None or S.dry) else bias.data_ptr()
     e.act, e.leak = act, leak
     if mask is not None:
         e.mask_src, e.mask_kind = (None if S.dry else mask[0].buf.data_ptr()), mask[1]
+        if bits_ok and mask[0].bits is not None and mask[1] in (K.ACT_RELU, K.ACT_LRELU):
+            e.mask_src, e.mask_bits, e.bits_pitch = None, mask[0].bits.data_ptr(), mask[0].bits.shape[1]
         if act == K.ACT_NONE:
             e.leak = mask[2]
         elif mask[1] == K.ACT_LRELU and act == K.ACT_LRELU and mask[2] != leak:
@@ -247,18 +253,23 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
     else:
         out_shape = (g.N, g.H, g.W, g.Cin)
     out = Tensor(empty(out_shape, F32 if out_f32 else BF16))
-    e = _epilogue(None if bias is None else bias.p32, act, leak, out_mask, out_f32)
+    opi = 0 if direction == "fprop" else 1
+    ws, wsb = _workspace(g, opi)
+    bits_ok = SIGN_BITMAPS and not S.dry and K.epilogue_bits(g, opi, ws is not None)
+    e = _epilogue(None if bias is None else bias.p32, act, leak, out_mask, out_f32, bits_ok=bits_ok)
+    if bits_ok and act in (K.ACT_RELU, K.ACT_LRELU) and not out_f32:
+        c = out_shape[-1]
+        out.bits = torch.empty((out.numel // c, (c + 15) // 16), dtype=torch.int16, device=out.buf.device)
+        e.bits_out, e.bits_pitch = out.bits.data_ptr(), out.bits.shape[1]
     if direction == "fprop":
         wt = W.transposed() if K.route(g, 0) == 1 else None
         tag, fl = _conv_tag("fprop", g) if S.profile is not None else (None, 0)
-        ws, wsb = _workspace(g, 0)
         launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e), _p(ws), wsb,
                flops=fl, tag=tag)
         if ws is not None:
             x.im2col = (_geom_key(g), ws)       # the filter gradient of this layer reads the same im2col
     else:
         tag, fl = _conv_tag("dgrad", g) if S.profile is not None else (None, 0)
-        ws, wsb = _workspace(g, 1)
         launch("b200_conv2d_dgrad", _p(x.buf), _p(W.p16), _p(out.buf), C.byref(g), C.byref(e), _p(ws), wsb, flops=fl,
                tag=tag)
     if act != K.ACT_NONE:

@@ -38,6 +38,14 @@ typedef struct {
   int mask_kind;
   int out_f32;            /* 0: bf16 output, 1: fp32 output */
   int accumulate;         /* fp32 only: out += result */
+  /* Sign bitmaps (optional, honoured where b200_conv2d_epilogue_bits() returns 1): one bit per output element,
+     uint16 words of 16 consecutive channels, bits_pitch words per output row (pixel).  relu / lrelu gradients
+     only need sign(activation) (ops/activations.py:28: slope = leak for x <= 0), so the layer that produces an
+     activation also writes its bitmap and the gradient of the layer above reads 2 bytes per 16 channels
+     instead of the bf16 activation itself. */
+  const void* mask_bits;  /* uint16 [rows, bits_pitch] of the tensor mask_src would name; used instead of it */
+  void* bits_out;         /* uint16 [rows, bits_pitch]: bit j of word (row, c/16) = out[row, c + j] > 0      */
+  int bits_pitch;
 } b200_epilogue;
 
 const char* b200_last_error(void);
@@ -67,6 +75,8 @@ long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op /*0 fprop,
 /* which kernel family a geometry maps to: 1 tensor core, 2 small-channel input (image side), 3 small-channel
  * output backward (<= 4 output channels, SIMT), negative = unsupported */
 int b200_conv2d_route(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
+/* 1 if that call honours b200_epilogue.bits_out / mask_bits (tensor-core epilogues), else 0: pass mask_src */
+int b200_conv2d_epilogue_bits(const b200_conv_geom* g, int op, int has_workspace);
 
 /* ---- dense with one output unit (critic fc2, models/gan.py:285; replaces tf.matmul ops/layers.py:57) */
 int b200_gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act, float leak,

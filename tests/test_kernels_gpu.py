@@ -168,3 +168,43 @@ def test_interp_sumsq_wgan_loss():
     assert abs(float(gl.buf.item()) + float(df.mean())) < 1e-5
     want = float(df.mean() - dr.mean()) + 10.0 * (s - 1) ** 2
     assert abs(float(dl.buf.item()) - want) < 1e-3 * abs(want)
+
+
+def test_sign_bitmaps_match_value_masks():
+    """relu/lrelu epilogues also write a 1-bit/element sign map; a gradient epilogue masked through the
+    bitmap must equal the one masked through the stored activation, bit for bit."""
+    import numpy as np
+    g = torch.Generator().manual_seed(3)
+    N = 6
+    chain = [(32, 3, 200), (16, 200, 400), (8, 400, 800)]          # IWGAN critic c1, c2, c3
+    x = P.dev(torch.randn(N, 32, 32, 3, generator=g))
+    acts = []
+    for (H, Cin, Cout) in chain:
+        geom = E.conv_geom(N, H, H, Cin, Cout, 5, 2)
+        Wp = P.make_param(torch.randn(5, 5, Cin, Cout, generator=g) * (0.3 / math.sqrt(25 * Cin)) * 5)
+        bp = P.make_param(torch.randn(Cout, generator=g) * 0.1)
+        y = E.conv_like("fprop", x, Wp, geom, bias=bp, act=K.ACT_LRELU, leak=0.2)
+        assert y.bits is not None, (H, Cin, Cout)
+        torch.cuda.synchronize()
+        words = y.bits.cpu().numpy().view(np.uint16)                # [rows, ceil(C/16)]
+        unpacked = ((words[:, :, None] >> np.arange(16, dtype=np.uint16)) & 1).reshape(words.shape[0], -1)[:, :Cout]
+        ref = (y.torch().float().cpu().numpy().reshape(-1, Cout) > 0)
+        assert (unpacked.astype(bool) == ref).all(), (H, Cin, Cout)
+        acts.append((x, y, geom, Wp))
+        x = y
+    for (xin, y, geom, Wp) in acts[1:]:
+        dy = P.dev(torch.randn(*y.shape, generator=g))
+        via_bits = E.conv_like("dgrad", dy, Wp, geom, out_mask=(xin, K.ACT_LRELU, 0.2))
+        saved, xin.bits = xin.bits, None
+        via_vals = E.conv_like("dgrad", dy, Wp, geom, out_mask=(xin, K.ACT_LRELU, 0.2))
+        xin.bits = saved
+        torch.cuda.synchronize()
+        assert torch.equal(via_bits.torch(), via_vals.torch())
+        # double-backward shape: fprop masked by the consumer's activation
+        v = P.dev(torch.randn(*xin.shape, generator=g))
+        f_bits = E.conv_like("fprop", v, Wp, geom, out_mask=(y, K.ACT_LRELU, 0.2))
+        saved, y.bits = y.bits, None
+        f_vals = E.conv_like("fprop", v, Wp, geom, out_mask=(y, K.ACT_LRELU, 0.2))
+        y.bits = saved
+        torch.cuda.synchronize()
+        assert torch.equal(f_bits.torch(), f_vals.torch())

@@ -60,9 +60,17 @@ for (N, H, Cin, Cout, k) in CASES:
     x = dev(torch.randn(N, H, H, Cin, generator=g)); dy = dev(torch.randn(N, geom.Ho, geom.Wo, Cout, generator=g))
     Wp = make_param(torch.randn(k, k, Cin, Cout, generator=g) * 0.05)
     fl = 2.0 * N * geom.Ho * geom.Wo * k * k * Cin * Cout
-    for name, fn in (("fprop", lambda: E.conv_like("fprop", x, Wp, geom)), ("dgrad", lambda: E.conv_like("dgrad", dy, Wp, geom))):
+    variants = [("fprop", lambda: E.conv_like("fprop", x, Wp, geom)), ("dgrad", lambda: E.conv_like("dgrad", dy, Wp, geom))]
+    if os.environ.get("WAVE_CASES") == "step":
+        bp = make_param(torch.randn(Cout, generator=g))
+        xm = dev(torch.randn(N, H, H, Cin, generator=g))
+        import numpy as np
+        xm.bits = torch.randint(-32768, 32767, (N * H * H, (Cin + 15) // 16), dtype=torch.int16, device="cuda")
+        variants += [("fprop+bias+lrelu+bits", lambda: E.conv_like("fprop", x, Wp, geom, bias=bp, act=K.ACT_LRELU, leak=0.2)),
+                     ("dgrad+maskbits", lambda: E.conv_like("dgrad", dy, Wp, geom, out_mask=(xm, K.ACT_LRELU, 0.2)))]
+    for name, fn in variants:
         if name == "dgrad" and k < 2:
             continue
         for _ in range(3): fn()
         t, tc = timed(fn)
-        print("N%4d H%2d %4d->%4d k%d %-6s warm %.3f ms (%5.0f TF/s)   cold %.3f ms (%5.0f TF/s)" % (N, H, Cin, Cout, k, name, t, fl / t / 1e9, tc, fl / tc / 1e9), flush=True)
+        print("N%4d H%2d %4d->%4d k%d %-22s warm %.3f ms (%5.0f TF/s)   cold %.3f ms (%5.0f TF/s)" % (N, H, Cin, Cout, k, name, t, fl / t / 1e9, tc, fl / tc / 1e9), flush=True)
