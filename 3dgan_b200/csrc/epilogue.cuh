@@ -11,14 +11,18 @@
 
 namespace b200 {
 
+// tanh / sigmoid use the hardware MUFU.TANH (tanh.approx.f32, relative error about 2^-11): results are stored
+// in bf16 (2^-9), and the libdevice tanhf expansion inlined into every epilogue bloats the hot loops
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float act_fwd(float v, int act, float leak) {
-  switch (act) {
-    case ACT_RELU: return fmaxf(v, 0.f);
-    case ACT_LRELU: return fmaxf(leak * v, v);
-    case ACT_TANH: return tanhf(v);
-    case ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
-    default: return v;
-  }
+  if (act == ACT_NONE) return v;
+  if (act == ACT_RELU || act == ACT_LRELU) return fmaxf(v, (act == ACT_RELU ? 0.f : leak) * v);
+  if (act == ACT_TANH) return tanh_fast(v);
+  return fmaf(0.5f, tanh_fast(0.5f * v), 0.5f);       // sigmoid(v) = (1 + tanh(v/2)) / 2
 }
 // derivative of act at the point whose OUTPUT is a (A.5: lrelu slope = leak for x <= 0)
 __device__ __forceinline__ float act_grad_from_out(float a, int act, float leak) {
@@ -66,11 +70,11 @@ struct MaskChunk {
 __device__ __forceinline__ MaskChunk epilogue_load_mask(const EpilogueArgs& e, long long off, int col) {
   MaskChunk m;
   m.loaded = false;
-  if (e.mask_src && e.pipelined && col + 16 <= e.ncols) {
+  if (e.mask_src && e.pipelined && col + 8 <= e.ncols) {
     const __nv_bfloat16* p = e.mask_src + off + col;
     if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
       m.lo = __ldg(reinterpret_cast<const uint4*>(p));
-      m.hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+      m.hi = (col + 16 <= e.ncols) ? __ldg(reinterpret_cast<const uint4*>(p) + 1) : make_uint4(0, 0, 0, 0);
       m.loaded = true;
     }
   }
@@ -113,44 +117,51 @@ __device__ __forceinline__ ChunkSide epilogue_load_side(const EpilogueArgs& e, l
   return s;
 }
 
-// general (ragged / unaligned) path: per-element guards
-__device__ __forceinline__ void epilogue_store16_slow(const EpilogueArgs& e, const uint32_t* acc, long long off, int col,
-                                                      uint32_t mbits, long long bits_row) {
+// general (ragged / unaligned) path: a compact per-element loop over a local copy of the accumulators
+__device__ __noinline__ static void epilogue_store16_slow(const EpilogueArgs& e, const float* acc, long long off, int col,
+                                                          uint32_t mbits, long long bits_row) {
   const int nvalid = min(16, e.ncols - col);
   const long long o = off + col;
   uint32_t obits = 0;
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    if (j < nvalid) {
-      float v = __uint_as_float(acc[j]) * e.alpha;
-      if (e.bias) v += __ldg(e.bias + col + j);
-      v = act_fwd(v, e.act, e.leak);
-      obits |= (v > 0.f ? 1u : 0u) << j;
-      if (e.mask_bits) v *= ((mbits >> j) & 1u) ? 1.f : (e.mask_kind == ACT_LRELU ? e.leak : 0.f);
-      else if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[o + j]), e.mask_kind, e.leak);
-      if (e.out_f32) {
-        float* dst = reinterpret_cast<float*>(e.out) + o + j;
-        *dst = e.accumulate ? *dst + v : v;
-      } else {
-        reinterpret_cast<__nv_bfloat16*>(e.out)[o + j] = __float2bfloat16(v);
-      }
+#pragma unroll 1
+  for (int j = 0; j < nvalid; ++j) {
+    float v = acc[j] * e.alpha;
+    if (e.bias) v += __ldg(e.bias + col + j);
+    v = act_fwd(v, e.act, e.leak);
+    obits |= (v > 0.f ? 1u : 0u) << j;
+    if (e.mask_bits) v *= ((mbits >> j) & 1u) ? 1.f : (e.mask_kind == ACT_LRELU ? e.leak : 0.f);
+    else if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[o + j]), e.mask_kind, e.leak);
+    if (e.out_f32) {
+      float* dst = reinterpret_cast<float*>(e.out) + o + j;
+      *dst = e.accumulate ? *dst + v : v;
+    } else {
+      reinterpret_cast<__nv_bfloat16*>(e.out)[o + j] = __float2bfloat16(v);
     }
   }
   if (e.bits_out) e.bits_out[bits_row + (col >> 4)] = (uint16_t)obits;
 }
 
 // 16 consecutive columns [col, col+16) of one output row starting at element offset `off`.
-// Fast path (full chunk, 16-byte aligned output, side data preloaded): straight-line code, the
-// activation / mask kind switches hoisted out of the element loops.
+// Fast path (full chunk, 16-byte aligned output, side data preloaded): straight-line code.
+// kSimple kernels are launched when the epilogue is bf16-out with none/relu/lrelu and no value mask (bias,
+// sign bitmaps in and out allowed): the other variants are compiled out of their hot loop.
+template <bool kSimple>
 __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const uint32_t* acc, long long off,
                                                  int col, const ChunkSide* side = nullptr, long long bits_row = 0) {
   const long long o = off + col;
-  const bool full = col + 16 <= e.ncols;
-  const uintptr_t oaddr = reinterpret_cast<uintptr_t>(e.out) + (uintptr_t)o * (e.out_f32 ? 4 : 2);
+  // channel counts are multiples of 8 on the tensor-core route: a chunk holds 16 or (the last one) 8 columns
+  const int nv = min(16, e.ncols - col);
+  const bool full = nv == 16 || nv == 8;
+  const bool f32 = !kSimple && e.out_f32;
+  const uintptr_t oaddr = reinterpret_cast<uintptr_t>(e.out) + (uintptr_t)o * (f32 ? 4 : 2);
+  const bool vmask = !kSimple && e.mask_src && !e.mask_bits;
   const bool fast = full && (oaddr & 15) == 0 && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
-                    (e.mask_bits || !e.mask_src || (side && side->m.loaded));
+                    (!vmask || (side && side->m.loaded));
   if (!fast) {
-    epilogue_store16_slow(e, acc, off, col, side ? side->bits : 0u, bits_row);
+    float tmp[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) tmp[j] = __uint_as_float(acc[j]);
+    epilogue_store16_slow(e, tmp, off, col, side ? side->bits : 0u, bits_row);
     return;
   }
   float v[16];
@@ -159,7 +170,7 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
     const float4* bp = reinterpret_cast<const float4*>(e.bias + col);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 b4 = __ldg(bp + j);
+      const float4 b4 = (4 * j < nv) ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       v[4 * j + 0] = fmaf(__uint_as_float(acc[4 * j + 0]), a, b4.x);
       v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), a, b4.y);
       v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), a, b4.z);
@@ -169,27 +180,20 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) * a;
   }
-  switch (e.act) {
-    case ACT_NONE: break;
-    case ACT_LRELU: {
-      const float leak = e.leak;
+  if (!kSimple && (e.act == ACT_TANH || e.act == ACT_SIGMOID)) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(leak * v[j], v[j]);
-      break;
-    }
-    case ACT_RELU:
+    for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act, e.leak);
+  } else {
+    // none / relu / lrelu in one branch-free form: max(v, slope * v) with slope 1 / 0 / leak
+    const float slope = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.leak);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-      break;
-    default:
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act, e.leak);
-      break;
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
   }
   if (e.bits_out) {
     uint32_t w = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+    if (nv == 8) w &= 0xffu;
     e.bits_out[bits_row + (col >> 4)] = (uint16_t)w;
   }
   if (e.mask_bits) {
@@ -197,7 +201,7 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
     const uint32_t w = side->bits;
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = ((w >> j) & 1u) ? v[j] : v[j] * neg;
-  } else if (e.mask_src) {
+  } else if (vmask) {
     const uint32_t mw[8] = {side->m.lo.x, side->m.lo.y, side->m.lo.z, side->m.lo.w,
                             side->m.hi.x, side->m.hi.y, side->m.hi.z, side->m.hi.w};
     if (e.mask_kind == ACT_LRELU || e.mask_kind == ACT_RELU) {
@@ -219,16 +223,18 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
       }
     }
   }
-  if (e.out_f32) {
+  if (f32) {
     float* dst = reinterpret_cast<float*>(e.out) + o;
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      if (e.accumulate) {
-        const float4 old = *reinterpret_cast<const float4*>(dst + j);
-        f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
+      if (j < nv) {
+        float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (e.accumulate) {
+          const float4 old = *reinterpret_cast<const float4*>(dst + j);
+          f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;
+        }
+        *reinterpret_cast<float4*>(dst + j) = f;
       }
-      *reinterpret_cast<float4*>(dst + j) = f;
     }
   } else {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + o;
@@ -239,45 +245,40 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
       pk[j] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    *(reinterpret_cast<uint4*>(dst) + 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    if (nv == 16) *(reinterpret_cast<uint4*>(dst) + 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
-// One output row's chunks c0, c0+step, ... of an accumulator row in TMEM: the TMEM load and the mask /
-// bias loads of chunk i+1 are issued before chunk i is processed (two register buffers).
+// host side: can this epilogue run in a kSimple kernel?
+inline bool epilogue_is_simple(int act, const void* mask_src, const void* mask_bits, int out_f32, int accumulate) {
+  return !out_f32 && !accumulate && (act == ACT_NONE || act == ACT_RELU || act == ACT_LRELU) &&
+         (mask_src == nullptr || mask_bits != nullptr);
+}
+
+// One output row's chunks c0, c0+step, ... of an accumulator row in TMEM: the TMEM load and the side loads
+// of chunk i+1 are issued before chunk i is processed.
+template <bool kSimple>
 __device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t trow, long long off, bool row_ok,
                                              int n0, int c_first, int c_step, int c_end) {
+  // c_end: first column offset (relative to the tile) that must not be processed
+  if (c_first >= c_end) return;
   // word offset of this output row in the sign bitmaps (the output is dense: row = element offset / row width)
   const long long bits_row = (e.mask_bits || e.bits_out) ? (off / e.row_elems) * e.bits_pitch : 0;
-  // c_end: first column offset (relative to the tile) that must not be processed
-  int c = c_first;
-  if (c >= c_end) return;
-  uint32_t va[16], vb[16];
-  tmem_ld16(trow + c, va);
-  ChunkSide cur = epilogue_load_side(e, off, n0 + c, row_ok, bits_row);
-  while (true) {
+  uint32_t vn[16], vc[16];
+  tmem_ld16(trow + c_first, vn);
+  ChunkSide nxt = epilogue_load_side(e, off, n0 + c_first, row_ok, bits_row);
+#pragma unroll 1
+  for (int c = c_first; c < c_end; c += c_step) {
+    tmem_ld_wait16(vn);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) vc[j] = vn[j];
+    const ChunkSide cur = nxt;
     const int c1 = c + c_step;
-    const bool more1 = c1 < c_end;
-    tmem_ld_wait16(va);
-    ChunkSide nxt;
-    nxt.m.loaded = false; nxt.bits = 0;
-    if (more1) {
-      tmem_ld16(trow + c1, vb);
+    if (c1 < c_end) {
+      tmem_ld16(trow + c1, vn);
       nxt = epilogue_load_side(e, off, n0 + c1, row_ok, bits_row);
     }
-    if (row_ok) epilogue_store16(e, va, off, n0 + c, &cur, bits_row);
-    if (!more1) break;
-    const int c2 = c1 + c_step;
-    const bool more2 = c2 < c_end;
-    tmem_ld_wait16(vb);
-    cur.m.loaded = false; cur.bits = 0;
-    if (more2) {
-      tmem_ld16(trow + c2, va);
-      cur = epilogue_load_side(e, off, n0 + c2, row_ok, bits_row);
-    }
-    if (row_ok) epilogue_store16(e, vb, off, n0 + c1, &nxt, bits_row);
-    if (!more2) break;
-    c = c2;
+    if (row_ok) epilogue_store16<kSimple>(e, vc, off, n0 + c, &cur, bits_row);
   }
 }
 

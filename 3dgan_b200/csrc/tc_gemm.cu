@@ -41,7 +41,7 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
 // share the same pixel tiles each load ONE of the two A tiles and multicast it to the other, so a CTA
 // pulls A/2 + B/2 from L2 for an (256 x bn_tile) output block.  These GEMMs are bound by the L2->SM
 // fill rate (about 12 TB/s chip-wide), so halving the operand traffic is what raises tensor-pipe use.
-template <int kCluster>
+template <int kCluster, bool kSimple>
 __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     for (int i = 0; i < 2; ++i) {
       if (i >= p.dual) break;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
-      epilogue_row(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols - n0));
+      epilogue_row<kSimple>(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols - n0));
     }
   }
 
@@ -418,22 +418,27 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(tapgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tapgemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tapgemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tapgemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tapgemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     configured = true;
   }
   const int tiles = (p.tiles_w * p.tiles_h * p.tiles_n + p.dual - 1) / p.dual;
   const int ntile_y = (p.ncols + p.bn_tile - 1) / p.bn_tile;
+  const bool simple = epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate);
   if (p.cluster == 2) {
     static int cy_env = -1;
     if (cy_env < 0) cy_env = env_int("B200GAN_CLUSTER_Y", 1);
     TapGemmParams q = p;
     q.cluster_y = (cy_env == 2 && p.dual == 2 && ntile_y >= 2) ? 2 : 1;
     dim3 grid((tiles + 1) / 2 * 2, (ntile_y + q.cluster_y - 1) / q.cluster_y * q.cluster_y, p.nphases);
-    launch_clustered(tapgemm_kernel<2>, q, grid, smem, 2, stream, q.cluster_y);
+    if (simple) launch_clustered(tapgemm_kernel<2, true>, q, grid, smem, 2, stream, q.cluster_y);
+    else launch_clustered(tapgemm_kernel<2, false>, q, grid, smem, 2, stream, q.cluster_y);
   } else {
     dim3 grid(tiles, ntile_y, p.nphases);
-    tapgemm_kernel<1><<<grid, gemm_threads(), smem, stream>>>(p);
+    if (simple) tapgemm_kernel<1, true><<<grid, gemm_threads(), smem, stream>>>(p);
+    else tapgemm_kernel<1, false><<<grid, gemm_threads(), smem, stream>>>(p);
   }
 }
 
@@ -449,6 +454,7 @@ struct SmallKSmem {
   uint32_t tmem_base;
 };
 
+template <bool kSimple>
 __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_constant__ SmallKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
       mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
       tc_fence_after();
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols;
-      epilogue_row(ea, trow, off, row_ok, 0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols));
+      epilogue_row<kSimple>(ea, trow, off, row_ok, 0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[acc]));
@@ -585,14 +591,18 @@ void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    cudaFuncSetAttribute(smallk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(smallk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(smallk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  smallk_kernel<<<grid, gemm_threads(), smem, stream>>>(p);
+  if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
+    smallk_kernel<true><<<grid, gemm_threads(), smem, stream>>>(p);
+  else
+    smallk_kernel<false><<<grid, gemm_threads(), smem, stream>>>(p);
 }
 
 // =============================================================================================

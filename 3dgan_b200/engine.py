@@ -209,13 +209,17 @@ def _act_code(act):
             "sigmoid": K.ACT_SIGMOID}[act] if not isinstance(act, int) else act
 
 
-def _epilogue(bias=None, act=K.ACT_NONE, leak=0.0, mask=None, out_f32=False, accumulate=False, bits_ok=False):
+def _epilogue(bias=None, act=K.ACT_NONE, leak=0.0, mask=None, out_f32=False, accumulate=False, bits_ok=False,
+              out_c=None):
     e = K.Epilogue()
     e.bias = None if (bias is None or S.dry) else bias.data_ptr()
     e.act, e.leak = act, leak
     if mask is not None:
         e.mask_src, e.mask_kind = (None if S.dry else mask[0].buf.data_ptr()), mask[1]
-        if bits_ok and mask[0].bits is not None and mask[1] in (K.ACT_RELU, K.ACT_LRELU):
+        # the bitmap is laid out per row of C channels: usable only when the mask tensor has this output's
+        # row width (a mask seen through a reshape keeps its values but not its bitmap layout)
+        if (bits_ok and mask[0].bits is not None and mask[1] in (K.ACT_RELU, K.ACT_LRELU)
+                and mask[0].shape[-1] == out_c):
             e.mask_src, e.mask_bits, e.bits_pitch = None, mask[0].bits.data_ptr(), mask[0].bits.shape[1]
         if act == K.ACT_NONE:
             e.leak = mask[2]
@@ -256,7 +260,8 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
     opi = 0 if direction == "fprop" else 1
     ws, wsb = _workspace(g, opi)
     bits_ok = SIGN_BITMAPS and not S.dry and K.epilogue_bits(g, opi, ws is not None)
-    e = _epilogue(None if bias is None else bias.p32, act, leak, out_mask, out_f32, bits_ok=bits_ok)
+    e = _epilogue(None if bias is None else bias.p32, act, leak, out_mask, out_f32, bits_ok=bits_ok,
+                  out_c=out_shape[-1])
     if bits_ok and act in (K.ACT_RELU, K.ACT_LRELU) and not out_f32:
         c = out_shape[-1]
         out.bits = torch.empty((out.numel // c, (c + 15) // 16), dtype=torch.int16, device=out.buf.device)
