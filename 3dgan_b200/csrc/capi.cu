@@ -43,7 +43,7 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor, dims[0] contiguous; strides in ELEMENTS for dims 1..rank-1; 128-byte swizzle, zero OOB fill
 static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long long* dims, const long long* strides,
-                     const int* box, const int* estride, int swizzle_bytes = 128) {
+                     const int* box, const int* estride, int swizzle_bytes = 128, int elem_bytes = 2) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15) return fail("tensor map base not 16-byte aligned");
@@ -55,14 +55,15 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long lon
     es[i] = (cuuint32_t)estride[i];
     if (box[i] < 1 || box[i] > 256) return fail("TMA box dim out of range");
     if (i > 0) {
-      gstr[i - 1] = (cuuint64_t)strides[i] * 2;
+      gstr[i - 1] = (cuuint64_t)strides[i] * elem_bytes;
       if (gstr[i - 1] & 15) return fail("TMA stride not a multiple of 16 bytes (channels must be a multiple of 8)");
     }
   }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, b, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
-                                       : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+  CUresult r = enc(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                         : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -92,6 +93,11 @@ static int pick_stages(int stage_bytes) {
   return std::max(2, std::min(s, std::min(cap, 8)));
 }
 
+static int tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200GAN_TMA_STORE"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static int weight_prefetch() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("B200GAN_PREFETCH_B"); v = e ? atoi(e) : 1; }
@@ -168,9 +174,26 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
     int slots = 0;
     const int kch = cdiv(K, kBlockK), bn = pick_bn_tile(ncols);
     const long long tiles = (M + kTileM - 1) / kTileM;
-    if (ncols <= 256 && tiles >= 296 && smallk_fits(kch, bn, &slots)) {
+    // bulk-store epilogue: possible when every 16-column chunk takes the epilogue's aligned fast path
+    const int elem = (e && e->out_f32) ? 4 : 2;
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(out) | (e ? reinterpret_cast<uintptr_t>(e->bias) : 0) |
+                             (e ? reinterpret_cast<uintptr_t>(e->mask_src) : 0)) & 15) == 0;
+    const bool tma_store = tma_store_enabled() && !(e && e->accumulate) && ncols % 8 == 0 && (ldo * elem) % 16 == 0 &&
+                           (ldo * 2) % 16 == 0 && aligned16 && epilogue_pipelined();
+    const int bits_pitch = e ? e->bits_pitch : 0;
+    const bool bits_stage = tma_store && e && e->bits_out && M % kTileM == 0 &&
+                            (reinterpret_cast<uintptr_t>(e->bits_out) & 15) == 0;
+    const int stage_bytes = tma_store ? (((kTileM * ncols * elem + 127) & ~127) +
+                                         (bits_stage ? ((kTileM * bits_pitch * 2 + 127) & ~127) : 0)) : 0;
+    if (ncols <= 256 && tiles >= 296 && smallk_fits(kch, bn, &slots, stage_bytes)) {
       SmallKParams q;
       memset(&q, 0, sizeof q);
+      if (tma_store) {
+        long long dimsO[2] = {ncols, M}, strO[2] = {1, ldo};
+        int boxO[2] = {ncols, kTileM}, esO[2] = {1, 1};
+        if (make_tmap(&q.tmOut, out, 2, dimsO, strO, boxO, esO, 0, elem)) return -1;
+        q.tma_store = 1; q.stage_pitch = ncols * elem; q.bits_stage = bits_stage ? 1 : 0;
+      }
       long long dimsA[2] = {K, M}, strA[2] = {1, lda};
       int boxA[2] = {kBlockK, kTileM}, es[2] = {1, 1};
       if (make_tmap(&q.tmA, A, 2, dimsA, strA, boxA, es)) return -1;

@@ -53,6 +53,13 @@ struct EpilogueArgs {
   uint16_t* bits_out;          // written next to the output: bit j of word (row, col/16) = out[row, col+j] > 0
   int bits_pitch;
   int row_elems;               // elements per output row: row index = element offset / row_elems
+  // shared-memory staging (TMA-store epilogue): when stage_row != 0 the chunk is written to
+  // stage_row + (col - stage_col0) * elem and its sign word to stage_bits + ((col - stage_col0) >> 4) * 2;
+  // one thread later moves the whole tile to global memory with a bulk tensor store.  Row-strided
+  // 16-byte global stores cost one L1 wavefront per lane; the bulk store writes full lines.
+  uint32_t stage_row;
+  uint32_t stage_bits;
+  int stage_col0;
 };
 
 // Epilogue warps are idle during the main loop: pull the mask rows they will need into L2 meanwhile.
@@ -155,13 +162,17 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
   const bool f32 = !kSimple && e.out_f32;
   const uintptr_t oaddr = reinterpret_cast<uintptr_t>(e.out) + (uintptr_t)o * (f32 ? 4 : 2);
   const bool vmask = !kSimple && e.mask_src && !e.mask_bits;
-  const bool fast = full && (oaddr & 15) == 0 && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
+  const bool fast = full && (e.stage_row || (oaddr & 15) == 0) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
                     (!vmask || (side && side->m.loaded));
   if (!fast) {
+    if (e.stage_row) __trap();            // the host enables staging only when every chunk takes the fast path
+    // cold: local copies, so that neither the accumulators nor the argument block of the hot path ever
+    // have their address taken (they would be demoted to local memory, and L1 is almost all shared memory here)
     float tmp[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) tmp[j] = __uint_as_float(acc[j]);
-    epilogue_store16_slow(e, tmp, off, col, side ? side->bits : 0u, bits_row);
+    const EpilogueArgs ecopy = e;
+    epilogue_store16_slow(ecopy, tmp, off, col, side ? side->bits : 0u, bits_row);
     return;
   }
   float v[16];
@@ -194,7 +205,8 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
 #pragma unroll
     for (int j = 0; j < 16; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
     if (nv == 8) w &= 0xffu;
-    e.bits_out[bits_row + (col >> 4)] = (uint16_t)w;
+    if (e.stage_bits) st_shared_u16(e.stage_bits + (((col - e.stage_col0) >> 4) << 1), (uint16_t)w);
+    else e.bits_out[bits_row + (col >> 4)] = (uint16_t)w;
   }
   if (e.mask_bits) {
     const float neg = e.mask_kind == ACT_LRELU ? e.leak : 0.f;
@@ -222,6 +234,27 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
         v[2 * j + 1] *= act_grad_from_out(hi, e.mask_kind, e.leak);
       }
     }
+  }
+  if (e.stage_row) {
+    if (f32) {
+      const uint32_t dst = e.stage_row + (uint32_t)(col - e.stage_col0) * 4;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        if (j < nv)
+          st_shared_v4(dst + j * 4, __float_as_uint(v[j]), __float_as_uint(v[j + 1]), __float_as_uint(v[j + 2]),
+                       __float_as_uint(v[j + 3]));
+    } else {
+      const uint32_t dst = e.stage_row + (uint32_t)(col - e.stage_col0) * 2;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      st_shared_v4(dst, pk[0], pk[1], pk[2], pk[3]);
+      if (nv == 16) st_shared_v4(dst + 16, pk[4], pk[5], pk[6], pk[7]);
+    }
+    return;
   }
   if (f32) {
     float* dst = reinterpret_cast<float*>(e.out) + o;
@@ -264,21 +297,33 @@ __device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t tro
   if (c_first >= c_end) return;
   // word offset of this output row in the sign bitmaps (the output is dense: row = element offset / row width)
   const long long bits_row = (e.mask_bits || e.bits_out) ? (off / e.row_elems) * e.bits_pitch : 0;
-  uint32_t vn[16], vc[16];
-  tmem_ld16(trow + c_first, vn);
-  ChunkSide nxt = epilogue_load_side(e, off, n0 + c_first, row_ok, bits_row);
+  if (kSimple) {
+    uint32_t vn[16], vc[16];
+    tmem_ld16(trow + c_first, vn);
+    ChunkSide nxt = epilogue_load_side(e, off, n0 + c_first, row_ok, bits_row);
 #pragma unroll 1
-  for (int c = c_first; c < c_end; c += c_step) {
-    tmem_ld_wait16(vn);
+    for (int c = c_first; c < c_end; c += c_step) {
+      tmem_ld_wait16(vn);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) vc[j] = vn[j];
-    const ChunkSide cur = nxt;
-    const int c1 = c + c_step;
-    if (c1 < c_end) {
-      tmem_ld16(trow + c1, vn);
-      nxt = epilogue_load_side(e, off, n0 + c1, row_ok, bits_row);
+      for (int j = 0; j < 16; ++j) vc[j] = vn[j];
+      const ChunkSide cur = nxt;
+      const int c1 = c + c_step;
+      if (c1 < c_end) {
+        tmem_ld16(trow + c1, vn);
+        nxt = epilogue_load_side(e, off, n0 + c1, row_ok, bits_row);
+      }
+      if (row_ok) epilogue_store16<kSimple>(e, vc, off, n0 + c, &cur, bits_row);
     }
-    if (row_ok) epilogue_store16<kSimple>(e, vc, off, n0 + c, &cur, bits_row);
+  } else {
+    // general epilogues (fp32 out, value masks, tanh/sigmoid) keep one accumulator buffer: fewer registers
+#pragma unroll 1
+    for (int c = c_first; c < c_end; c += c_step) {
+      uint32_t v[16];
+      tmem_ld16(trow + c, v);
+      const ChunkSide cur = epilogue_load_side(e, off, n0 + c, row_ok, bits_row);
+      tmem_ld_wait16(v);
+      if (row_ok) epilogue_store16<kSimple>(e, v, off, n0 + c, &cur, bits_row);
+    }
   }
 }
 

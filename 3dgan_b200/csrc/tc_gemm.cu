@@ -6,6 +6,7 @@
 #include "tc_gemm.cuh"
 #include "ptx.cuh"
 #include "epilogue.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -289,6 +290,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
     ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
+    ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
 
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     bool row_ok[2];
@@ -452,6 +454,7 @@ struct SmallKSmem {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
+  long long trace[5][12];      // B200GAN_SMALLK_TRACE: per-tile clock stamps of CTA 0 (debug)
 };
 
 template <bool kSimple>
@@ -464,7 +467,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
   const int slot_bytes = p.kchunks * kABytes;             // one A tile: 128 rows x full K
   uint8_t* smem_b = smem;
   uint8_t* smem_a = smem + (size_t)p.kchunks * b_bytes;
-  SmallKSmem* ps = reinterpret_cast<SmallKSmem*>(smem_a + (size_t)p.slots * slot_bytes);
+  uint8_t* smem_out = smem_a + (size_t)p.slots * slot_bytes;                     // staged output tile (tma_store)
+  const int out_stage_bytes = p.tma_store ? ((kTileM * p.stage_pitch + 127) & ~127) : 0;
+  uint8_t* smem_bits = smem_out + out_stage_bytes;
+  const int bits_stage_bytes = p.bits_stage ? ((kTileM * p.bits_pitch * 2 + 127) & ~127) : 0;
+  SmallKSmem* ps = reinterpret_cast<SmallKSmem*>(smem_bits + bits_stage_bytes);
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmA);
@@ -494,8 +501,20 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
         tma_load_2d(smem_u32(smem_b + (size_t)kc * b_bytes), &p.tmB, bfull, kc * kBlockK, 0);
       int s = 0;
       uint32_t par = 0;
+      // A is streamed once from HBM: the few smem slots do not keep enough requests in flight to cover the
+      // DRAM latency, so tiles are pulled into L2 p.l2_ahead tiles before their loads
+      auto prefetch_tile = [&](int tile) {
+        if (tile < p.num_tiles)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            int c[2] = {kc * kBlockK, tile * kTileM};
+            tma_prefetch_nd(2, &p.tmA, c);
+          }
+      };
+      for (int i = 0; i < p.l2_ahead; ++i) prefetch_tile(blockIdx.x + i * gridDim.x);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (p.l2_ahead) prefetch_tile(tile + p.l2_ahead * gridDim.x);
         mbar_wait(smem_u32(&ps->a_empty[s]), par ^ 1);
+        if (p.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 12) ps->trace[0][tile / gridDim.x] = clock64();
         const uint32_t full = smem_u32(&ps->a_full[s]);
         mbar_arrive_expect_tx(full, slot_bytes);
         const uint32_t dst = smem_u32(smem_a + (size_t)s * slot_bytes);
@@ -516,7 +535,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
       uint32_t par = 0, accpar = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(smem_u32(&ps->acc_empty[acc]), accpar ^ 1);   // epilogue has drained this accumulator
+        if (p.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 12) ps->trace[1][tile / gridDim.x] = clock64();
         mbar_wait(smem_u32(&ps->a_full[s]), par);
+        if (p.trace && blockIdx.x == 0 && tile / (int)gridDim.x < 12) ps->trace[2][tile / gridDim.x] = clock64();
         tc_fence_after();
         const uint64_t adesc = adesc0 + (uint64_t)(((uint32_t)slot_bytes >> 4) * s);
         uint32_t accum = 0;
@@ -550,43 +571,77 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
     ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
     ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
+    ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
     int acc = 0;
     uint32_t accpar = 0;
+    const int nepi = (int)blockDim.x - 64;
+    const bool issuer = threadIdx.x == 64;
+    if (p.tma_store) {
+      ea.stage_row = smem_u32(smem_out) + (uint32_t)(r * p.stage_pitch);
+      ea.stage_bits = p.bits_stage ? smem_u32(smem_bits) + (uint32_t)(r * p.bits_pitch * 2) : 0u;
+      ea.stage_col0 = 0;
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long row = (long long)tile * kTileM + r;
       const bool row_ok = row < p.M;
       const long long off = row * p.ldo;
       if (row_ok && cg == 0) epilogue_prefetch_mask(ea, off, 0, p.bn_tile);
       mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && tile / (int)gridDim.x < 12) ps->trace[3][tile / gridDim.x] = clock64();
       tc_fence_after();
+      if (p.tma_store) {
+        if (issuer) bulk_wait_read0();          // the previous tile's bulk store has drained the staging buffer
+        named_barrier(1, nepi);
+      }
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols;
       epilogue_row<kSimple>(ea, trow, off, row_ok, 0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols));
       tc_fence_before();
       __syncwarp();
+      if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && tile / (int)gridDim.x < 12) ps->trace[4][tile / gridDim.x] = clock64();
       if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[acc]));
+      if (p.tma_store) {
+        fence_proxy_async_smem();               // staged rows (generic proxy) -> visible to the bulk copy engine
+        named_barrier(1, nepi);
+        if (issuer) {
+          tma_store_2d(&p.tmOut, smem_u32(smem_out), 0, tile * kTileM);
+          if (p.bits_stage)
+            bulk_store_1d(p.bits_out + (size_t)tile * kTileM * p.bits_pitch, smem_u32(smem_bits),
+                          (uint32_t)(kTileM * p.bits_pitch * 2));
+          bulk_commit();
+        }
+      }
       acc ^= 1;
       if (acc == 0) accpar ^= 1;
     }
+    if (p.tma_store && issuer) bulk_wait0();
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = ps->trace[0][0];
+    for (int i = 0; i < 7; ++i)
+      printf("tile %d: load_issue %lld  mma_acc_free %lld  mma_a_full %lld  epi_start %lld  epi_end %lld\n", i,
+             ps->trace[0][i] - t0, ps->trace[1][i] - t0, ps->trace[2][i] - t0, ps->trace[3][i] - t0, ps->trace[4][i] - t0);
+  }
   if (warp == 1) tmem_dealloc<2 * kTmemCols>(tmem);
 }
 
-bool smallk_fits(int kchunks, int bn_tile, int* slots) {
+bool smallk_fits(int kchunks, int bn_tile, int* slots, int stage_bytes) {
   if (getenv("B200GAN_NO_SMALLK")) return false;
   if (kchunks < 1 || kchunks > 4 || bn_tile > 256) return false;
   const int b_total = kchunks * bn_tile * kBlockK * 2;
   const int slot = kchunks * kABytes;
-  int n = (227 * 1024 - 2048 - b_total) / slot;
+  int n = (227 * 1024 - 2048 - b_total - stage_bytes) / slot;
   if (n < 2) return false;
   *slots = n > 8 ? 8 : n;
   return true;
 }
 
 void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
-  const size_t smem = (size_t)p.kchunks * p.bn_tile * kBlockK * 2 + (size_t)p.slots * p.kchunks * kABytes +
+  const size_t stage = (p.tma_store ? ((kTileM * p.stage_pitch + 127) & ~127) : 0) +
+                       (p.bits_stage ? ((kTileM * p.bits_pitch * 2 + 127) & ~127) : 0);
+  const size_t smem = (size_t)p.kchunks * p.bn_tile * kBlockK * 2 + (size_t)p.slots * p.kchunks * kABytes + stage +
                       sizeof(SmallKSmem) + 1024;
   static bool configured = false;
   static int sms = 148;
@@ -599,10 +654,17 @@ void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
     configured = true;
   }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  static int ahead = -1;
+  if (ahead < 0) ahead = env_int("B200GAN_SMALLK_AHEAD", 0);
+  SmallKParams q = p;
+  q.l2_ahead = ahead;
+  static int trace = -1;
+  if (trace < 0) trace = env_int("B200GAN_SMALLK_TRACE", 0);
+  q.trace = trace;
   if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
-    smallk_kernel<true><<<grid, gemm_threads(), smem, stream>>>(p);
+    smallk_kernel<true><<<grid, gemm_threads(), smem, stream>>>(q);
   else
-    smallk_kernel<false><<<grid, gemm_threads(), smem, stream>>>(p);
+    smallk_kernel<false><<<grid, gemm_threads(), smem, stream>>>(q);
 }
 
 // =============================================================================================

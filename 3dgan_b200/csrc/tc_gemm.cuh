@@ -109,6 +109,12 @@ struct SmallKParams {
   long long M;
   int ncols, bn_tile;
   int slots;                          // A ring depth
+  int trace;                          // debug: print per-tile clock stamps of CTA 0
+  CUtensorMap tmOut;                  // [M, ncols] output, box ncols x 128, no swizzle (tma_store)
+  int tma_store;                      // 1: tiles are staged in shared memory and written with one bulk tensor store
+  int stage_pitch;                    // bytes per staged row (ncols * element size)
+  int bits_stage;                     // 1: the tile's sign words are staged and written with one bulk copy
+  int l2_ahead;                       // tiles prefetched into L2 ahead of their loads (set by launch_smallk)
   int epi_pipe;
   long long ldo;
   void* out;
@@ -123,7 +129,7 @@ struct SmallKParams {
   int bits_pitch, row_elems;
   float alpha;
 };
-bool smallk_fits(int kchunks, int bn_tile, int* slots);
+bool smallk_fits(int kchunks, int bn_tile, int* slots, int stage_bytes = 0);
 void launch_smallk(const SmallKParams& p, cudaStream_t stream);
 int wgrad_dual(int m_tiles);
 void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream);
