@@ -582,8 +582,53 @@ int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B
 // Column reductions over a row-major [R, C] bf16 matrix (C contiguous)
 // =============================================================================================
 // out[c] += alpha * sum_r x[r,c] * (wrow ? wrow[r] : 1);   out2[c] += alpha * sum_r x[r,c]^2 (optional)
-// block = 32 column-pairs x 8 row lanes: each warp reads 128 contiguous bytes of a row, 8 rows in flight per
-// block iteration, 4-way unrolled; row lanes are combined through shared memory, one atomic per column.
+// Vector path (C % 8 == 0): block = 32 column-octets x 8 row lanes, one 16-byte load per thread and row, 4 rows
+// in flight per thread; row lanes are combined through shared memory, one atomic per column.
+template <bool kSquares>
+__global__ void colsum_vec_kernel(const bf16* __restrict__ x, const float* __restrict__ wrow, float* out, float* out2,
+                                  long long R, int C, float alpha, int rows_per_block) {
+  __shared__ float red[kSquares ? 2 : 1][8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 8;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (c < C) {
+#pragma unroll 4
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const float wr = wrow ? wrow[r] : 1.f;
+      const uint4 raw = *reinterpret_cast<const uint4*>(x + r * C + c);
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+        s[2 * j] = fmaf(lo, wr, s[2 * j]); s[2 * j + 1] = fmaf(hi, wr, s[2 * j + 1]);
+        if (kSquares) { q[2 * j] = fmaf(lo, lo, q[2 * j]); q[2 * j + 1] = fmaf(hi, hi, q[2 * j + 1]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][ty][tx * 8 + j] = s[j];
+    if (kSquares) red[kSquares ? 1 : 0][ty][tx * 8 + j] = q[j];
+  }
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a += red[0][j][threadIdx.x];
+      if (kSquares) b += red[kSquares ? 1 : 0][j][threadIdx.x];
+    }
+    atomicAdd(out + cc, a * alpha);
+    if (kSquares) atomicAdd(out2 + cc, b * alpha);
+  }
+}
+// block = 32 column-pairs x 8 row lanes (any C)
 __global__ void colsum_kernel(const bf16* __restrict__ x, const float* __restrict__ wrow, float* out, float* out2,
                               long long R, int C, float alpha, int rows_per_block) {
   __shared__ float red[4][8][64];
@@ -626,13 +671,16 @@ __global__ void colsum_kernel(const bf16* __restrict__ x, const float* __restric
 }
 static void colsum_launch(const bf16* x, const float* wrow, float* out, float* out2, long long R, int C, float alpha,
                           cudaStream_t st) {
-  const int gx = (C + 63) / 64;
+  const bool vec = (C & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int gx = vec ? (C + 255) / 256 : (C + 63) / 64;
   long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
   if (want > (R + 31) / 32) want = (R + 31) / 32;
   if (want < 1) want = 1;
   const int rpb = (int)((R + want - 1) / want);
   const int gy = (int)((R + rpb - 1) / rpb);
-  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
+  if (vec && out2) colsum_vec_kernel<true><<<dim3(gx, gy), 256, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
+  else if (vec) colsum_vec_kernel<false><<<dim3(gx, gy), 256, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
+  else colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, wrow, out, out2, R, C, alpha, rpb);
 }
 int colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, cudaStream_t st) {
   colsum_launch((const bf16*)x, wrow, out, nullptr, R, C, alpha, st);
@@ -645,28 +693,43 @@ int bn_sums(const void* z, float* stats, long long R, int C, cudaStream_t st) {
   colsum_launch((const bf16*)z, nullptr, stats, stats + C, R, C, 1.f, st);
   return 0;
 }
-// a = act((z-mean)*rstd + beta)
+// a = act((z-mean)*rstd + beta).  A block owns a slab of up to 1024 channels x a range of rows: the slab's
+// rstd and shift are computed once into shared memory, then the rows are streamed with 16-byte accesses.
+constexpr int kBnSlab = 1024;
 __global__ void bn_apply_vec_kernel(const bf16* __restrict__ z, const float* __restrict__ stats,
                                     const float* __restrict__ beta, bf16* out, long long R, int C, float eps, int act,
-                                    float leak) {
-  const long long n8 = R * C / 8;
+                                    float leak, int rows_per_block) {
+  __shared__ float sc[kBnSlab], sh[kBnSlab];
+  const int cs0 = blockIdx.x * kBnSlab;
+  const int cw = min(kBnSlab, C - cs0);
   const float invR = 1.f / (float)R;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    const int c0 = (int)((i * 8) % C);
-    uint4 zv = *reinterpret_cast<const uint4*>(z + i * 8);
-    const bf16* zp = reinterpret_cast<const bf16*>(&zv);
-    uint4 ov;
-    bf16* op = reinterpret_cast<bf16*>(&ov);
+  for (int c = threadIdx.x; c < cw; c += blockDim.x) {
+    const float mean = stats[cs0 + c] * invR;
+    const float rstd = rsqrtf(fmaxf(stats[C + cs0 + c] * invR - mean * mean, 0.f) + eps);
+    sc[c] = rstd;
+    sh[c] = beta[cs0 + c] - mean * rstd;
+  }
+  __syncthreads();
+  const int cpr = cw >> 3;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  const int total = (int)(r1 - r0) * cpr;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int rr = t / cpr, ch = t - rr * cpr;
+    const long long e0 = (r0 + rr) * C + cs0 + ch * 8;
+    const uint4 zv = *reinterpret_cast<const uint4*>(z + e0);
+    const uint32_t w4[4] = {zv.x, zv.y, zv.z, zv.w};
+    uint32_t o4[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = c0 + e;
-      const float mean = stats[c] * invR;
-      const float var = fmaxf(stats[C + c] * invR - mean * mean, 0.f);
-      const float v = (__bfloat162float(zp[e]) - mean) * rsqrtf(var + eps) + beta[c];
-      op[e] = __float2bfloat16(act_fwd(v, act, leak));
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + 2 * j;
+      const float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+      const float a = act_fwd(fmaf(lo, sc[c], sh[c]), act, leak);
+      const float b = act_fwd(fmaf(hi, sc[c + 1], sh[c + 1]), act, leak);
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      o4[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = ov;
+    *reinterpret_cast<uint4*>(out + e0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
   }
 }
 __global__ void bn_apply_kernel(const bf16* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ beta,
@@ -684,8 +747,14 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ z, const float* __restr
 }
 int bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps, int act,
              float leak, cudaStream_t st) {
-  if ((C & 7) == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
-    bn_apply_vec_kernel<<<stride_grid(R * C / 8, 256, 2), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
+  if ((C & 7) == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int gx = (C + kBnSlab - 1) / kBnSlab;
+    long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
+    if (want > R) want = R;
+    const int rpb = (int)((R + want - 1) / want);
+    const int gy = (int)((R + rpb - 1) / rpb);
+    bn_apply_vec_kernel<<<dim3(gx, gy), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak, rpb);
+  }
   else
     bn_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
   return 0;
@@ -743,16 +812,17 @@ int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* 
 // =============================================================================================
 // GEMV family for 1-unit dense layers (critic fc2, models/gan.py:285)
 // =============================================================================================
-// out[m] = act( sum_k a[m,k]*w[k] + bias[0] )    one warp per row
+// out[m] = act( sum_k a[m,k]*w[k] + bias[0] )    one block (4 warps) per row: enough loads in flight for HBM
 __global__ void gemv_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ w, const float* bias, float* out,
                                  int M, int K, int act, float leak) {
-  const int lane = threadIdx.x & 31;
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= M) return;
+  __shared__ float part[4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x;
   const bf16* ar = a + (long long)row * K;
   float s = 0.f;
   if ((K & 7) == 0) {
-    for (int k = lane * 8; k < K; k += 256) {
+#pragma unroll 4
+    for (int k = threadIdx.x * 8; k < K; k += 128 * 8) {
       uint4 av = *reinterpret_cast<const uint4*>(ar + k);
       uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + k));
       const bf16* ap = reinterpret_cast<const bf16*>(&av);
@@ -761,15 +831,16 @@ __global__ void gemv_rows_kernel(const bf16* __restrict__ a, const bf16* __restr
       for (int j = 0; j < 8; ++j) s = fmaf(__bfloat162float(ap[j]), __bfloat162float(wp[j]), s);
     }
   } else {
-    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(ar[k]), __bfloat162float(w[k]), s);
+    for (int k = threadIdx.x; k < K; k += 128) s = fmaf(__bfloat162float(ar[k]), __bfloat162float(w[k]), s);
   }
   s = warp_sum(s);
-  if (lane == 0) out[row] = act_fwd(s + (bias ? bias[0] : 0.f), act, leak);
+  if (lane == 0) part[wid] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) out[row] = act_fwd(part[0] + part[1] + part[2] + part[3] + (bias ? bias[0] : 0.f), act, leak);
 }
 int gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act, float leak,
               cudaStream_t st) {
-  const int threads = 256;
-  gemv_rows_kernel<<<(M * 32 + threads - 1) / threads, threads, 0, st>>>((const bf16*)a, (const bf16*)w, bias, out, M, K, act, leak);
+  gemv_rows_kernel<<<M, 128, 0, st>>>((const bf16*)a, (const bf16*)w, bias, out, M, K, act, leak);
   return 0;
 }
 // out[m,k] = g[m] * w[k] * act'(mask[m,k])

@@ -21,6 +21,7 @@ struct PipeSmem {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full;
+  uint64_t tmem_empty;
   uint32_t tmem_base;
 };
 
@@ -670,6 +671,11 @@ void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
 // =============================================================================================
 // Weight gradient (MN-major operands, split-K, fp32 atomics)
 // =============================================================================================
+// Work decomposition ("stream-K"): the (unit, K chunk) space -- unit = (filter tap, M tile pair, N tile), K chunks
+// = 64-pixel slabs -- is linearised and cut into gridDim.x equal ranges, one per CTA (one CTA per SM).  A range
+// that crosses a unit boundary is processed as consecutive segments: the accumulators are flushed to the fp32
+// gradient with red.global.add after each segment and the pipeline keeps streaming into the next one.  Every SM
+// gets the same number of chunks (no wave quantisation) and each unit is reduced by as few CTAs as possible.
 __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -681,21 +687,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
   const int stage_bytes = a_bytes + p.nb_boxes * kBox;
   PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
 
-  int t = blockIdx.x;
-  const int nt = t % p.n_tiles; t /= p.n_tiles;
+  const long long range_begin = (long long)blockIdx.x * p.chunks_per_cta;
+  const long long range_end = min(range_begin + p.chunks_per_cta, (long long)p.units * p.total_chunks);
+  if (range_begin >= range_end) return;
   const int md_tiles = (p.m_tiles + p.dual - 1) / p.dual;
-  const int mt = t % md_tiles; t /= md_tiles;
-  const int tap = t;
-  const int m0 = mt * p.dual * kTileM, n0 = nt * p.bn_tile;
-  const int chunk_begin = blockIdx.y * p.chunks_per_split;
-  const int chunk_end = min(chunk_begin + p.chunks_per_split, p.total_chunks);
-  const int iters = chunk_end - chunk_begin;
-  if (iters <= 0) return;
 
-  // number of 64-channel boxes that actually hold data (the rest of the tile is never loaded
-  // nor stored; stale smem feeds accumulator rows/columns that the epilogue masks off)
-  const int a_boxes = min(2 * p.dual, (p.Ca - m0 + 63) / 64);
-  const int b_boxes = min(p.nb_boxes, (p.Cb - n0 + 63) / 64);
+  // segment starting at linear position pos: its unit, first chunk and length
+  struct Seg { int tap, m0, n0, a_boxes, b_boxes, cbeg, len; };
+  auto segment = [&](long long pos) {
+    Seg g;
+    int u = (int)(pos / p.total_chunks);
+    g.cbeg = (int)(pos - (long long)u * p.total_chunks);
+    g.len = (int)min((long long)(p.total_chunks - g.cbeg), range_end - pos);
+    const int nt = u % p.n_tiles; u /= p.n_tiles;
+    const int mt = u % md_tiles; u /= md_tiles;
+    g.tap = u;
+    g.m0 = mt * p.dual * kTileM; g.n0 = nt * p.bn_tile;
+    // number of 64-channel boxes that actually hold data (the rest of the tile is never loaded nor stored;
+    // stale smem feeds accumulator rows/columns that the epilogue masks off)
+    g.a_boxes = min(2 * p.dual, (p.Ca - g.m0 + 63) / 64);
+    g.b_boxes = min(p.nb_boxes, (p.Cb - g.n0 + 63) / 64);
+    return g;
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmA);
@@ -705,6 +718,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
       mbar_init(smem_u32(&ps->empty[s]), 1);
     }
     mbar_init(smem_u32(&ps->tmem_full), 1);
+    mbar_init(smem_u32(&ps->tmem_empty), (blockDim.x >> 5) - 2);     // one arrival per epilogue warp
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -718,63 +732,43 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
 
   if (warp == 0) {
     if (elect_one()) {
-      // running (w,h,n) chunk coordinates: one division at the start, increments afterwards
-      int jw, jh, jn;
-      {
-        int ch = chunk_begin;
-        jw = ch % p.chunks_w; ch /= p.chunks_w;
-        jh = ch % p.chunks_h; ch /= p.chunks_h;
-        jn = ch;
-      }
       int s = 0;
       uint32_t par = 0;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       const uint32_t smem0 = smem_u32(smem);
-      // L2 prefetch iterator, p.l2_prefetch chunks ahead
-      int qw = jw, qh = jh, qn = jn, qit = 0;
-      auto prefetch_next = [&]() {
-        if (qit < iters) {
-          const int w0 = qw * p.bw, h0 = qh * p.bh, n0p = qn * p.bn;
+      for (long long pos = range_begin; pos < range_end;) {
+        const Seg g = segment(pos);
+        // running (w,h,n) chunk coordinates: one division per segment, increments afterwards
+        int jw, jh, jn;
+        {
+          int ch = g.cbeg;
+          jw = ch % p.chunks_w; ch /= p.chunks_w;
+          jh = ch % p.chunks_h; ch /= p.chunks_h;
+          jn = ch;
+        }
+        for (int it = 0; it < g.len; ++it) {
+          const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
+          mbar_wait(empty0 + 8 * s, par ^ 1);
+          const uint32_t full = full0 + 8 * s;
+          mbar_arrive_expect_tx(full, (g.a_boxes + g.b_boxes) * kBox);
+          const uint32_t a_dst = smem0 + s * stage_bytes;
           int c[5];
 #pragma unroll
           for (int d = 0; d < 4; ++d)
-            c[d + 1] = p.tap_a_off[tap][d] + w0 * p.a_mul[0][d] + h0 * p.a_mul[1][d] + n0p * p.a_mul[2][d];
-          for (int b = 0; b < a_boxes; ++b) {
-            c[0] = m0 + b * 64;
-            tma_prefetch_nd(p.a_rank, &p.tmA, c);
+            c[d + 1] = p.tap_a_off[g.tap][d] + pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
+          for (int b = 0; b < g.a_boxes; ++b) {
+            c[0] = g.m0 + b * 64;
+            tma_load_nd(p.a_rank, a_dst + b * kBox, &p.tmA, full, c);
           }
-          int cb[5] = {0, w0, h0, n0p, 0};
-          for (int b = 0; b < b_boxes; ++b) {
-            cb[0] = n0 + b * 64;
-            tma_prefetch_nd(p.b_rank, &p.tmB, cb);
+          int cb[5] = {0, pw0, ph0, pn0, 0};
+          for (int b = 0; b < g.b_boxes; ++b) {
+            cb[0] = g.n0 + b * 64;
+            tma_load_nd(p.b_rank, a_dst + a_bytes + b * kBox, &p.tmB, full, cb);
           }
-          ++qit;
-          if (++qw == p.chunks_w) { qw = 0; if (++qh == p.chunks_h) { qh = 0; ++qn; } }
+          if (++s == p.stages) { s = 0; par ^= 1; }
+          if (++jw == p.chunks_w) { jw = 0; if (++jh == p.chunks_h) { jh = 0; ++jn; } }
         }
-      };
-      for (int i = 0; i < p.l2_prefetch; ++i) prefetch_next();
-      for (int it = 0; it < iters; ++it) {
-        if (p.l2_prefetch) prefetch_next();
-        const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
-        mbar_wait(empty0 + 8 * s, par ^ 1);
-        const uint32_t full = full0 + 8 * s;
-        mbar_arrive_expect_tx(full, (a_boxes + b_boxes) * kBox);
-        const uint32_t a_dst = smem0 + s * stage_bytes;
-        int c[5];
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-          c[d + 1] = p.tap_a_off[tap][d] + pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
-        for (int b = 0; b < a_boxes; ++b) {
-          c[0] = m0 + b * 64;
-          tma_load_nd(p.a_rank, a_dst + b * kBox, &p.tmA, full, c);
-        }
-        int cb[5] = {0, pw0, ph0, pn0, 0};
-        for (int b = 0; b < b_boxes; ++b) {
-          cb[0] = n0 + b * 64;
-          tma_load_nd(p.b_rank, a_dst + a_bytes + b * kBox, &p.tmB, full, cb);
-        }
-        if (++s == p.stages) { s = 0; par ^= 1; }
-        if (++jw == p.chunks_w) { jw = 0; if (++jh == p.chunks_h) { jh = 0; ++jn; } }
+        pos += g.len;
       }
     }
     __syncwarp();
@@ -787,76 +781,99 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
       const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, kBox, 1024);
       const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
-      const bool second = a_boxes > 2;       // the second 128-channel tile exists
       int s = 0;
-      uint32_t par = 0, acc = 0;
-      for (int it = 0; it < iters; ++it) {
-        mbar_wait(full0 + 8 * s, par);
-        tc_fence_after();
-        const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
-        const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // 16 pixels per MMA = two 8-pixel groups = 2048 bytes (addr field is >>4); the second channel
-          // tile (A + 16 KiB) accumulates into TMEM columns [256, 256 + N)
-          umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, acc);
-          if (second) umma_bf16(tmem + kTmemCols, adesc + ((2 * kBox) >> 4) + 128 * k, bdesc + 128 * k, idesc, acc);
-          acc = 1;
+      uint32_t par = 0, seg_par = 0;
+      bool first = true;
+      for (long long pos = range_begin; pos < range_end;) {
+        const Seg g = segment(pos);
+        const bool second = g.a_boxes > 2;       // the second 128-channel tile exists
+        if (!first) {
+          // the epilogue warps have read the previous segment's accumulators out of TMEM
+          mbar_wait(smem_u32(&ps->tmem_empty), seg_par);
+          tc_fence_after();
         }
-        umma_commit(empty0 + 8 * s);
-        if (++s == p.stages) { s = 0; par ^= 1; }
+        uint32_t acc = 0;
+        for (int it = 0; it < g.len; ++it) {
+          mbar_wait(full0 + 8 * s, par);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // 16 pixels per MMA = two 8-pixel groups = 2048 bytes (addr field is >>4); the second channel
+            // tile (A + 16 KiB) accumulates into TMEM columns [256, 256 + N)
+            umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, acc);
+            if (second) umma_bf16(tmem + kTmemCols, adesc + ((2 * kBox) >> 4) + 128 * k, bdesc + 128 * k, idesc, acc);
+            acc = 1;
+          }
+          umma_commit(empty0 + 8 * s);
+          if (++s == p.stages) { s = 0; par ^= 1; }
+        }
+        umma_commit(smem_u32(&ps->tmem_full));
+        if (!first) seg_par ^= 1;
+        first = false;
+        pos += g.len;
       }
-      umma_commit(smem_u32(&ps->tmem_full));
     }
     __syncwarp();
   } else {
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
     const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
-    mbar_wait(smem_u32(&ps->tmem_full), 0);
-    tc_fence_after();
     const bool vec_ok = (p.ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
                         ((p.out_tap_stride & 3) == 0);
-    for (int i = 0; i < p.dual; ++i) {
-      if (m0 + i * kTileM >= p.Ca) break;
-      const int ca = m0 + i * kTileM + q * 32 + lane;
-      const bool row_ok = ca < p.Ca;
-      float* orow = p.out + (long long)tap * p.out_tap_stride + (long long)ca * p.ldo;
-      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
-      // chunks cg, cg+ncg, ...: the TMEM load of the next chunk is in flight while this one is reduced
-      auto reduce16 = [&](const uint32_t* v, int col) {
-        if (!row_ok) return;
-        if (vec_ok && col + 16 <= p.Cb) {
+    uint32_t full_par = 0;
+    for (long long pos = range_begin; pos < range_end;) {
+      const Seg g = segment(pos);
+      mbar_wait(smem_u32(&ps->tmem_full), full_par);
+      full_par ^= 1;
+      tc_fence_after();
+      for (int i = 0; i < p.dual; ++i) {
+        if (g.m0 + i * kTileM >= p.Ca) break;
+        const int ca = g.m0 + i * kTileM + q * 32 + lane;
+        const bool row_ok = ca < p.Ca;
+        float* orow = p.out + (long long)g.tap * p.out_tap_stride + (long long)ca * p.ldo;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+        // chunks cg, cg+ncg, ...: the TMEM load of the next chunk is in flight while this one is reduced
+        auto reduce16 = [&](const uint32_t* v, int col) {
+          if (!row_ok) return;
+          if (vec_ok && col + 16 <= p.Cb) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j),
-                         "f"(__uint_as_float(v[j]) * p.alpha), "f"(__uint_as_float(v[j + 1]) * p.alpha),
-                         "f"(__uint_as_float(v[j + 2]) * p.alpha), "f"(__uint_as_float(v[j + 3]) * p.alpha)
-                         : "memory");
+            for (int j = 0; j < 16; j += 4) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + col + j),
+                           "f"(__uint_as_float(v[j]) * p.alpha), "f"(__uint_as_float(v[j + 1]) * p.alpha),
+                           "f"(__uint_as_float(v[j + 2]) * p.alpha), "f"(__uint_as_float(v[j + 3]) * p.alpha)
+                           : "memory");
+            }
+          } else {
+            for (int j = 0; j < 16 && col + j < p.Cb; ++j) atomicAdd(orow + col + j, __uint_as_float(v[j]) * p.alpha);
           }
-        } else {
-          for (int j = 0; j < 16 && col + j < p.Cb; ++j) atomicAdd(orow + col + j, __uint_as_float(v[j]) * p.alpha);
-        }
-      };
-      const int c_end = min(p.bn_tile, p.Cb - n0), step = ncg * 16;
-      int c = cg * 16;
-      if (c < c_end) {
-        uint32_t va[16], vb[16];
-        tmem_ld16(trow + c, va);
-        while (true) {
-          const int c1 = c + step;
-          tmem_ld_wait16(va);
-          if (c1 < c_end) tmem_ld16(trow + c1, vb);
-          reduce16(va, n0 + c);
-          if (c1 >= c_end) break;
-          const int c2 = c1 + step;
-          tmem_ld_wait16(vb);
-          if (c2 < c_end) tmem_ld16(trow + c2, va);
-          reduce16(vb, n0 + c1);
-          if (c2 >= c_end) break;
-          c = c2;
+        };
+        const int c_end = min(p.bn_tile, p.Cb - g.n0), step = ncg * 16;
+        int c = cg * 16;
+        if (c < c_end) {
+          uint32_t va[16], vb[16];
+          tmem_ld16(trow + c, va);
+          while (true) {
+            const int c1 = c + step;
+            tmem_ld_wait16(va);
+            if (c1 < c_end) tmem_ld16(trow + c1, vb);
+            reduce16(va, g.n0 + c);
+            if (c1 >= c_end) break;
+            const int c2 = c1 + step;
+            tmem_ld_wait16(vb);
+            if (c2 < c_end) tmem_ld16(trow + c2, va);
+            reduce16(vb, g.n0 + c1);
+            if (c2 >= c_end) break;
+            c = c2;
+          }
         }
       }
+      // accumulators are in registers / reduced: the MMA warp may overwrite TMEM with the next segment
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ps->tmem_empty));
+      pos += g.len;
     }
   }
 
@@ -874,15 +891,27 @@ int wgrad_dual(int m_tiles) {
   return (v == 2 && m_tiles >= 2) ? 2 : 1;
 }
 
-void launch_wgrad(const WgradParams& p, int splits, cudaStream_t stream) {
+void launch_wgrad(const WgradParams& p0, int /*splits_hint*/, cudaStream_t stream) {
+  WgradParams p = p0;
   const int stage_bytes = (2 * p.dual + p.nb_boxes) * 64 * 64 * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   static bool configured = false;
+  static int sms = 148;
   if (!configured) {
     cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
-  dim3 grid(((p.m_tiles + p.dual - 1) / p.dual) * p.n_tiles * p.ntaps, splits, 1);
+  // equal share of the (unit, chunk) space per CTA, one CTA per SM; a CTA gets at least 4 chunks
+  p.units = ((p.m_tiles + p.dual - 1) / p.dual) * p.n_tiles * p.ntaps;
+  const long long total = (long long)p.units * p.total_chunks;
+  long long ctas = total / 4;
+  if (ctas > sms) ctas = sms;
+  if (ctas < 1) ctas = 1;
+  p.chunks_per_cta = (int)((total + ctas - 1) / ctas);
+  const int grid = (int)((total + p.chunks_per_cta - 1) / p.chunks_per_cta);
   wgrad_kernel<<<grid, gemm_threads(), smem, stream>>>(p);
 }
 

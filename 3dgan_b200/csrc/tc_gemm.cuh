@@ -80,6 +80,7 @@ struct WgradParams {
   int bw, bh, bn;                     // pixels per K-chunk along w, h, n (product 64)
   int chunks_w, chunks_h, chunks_n;
   int total_chunks, chunks_per_split;
+  int units, chunks_per_cta;          // set by launch_wgrad: (tap, M pair, N tile) units; linear chunk range per CTA
   int Ca, Cb;
   int m_tiles, n_tiles, bn_tile, nb_boxes;
   int l2_prefetch;                    // K chunks prefetched into L2 ahead of the loads
