@@ -83,8 +83,9 @@ def _conv_tag(op, g):
     (SURVEY 8d); tc: tensor-core route, simt: small-channel route."""
     opi = {"fprop": 0, "dgrad": 1, "wgrad": 2}[op]
     fam = "tc" if K.route(g, opi) == 1 else ("smallc-gemm" if SMALL_CHANNEL_GEMM and K.workspace_bytes(g, opi) else "simt")
-    tag = "%s:%s N%d %dx%dx%d->%dx%dx%d k%ds%d" % (fam, op, g.N, g.H, g.W, g.Cin, g.Ho, g.Wo, g.Cout, g.k, g.stride)
-    return tag, 2.0 * g.N * g.Ho * g.Wo * g.k * g.k * g.Cin * g.Cout
+    cin, cout = getattr(g, "logical", (g.Cin, g.Cout))       # zero-padded channels do no algorithmic work
+    tag = "%s:%s N%d %dx%dx%d->%dx%dx%d k%ds%d" % (fam, op, g.N, g.H, g.W, cin, g.Ho, g.Wo, cout, g.k, g.stride)
+    return tag, 2.0 * g.N * g.Ho * g.Wo * g.k * g.k * cin * cout
 
 
 def empty(shape, dtype=BF16):
@@ -118,7 +119,8 @@ class recording:
 
 # ------------------------------------------------------------------------------------------ tensors
 class Tensor:
-    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "im2col", "bits", "__weakref__")
+    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "im2col", "bits", "logical_c",
+                 "__weakref__")
 
     def __init__(self, buf, shape=None, requires_grad=False, mask=None):
         self.buf = buf
@@ -129,6 +131,7 @@ class Tensor:
         self.grad_f32 = False      # leaf whose gradient is wanted in fp32 (the GP interpolates)
         self.im2col = None         # (geometry key, workspace) left by a small-channel fprop of this tensor
         self.bits = None           # int16 [rows, ceil(C/16)] sign bitmap written by the producing relu/lrelu epilogue
+        self.logical_c = None      # channels that carry data when the last dim is zero-padded (ops/layers.py)
 
     @property
     def f32(self):
@@ -168,8 +171,10 @@ class Param:
     """One trainable variable: fp32 master / gradient views into the group's flat buckets, a bf16
     compute copy, and (lazily) a per-tap transposed bf16 copy for the K-major fprop operand."""
 
-    def __init__(self, name, shape):
+    def __init__(self, name, shape, logical_shape=None):
         self.name, self.shape = name, tuple(shape)
+        # physical shape may be zero-padded along the channel dims; the TF variable is the leading block
+        self.logical_shape = tuple(shape if logical_shape is None else logical_shape)
         self.numel = int(math.prod(shape))
         self.p32 = self.g32 = self.p16 = self.p16_t = None
         self.group = None
@@ -185,6 +190,13 @@ class Param:
         if not S.accumulate or id(self) not in S.active:
             return False
         return S.accumulate is True or id(self) in S.accumulate
+
+    def logical(self, flat):
+        """The TF variable's view of one of this variable's flat buffers (p32 / g32 / ...)."""
+        t = flat.reshape(self.shape)
+        if self.logical_shape != self.shape:
+            t = t[tuple(slice(0, d) for d in self.logical_shape)]
+        return t
 
     def transposed(self):
         """bf16 [T, B, A] copy of a [T, A, B] weight (T = k*k taps)."""

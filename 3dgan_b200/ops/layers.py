@@ -5,6 +5,7 @@ again when `reuse=True` (ops/layers.py:50-53); op order is conv -> +bias -> batc
 (ops/layers.py:101-105).  Underneath: tcgen05 implicit-GEMM kernels through the C ABI.
 """
 import contextlib
+import os
 
 from .. import _capi as K
 from .. import engine as E
@@ -36,6 +37,27 @@ def variable_scope(name):
         st.scope.pop()
 
 
+# Channel counts C with C % 16 == 8 (the reference's 200-channel layers) make every NHWC pixel row start on an
+# odd 16-byte boundary, which costs the TMA loads of the GEMM operands about 20%.  Such layers are stored with
+# 8 extra zero channels: the padded weights / biases are zero, get zero gradients and stay zero, so the TF
+# variables (the leading block of each padded array) see exactly the reference's arithmetic.
+CHANNEL_PAD = os.environ.get("B200GAN_CHANNEL_PAD", "1") != "0"
+
+
+def physical_channels(c):
+    return c + 8 if (CHANNEL_PAD and c % 16 == 8 and c >= 24) else c
+
+
+def _logical_c(x):
+    return x.shape[-1] if x.logical_c is None else x.logical_c
+
+
+def _mark(t, logical_c):
+    if t.shape[-1] != logical_c:
+        t.logical_c = logical_c
+    return t
+
+
 def weight_name(name):
     return name if name is None else name + '/weights'
 
@@ -44,12 +66,12 @@ def bias_name(name):
     return name if name is None else name + '/bias'
 
 
-def _variables(name, w_shape, b_shape, init):
+def _variables(name, w_shape, b_shape, init, w_phys=None, b_phys=None):
     st = get_store()
     st.scope.append('vars')
     try:
-        W = st.get_variable(weight_name(name), w_shape, init())
-        b = st.get_variable(bias_name(name), b_shape, init())
+        W = st.get_variable(weight_name(name), w_shape, init(), w_phys)
+        b = st.get_variable(bias_name(name), b_shape, init(), b_phys)
     finally:
         st.scope.pop()
     return W, b
@@ -70,19 +92,19 @@ def batch_norm(h, activation=None):
     st = get_store()
     st.scope.append(st.unique_bn_scope())
     try:
-        beta = st.get_variable('beta', (h.shape[-1],), zeros_initializer())
+        beta = st.get_variable('beta', (_logical_c(h),), zeros_initializer(), (h.shape[-1],))
     finally:
         st.scope.pop()
     act, leak, ok = _fusable(activation)
-    out = E.batch_norm_act(h, beta, act, leak)
-    return out if ok else activation(out)
+    out = _mark(E.batch_norm_act(h, beta, act, leak), _logical_c(h))
+    return out if ok else _mark(activation(out), _logical_c(h))
 
 
 def _finish(h, use_batch_norm, activation, fused):
     if use_batch_norm:
         return batch_norm(h, activation)
     if activation is not None and not fused:
-        return activation(h)
+        return _mark(activation(h), _logical_c(h))
     return h
 
 
@@ -109,13 +131,16 @@ def dense(x, input_size, output_size, init=xavier_initializer, use_batch_norm=Fa
 def conv2d(x, input_size, output_size, filter_size=3, stride=1, init=xavier_initializer, use_batch_norm=False,
            activation=None, reuse=False, name=None):
     """ops/layers.py:66-107 — act(BN(conv_SAME(x, K) + b)), K [k,k,input_size,output_size]."""
-    W, b = _variables(name, (filter_size, filter_size, input_size, output_size), (output_size,), init)
+    N, H, Wd, C = x.shape
+    assert _logical_c(x) == input_size, "conv2d %s: input has %d channels, input_size=%d" % (name, _logical_c(x), input_size)
+    cout = physical_channels(output_size)
+    W, b = _variables(name, (filter_size, filter_size, input_size, output_size), (output_size,), init,
+                      (filter_size, filter_size, C, cout), (cout,))
     act, leak, ok = _fusable(activation)
     fuse = ok and not use_batch_norm
-    N, H, Wd, C = x.shape
-    assert C == input_size, "conv2d %s: input has %d channels, input_size=%d" % (name, C, input_size)
-    g = E.conv_geom(N, H, Wd, input_size, output_size, filter_size, stride)
-    h = E.conv_like('fprop', x, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak)
+    g = E.conv_geom(N, H, Wd, C, cout, filter_size, stride)
+    g.logical = (input_size, output_size)
+    h = _mark(E.conv_like('fprop', x, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak), output_size)
     return _finish(h, use_batch_norm, activation, fuse)
 
 
@@ -125,20 +150,25 @@ def deconv2d(x, input_size, output_size, filter_size=3, stride=2, init=xavier_in
     """ops/layers.py:111-148 — act(BN(conv2d_transpose_SAME(x, K) + b)), K [k,k,output_size,input_size];
     output is 2x the input (ops/layers.py:141) unless output_shape=(H,W) is given (the Gen-2 kwarg,
     hem/ops/layers.py:185-187, used by the shape-generalised autoencoders)."""
-    W, b = _variables(name, (filter_size, filter_size, output_size, input_size), (output_size,), init)
+    N, h_in, w_in, C = x.shape
+    assert _logical_c(x) == input_size, "deconv2d %s: input has %d channels, input_size=%d" % (name, _logical_c(x), input_size)
+    cout = physical_channels(output_size)
+    W, b = _variables(name, (filter_size, filter_size, output_size, input_size), (output_size,), init,
+                      (filter_size, filter_size, cout, C), (cout,))
     act, leak, ok = _fusable(activation)
     fuse = ok and not use_batch_norm
-    N, h_in, w_in, C = x.shape
-    assert C == input_size, "deconv2d %s: input has %d channels, input_size=%d" % (name, C, input_size)
     Ho, Wo = (h_in * 2, w_in * 2) if output_shape is None else output_shape
     # the forward conv whose adjoint this is: [N,Ho,Wo,output_size] -> [N,h_in,w_in,input_size]
-    g = E.conv_geom(N, Ho, Wo, output_size, input_size, filter_size, stride)
+    g = E.conv_geom(N, Ho, Wo, cout, C, filter_size, stride)
+    g.logical = (output_size, input_size)
     assert (g.Ho, g.Wo) == (h_in, w_in), "deconv2d %s: output_shape incompatible with stride" % name
-    h = E.conv_like('dgrad', x, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak)
+    h = _mark(E.conv_like('dgrad', x, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak), output_size)
     return _finish(h, use_batch_norm, activation, fuse)
 
 
 @add_arg_scope
 def flatten(x, name=None):
     """ops/layers.py:152-166 — [B, -1]."""
+    if x.logical_c is not None:
+        raise K.B200Error("flatten of a channel-padded tensor (set B200GAN_CHANNEL_PAD=0 for this model)")
     return E.reshape(x, (x.shape[0], -1))

@@ -42,17 +42,21 @@ class VariableStore:
         self.bn_counters[base] = k + 1
         return "BatchNorm" if k == 0 else "BatchNorm_%d" % k
 
-    def get_variable(self, name, shape, init):
+    def get_variable(self, name, shape, init, physical_shape=None):
+        """`shape` is the TF variable's shape; `physical_shape` (>= shape per dim) is how it is stored when
+        a layer zero-pads its channels: the extra entries are initialised to zero and, receiving zero
+        gradients, stay zero under every optimizer here."""
         full = self.path(name)
         p = self.params.get(full)
+        phys = tuple(shape if physical_shape is None else physical_shape)
         if p is None:
             if self.finalized:
                 raise K.B200Error("variable %s requested after the store was finalized" % full)
-            p = E.Param(full, shape)
+            p = E.Param(full, phys, logical_shape=shape)
             p.init = init
             self.params[full] = p
-        elif tuple(shape) != p.shape:
-            raise ValueError("variable %s: shape %s != existing %s" % (full, tuple(shape), p.shape))
+        elif tuple(shape) != p.logical_shape or phys != p.shape:
+            raise ValueError("variable %s: shape %s != existing %s" % (full, tuple(shape), p.logical_shape))
         return p
 
     def collection(self, prefix):
@@ -66,7 +70,7 @@ class VariableStore:
         gen = torch.Generator().manual_seed(self.seed)
         host = OrderedDict()
         for name, p in self.params.items():           # creation order, like TF's initializer run
-            host[name] = p.init(p.shape, gen)
+            host[name] = _pad_to(p.init(p.logical_shape, gen), p.shape)
         seen = set()
         for gname, params, cfg in groups:
             for p in params:
@@ -82,12 +86,21 @@ class VariableStore:
         """Overwrite variables from {tf_name: tensor} (parity tests, checkpoints)."""
         for name, v in values.items():
             p = self.params[name]
-            p.p32.copy_(v.reshape(-1).to(torch.float32))
+            p.p32.copy_(_pad_to(v.reshape(p.logical_shape).to(torch.float32), p.shape).reshape(-1))
         for g in self.groups:
             g.sync_compute_copies()
 
     def state_dict(self):
-        return OrderedDict((n, p.p32.detach().cpu().reshape(p.shape).clone()) for n, p in self.params.items())
+        return OrderedDict((n, p.logical(p.p32.detach()).cpu().clone()) for n, p in self.params.items())
+
+
+def _pad_to(t, shape):
+    """zero-pad tensor t (logical shape) to `shape` (leading-block placement)."""
+    if tuple(t.shape) == tuple(shape):
+        return t
+    out = torch.zeros(shape, dtype=t.dtype, device=t.device)
+    out[tuple(slice(0, d) for d in t.shape)] = t
+    return out
 
 
 def xavier_initializer():

@@ -152,7 +152,7 @@ def iwgan_step_parity(H=32, C=3, L=16, B=8, model="iwgan", seed=0, verbose=False
             if not name.startswith(group_prefix):
                 continue
             want = ref["grads"][name]
-            got = prm.g32.reshape(prm.shape).float().cpu()
+            got = prm.logical(prm.g32).float().cpu()
             wn = scale[name]
             if wn < 1e-5:
                 # analytically-zero gradient (a bias feeding batch-norm): ours is rounding noise of the
@@ -218,7 +218,7 @@ def iwgan_trajectory_parity(H=32, C=3, L=16, B=16, iters=3, n_disc=2, model="iwg
     worst = 0.0
     for name, prm in sess.store.params.items():
         d_ref = tr.p[name] - p0[name]
-        d_got = prm.p32.reshape(prm.shape).float().cpu() - p0[name]
+        d_got = prm.logical(prm.p32).float().cpu() - p0[name]
         under_bn = name.startswith("generator/vars/") and name.endswith("/bias") and \
             ("generator/vars/dc%d/bias" % OM.n_up_stages(H)) != name
         if float(d_ref.norm()) < 1e-9 or under_bn:
@@ -281,7 +281,7 @@ def ae_step_parity(model="cnn", H=28, C=1, L=16, B=8, seed=0, verbose=False, gra
     worst = 0.0
     for name, prm in sess.store.params.items():
         want = ref["grads"][name]
-        got = prm.g32.reshape(prm.shape).float().cpu()
+        got = prm.logical(prm.g32).float().cpu()
         wn = float(want.norm())
         under_bn = model == "vae" and name.startswith("encoder/vars/") and name.endswith("/bias")
         if wn < 1e-6 or under_bn:
@@ -330,7 +330,7 @@ def smooth_chain_parity(B=16, seed=0, verbose=False):
     x_in.materialize(sess.device)
     sess.store.finalize([('all', list(sess.store.params.values()), optimizer_cfg(args))], sess.device)
     gen = torch.Generator().manual_seed(seed)
-    p = OrderedDict((n_, bf16_round(OT.xavier_uniform(prm.shape, gen))) for n_, prm in sess.store.params.items())
+    p = OrderedDict((n_, bf16_round(OT.xavier_uniform(prm.logical_shape, gen))) for n_, prm in sess.store.params.items())
     sess.store.load(p)
     x01 = bf16_round(torch.rand(B, 16, 16, 3, generator=gen))
     x_in.feed(0, x01.cuda())
@@ -353,7 +353,7 @@ def smooth_chain_parity(B=16, seed=0, verbose=False):
               "loss": (float(loss.buf.item()), float(ref_loss))}
     worst = 0.0
     for (name, prm), want in zip(sess.store.params.items(), grads):
-        e = rel_err(prm.g32.reshape(prm.shape), want)
+        e = rel_err(prm.logical(prm.g32), want)
         worst = max(worst, e)
         if verbose or e > 1.5e-2:
             print("  [smooth] %-28s err %.3e" % (name, e))
@@ -408,7 +408,7 @@ def pix2pix_step_parity(B=2, add_l1=True, seed=0, verbose=False, grad_tol=0.25, 
             if not name.startswith(prefix):
                 continue
             want = ref["grads"][name]
-            got = prm.g32.reshape(prm.shape).float().cpu()
+            got = prm.logical(prm.g32).float().cpu()
             wn = float(want.norm())
             under_bn = name.startswith("generator/decoder/vars/") and name.endswith("/bias")
             if wn < 1e-7 or under_bn:

@@ -32,7 +32,7 @@ def test_build_pass_creates_reference_variables(model, H):
     gan_model.gan(x, _args(model))
     gs, ds = OM.gan_param_specs(model, H, 3, 16)
     want = OrderedDict(list(gs.items()) + list(ds.items()))
-    got = OrderedDict((n, p.shape) for n, p in sess.store.params.items())
+    got = OrderedDict((n, p.logical_shape) for n, p in sess.store.params.items())
     assert set(got) == set(want)
     for n in want:
         assert tuple(want[n]) == got[n], n
@@ -199,7 +199,7 @@ def test_pix2pix_build_pass_matches_reference_variables():
     pix2pix((S.Input(2, (256, 256, 3), slots=3), S.Input(2, (256, 256, 1), slots=3)), a)
     gs, ds = OP.param_specs()
     want = OrderedDict(list(gs.items()) + list(ds.items()))
-    got = OrderedDict((n, p.shape) for n, p in sess.store.params.items())
+    got = OrderedDict((n, p.logical_shape) for n, p in sess.store.params.items())
     assert list(got) == list(want)
     assert all(tuple(want[n]) == got[n] for n in want)
     assert abs(sum(p.numel for n, p in sess.store.params.items() if n.startswith("generator")) - 54.408e6) < 1e3
