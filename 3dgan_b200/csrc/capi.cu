@@ -425,7 +425,9 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
     b200_epilogue te;
     memset(&te, 0, sizeof te);
     te.out_f32 = 1;
-    if (dense_gemm(dy, M, g->Cout, g->Cout, w, kk, g->Cout, workspace, Kp, kk, &te, st)) return -1;
+    // all Kp columns are produced (the weight rows past k*k*Cin are TMA zero fill): every 16-column chunk of the
+    // epilogue is then full, the ragged 11-column tail used to cost more than the rest of the kernel
+    if (dense_gemm(dy, M, g->Cout, g->Cout, w, kk, g->Cout, workspace, Kp, Kp, &te, st)) return -1;
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
                     e ? e->mask_kind : 0, dx, e ? e->out_f32 : 0};

@@ -150,8 +150,8 @@ __device__ __noinline__ static void epilogue_store16_slow(const EpilogueArgs& e,
 
 // 16 consecutive columns [col, col+16) of one output row starting at element offset `off`.
 // Fast path (full chunk, 16-byte aligned output, side data preloaded): straight-line code.
-// kSimple kernels are launched when the epilogue is bf16-out with none/relu/lrelu and no value mask (bias,
-// sign bitmaps in and out allowed): the other variants are compiled out of their hot loop.
+// kSimple kernels are launched when the epilogue is none/relu/lrelu with no value mask and no accumulate (bias,
+// fp32 or bf16 output, sign bitmaps in and out allowed): the other variants are compiled out of their hot loop.
 template <bool kSimple>
 __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const uint32_t* acc, long long off,
                                                  int col, const ChunkSide* side = nullptr, long long bits_row = 0) {
@@ -159,7 +159,7 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
   // channel counts are multiples of 8 on the tensor-core route: a chunk holds 16 or (the last one) 8 columns
   const int nv = min(16, e.ncols - col);
   const bool full = nv == 16 || nv == 8;
-  const bool f32 = !kSimple && e.out_f32;
+  const bool f32 = e.out_f32 != 0;
   const uintptr_t oaddr = reinterpret_cast<uintptr_t>(e.out) + (uintptr_t)o * (f32 ? 4 : 2);
   const bool vmask = !kSimple && e.mask_src && !e.mask_bits;
   const bool fast = full && (e.stage_row || (oaddr & 15) == 0) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
@@ -284,7 +284,8 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
 
 // host side: can this epilogue run in a kSimple kernel?
 inline bool epilogue_is_simple(int act, const void* mask_src, const void* mask_bits, int out_f32, int accumulate) {
-  return !out_f32 && !accumulate && (act == ACT_NONE || act == ACT_RELU || act == ACT_LRELU) &&
+  (void)out_f32;
+  return !accumulate && (act == ACT_NONE || act == ACT_RELU || act == ACT_LRELU) &&
          (mask_src == nullptr || mask_bits != nullptr);
 }
 
