@@ -227,3 +227,40 @@ def test_train_cli_flags_and_config_file(tmp_path):
     d = tr.build_parser().parse_args([])
     assert (d.optimizer, d.lr, d.momentum, d.decay, d.latent_size, d.n_disc_train, d.batch_size) == \
         ("rmsprop", 0.001, 0.01, 0.9, 200, 5, 256)          # reference defaults, train.py:87-153
+
+
+def test_channel_padding_is_layout_only():
+    """200-channel layers are stored with 8 zero channels: the TF variables keep the reference's
+    names and shapes (logical view), only the physical arrays grow; initialisation / load / state_dict go
+    through the logical block and leave the padding at exactly zero."""
+    import torch
+    from b200gan.ops import layers as L
+    from b200gan import variables as V
+    assert [L.physical_channels(c) for c in (3, 8, 24, 72, 200, 208, 400, 800)] == [3, 8, 32, 80, 208, 208, 400, 800]
+    sess = S.Session()
+    x = S.Input(8, (32, 32, 3), slots=6)
+    gan_model.gan(x, _args("iwgan", Lz=200))
+    prm = sess.store.params
+    want = {"discriminator/vars/c1/weights": ((5, 5, 3, 200), (5, 5, 3, 208)),
+            "discriminator/vars/c1/bias": ((200,), (208,)),
+            "discriminator/vars/c2/weights": ((5, 5, 200, 400), (5, 5, 208, 400)),
+            "generator/vars/dc2/weights": ((5, 5, 200, 400), (5, 5, 208, 400)),
+            "generator/BatchNorm_2/beta": ((200,), (208,)),
+            "generator/vars/dc3/weights": ((5, 5, 3, 200), (5, 5, 3, 208)),
+            "discriminator/vars/c3/weights": ((5, 5, 400, 800), (5, 5, 400, 800))}
+    for name, (logical, physical) in want.items():
+        assert prm[name].logical_shape == logical and prm[name].shape == physical, name
+    # pad / slice round trip on host tensors
+    t = torch.arange(2 * 3 * 5, dtype=torch.float32).reshape(2, 3, 5)
+    padded = V._pad_to(t, (2, 4, 8))
+    assert padded.shape == (2, 4, 8) and padded.sum() == t.sum() and torch.equal(padded[:, :3, :5], t)
+    p = E.Param("x", (2, 4, 8), logical_shape=(2, 3, 5))
+    assert torch.equal(p.logical(padded.reshape(-1)), t)
+    # switch: no padding, physical == logical
+    L.CHANNEL_PAD = False
+    try:
+        sess2 = S.Session()
+        gan_model.gan(S.Input(8, (32, 32, 3), slots=6), _args("iwgan", Lz=200))
+        assert all(q.shape == q.logical_shape for q in sess2.store.params.values())
+    finally:
+        L.CHANNEL_PAD = True

@@ -12,6 +12,17 @@ def test_iwgan_step_matches_oracle(H, C, L, B):
     assert res["ok"], res
 
 
+def test_iwgan_step_without_channel_padding_matches_oracle():
+    """BASELINE's L=200 config with the 200 -> 208 channel padding switched off: same parity bar."""
+    from b200gan.ops import layers as L
+    L.CHANNEL_PAD = False
+    try:
+        res = P.iwgan_step_parity(H=32, C=3, L=200, B=32, verbose=True)
+    finally:
+        L.CHANNEL_PAD = True
+    assert res["ok"], res
+
+
 def test_iwgan_training_trajectory_matches_oracle():
     """3 iterations x (2 critic + 1 generator) Adam updates: losses per iteration and the parameter
     displacement.  Adam's m/sqrt(v) is sign-like in the first steps, so tiny gradient differences on
