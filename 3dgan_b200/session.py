@@ -39,6 +39,29 @@ class Input:
     def feed(self, slot, host_or_device_batch, non_blocking=True):
         self.ring[slot].copy_(host_or_device_batch, non_blocking=non_blocking)
 
+    # ---- prefetching feed (the role of the reference's queue runners, data.py:34-60): the next iteration's
+    # batches travel host -> device on a copy stream while the current iteration computes
+    def prefetch(self, pinned_host_batches):
+        """Start the asynchronous copy of one iteration's batches ([slots, B, H, W, C] pinned host tensor)
+        into the staging buffer.  Call `commit()` before the iteration that consumes them."""
+        if getattr(self, "_staging", None) is None:
+            self._staging = torch.empty_like(self.ring)
+            self._copy_stream = torch.cuda.Stream(device=self.ring.device)
+            self._staged = torch.cuda.Event()
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)           # the previous commit has read the staging buffer
+        with torch.cuda.stream(self._copy_stream):
+            self._staging.copy_(pinned_host_batches, non_blocking=True)
+            self._staged.record()
+
+    def commit(self):
+        """Make the prefetched batches the ring's contents (device-to-device, on the compute stream)."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        self.ring.copy_(self._staging, non_blocking=True)
+        self._consumed.record(cur)
+
     def reset(self):
         self.cursor = 0
 
