@@ -89,7 +89,7 @@ static int pick_bn_tile(int cols) {
 static int pick_stages(int stage_bytes) {
   static int cap = -1;          // B200GAN_STAGES: cap the pipeline depth (2 leaves room for two CTAs per SM)
   if (cap < 0) { const char* e = getenv("B200GAN_STAGES"); cap = e ? atoi(e) : 8; }
-  int s = (227 * 1024 - 2048) / stage_bytes;
+  int s = (227 * 1024 - 3072) / stage_bytes;
   return std::max(2, std::min(s, std::min(cap, 8)));
 }
 
@@ -161,6 +161,35 @@ static int pick_splits(int base, int total_chunks, int bn_tile, int dual = 1) {
     if (cost < best_cost) { best_cost = cost; best = s; }
   }
   return best;
+}
+
+
+// Output tensor maps for the bulk-store epilogue of the tap GEMM: per phase the output is the strided view
+// [ext_n, ext_h, ext_w, ncols] the phase's pixels form; the box is the CTA tile.  Returns with p.tma_store = 0
+// when a precondition fails (the epilogue then stores from registers).
+static void setup_out_maps(TapGemmParams& p, const b200_epilogue* e) {
+  p.tma_store = 0;
+  if (!tma_store_enabled() || !epilogue_pipelined()) return;
+  if (e && e->accumulate) return;
+  const int elem = p.out_f32 ? 4 : 2;
+  if (p.ncols % 8) return;
+  const uintptr_t align = reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.mask_src);
+  if (align & 15) return;
+  if ((p.o_sw * elem) % 16 || (p.o_sh * elem) % 16 || (p.o_sn * elem) % 16 || (p.o_sw * 2) % 16) return;
+  const long long need = (long long)p.dual * kTileM * p.bn_tile * elem;
+  if (need > (long long)p.stages * tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)) return;
+  for (int i = 0; i < p.nphases; ++i) {
+    const char* base = reinterpret_cast<const char*>(p.out) + p.phase_o_off[i] * elem;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return;
+    long long dims[4] = {p.ncols, p.phase_ext_w[i], p.phase_ext_h[i], p.ext_n};
+    long long str[4] = {1, p.o_sw, std::max<long long>(p.o_sh, 1), std::max<long long>(p.o_sn, 1)};
+    int box[4] = {p.bn_tile, p.bw, p.bh, p.bn};
+    int es[4] = {1, 1, 1, 1};
+    if (dims[1] < 1 || dims[2] < 1) return;
+    if (make_tmap(&p.tmOut[i], base, 4, dims, str, box, es, 0, elem)) return;
+  }
+  p.stage_pitch = p.bn_tile * elem;
+  p.tma_store = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,6 +436,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.stages = std::min(pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)),
                       std::max(2, (p.kchunks - p.merge_tail) * g->k * g->k));
   p.out = y;
+  setup_out_maps(p, e);
   launch_tapgemm(p, st);
   return check_launch("conv2d_fprop");
 }
@@ -530,6 +560,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
   p.stages = pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail));
   p.out = dx;
+  setup_out_maps(p, e);
   launch_tapgemm(p, st);
   return check_launch("conv2d_dgrad");
 }

@@ -60,6 +60,11 @@ struct EpilogueArgs {
   uint32_t stage_row;
   uint32_t stage_bits;
   int stage_col0;
+  // the tile's bias row staged in shared memory by the epilogue warps while they wait for the accumulators
+  // (fp32, element i = bias[bias_col0 + i], zero past ncols): the global bias loads were the top stall of the
+  // epilogue (L1 is almost all shared memory here, so they usually went to L2)
+  uint32_t bias_smem;
+  int bias_col0;
 };
 
 // Epilogue warps are idle during the main loop: pull the mask rows they will need into L2 meanwhile.
@@ -162,7 +167,8 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
   const bool f32 = e.out_f32 != 0;
   const uintptr_t oaddr = reinterpret_cast<uintptr_t>(e.out) + (uintptr_t)o * (f32 ? 4 : 2);
   const bool vmask = !kSimple && e.mask_src && !e.mask_bits;
-  const bool fast = full && (e.stage_row || (oaddr & 15) == 0) && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
+  const bool fast = full && (e.stage_row || (oaddr & 15) == 0) &&
+                    (!e.bias || e.bias_smem || (reinterpret_cast<uintptr_t>(e.bias + col) & 15) == 0) &&
                     (!vmask || (side && side->m.loaded));
   if (!fast) {
     if (e.stage_row) __trap();            // the host enables staging only when every chunk takes the fast path
@@ -181,7 +187,8 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
     const float4* bp = reinterpret_cast<const float4*>(e.bias + col);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 b4 = (4 * j < nv) ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b4 = e.bias_smem ? ld_shared_f4(e.bias_smem + (uint32_t)(col - e.bias_col0 + 4 * j) * 4)
+                                    : ((4 * j < nv) ? __ldg(bp + j) : make_float4(0.f, 0.f, 0.f, 0.f));
       v[4 * j + 0] = fmaf(__uint_as_float(acc[4 * j + 0]), a, b4.x);
       v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), a, b4.y);
       v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), a, b4.z);

@@ -23,6 +23,8 @@ struct PipeSmem {
   uint64_t tmem_full;
   uint64_t tmem_empty;
   uint32_t tmem_base;
+  long long trace[6];          // B200GAN_GEMM_TRACE: clock stamps of CTA (0,0,0) (debug)
+  alignas(16) float bias[256]; // this N tile's bias row (epilogue)
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
   const uint32_t crank = kCluster > 1 ? cluster_ctarank() : 0;
   // cluster dims (2, cluster_y, 1): rank = x + 2*y.  cx pairs pixel tiles (shares B), cyi pairs N tiles (shares A)
   const uint32_t cx = crank & 1, cyi = crank >> 1;
@@ -84,6 +87,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;     // pipeline iterations per tap
   const int iters = ntaps * kloops;
 
+  const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (tr && threadIdx.x == 0) ps->trace[0] = clock64();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
@@ -103,6 +108,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   if (kCluster > 1) cluster_sync_all();       // peer barriers are initialised before anything lands on them
   tc_fence_after();
   const uint32_t tmem = ps->tmem_base;
+  griddep_wait();      // everything above touched only shared memory / TMEM / kernel parameters
 
   if (warp == 0) {
     if (elect_one()) {
@@ -218,8 +224,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
       const bool dual = p.dual == 2;
       int s = 0, kc = 0;
       uint32_t par = 0, acc = 0;
+      if (tr) ps->trace[1] = clock64();
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full0 + 8 * s, par);
+        if (tr && it == 0) ps->trace[2] = clock64();
         tc_fence_after();
         const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
         const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
@@ -275,6 +283,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
         if (++s == p.stages) { s = 0; par ^= 1; }
       }
       umma_commit(smem_u32(&ps->tmem_full));
+      if (tr) ps->trace[3] = clock64();
     }
     __syncwarp();
   } else {
@@ -292,6 +301,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
     ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
+    ea.bias_smem = 0; ea.bias_col0 = n0;
+    if (p.bias) {
+      for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += (int)blockDim.x - 64)
+        ps->bias[i] = (n0 + i < p.ncols) ? __ldg(p.bias + n0 + i) : 0.f;
+      named_barrier(2, (int)blockDim.x - 64);
+      ea.bias_smem = smem_u32(&ps->bias[0]);
+    }
 
     const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     bool row_ok[2];
@@ -323,17 +339,43 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
       }
     }
     mbar_wait(smem_u32(&ps->tmem_full), 0);
+    if (tr && threadIdx.x == 64) ps->trace[4] = clock64();
     tc_fence_after();
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       if (i >= p.dual) break;
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+      if (p.tma_store) {
+        // all MMAs have completed (tmem_full), so the pipeline stages are idle: tile i is staged at
+        // smem + i * 128 rows and leaves through one bulk tensor store
+        ea.stage_row = smem_u32(smem) + (uint32_t)((i * kTileM + r) * p.stage_pitch);
+        ea.stage_col0 = n0;
+      }
       epilogue_row<kSimple>(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols - n0));
+    }
+    if (p.tma_store) {
+      fence_proxy_async_smem();
+      named_barrier(1, (int)blockDim.x - 64);
+      if (threadIdx.x == 64) {
+        for (int i = 0; i < p.dual; ++i)
+          if ((int)(blockIdx.x * p.dual + i) < total_tiles)
+            tma_store_4d(&p.tmOut[phase], smem_u32(smem) + (uint32_t)(i * kTileM * p.stage_pitch), n0, pw0[i], ph0[i],
+                         pn0[i]);
+        bulk_commit();
+        bulk_wait_read0();       // shared memory must outlive the copy engine's reads
+      }
     }
   }
 
+  if (tr && threadIdx.x == 64) ps->trace[5] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) {
+    const long long t0 = ps->trace[0];
+    printf("tapgemm grid(%d,%d,%d) iters %d: setup_done %lld first_data %lld mma_issued %lld epi_start %lld epi_end(warp2) %lld all_done %lld\n",
+           gridDim.x, gridDim.y, gridDim.z, iters, ps->trace[1] - t0, ps->trace[2] - t0, ps->trace[3] - t0, ps->trace[4] - t0,
+           ps->trace[5] - t0, (long long)clock64() - t0);
+  }
   if (kCluster > 1) cluster_sync_all();       // the peer may still be signalling our barriers
   if (warp == 1) {
     if (p.dual == 2) tmem_dealloc<2 * kTmemCols>(tmem);
@@ -388,6 +430,14 @@ static int env_cluster() {
   return v;
 }
 
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = env_int("B200GAN_PDL", 0);   // measured neutral (21.17 vs 21.16 ms/step): off by default
+  return v;
+}
+
+// cluster == 1: plain launch.  All GEMM kernels are launched as programmatic dependents of their predecessor
+// (B200GAN_PDL): their prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps its tail.
 template <typename Params>
 static void launch_clustered(void (*kern)(Params), const Params& p, dim3 grid, size_t smem, int cluster,
                              cudaStream_t stream, int cluster_y = 1) {
@@ -397,13 +447,22 @@ static void launch_clustered(void (*kern)(Params), const Params& p, dim3 grid, s
   cfg.blockDim = dim3(gemm_threads());
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster;
-  attr[0].val.clusterDim.y = cluster_y;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster > 1 || cluster_y > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = cluster_y;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, p);
 }
 
@@ -434,14 +493,17 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     static int cy_env = -1;
     if (cy_env < 0) cy_env = env_int("B200GAN_CLUSTER_Y", 1);
     TapGemmParams q = p;
+    static int trace_env = -1;
+    if (trace_env < 0) trace_env = env_int("B200GAN_GEMM_TRACE", 0);
+    q.trace = trace_env;
     q.cluster_y = (cy_env == 2 && p.dual == 2 && ntile_y >= 2) ? 2 : 1;
     dim3 grid((tiles + 1) / 2 * 2, (ntile_y + q.cluster_y - 1) / q.cluster_y * q.cluster_y, p.nphases);
     if (simple) launch_clustered(tapgemm_kernel<2, true>, q, grid, smem, 2, stream, q.cluster_y);
     else launch_clustered(tapgemm_kernel<2, false>, q, grid, smem, 2, stream, q.cluster_y);
   } else {
     dim3 grid(tiles, ntile_y, p.nphases);
-    if (simple) tapgemm_kernel<1, true><<<grid, gemm_threads(), smem, stream>>>(p);
-    else tapgemm_kernel<1, false><<<grid, gemm_threads(), smem, stream>>>(p);
+    if (simple) launch_clustered(tapgemm_kernel<1, true>, p, grid, smem, 1, stream);
+    else launch_clustered(tapgemm_kernel<1, false>, p, grid, smem, 1, stream);
   }
 }
 
@@ -456,6 +518,7 @@ struct SmallKSmem {
   uint64_t acc_empty[2];
   uint32_t tmem_base;
   long long trace[5][12];      // B200GAN_SMALLK_TRACE: per-tile clock stamps of CTA 0 (debug)
+  alignas(16) float bias[256]; // the bias row (epilogue)
 };
 
 template <bool kSimple>
@@ -464,6 +527,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
   const int b_bytes = p.bn_tile * kBlockK * 2;            // one K chunk of B
   const int slot_bytes = p.kchunks * kABytes;             // one A tile: 128 rows x full K
   uint8_t* smem_b = smem;
@@ -493,6 +557,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ps->tmem_base;
+  griddep_wait();      // everything above touched only shared memory / TMEM / kernel parameters
 
   if (warp == 0) {
     if (elect_one()) {
@@ -573,6 +638,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
     ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
     ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
+    ea.bias_smem = 0; ea.bias_col0 = 0;
+    if (p.bias) {
+      for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += (int)blockDim.x - 64)
+        ps->bias[i] = (i < p.ncols) ? __ldg(p.bias + i) : 0.f;
+      named_barrier(2, (int)blockDim.x - 64);
+      ea.bias_smem = smem_u32(&ps->bias[0]);
+    }
     int acc = 0;
     uint32_t accpar = 0;
     const int nepi = (int)blockDim.x - 64;
@@ -633,7 +705,7 @@ bool smallk_fits(int kchunks, int bn_tile, int* slots, int stage_bytes) {
   if (kchunks < 1 || kchunks > 4 || bn_tile > 256) return false;
   const int b_total = kchunks * bn_tile * kBlockK * 2;
   const int slot = kchunks * kABytes;
-  int n = (227 * 1024 - 2048 - b_total - stage_bytes) / slot;
+  int n = (227 * 1024 - 3072 - b_total - stage_bytes) / slot;
   if (n < 2) return false;
   *slots = n > 8 ? 8 : n;
   return true;
@@ -663,9 +735,9 @@ void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
   if (trace < 0) trace = env_int("B200GAN_SMALLK_TRACE", 0);
   q.trace = trace;
   if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
-    smallk_kernel<true><<<grid, gemm_threads(), smem, stream>>>(q);
+    launch_clustered(smallk_kernel<true>, q, dim3(grid), smem, 1, stream);
   else
-    smallk_kernel<false><<<grid, gemm_threads(), smem, stream>>>(q);
+    launch_clustered(smallk_kernel<false>, q, dim3(grid), smem, 1, stream);
 }
 
 // =============================================================================================
@@ -681,6 +753,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
   uint8_t* smem = align1024(smem_raw);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();
 
   constexpr int kBox = 64 * 64 * 2;                     // 8 KiB: 64 pixels x 64 channels
   const int a_bytes = p.dual * 2 * kBox;                // p.dual x 128 "M" channels share one B tile
@@ -729,6 +802,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ps->tmem_base;
+  griddep_wait();      // everything above touched only shared memory / TMEM / kernel parameters
 
   if (warp == 0) {
     if (elect_one()) {
@@ -912,7 +986,7 @@ void launch_wgrad(const WgradParams& p0, int /*splits_hint*/, cudaStream_t strea
   if (ctas < 1) ctas = 1;
   p.chunks_per_cta = (int)((total + ctas - 1) / ctas);
   const int grid = (int)((total + p.chunks_per_cta - 1) / p.chunks_per_cta);
-  wgrad_kernel<<<grid, gemm_threads(), smem, stream>>>(p);
+  launch_clustered(wgrad_kernel, p, dim3(grid), smem, 1, stream);
 }
 
 }  // namespace b200

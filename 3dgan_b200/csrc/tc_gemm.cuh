@@ -52,6 +52,10 @@ struct TapGemmParams {
   int b_pitch_bytes;
   int b_rows_total;
   int b_prefetch;                     // 1: CTAs of the first pixel tile pull their N tile's weight rows into L2 at kernel start
+  int trace;                          // debug: CTA (0,0,0) prints clock stamps of its phases
+  CUtensorMap tmOut[kMaxPhases];      // per phase: output viewed as [ext_n, ext_h, ext_w, ncols], box = the tile (tma_store)
+  int tma_store;                      // 1: the epilogue stages its tiles in the (idle) pipeline smem and bulk-stores them
+  int stage_pitch;                    // bytes per staged row = bn_tile * element size
   int cluster_y;                      // set by launch_tapgemm: 2 -> 2x2 clusters, the N-tile pair also shares A
   void* out;
   int out_f32;                        // 0: bf16, 1: fp32
