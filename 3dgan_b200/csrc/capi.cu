@@ -177,7 +177,8 @@ static void setup_out_maps(TapGemmParams& p, const b200_epilogue* e) {
   if (align & 15) return;
   if ((p.o_sw * elem) % 16 || (p.o_sh * elem) % 16 || (p.o_sn * elem) % 16 || (p.o_sw * 2) % 16) return;
   const long long need = (long long)p.dual * kTileM * p.bn_tile * elem;
-  if (need > (long long)p.stages * tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)) return;
+  if (need > (long long)p.stages * (p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
+                                           : tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail))) return;
   for (int i = 0; i < p.nphases; ++i) {
     const char* base = reinterpret_cast<const char*>(p.out) + p.phase_o_off[i] * elem;
     if (reinterpret_cast<uintptr_t>(base) & 15) return;
@@ -433,7 +434,9 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
   p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks * g->k * g->k);
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
-  p.stages = std::min(pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)),
+  p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
+  p.stages = std::min(pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
+                                         : tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)),
                       std::max(2, (p.kchunks - p.merge_tail) * g->k * g->k));
   p.out = y;
   setup_out_maps(p, e);
@@ -558,7 +561,9 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
   p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks);
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
-  p.stages = pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail));
+  p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
+  p.stages = pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
+                                : tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail));
   p.out = dx;
   setup_out_maps(p, e);
   launch_tapgemm(p, st);

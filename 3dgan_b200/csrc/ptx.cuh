@@ -192,6 +192,73 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
+// ---- 2-CTA (cta_group::2) variants: a CTA pair (even rank = leader) runs one UMMA with M = 256; each CTA holds
+// its 128 A rows and HALF of the B rows at the same shared-memory offsets; TMA loads of either CTA complete
+// bytes on the LEADER's mbarrier (barrier address with the peer bit cleared, as in cute::SM100_TMA_2SM_LOAD)
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_nd_2sm(int rank, uint32_t dst, const void* tmap, uint32_t bar, const int* c) {
+  switch (rank) {
+    case 2: tma_load_2d_2sm(dst, tmap, bar, c[0], c[1]); break;
+    case 3: tma_load_3d_2sm(dst, tmap, bar, c[0], c[1], c[2]); break;
+    case 4: tma_load_4d_2sm(dst, tmap, bar, c[0], c[1], c[2], c[3]); break;
+    default: tma_load_5d_2sm(dst, tmap, bar, c[0], c[1], c[2], c[3], c[4]); break;
+  }
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B, M = 256 across the pair; issued by one thread of the leader CTA
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all prior MMAs of the pair have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
 // programmatic dependent launch: `launch_dependents` lets the next kernel of the stream (launched with the
 // programmatic-serialization attribute) start its prologue on SMs this grid no longer uses; `wait` blocks that
 // kernel until every prerequisite grid has completed and its memory is visible

@@ -383,6 +383,237 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   }
 }
 
+// =============================================================================================
+// Tap GEMM, 2-CTA form (tcgen05 cta_group::2)
+// =============================================================================================
+// The cluster pair runs UMMA instructions with M = 256: rows 0..127 are the leader's pixel tile, rows 128..255
+// the peer's, the accumulators land in each CTA's own TMEM; each CTA keeps only HALF of the B tile in shared
+// memory (rows [rank * N/2, (rank+1) * N/2)), the tensor core reads both halves.  Per 64-wide K block a CTA
+// therefore receives 2 A tiles + B/2 = 45 KB instead of 58 KB: the 1-CTA kernel is bound by the shared-memory
+// fill rate (about 64 B/clk/SM; 58 KB per 832 MMA cycles), this one is not.  Protocol (as CUTLASS's
+// PipelineTmaUmmaAsync): both producers wait on their own empty barrier and issue cta_group::2 TMA loads that
+// complete bytes on the LEADER's full barrier; the leader's producer alone arms it with the pair's byte count;
+// the leader's MMA thread issues every MMA and releases stages / publishes the accumulators with multicast commits.
+// Requires dual pixel tiles and (no K tail or the merged 16-wide tail).
+template <bool kSimple>
+__global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid_constant__ TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // cluster dims (2,1,1): 0 = leader
+  const bool leader = crank == 0;
+
+  const int half_rows = p.bn_tile / 2;
+  const int b_bytes = half_rows * kBlockK * 2;        // this CTA's half of the B tile
+  const int a_bytes = 2 * kABytes;                    // two pixel tiles per CTA
+  const int tail_area = p.merge_tail ? (2 * kTileM + half_rows) * 32 : 0;
+  const int stage_bytes = a_bytes + b_bytes + tail_area;
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
+
+  const int phase = blockIdx.z;
+  int pw0[2], ph0[2], pn0[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int t = blockIdx.x * 2 + i;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    pw0[i] = tw * p.bw; ph0[i] = th * p.bh; pn0[i] = t * p.bn;
+  }
+  const int n0 = blockIdx.y * p.bn_tile;
+  const int ext_w = p.phase_ext_w[phase], ext_h = p.phase_ext_h[phase];
+  const int tap_begin = p.phase_tap_begin[phase];
+  const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
+  const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;
+  const int iters = ntaps * kloops;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ps->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // both CTAs' barriers and TMEM exist before any load / MMA touches them
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ TMA producer (both CTAs)
+      int base[2][5];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        base[i][0] = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+          base[i][d + 1] = pw0[i] * p.a_mul[0][d] + ph0[i] * p.a_mul[1][d] + pn0[i] * p.a_mul[2][d];
+      }
+      int s = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const uint32_t smem0 = smem_u32(smem);
+      const int a_tile = kABytes, t_tile = kTileM * 32;
+      for (int tp = 0; tp < ntaps; ++tp) {
+        const int tap = tap_begin + tp;
+        int c0[5], c1[5];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          c0[d + 1] = base[0][d + 1] + p.tap_a_off[tap][d];
+          c1[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
+        }
+        const int brow = p.tap_b_row[tap] + n0 + (int)crank * half_rows;
+        for (int kc = 0; kc < kloops; ++kc) {
+          mbar_wait(empty0 + 8 * s, par ^ 1);
+          const uint32_t full = full0 + 8 * s;
+          const uint32_t a_dst = smem0 + s * stage_bytes;
+          const bool with_tail = p.merge_tail && kc == kloops - 1;
+          // the leader arms its barrier with the bytes BOTH CTAs will deliver for this stage
+          if (leader) mbar_arrive_expect_tx(full, 2 * (a_bytes + b_bytes + (with_tail ? tail_area : 0)));
+          c0[0] = kc * kBlockK;
+          c1[0] = kc * kBlockK;
+          tma_load_nd_2sm(p.a_rank, a_dst, &p.tmA, full, c0);
+          tma_load_nd_2sm(p.a_rank, a_dst + a_tile, &p.tmA, full, c1);
+          tma_load_2d_2sm(a_dst + 2 * a_tile, &p.tmB, full, kc * kBlockK, brow);
+          if (with_tail) {
+            const uint32_t t_dst = a_dst + a_bytes + b_bytes;
+            c0[0] = (kc + 1) * kBlockK;
+            c1[0] = (kc + 1) * kBlockK;
+            tma_load_nd_2sm(p.a_rank, t_dst, &p.tmA_tail, full, c0);
+            tma_load_nd_2sm(p.a_rank, t_dst + t_tile, &p.tmA_tail, full, c1);
+            tma_load_2d_2sm(t_dst + 2 * t_tile, &p.tmB_tail, full, (kc + 1) * kBlockK, brow);
+          }
+          if (++s == p.stages) { s = 0; par ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+      const uint32_t idesc = make_idesc_bf16(2 * kTileM, p.bn_tile, 0, 0);
+      const int tail_steps = (p.k_total - (p.kchunks - 1) * kBlockK + 15) / 16;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem0, 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, 16, 1024);
+      const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      int s = 0, kc = 0;
+      uint32_t par = 0, acc = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full0 + 8 * s, par);
+        tc_fence_after();
+        const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
+        const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
+        const int nsteps = (p.merge_tail || kc != p.kchunks - 1 || p.tail_mode == 0) ? kBlockK / 16 : tail_steps;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          if (k < nsteps) {
+            // pair tile 0 -> TMEM columns [0, N), pair tile 1 (A + 16 KiB) -> [256, 256 + N), in both CTAs
+            umma_bf16_2sm(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            umma_bf16_2sm(tmem + kTmemCols, adesc + (kABytes >> 4) + 2 * k, bdesc + 2 * k, idesc, acc);
+            acc = 1;
+          }
+        }
+        if (p.merge_tail && kc == kloops - 1) {
+          // the tap's 16-wide tail (SWIZZLE_32B tiles behind the full tiles of this stage): one K step
+          const uint32_t tb0 = smem0 + s * stage_bytes + a_bytes + b_bytes;
+          const uint32_t t_tile = kTileM * 32;
+          const uint64_t tbd = make_smem_desc(tb0 + 2 * t_tile, 16, 256, 6);
+          umma_bf16_2sm(tmem, make_smem_desc(tb0, 16, 256, 6), tbd, idesc, 1);
+          umma_bf16_2sm(tmem + kTmemCols, make_smem_desc(tb0 + t_tile, 16, 256, 6), tbd, idesc, 1);
+        }
+        umma_commit_2sm(empty0 + 8 * s, (uint16_t)0x3);       // stage free in both CTAs
+        if (++kc == kloops) kc = 0;
+        if (++s == p.stages) { s = 0; par ^= 1; }
+      }
+      umma_commit_2sm(smem_u32(&ps->tmem_full), (uint16_t)0x3);   // accumulators final in both CTAs
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------------------------------------------- epilogue (each CTA: its own rows)
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int iw = r % p.bw;
+    const int ih = (r / p.bw) % p.bh;
+    const int in = r / (p.bw * p.bh);
+    EpilogueArgs ea;
+    ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
+    ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
+    ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
+    ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
+    ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
+    ea.bias_smem = 0; ea.bias_col0 = n0;
+    if (p.bias) {
+      for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += (int)blockDim.x - 64)
+        ps->bias[i] = (n0 + i < p.ncols) ? __ldg(p.bias + n0 + i) : 0.f;
+      named_barrier(2, (int)blockDim.x - 64);
+      ea.bias_smem = smem_u32(&ps->bias[0]);
+    }
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    bool row_ok[2];
+    long long off[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int pw = pw0[i] + iw, ph = ph0[i] + ih, pn = pn0[i] + in;
+      const bool tile_ok = (int)(blockIdx.x * 2 + i) < total_tiles;
+      row_ok[i] = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
+      off[i] = p.phase_o_off[phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh + (long long)pw * p.o_sw;
+      if (row_ok[i] && cg == 0) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
+    }
+    if (p.b_prefetch && blockIdx.x < 2) {
+      const int row0 = n0 + (int)crank * half_rows;
+      const int lines = (p.k_total * 2 + 127) >> 7;
+      const int per_tap = half_rows * lines;
+      const int total = ntaps * per_tap;
+      const char* base = reinterpret_cast<const char*>(p.b_base);
+      for (int i = (int)threadIdx.x - 64; i < total; i += (int)blockDim.x - 64) {
+        const int tp = i / per_tap, rem = i - tp * per_tap;
+        const int rr = rem / lines, ln = rem - rr * lines;
+        const int row = p.tap_b_row[tap_begin + tp] + row0 + rr;
+        if (row < p.b_rows_total)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)row * p.b_pitch_bytes + ln * 128));
+      }
+    }
+    mbar_wait(smem_u32(&ps->tmem_full), 0);
+    tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+      if (p.tma_store) {
+        ea.stage_row = smem_u32(smem) + (uint32_t)((i * kTileM + r) * p.stage_pitch);
+        ea.stage_col0 = n0;
+      }
+      epilogue_row<kSimple>(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols - n0));
+    }
+    if (p.tma_store) {
+      fence_proxy_async_smem();
+      named_barrier(1, (int)blockDim.x - 64);
+      if (threadIdx.x == 64) {
+        for (int i = 0; i < 2; ++i)
+          if ((int)(blockIdx.x * 2 + i) < total_tiles)
+            tma_store_4d(&p.tmOut[phase], smem_u32(smem) + (uint32_t)(i * kTileM * p.stage_pitch), n0, pw0[i], ph0[i],
+                         pn0[i]);
+        bulk_commit();
+        bulk_wait_read0();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();       // the pair's MMAs / barrier traffic are finished in both CTAs
+  if (warp == 1) tmem_dealloc_2sm<2 * kTmemCols>(tmem);
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -475,7 +706,34 @@ int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail) {
   return dual * kABytes + bn_tile * kBlockK * 2 + (merge_tail ? (dual * kTileM + bn_tile) * 32 : 0);
 }
 
+// 2-CTA form: usable with two pixel tiles per CTA and either no K tail or the merged 16-wide tail
+int tapgemm_2sm(int cluster, int dual, int tail_mode, int merge_tail, int bn_tile) {
+  static int v = -1;
+  if (v < 0) v = env_int("B200GAN_CTA2", 1);
+  return v && cluster == 2 && dual == 2 && (tail_mode == 0 || merge_tail) && bn_tile % 16 == 0;
+}
+int tapgemm_stage_bytes_2sm(int bn_tile, int merge_tail) {
+  return 2 * kABytes + (bn_tile / 2) * kBlockK * 2 + (merge_tail ? (2 * kTileM + bn_tile / 2) * 32 : 0);
+}
+
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+  if (p.cta2) {
+    const size_t smem2 = (size_t)p.stages * tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail) + sizeof(PipeSmem) + 1024;
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaFuncSetAttribute(tapgemm2sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(tapgemm2sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      configured2 = true;
+    }
+    const int tiles2 = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
+    const int ny = (p.ncols + p.bn_tile - 1) / p.bn_tile;
+    dim3 grid((tiles2 + 1) / 2 * 2, ny, p.nphases);
+    if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
+      launch_clustered(tapgemm2sm_kernel<true>, p, grid, smem2, 2, stream);
+    else
+      launch_clustered(tapgemm2sm_kernel<false>, p, grid, smem2, 2, stream);
+    return;
+  }
   const int stage_bytes = tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail);
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   static bool configured = false;
@@ -808,6 +1066,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
     if (elect_one()) {
       int s = 0;
       uint32_t par = 0;
+      long long prod_wait = 0;
+      const long long prod_t0 = clock64();
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       const uint32_t smem0 = smem_u32(smem);
       for (long long pos = range_begin; pos < range_end;) {
@@ -822,7 +1082,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
         }
         for (int it = 0; it < g.len; ++it) {
           const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
+          const long long tw0 = p.trace ? clock64() : 0;
           mbar_wait(empty0 + 8 * s, par ^ 1);
+          if (p.trace) prod_wait += clock64() - tw0;
           const uint32_t full = full0 + 8 * s;
           mbar_arrive_expect_tx(full, (g.a_boxes + g.b_boxes) * kBox);
           const uint32_t a_dst = smem0 + s * stage_bytes;
@@ -844,6 +1106,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
         }
         pos += g.len;
       }
+      if (p.trace && blockIdx.x == 0)
+        printf("wgrad producer: total %lld cycles, waiting for free stages %lld, chunks %lld\n",
+               (long long)clock64() - prod_t0, prod_wait, range_end - range_begin);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -858,6 +1123,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
       int s = 0;
       uint32_t par = 0, seg_par = 0;
       bool first = true;
+      long long mma_wait = 0;
+      const long long mma_t0 = clock64();
       for (long long pos = range_begin; pos < range_end;) {
         const Seg g = segment(pos);
         const bool second = g.a_boxes > 2;       // the second 128-channel tile exists
@@ -868,7 +1135,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
         }
         uint32_t acc = 0;
         for (int it = 0; it < g.len; ++it) {
+          const long long tw0 = p.trace ? clock64() : 0;
           mbar_wait(full0 + 8 * s, par);
+          if (p.trace) mma_wait += clock64() - tw0;
           tc_fence_after();
           const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
           const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
@@ -888,6 +1157,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
         first = false;
         pos += g.len;
       }
+      if (p.trace && blockIdx.x == 0)
+        printf("wgrad mma: total %lld cycles, waiting for data %lld\n", (long long)clock64() - mma_t0, mma_wait);
     }
     __syncwarp();
   } else {
@@ -985,6 +1256,9 @@ void launch_wgrad(const WgradParams& p0, int /*splits_hint*/, cudaStream_t strea
   if (ctas > sms) ctas = sms;
   if (ctas < 1) ctas = 1;
   p.chunks_per_cta = (int)((total + ctas - 1) / ctas);
+  static int trace_env = -1;
+  if (trace_env < 0) trace_env = env_int("B200GAN_GEMM_TRACE", 0);
+  p.trace = trace_env;
   const int grid = (int)((total + p.chunks_per_cta - 1) / p.chunks_per_cta);
   launch_clustered(wgrad_kernel, p, dim3(grid), smem, 1, stream);
 }

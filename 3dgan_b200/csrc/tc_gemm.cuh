@@ -53,6 +53,7 @@ struct TapGemmParams {
   int b_rows_total;
   int b_prefetch;                     // 1: CTAs of the first pixel tile pull their N tile's weight rows into L2 at kernel start
   int trace;                          // debug: CTA (0,0,0) prints clock stamps of its phases
+  int cta2;                           // 1: 2-CTA kernel (cta_group::2): B split across the pair, M = 256 per MMA
   CUtensorMap tmOut[kMaxPhases];      // per phase: output viewed as [ext_n, ext_h, ext_w, ncols], box = the tile (tma_store)
   int tma_store;                      // 1: the epilogue stages its tiles in the (idle) pipeline smem and bulk-stores them
   int stage_pitch;                    // bytes per staged row = bn_tile * element size
@@ -84,6 +85,7 @@ struct WgradParams {
   int bw, bh, bn;                     // pixels per K-chunk along w, h, n (product 64)
   int chunks_w, chunks_h, chunks_n;
   int total_chunks, chunks_per_split;
+  int trace;                          // debug: CTA 0 prints where its producer / MMA threads wait
   int units, chunks_per_cta;          // set by launch_wgrad: (tap, M pair, N tile) units; linear chunk range per CTA
   int Ca, Cb;
   int m_tiles, n_tiles, bn_tile, nb_boxes;
@@ -99,6 +101,8 @@ struct WgradParams {
 int tapgemm_cluster_size(const TapGemmParams& p);
 int tapgemm_dual(int m_tiles, int iters);
 int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail);
+int tapgemm_2sm(int cluster, int dual, int tail_mode, int merge_tail, int bn_tile);
+int tapgemm_stage_bytes_2sm(int bn_tile, int merge_tail);
 int epilogue_pipelined();
 int l2_prefetch_distance();
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream);

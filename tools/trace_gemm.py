@@ -16,3 +16,8 @@ for (N, H, Cin, Cout) in [(512, 16, 208, 400), (512, 8, 400, 800)]:
     for i in range(2):
         print("== dgrad", Cin, Cout, i, flush=True)
         E.conv_like("dgrad", dy, Wp, geom); torch.cuda.synchronize()
+
+    print("== wgrad", Cin, Cout, flush=True)
+    for i in range(2):
+        ws, wsb = E._workspace(geom, 2)
+        E.launch("b200_conv2d_wgrad", E._p(x.buf), E._p(dy.buf), E._p(Wp.g32), E.C.byref(geom), 1.0, E._p(ws), wsb, 0); torch.cuda.synchronize()
