@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
 // PipelineTmaUmmaAsync): both producers wait on their own empty barrier and issue cta_group::2 TMA loads that
 // complete bytes on the LEADER's full barrier; the leader's producer alone arms it with the pair's byte count;
 // the leader's MMA thread issues every MMA and releases stages / publishes the accumulators with multicast commits.
-// Requires dual pixel tiles and (no K tail or the merged 16-wide tail).
+// Requires two pixel tiles per CTA.
 template <bool kSimple>
 __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
   const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
   const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;
   const int iters = ntaps * kloops;
+  const int tail_row_bytes = p.tail_mode == 1 ? 32 : 64;      // bytes per row of a narrow (not merged) tail box
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmA);
@@ -474,10 +475,21 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
           const uint32_t full = full0 + 8 * s;
           const uint32_t a_dst = smem0 + s * stage_bytes;
           const bool with_tail = p.merge_tail && kc == kloops - 1;
-          // the leader arms its barrier with the bytes BOTH CTAs will deliver for this stage
-          if (leader) mbar_arrive_expect_tx(full, 2 * (a_bytes + b_bytes + (with_tail ? tail_area : 0)));
+          // a tail chunk that is not merged moves only its 16 / 32 valid channels (narrow box, 32B / 64B swizzle)
+          const bool tail = !p.merge_tail && p.tail_mode != 0 && kc == p.kchunks - 1;
           c0[0] = kc * kBlockK;
           c1[0] = kc * kBlockK;
+          if (tail) {
+            const int n_tile = kTileM * tail_row_bytes;
+            if (leader) mbar_arrive_expect_tx(full, 2 * (2 * n_tile + half_rows * tail_row_bytes));
+            tma_load_nd_2sm(p.a_rank, a_dst, &p.tmA_tail, full, c0);
+            tma_load_nd_2sm(p.a_rank, a_dst + n_tile, &p.tmA_tail, full, c1);
+            tma_load_2d_2sm(a_dst + 2 * n_tile, &p.tmB_tail, full, kc * kBlockK, brow);
+            if (++s == p.stages) { s = 0; par ^= 1; }
+            continue;
+          }
+          // the leader arms its barrier with the bytes BOTH CTAs will deliver for this stage
+          if (leader) mbar_arrive_expect_tx(full, 2 * (a_bytes + b_bytes + (with_tail ? tail_area : 0)));
           tma_load_nd_2sm(p.a_rank, a_dst, &p.tmA, full, c0);
           tma_load_nd_2sm(p.a_rank, a_dst + a_tile, &p.tmA, full, c1);
           tma_load_2d_2sm(a_dst + 2 * a_tile, &p.tmB, full, kc * kBlockK, brow);
@@ -511,6 +523,28 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
         tc_fence_after();
         const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
         const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
+        if (!p.merge_tail && p.tail_mode != 0 && kc == p.kchunks - 1) {
+          // narrow tail tile: rows of 32 B (SWIZZLE_32B, 8-row groups 256 B apart) or 64 B (SWIZZLE_64B, 512 B)
+          const uint32_t base = smem0 + s * stage_bytes;
+          const uint32_t n_tile = kTileM * tail_row_bytes;
+          const uint32_t layout = p.tail_mode == 1 ? 6u : 4u;
+          const uint32_t sbo = 8 * tail_row_bytes;
+          const uint64_t ta0 = make_smem_desc(base, 16, sbo, layout);
+          const uint64_t ta1 = make_smem_desc(base + n_tile, 16, sbo, layout);
+          const uint64_t tb = make_smem_desc(base + 2 * n_tile, 16, sbo, layout);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            if (k < tail_steps) {
+              umma_bf16_2sm(tmem, ta0 + 2 * k, tb + 2 * k, idesc, acc);
+              umma_bf16_2sm(tmem + kTmemCols, ta1 + 2 * k, tb + 2 * k, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit_2sm(empty0 + 8 * s, (uint16_t)0x3);
+          if (++kc == kloops) kc = 0;
+          if (++s == p.stages) { s = 0; par ^= 1; }
+          continue;
+        }
         const int nsteps = (p.merge_tail || kc != p.kchunks - 1 || p.tail_mode == 0) ? kBlockK / 16 : tail_steps;
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
@@ -706,11 +740,12 @@ int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail) {
   return dual * kABytes + bn_tile * kBlockK * 2 + (merge_tail ? (dual * kTileM + bn_tile) * 32 : 0);
 }
 
-// 2-CTA form: usable with two pixel tiles per CTA and either no K tail or the merged 16-wide tail
+// 2-CTA form: usable with two pixel tiles per CTA
 int tapgemm_2sm(int cluster, int dual, int tail_mode, int merge_tail, int bn_tile) {
   static int v = -1;
   if (v < 0) v = env_int("B200GAN_CTA2", 1);
-  return v && cluster == 2 && dual == 2 && (tail_mode == 0 || merge_tail) && bn_tile % 16 == 0;
+  (void)tail_mode; (void)merge_tail;
+  return v && cluster == 2 && dual == 2 && bn_tile % 16 == 0;
 }
 int tapgemm_stage_bytes_2sm(int bn_tile, int merge_tail) {
   return 2 * kABytes + (bn_tile / 2) * kBlockK * 2 + (merge_tail ? (2 * kTileM + bn_tile / 2) * 32 : 0);
