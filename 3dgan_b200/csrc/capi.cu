@@ -311,6 +311,7 @@ static int dense_wgrad(const void* A, int Ca, int Ka, const void* B, int Cb, lon
   p.bn_tile = pick_bn_tile(Cb);
   p.n_tiles = cdiv(Cb, p.bn_tile);
   p.nb_boxes = cdiv(p.bn_tile, 64);
+  p.bn_tile_t = pick_bn_tile(p.Ca);       // N tile (over X channels) of the transposed 2-CTA kernel
   p.dual = wgrad_dual(p.m_tiles);
   p.l2_prefetch = l2_prefetch_distance();
   p.stages = pick_stages((2 * p.dual + p.nb_boxes) * 64 * 64 * 2);
@@ -635,6 +636,7 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
   p.bn_tile = pick_bn_tile(g->Cout);
   p.n_tiles = cdiv(g->Cout, p.bn_tile);
   p.nb_boxes = cdiv(p.bn_tile, 64);
+  p.bn_tile_t = pick_bn_tile(p.Ca);       // N tile (over X channels) of the transposed 2-CTA kernel
   p.dual = wgrad_dual(p.m_tiles);
   p.l2_prefetch = l2_prefetch_distance();
   p.stages = pick_stages((2 * p.dual + p.nb_boxes) * 64 * 64 * 2);

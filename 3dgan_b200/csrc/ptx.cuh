@@ -259,6 +259,15 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask) : "memory");
 }
 
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+
 // programmatic dependent launch: `launch_dependents` lets the next kernel of the stream (launched with the
 // programmatic-serialization attribute) start its prologue on SMs this grid no longer uses; `wait` blocks that
 // kernel until every prerequisite grid has completed and its memory is visible

@@ -1265,13 +1265,263 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad_kernel(const __grid_cons
   }
 }
 
+// =============================================================================================
+// Weight gradient, 2-CTA form (tcgen05 cta_group::2), transposed orientation
+// =============================================================================================
+// M = output channels (dY^T, plain box), N = input channels (X^T, the tap gather), K = pixels.  A cluster pair
+// owns a unit of 512 dY channels x n_tile X channels x one filter tap: CTA r holds M tiles {2r, 2r+1} (two
+// accumulators in its TMEM) and HALF of the X tile (n_tile/2 channels), so a 64-pixel K chunk costs a CTA
+// 32 KB + 16 KB of shared-memory fill for 2 x (256 x n_tile x 64) MACs -- the 1-CTA kernel needs 64 KB for the
+// same MMA time and is bound by that fill rate.  Work is cut stream-K style over the 74 pairs; the epilogue
+// writes dW[tap][ci][co] with co along the TMEM lanes, i.e. warp-coalesced scalar red.global.add.
+__global__ void __launch_bounds__(kMaxThreads, 1) wgrad2sm_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  constexpr int kBox = 64 * 64 * 2;                     // 8 KiB: 64 pixels x 64 channels
+  const int half_n = p.bn_tile / 2;                     // X channels held by one CTA
+  const int nb_half = (half_n + 63) / 64;               // 64-channel boxes per CTA for its half
+  const int a_bytes = 4 * kBox;                         // two 128-channel dY tiles
+  const int stage_bytes = a_bytes + nb_half * kBox;
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
+
+  const long long pair = blockIdx.x >> 1;
+  const long long range_begin = pair * p.chunks_per_cta;
+  const long long range_end = min(range_begin + p.chunks_per_cta, (long long)p.units * p.total_chunks);
+  const bool has_work = range_begin < range_end;        // (both CTAs of a pair agree; they must stay for the syncs)
+  const int m_units = (p.Cb + 511) / 512;
+
+  struct Seg { int tap, m0, n0, cbeg, len; };
+  auto segment = [&](long long pos) {
+    Seg g;
+    int u = (int)(pos / p.total_chunks);
+    g.cbeg = (int)(pos - (long long)u * p.total_chunks);
+    g.len = (int)min((long long)(p.total_chunks - g.cbeg), range_end - pos);
+    const int nt = u % p.n_tiles; u /= p.n_tiles;
+    const int mu = u % m_units; u /= m_units;
+    g.tap = u;
+    g.m0 = mu * 512; g.n0 = nt * p.bn_tile;
+    return g;
+  };
+  // valid 64-channel boxes of CTA `r` for a segment (identical formulas in both CTAs: the leader arms the
+  // barrier with the bytes of both)
+  auto a_boxes_of = [&](const Seg& g, int r) { return max(0, min(4, (p.Cb - (g.m0 + r * 256) + 63) / 64)); };
+  auto b_boxes_of = [&](const Seg& g, int r) { return max(0, min(nb_half, (p.Ca - (g.n0 + r * half_n) + 63) / 64)); };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ps->tmem_full), 1);
+    mbar_init(smem_u32(&ps->tmem_empty), 2 * ((blockDim.x >> 5) - 2));   // the epilogue warps of BOTH CTAs
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (has_work && warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ TMA producer (both CTAs)
+      int s = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const uint32_t smem0 = smem_u32(smem);
+      for (long long pos = range_begin; pos < range_end;) {
+        const Seg g = segment(pos);
+        const int my_a = a_boxes_of(g, (int)crank), my_b = b_boxes_of(g, (int)crank);
+        const int pair_boxes = a_boxes_of(g, 0) + a_boxes_of(g, 1) + b_boxes_of(g, 0) + b_boxes_of(g, 1);
+        const int ma = g.m0 + (int)crank * 256, nb = g.n0 + (int)crank * half_n;
+        int jw, jh, jn;
+        {
+          int ch = g.cbeg;
+          jw = ch % p.chunks_w; ch /= p.chunks_w;
+          jh = ch % p.chunks_h; ch /= p.chunks_h;
+          jn = ch;
+        }
+        for (int it = 0; it < g.len; ++it) {
+          const int pw0 = jw * p.bw, ph0 = jh * p.bh, pn0 = jn * p.bn;
+          mbar_wait(empty0 + 8 * s, par ^ 1);
+          const uint32_t full = full0 + 8 * s;
+          if (leader) mbar_arrive_expect_tx(full, pair_boxes * kBox);
+          const uint32_t a_dst = smem0 + s * stage_bytes;
+          // M side: dY channels [ma, ma + 256) of the chunk's 64 pixels
+          int cb[5] = {0, pw0, ph0, pn0, 0};
+          for (int b = 0; b < my_a; ++b) {
+            cb[0] = ma + b * 64;
+            tma_load_nd_2sm(p.b_rank, a_dst + b * kBox, &p.tmB, full, cb);
+          }
+          // N side: X channels [nb, nb + half_n) of the tap-shifted, strided pixels
+          int c[5];
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            c[d + 1] = p.tap_a_off[g.tap][d] + pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
+          for (int b = 0; b < my_b; ++b) {
+            c[0] = nb + b * 64;
+            tma_load_nd_2sm(p.a_rank, a_dst + a_bytes + b * kBox, &p.tmA, full, c);
+          }
+          if (++s == p.stages) { s = 0; par ^= 1; }
+          if (++jw == p.chunks_w) { jw = 0; if (++jh == p.chunks_h) { jh = 0; ++jn; } }
+        }
+        pos += g.len;
+      }
+    }
+    __syncwarp();
+  } else if (has_work && warp == 1) {
+    if (leader && elect_one()) {
+      // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+      const uint32_t idesc = make_idesc_bf16(2 * kTileM, p.bn_tile, 1, 1);
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem0, kBox, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, kBox, 1024);
+      const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      int s = 0;
+      uint32_t par = 0, seg_par = 0;
+      bool first = true;
+      for (long long pos = range_begin; pos < range_end;) {
+        const Seg g = segment(pos);
+        const bool second = p.Cb - g.m0 > 128;       // some CTA has a second 128-channel tile
+        if (!first) {
+          mbar_wait(smem_u32(&ps->tmem_empty), seg_par);     // both CTAs' epilogues have drained TMEM
+          tc_fence_after();
+          seg_par ^= 1;
+        }
+        first = false;
+        uint32_t acc = 0;
+        for (int it = 0; it < g.len; ++it) {
+          mbar_wait(full0 + 8 * s, par);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16_2sm(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, acc);
+            if (second) umma_bf16_2sm(tmem + kTmemCols, adesc + ((2 * kBox) >> 4) + 128 * k, bdesc + 128 * k, idesc, acc);
+            acc = 1;
+          }
+          umma_commit_2sm(empty0 + 8 * s, (uint16_t)0x3);
+          if (++s == p.stages) { s = 0; par ^= 1; }
+        }
+        umma_commit_2sm(smem_u32(&ps->tmem_full), (uint16_t)0x3);
+        pos += g.len;
+      }
+    }
+    __syncwarp();
+  } else if (has_work && warp >= 2) {
+    // -------------------------------------------------------------------- epilogue: dW[tap][ci][co] += acc
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
+    uint32_t full_par = 0;
+    for (long long pos = range_begin; pos < range_end;) {
+      const Seg g = segment(pos);
+      mbar_wait(smem_u32(&ps->tmem_full), full_par);
+      full_par ^= 1;
+      tc_fence_after();
+      const int c_end = min(p.bn_tile, p.Ca - g.n0), step = ncg * 16;
+      for (int i = 0; i < 2; ++i) {
+        const int co0 = g.m0 + (int)crank * 256 + i * kTileM;
+        if (co0 >= p.Cb) break;
+        const int co = co0 + q * 32 + lane;
+        const bool row_ok = co < p.Cb;
+        float* obase = p.out + (long long)g.tap * p.out_tap_stride + co;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+        auto reduce16 = [&](const uint32_t* v, int c) {
+          if (!row_ok) return;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int ci = g.n0 + c + j;
+            if (ci < p.Ca)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(obase + (long long)ci * p.ldo),
+                           "f"(__uint_as_float(v[j]) * p.alpha) : "memory");
+          }
+        };
+        int c = cg * 16;
+        if (c < c_end) {
+          uint32_t va[16], vb[16];
+          tmem_ld16(trow + c, va);
+          while (true) {
+            const int c1 = c + step;
+            tmem_ld_wait16(va);
+            if (c1 < c_end) tmem_ld16(trow + c1, vb);
+            reduce16(va, c);
+            if (c1 >= c_end) break;
+            const int c2 = c1 + step;
+            tmem_ld_wait16(vb);
+            if (c2 < c_end) tmem_ld16(trow + c2, va);
+            reduce16(vb, c1);
+            if (c2 >= c_end) break;
+            c = c2;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&ps->tmem_empty), 0);    // on the leader's barrier
+      pos += g.len;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm<2 * kTmemCols>(tmem);
+}
+
 int wgrad_dual(int m_tiles) {
   static int v = -1;
   if (v < 0) v = env_int("B200GAN_DUAL", 2);
   return (v == 2 && m_tiles >= 2) ? 2 : 1;
 }
 
+static void launch_wgrad_2sm(const WgradParams& p0, cudaStream_t stream) {
+  WgradParams p = p0;
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    cudaFuncSetAttribute(wgrad2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  // transposed orientation: M = Cb (dY channels, units of 512), N = Ca (X channels)
+  p.bn_tile = p.bn_tile_t;
+  p.n_tiles = (p.Ca + p.bn_tile - 1) / p.bn_tile;
+  const int nb_half = (p.bn_tile / 2 + 63) / 64;
+  const int stage_bytes = (4 + nb_half) * 64 * 64 * 2;
+  p.stages = (227 * 1024 - 3072) / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
+  p.units = ((p.Cb + 511) / 512) * p.n_tiles * p.ntaps;
+  const long long total = (long long)p.units * p.total_chunks;
+  long long pairs = total / 4;
+  if (pairs > sms / 2) pairs = sms / 2;
+  if (pairs < 1) pairs = 1;
+  p.chunks_per_cta = (int)((total + pairs - 1) / pairs);
+  const int npairs = (int)((total + p.chunks_per_cta - 1) / p.chunks_per_cta);
+  launch_clustered(wgrad2sm_kernel, p, dim3(2 * npairs), smem, 2, stream);
+}
+
 void launch_wgrad(const WgradParams& p0, int /*splits_hint*/, cudaStream_t stream) {
+  static int w2 = -1;
+  if (w2 < 0) w2 = env_int("B200GAN_WGRAD2", 1);
+  // the 2-CTA kernel needs at least three 128-channel dY tiles to fill its 512-row unit reasonably
+  if (w2 && p0.bn_tile_t > 0 && p0.Cb > 256 && (p0.ldo & 3) == 0) {
+    launch_wgrad_2sm(p0, stream);
+    return;
+  }
   WgradParams p = p0;
   const int stage_bytes = (2 * p.dual + p.nb_boxes) * 64 * 64 * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;

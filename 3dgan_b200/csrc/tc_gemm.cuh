@@ -89,6 +89,7 @@ struct WgradParams {
   int units, chunks_per_cta;          // set by launch_wgrad: (tap, M pair, N tile) units; linear chunk range per CTA
   int Ca, Cb;
   int m_tiles, n_tiles, bn_tile, nb_boxes;
+  int bn_tile_t;                      // N tile of the transposed 2-CTA kernel (over Ca); 0 = not eligible
   int l2_prefetch;                    // K chunks prefetched into L2 ahead of the loads
   int dual;                           // 128-channel M tiles per CTA (1|2) sharing one B tile
   int stages;
