@@ -299,7 +299,7 @@ def roofline(sess, train, x, pool, a, step_ms):
     achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": ncu_traffic_bytes(), "peak_source": src,
-            "kernel": "tapgemm_kernel+wgrad_kernel (tcgen05 implicit GEMM: conv fprop/dgrad/wgrad, dense)",
+            "kernel": "tapgemm2sm_kernel+wgrad2sm_kernel (tcgen05 cta_group::2 implicit GEMM: conv fprop/dgrad/wgrad, dense)",
             "launches": n_tc, "flops_per_launch_avg": tot_f / max(n_tc, 1), "ms_per_launch_avg": tot_ms / max(n_tc, 1),
             "step_share": tot_ms / step_ms if step_ms > 0 else None,
             "note": "achieved = sum(2*N*Ho*Wo*k*k*Cin*Cout over the launches) / sum(CUDA-event durations), one eager "
@@ -319,7 +319,7 @@ def ncu_traffic_bytes():
         ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     except ValueError:
         return None
-    vals = [(float(r[ri]) + float(r[wi])) * 1e6 for r in rows[3:] if r and ("tapgemm" in r[0] or "wgrad_kernel" in r[0])
+    vals = [(float(r[ri]) + float(r[wi])) * 1e6 for r in rows[3:] if r and ("tapgemm" in r[0] or "wgrad" in r[0])
             and float(r[hdr.index("gpu__time_duration.sum")]) > 100.0]
     return sum(vals) / len(vals) if vals else None
 
