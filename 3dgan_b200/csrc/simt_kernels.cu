@@ -227,9 +227,46 @@ __global__ void im2col_small_kernel(const bf16* __restrict__ xs, bf16* __restric
     *reinterpret_cast<uint4*>(A + m * Kp + ch * 8) = outv;
   }
 }
+// specialisation for k = 5, Cs = 3, Kp = 80 (IWGAN c1 and the generator's last deconv): one thread builds a whole
+// 160-byte row -- each of the 5 filter rows is 15 consecutive bf16 of the input -- and stores it with ten
+// 16-byte writes (a quarter of the instructions of the generic kernel)
+__global__ void im2col_k5c3_kernel(const bf16* __restrict__ xs, bf16* __restrict__ A, ConvGeom g, long long rows) {
+  const unsigned short* x16 = reinterpret_cast<const unsigned short*>(xs);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < rows; m += stride) {
+    const int ow = (int)(m % g.Wo);
+    const int oh = (int)((m / g.Wo) % g.Ho);
+    const int n = (int)(m / ((long long)g.Wo * g.Ho));
+    const int ih0 = oh * g.stride - g.pad_t, iw0 = ow * g.stride - g.pad_l;
+    const long long base = (((long long)n * g.H + ih0) * g.W + iw0) * 3;
+    uint32_t w[40];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const bool rok = (unsigned)(ih0 + r) < (unsigned)g.H;
+      const long long rb = base + (long long)r * g.W * 3;
+#pragma unroll
+      for (int e = 0; e < 15; ++e) {
+        const bool ok = rok && (unsigned)(iw0 + e / 3) < (unsigned)g.W;
+        const uint32_t v = ok ? (uint32_t)x16[rb + e] : 0u;
+        const int j = r * 15 + e;
+        if (j & 1) w[j >> 1] |= v << 16;
+        else w[j >> 1] = v;
+      }
+    }
+    w[38] = 0u; w[39] = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(A + m * 80);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  }
+}
 int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaStream_t st) {
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
   if (Kp > 128) return -1;
+  if (a.k == 5 && a.Cs == 3 && Kp == 80 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {
+    const long long rows = (long long)a.N * a.Ho * a.Wo;
+    im2col_k5c3_kernel<<<stride_grid(rows, 128, 1), 128, 0, st>>>((const bf16*)xs, (bf16*)A, g, rows);
+    return 0;
+  }
   const long long total = (long long)a.N * a.Ho * a.Wo * (Kp / 8);
   im2col_small_kernel<<<stride_grid(total, 256, 1), 256, 0, st>>>((const bf16*)xs, (bf16*)A, g, Kp, total);
   return 0;
@@ -795,6 +832,48 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __re
     dz[i] = __float2bfloat16(v);
   }
 }
+// slab version (C % 8 == 0): per-channel coefficients once per block in shared memory, 16-byte accesses
+//   dz = a*g + b*z + c   with  a = rstd,  b = -rstd^2*s2/R,  c = -rstd*s1/R + rstd^2*s2/R*mean
+__global__ void bn_bwd_apply_vec_kernel(const bf16* __restrict__ g, const bf16* __restrict__ z, const float* __restrict__ stats,
+                                        const float* __restrict__ bsum, bf16* dz, long long R, int C, float eps,
+                                        int rows_per_block) {
+  __shared__ float ca[kBnSlab], cb[kBnSlab], cc[kBnSlab];
+  const int cs0 = blockIdx.x * kBnSlab;
+  const int cw = min(kBnSlab, C - cs0);
+  const float invR = 1.f / (float)R;
+  for (int c = threadIdx.x; c < cw; c += blockDim.x) {
+    const float mean = stats[cs0 + c] * invR;
+    const float rstd = rsqrtf(fmaxf(stats[C + cs0 + c] * invR - mean * mean, 0.f) + eps);
+    const float s1 = bsum[cs0 + c] * invR, s2 = bsum[C + cs0 + c] * invR;
+    ca[c] = rstd;
+    cb[c] = -rstd * rstd * s2;
+    cc[c] = -rstd * s1 + rstd * rstd * s2 * mean;
+  }
+  __syncthreads();
+  const int cpr = cw >> 3;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  const int total = (int)(r1 - r0) * cpr;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int rr = t / cpr, ch = t - rr * cpr;
+    const long long e0 = (r0 + rr) * C + cs0 + ch * 8;
+    const uint4 gv = *reinterpret_cast<const uint4*>(g + e0);
+    const uint4 zv = *reinterpret_cast<const uint4*>(z + e0);
+    const uint32_t g4[4] = {gv.x, gv.y, gv.z, gv.w}, z4[4] = {zv.x, zv.y, zv.z, zv.w};
+    uint32_t o4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ch * 8 + 2 * j;
+      const float glo = __uint_as_float(g4[j] << 16), ghi = __uint_as_float(g4[j] & 0xffff0000u);
+      const float zlo = __uint_as_float(z4[j] << 16), zhi = __uint_as_float(z4[j] & 0xffff0000u);
+      const float a = fmaf(ca[c], glo, fmaf(cb[c], zlo, cc[c]));
+      const float b = fmaf(ca[c + 1], ghi, fmaf(cb[c + 1], zhi, cc[c + 1]));
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      o4[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dz + e0) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+  }
+}
 int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* dz, long long R, int C, float eps,
            cudaStream_t st) {
   const int threads = 128;
@@ -805,7 +884,17 @@ int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* 
   const int rpb = (int)((R + want - 1) / want);
   const int gy = (int)((R + rpb - 1) / rpb);
   bn_bwd_sums_kernel<<<dim3(gx, gy), threads, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, R, C, eps, rpb);
-  bn_bwd_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, (bf16*)dz, R, C, eps);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz);
+  if ((C & 7) == 0 && (al & 15) == 0) {
+    const int sx = (C + kBnSlab - 1) / kBnSlab;
+    long long w2 = ((long long)num_sms() * 8 + sx - 1) / sx;
+    if (w2 > R) w2 = R;
+    const int rpb2 = (int)((R + w2 - 1) / w2);
+    const int sy = (int)((R + rpb2 - 1) / rpb2);
+    bn_bwd_apply_vec_kernel<<<dim3(sx, sy), 256, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, (bf16*)dz, R, C, eps, rpb2);
+  } else {
+    bn_bwd_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, (bf16*)dz, R, C, eps);
+  }
   return 0;
 }
 
