@@ -26,9 +26,11 @@ def gan(x, args):
     H, W, C = x.shape
     assert H == W, "GAN family expects square images"
 
-    def tower(batch01, train):
+    def tower(batch01, train, before_critic=None):
         """One sess.run-equivalent on this rank's tower: forward + losses.  `train` in {'d','g'}
-        selects whose variables are being differentiated (models/gan.py:55-68)."""
+        selects whose variables are being differentiated (models/gan.py:55-68).  `before_critic` runs
+        between the generator forward and the first critic kernel (the previous run's critic update, which
+        overlaps the generator forward, is joined there)."""
         g_params = store.collection('generator')
         d_params = store.collection('discriminator')
         active = {'d': d_params, 'g': g_params, 'dg': d_params + g_params}[train]
@@ -36,6 +38,8 @@ def gan(x, args):
         with E.recording(True, active=active):
             with variable_scope('generator'), E.recording(train != 'd'):   # G is a constant for d_loss
                 g = generator(B, args.latent_size, args, H, C)
+            if before_critic is not None:
+                before_critic()
             with variable_scope('discriminator'):
                 d_real = discriminator(xr, args, H, C)
                 d_fake = discriminator(g, args, H, C, reuse=True)
@@ -59,16 +63,34 @@ def gan(x, args):
 
     clip = 0.01 if args.model == 'wgan' else 0.0                      # gan.py:142-143
 
-    def d_run():
+    pending = [False]                             # a critic exchange is in flight on the side stream
+
+    def finish_pending():
+        """Join the deferred gradient exchange of the previous critic run and apply its update."""
+        if pending[0]:
+            sess.join_updates()
+            d_group.apply_gradients(1.0 / sess.world, clip)
+            pending[0] = False
+
+    def before_critic_d():
+        finish_pending()
         d_group.zero_grad()
-        g_loss, d_loss = tower(x.next(), 'd')
+
+    def d_run():
+        g_loss, d_loss = tower(x.next(), 'd', before_critic_d)
         E.backward([(d_loss, None)])
-        d_group.apply_gradients(sess.all_reduce_grads(d_group), clip)
+        if sess.dist is not None and sess.overlap_updates:
+            # multi-GPU: the all-reduce runs on a side stream and overlaps the next run's generator forward
+            # (which reads no critic variable); the update itself is applied when that run reaches the critic
+            sess.defer_update(lambda: sess.all_reduce_grads(d_group))
+            pending[0] = True
+        else:
+            d_group.apply_gradients(sess.all_reduce_grads(d_group), clip)
         return g_loss, d_loss
 
     def g_run():
         g_group.zero_grad()
-        g_loss, d_loss = tower(x.next(), 'g')
+        g_loss, d_loss = tower(x.next(), 'g', finish_pending)
         E.backward([(g_loss, None)])
         g_group.apply_gradients(sess.all_reduce_grads(g_group), clip)
         return g_loss, d_loss
@@ -91,6 +113,7 @@ def gan(x, args):
                 d_run()
                 store.begin_pass()
             gl, dl = g_run()
+        finish_pending()
         return {'g_loss': gl.buf, 'd_loss': dl.buf}
 
     def helper(sess_, args_):

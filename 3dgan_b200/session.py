@@ -93,6 +93,10 @@ class Session:
         self.graphs = {}
         self.use_graphs = os.environ.get("B200GAN_CUDA_GRAPHS", "1") != "0"
         self.dist = None
+        # gradient exchange + optimizer update of one run overlap the start of the next run (side stream)
+        self.overlap_updates = os.environ.get("B200GAN_OVERLAP_UPDATE", "1") != "0"
+        self._side = None
+        self._join_event = None
         _current = self
 
     # ---------------------------------------------------------------- build / run modes
@@ -143,6 +147,39 @@ class Session:
         if self.dist is not None:
             self.dist.all_reduce(group.g32)
         return 1.0 / self.world
+
+    # ---------------------------------------------------------------- overlapped parameter updates
+    def defer_update(self, fn):
+        """Run `fn` (the gradient all-reduce of one optimizer group: it touches only that group's gradient
+        bucket and allocates nothing) on a side stream, ordered after everything issued so far.  The caller
+        goes on with work that does not touch that bucket and calls `join_updates()` before the update.
+        Inside a CUDA-graph capture the fork / join become graph edges, so the exchange runs concurrently
+        with the next run's generator forward.  (Also running the optimizer kernel there was measured
+        slower on one GPU: its blocks crowd the GEMM CTAs out of the SMs.)"""
+        if not self.overlap_updates or E.S.dry:
+            fn()
+            return
+        import ctypes
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        prev = E.S.stream
+        E.S.stream = ctypes.c_void_p(self._side.cuda_stream)
+        try:
+            with torch.cuda.stream(self._side):
+                fn()
+                self._join_event = torch.cuda.Event()
+                self._join_event.record(self._side)
+        finally:
+            E.S.stream = prev
+
+    def join_updates(self):
+        if self._join_event is not None:
+            torch.cuda.current_stream().wait_event(self._join_event)
+            self._join_event = None
 
     # ---------------------------------------------------------------- CUDA graphs
     def run(self, key, fn):
