@@ -38,14 +38,16 @@ def variable_scope(name):
 
 
 # Channel counts C with C % 16 == 8 (the reference's 200-channel layers) make every NHWC pixel row start on an
-# odd 16-byte boundary, which costs the TMA loads of the GEMM operands about 20%.  Such layers are stored with
-# 8 extra zero channels: the padded weights / biases are zero, get zero gradients and stay zero, so the TF
-# variables (the leading block of each padded array) see exactly the reference's arithmetic.
+# odd 16-byte boundary, which costs the TMA loads of the GEMM operands about 20%; counts that are not a
+# multiple of 8 (the 100-channel deconv of the 64x64 generator at L=200) cannot be addressed by TMA at all.
+# Layers wider than 8 channels are therefore stored with their channel count rounded up to a multiple of 16:
+# the padded weights / biases are zero, get zero gradients and stay zero, so the TF variables (the leading
+# block of each padded array) see exactly the reference's arithmetic.
 CHANNEL_PAD = os.environ.get("B200GAN_CHANNEL_PAD", "1") != "0"
 
 
 def physical_channels(c):
-    return c + 8 if (CHANNEL_PAD and c % 16 == 8 and c >= 24) else c
+    return (c + 15) // 16 * 16 if (CHANNEL_PAD and c > 8) else c
 
 
 def _logical_c(x):

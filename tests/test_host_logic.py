@@ -236,7 +236,7 @@ def test_channel_padding_is_layout_only():
     import torch
     from b200gan.ops import layers as L
     from b200gan import variables as V
-    assert [L.physical_channels(c) for c in (3, 8, 24, 72, 200, 208, 400, 800)] == [3, 8, 32, 80, 208, 208, 400, 800]
+    assert [L.physical_channels(c) for c in (3, 8, 24, 72, 100, 200, 208, 400, 800)] == [3, 8, 32, 80, 112, 208, 208, 400, 800]
     sess = S.Session()
     x = S.Input(8, (32, 32, 3), slots=6)
     gan_model.gan(x, _args("iwgan", Lz=200))

@@ -12,6 +12,14 @@ def test_iwgan_step_matches_oracle(H, C, L, B):
     assert res["ok"], res
 
 
+def test_iwgan_reference_native_64x64_L200_step_matches_oracle():
+    """The reference's own default shape (64x64x3, latent 200): its 100-channel deconv only runs because the
+    layer API pads channel counts to multiples of 16.  The generator has one more BN+ReLU stage than at 32x32,
+    so the bf16 mask-flip noise of the earliest generator layers is larger (measured 4.3e-2; critic <= 1.6e-2)."""
+    res = P.iwgan_step_parity(H=64, C=3, L=200, B=16, verbose=True, grad_tol=6e-2)
+    assert res["ok"], res
+
+
 def test_iwgan_step_without_channel_padding_matches_oracle():
     """BASELINE's L=200 config with the 200 -> 208 channel padding switched off: same parity bar."""
     from b200gan.ops import layers as L
