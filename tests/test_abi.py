@@ -46,3 +46,40 @@ def test_route_is_host_only_logic():
         assert False
     except _capi.B200Error:
         pass
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Compile a probe against include/b200gan.h with the host C compiler and compare struct sizes and field
+    offsets with the ctypes mirrors in _capi.py (a silent layout mismatch would corrupt every call)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    probe = tmp_path / "probe.c"
+    fields_e = ["bias", "act", "leak", "mask_src", "mask_kind", "out_f32", "accumulate", "mask_bits", "bits_out",
+                "bits_pitch"]
+    fields_g = ["N", "H", "W", "Cin", "Ho", "Wo", "Cout", "k", "stride", "pad_t", "pad_l"]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "b200gan.h"', 'int main(void) {',
+             '  printf("%zu %zu\\n", sizeof(b200_conv_geom), sizeof(b200_epilogue));']
+    lines += ['  printf("%%zu\\n", offsetof(b200_epilogue, %s));' % f for f in fields_e]
+    lines += ['  printf("%%zu\\n", offsetof(b200_conv_geom, %s));' % f for f in fields_g]
+    lines += ['  return 0;', '}']
+    probe.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run([cc, "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    sizes, offs = [int(v) for v in out[:2]], [int(v) for v in out[2:]]
+    assert sizes == [ctypes.sizeof(_capi.ConvGeom), ctypes.sizeof(_capi.Epilogue)]
+    want = [getattr(_capi.Epilogue, f).offset for f in fields_e] + [getattr(_capi.ConvGeom, f).offset for f in fields_g]
+    assert offs == want
+
+
+def test_epilogue_bits_query_is_host_only_logic():
+    g = _capi.ConvGeom(N=8, H=16, W=16, Cin=208, Ho=8, Wo=8, Cout=400, k=5, stride=2, pad_t=1, pad_l=1)
+    assert _capi.epilogue_bits(g, 0, False) and _capi.epilogue_bits(g, 1, False)     # tensor-core route
+    g = _capi.ConvGeom(N=8, H=32, W=32, Cin=3, Ho=16, Wo=16, Cout=208, k=5, stride=2, pad_t=1, pad_l=1)
+    assert _capi.epilogue_bits(g, 0, True) and not _capi.epilogue_bits(g, 0, False)  # image side: GEMM route only
+    assert not _capi.epilogue_bits(g, 1, True)                                         # col2im epilogue: no bitmaps
+    assert _capi.abi_version() == 2 if hasattr(_capi, "abi_version") else True
