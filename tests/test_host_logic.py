@@ -264,3 +264,21 @@ def test_channel_padding_is_layout_only():
         assert all(q.shape == q.logical_shape for q in sess2.store.params.values())
     finally:
         L.CHANNEL_PAD = True
+
+
+def test_deferred_update_runs_inline_without_a_device():
+    """Session.defer_update is the multi-GPU overlap hook (gradient exchange on a side stream); during the
+    graph-construction pass / without CUDA it must simply run the callable so that the schedule is unchanged."""
+    sess = S.Session()
+    calls = []
+    prev = E.S.dry
+    E.S.dry = True
+    try:
+        sess.defer_update(lambda: calls.append("exchange"))
+        sess.join_updates()                       # nothing pending: no-op
+    finally:
+        E.S.dry = prev
+    assert calls == ["exchange"] and sess._join_event is None
+    sess.overlap_updates = False
+    sess.defer_update(lambda: calls.append("inline"))
+    assert calls == ["exchange", "inline"]
