@@ -46,8 +46,8 @@ if os.path.exists(rep):
     idx = [hdr.index(w) for w in want if w in hdr]
     with open(os.path.join(out_dir, "%s_ncu_kernels.csv" % tag), "w") as f:
         w = csv.writer(f)
-        w.writerow(["# ncu --set full --clock-control none, tools/prof_kernels.py: c2 (16x16x200->8x8x400), c3 (8x8x400->4x4x800), "
-                    "c1 (32x32x3->16x16x200) fprop/dgrad/wgrad at B=512"])
+        w.writerow(["# ncu --set full --clock-control none, tools/prof_kernels.py: c2 (16x16x208->8x8x400, 200 logical channels), c3 (8x8x400->4x4x800), "
+                    "c1 (32x32x3->16x16x208) fprop/dgrad/wgrad at B=512"])
         w.writerow([hdr[i] for i in idx])
         w.writerow([units[i] for i in idx])
         for r in rows[2:]:
