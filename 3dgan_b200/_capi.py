@@ -50,11 +50,12 @@ SIGNATURES = {
     "b200_fill_f32": [_P, _LL, _F, _P],
     "b200_interp": [_P, _P, _P, _P, _I, _I, _P],
     "b200_rowscale": [_P, _P, _F, _F, _P, _I, _I, _P],
+    "b200_slice_cols": [_P, _LL, _I, _P, _LL, _I, _LL, _I, _P, _I, _F, _P],
     "b200_transpose_to_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "b200_colsum": [_P, _P, _P, _LL, _I, _F, _P],
     "b200_reduce_sum": [_P, _I, _LL, _P, _F, _I, _P],
     "b200_wgan_loss": [_P, _I, _I, _F, _P, _P],
-    "b200_eltloss": [_P, _I, _P, _LL, _I, _F, _F, _F, _P, _P, _I, _P],
+    "b200_eltloss": [_P, _I, _P, _LL, _I, _F, _F, _F, _P, _P, _I, _I, _F, _P],
     "b200_philox": [_P, _I, _LL, _ULL, _P, _U, _I, _P],
     "b200_optim_step": [_P, _P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _F, _P, _P],
     "b200_device_check": [],

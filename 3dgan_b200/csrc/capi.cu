@@ -656,7 +656,7 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
 // thin wrappers
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
-extern "C" int b200_abi_version(void) { return 2; }
+extern "C" int b200_abi_version(void) { return 3; }
 extern "C" int b200_device_check(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device"); }
@@ -712,6 +712,11 @@ extern "C" int b200_rowscale(const void* in, const float* s_row, float mul, floa
                              b200_stream s) {
   WRAP(rowscale(in, s_row, mul, add, out, B, D, (cudaStream_t)s), "rowscale");
 }
+extern "C" int b200_slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off,
+                               long long rows, int cols, const void* mask, int mask_kind, float leak, b200_stream s) {
+  WRAP(slice_cols(in, in_ld, in_off, out, out_ld, out_off, rows, cols, mask, mask_kind, leak, (cudaStream_t)s),
+       "slice_cols");
+}
 extern "C" int b200_transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, b200_stream s) {
   WRAP(transpose_to_bf16(in, in_f32, out, T, A, B, (cudaStream_t)s), "transpose_to_bf16");
 }
@@ -727,8 +732,10 @@ extern "C" int b200_wgan_loss(const float* sums, int B, int use_gp, float lambda
   WRAP(wgan_loss(sums, B, use_gp, lambda, out4, (cudaStream_t)s), "wgan_loss");
 }
 extern "C" int b200_eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float label, float scale,
-                            float gscale, float* out_sum, void* grad, int grad_f32, b200_stream s) {
-  WRAP(eltloss(a, a_f32, b, n, kind, label, scale, gscale, out_sum, grad, grad_f32, (cudaStream_t)s), "eltloss");
+                            float gscale, float* out_sum, void* grad, int grad_f32, int mask_kind, float leak,
+                            b200_stream s) {
+  WRAP(eltloss(a, a_f32, b, n, kind, label, scale, gscale, out_sum, grad, grad_f32, mask_kind, leak, (cudaStream_t)s),
+       "eltloss");
 }
 extern "C" int b200_philox(void* out, int out_f32, long long n, unsigned long long seed,
                            unsigned long long* dev_draw_counter, unsigned int stream_id, int normal, b200_stream s) {

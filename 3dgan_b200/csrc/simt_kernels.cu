@@ -592,6 +592,54 @@ int rowscale(const void* in, const float* s, float mul, float add, void* out, in
   return 0;
 }
 
+// out[r, out_off + c] = in[r, in_off + c] * act'(mask[r, c])  for c < cols: column-slice copy between row-major bf16
+// matrices with different row strides.  Channel concatenation (pix2pix skip connections, hem/models/pix2pix.py:
+// 210-222) writes each piece into its slice of the concat buffer; its backward reads the slice back and applies
+// the piece's activation gradient in the same pass; also strips / restores zero channel padding.
+template <int kVec>
+__global__ void slice_cols_kernel(const bf16* __restrict__ in, long long in_ld, int in_off, bf16* __restrict__ out,
+                                  long long out_ld, int out_off, long long rows, int cols,
+                                  const bf16* __restrict__ mask, int mask_kind, float leak) {
+  const int cpr = cols / kVec;                               // chunks per row
+  const long long total = rows * cpr;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long r = i / cpr;
+    const int c = (int)(i - r * cpr) * kVec;
+    const bf16* src = in + r * in_ld + in_off + c;
+    bf16* dst = out + r * out_ld + out_off + c;
+    if (kVec == 8) {
+      uint4 v = *reinterpret_cast<const uint4*>(src);
+      if (mask) {
+        const uint4 mv = *reinterpret_cast<const uint4*>(mask + r * cols + c);
+        bf16* vp = reinterpret_cast<bf16*>(&v);
+        const bf16* mp = reinterpret_cast<const bf16*>(&mv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          vp[j] = __float2bfloat16(__bfloat162float(vp[j]) * act_grad_from_out(__bfloat162float(mp[j]), mask_kind, leak));
+      }
+      *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+      float v = __bfloat162float(*src);
+      if (mask) v *= act_grad_from_out(__bfloat162float(mask[r * cols + c]), mask_kind, leak);
+      *dst = __float2bfloat16(v);
+    }
+  }
+}
+int slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off, long long rows,
+               int cols, const void* mask, int mask_kind, float leak, cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return -1;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask);
+  const bool vec = ((cols | in_off | out_off) & 7) == 0 && ((in_ld | out_ld) & 7) == 0 && (al & 15) == 0;
+  if (vec)
+    slice_cols_kernel<8><<<stride_grid(rows * (cols / 8), 256, 2), 256, 0, st>>>(
+        (const bf16*)in, in_ld, in_off, (bf16*)out, out_ld, out_off, rows, cols, (const bf16*)mask, mask_kind, leak);
+  else
+    slice_cols_kernel<1><<<stride_grid(rows * cols, 256, 4), 256, 0, st>>>(
+        (const bf16*)in, in_ld, in_off, (bf16*)out, out_ld, out_off, rows, cols, (const bf16*)mask, mask_kind, leak);
+  return 0;
+}
+
 // [T][A][B] -> [T][B][A], fp32 or bf16 in, bf16 out (weight re-layout for the K-major GEMM operand)
 template <typename TI>
 __global__ void transpose_kernel(const TI* __restrict__ in, bf16* out, int A, int B) {
@@ -1032,10 +1080,13 @@ int wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out, cu
 //   kind 4  sigmoid-CE(logits a, label scalar `lab`)          dl/da = sigmoid(a)-lab
 //   kind 5  squared error (a-b)^2                             dl/da = 2(a-b)
 //   kind 6  0.5 a^2 ; kind 7  0.5 (a^2 - log(eps+a^2) - 1)    VAE latent loss pieces (models/vae.py:80-81)
-// out_sum[0] += scale * sum l ;  grad[i] = gscale * dl/da  (bf16 or fp32), optional
+// out_sum[0] += scale * sum l ;  grad[i] = gscale * dl/da * act'(a)  (bf16 or fp32), optional; act' is the
+// derivative of the activation `mask_kind` that PRODUCED a, evaluated at a (0 = none): the gradient w.r.t. the
+// pre-activation in one fp32 expression (Bernoulli loss behind a sigmoid: (1-b)/(1-a) * a(1-a) must not be
+// rounded in between)
 template <typename TA, typename TG>
 __global__ void eltloss_kernel(const TA* __restrict__ a, const bf16* __restrict__ b, long long n, int kind, float lab,
-                               float scale, float gscale, float* out_sum, TG* grad) {
+                               float scale, float gscale, float* out_sum, TG* grad, int mask_kind, float leak) {
   float s = 0.f;
   const float eps = 1e-8f;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1055,7 +1106,7 @@ __global__ void eltloss_kernel(const TA* __restrict__ a, const bf16* __restrict_
       default: l = (av - bv) * (av - bv); d = 2.f * (av - bv); break;
     }
     s += l;
-    if (grad) grad[i] = (TG)(d * gscale);
+    if (grad) grad[i] = (TG)(d * gscale * act_grad_from_out(av, mask_kind, leak));
   }
   __shared__ float ws[32];
   s = warp_sum(s);
@@ -1068,13 +1119,13 @@ __global__ void eltloss_kernel(const TA* __restrict__ a, const bf16* __restrict_
   }
 }
 int eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float lab, float scale, float gscale,
-            float* out_sum, void* grad, int grad_f32, cudaStream_t st) {
+            float* out_sum, void* grad, int grad_f32, int mask_kind, float leak, cudaStream_t st) {
   int grid = stride_grid(n, 256, 8);
   if (grid > num_sms() * 2) grid = num_sms() * 2;
-  if (a_f32 && grad_f32) eltloss_kernel<float, float><<<grid, 256, 0, st>>>((const float*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (float*)grad);
-  else if (a_f32) eltloss_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (bf16*)grad);
-  else if (grad_f32) eltloss_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (float*)grad);
-  else eltloss_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (bf16*)grad);
+  if (a_f32 && grad_f32) eltloss_kernel<float, float><<<grid, 256, 0, st>>>((const float*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (float*)grad, mask_kind, leak);
+  else if (a_f32) eltloss_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (bf16*)grad, mask_kind, leak);
+  else if (grad_f32) eltloss_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (float*)grad, mask_kind, leak);
+  else eltloss_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)a, (const bf16*)b, n, kind, lab, scale, gscale, out_sum, (bf16*)grad, mask_kind, leak);
   return 0;
 }
 

@@ -37,6 +37,8 @@ int mul_add(const void* a, const void* b, const void* c, void* out, long long n,
 int fill_f32(float* out, long long n, float v, cudaStream_t st);
 int interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, cudaStream_t st);
 int rowscale(const void* in, const float* s, float mul, float add, void* out, int B, int D, cudaStream_t st);
+int slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off, long long rows,
+               int cols, const void* mask, int mask_kind, float leak, cudaStream_t st);
 int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, cudaStream_t st);
 int colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, cudaStream_t st);
 int bn_sums(const void* z, float* stats, long long R, int C, cudaStream_t st);
@@ -51,7 +53,7 @@ int outer_mask(const float* g, const void* w, const void* mask, void* out, int M
 int reduce_sum(const void* x, int x_f32, long long n, float* out, float alpha, int sq, cudaStream_t st);
 int wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out, cudaStream_t st);
 int eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float lab, float scale, float gscale,
-            float* out_sum, void* grad, int grad_f32, cudaStream_t st);
+            float* out_sum, void* grad, int grad_f32, int mask_kind, float leak, cudaStream_t st);
 int philox_fill(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* draw,
                 unsigned int stream_id, int normal, cudaStream_t st);
 int optim_step(float* p, float* m, float* v, const float* g, void* p16, long long n, int kind, float lr, float b1,

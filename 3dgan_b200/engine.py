@@ -14,6 +14,7 @@ backward receives the gradient w.r.t. its raw (pre-activation) output.
 import ctypes as C
 import math
 import os
+import weakref
 
 import torch
 
@@ -32,6 +33,9 @@ class _State:
     device = None
     launches = 0               # kernels launched through the C ABI (bench.py reports it)
     profile = None             # list -> per-launch CUDA-event records of the conv-family launches
+    decisions = None           # list -> (kind, tensors) of every discontinuous decision of the forward (tests)
+    cyclic = []                # weak refs to tensors that sit on a reference cycle (self-mask, tape node)
+    f32_out = False            # layer outputs are kept in fp32 (loss heads of the autoencoders)
 
 
 S = _State()
@@ -42,9 +46,21 @@ def _p(t):
 
 
 def begin(device=None):
-    """Bind the engine to torch's current device/stream for the calls that follow."""
+    """Bind the engine to torch's current device/stream for the calls that follow.  The previous step's tape is
+    dropped: its tensors reference themselves (`t.mask = (t, ...)`) and their nodes, which would otherwise keep
+    the step's activations alive until Python's cyclic collector runs."""
     S.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
     S.stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    release_tape()
+
+
+def release_tape():
+    live, S.cyclic = S.cyclic, []
+    for r in live:
+        t = r()
+        if t is not None:
+            t.mask = None
+            t.node = None
 
 
 def launch(name, *args, n=1, flops=0, tag=None):
@@ -92,6 +108,26 @@ def empty(shape, dtype=BF16):
     return torch.empty(shape, dtype=dtype, device="meta" if S.dry else S.device)
 
 
+class f32_outputs:
+    """Layers built inside this context store their output in fp32 instead of bf16.  The autoencoders use it
+    for the final tanh / sigmoid layer, whose values feed the reconstruction loss directly: rounding a
+    sigmoid output near 0 or 1 to bf16 destroys the Bernoulli loss gradient there (models/vae.py:76-79)."""
+
+    def __enter__(self):
+        self.prev, S.f32_out = S.f32_out, True
+
+    def __exit__(self, *a):
+        S.f32_out = self.prev
+
+
+def _decision(kind, *tensors):
+    """Verification hook (tests/parity.py): remember where the forward pass took a discontinuous decision —
+    the sign masks of relu / lrelu outputs, the sign of an L1 residual — so that the oracle can be evaluated
+    on the same linear piece (oracle.tf_ops.inject_decisions)."""
+    if S.decisions is not None and not S.dry:
+        S.decisions.append((kind,) + tensors)
+
+
 class _All(frozenset):
     """Sentinel active-set: every variable is trainable (single-optimizer models)."""
 
@@ -119,19 +155,29 @@ class recording:
 
 # ------------------------------------------------------------------------------------------ tensors
 class Tensor:
-    __slots__ = ("buf", "shape", "requires_grad", "mask", "node", "grad_f32", "im2col", "bits", "logical_c",
+    __slots__ = ("buf", "shape", "requires_grad", "_mask", "node", "grad_f32", "im2col", "bits", "logical_c",
                  "__weakref__")
 
     def __init__(self, buf, shape=None, requires_grad=False, mask=None):
         self.buf = buf
         self.shape = tuple(buf.shape if shape is None else shape)
         self.requires_grad = requires_grad
-        self.mask = mask
+        self._mask = mask
         self.node = None
         self.grad_f32 = False      # leaf whose gradient is wanted in fp32 (the GP interpolates)
         self.im2col = None         # (geometry key, workspace) left by a small-channel fprop of this tensor
         self.bits = None           # int16 [rows, ceil(C/16)] sign bitmap written by the producing relu/lrelu epilogue
         self.logical_c = None      # channels that carry data when the last dim is zero-padded (ops/layers.py)
+
+    @property
+    def mask(self):
+        return self._mask
+
+    @mask.setter
+    def mask(self, m):
+        self._mask = m
+        if m is not None and m[0] is self:
+            S.cyclic.append(weakref.ref(self))
 
     @property
     def f32(self):
@@ -165,6 +211,7 @@ def _record(inputs, outputs, bw, uses_active_param=False):
     for o in outputs:
         o.requires_grad = True
         o.node = n
+        S.cyclic.append(weakref.ref(o))
 
 
 class Param:
@@ -268,6 +315,7 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
         out_shape = (g.N, g.Ho, g.Wo, g.Cout)
     else:
         out_shape = (g.N, g.H, g.W, g.Cin)
+    out_f32 = out_f32 or S.f32_out
     out = Tensor(empty(out_shape, F32 if out_f32 else BF16))
     opi = 0 if direction == "fprop" else 1
     ws, wsb = _workspace(g, opi)
@@ -293,6 +341,8 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
         if out_mask is not None:
             raise K.B200Error("conv_like: activation and out_mask are mutually exclusive")
         out.mask = (out, act, leak)
+        if act in (K.ACT_RELU, K.ACT_LRELU):
+            _decision("act", out)
     else:
         out.mask = out_mask
 
@@ -387,6 +437,8 @@ def batch_norm_act(z, beta, act=K.ACT_NONE, leak=0.0, eps=1e-3):
     launch("b200_bn_apply", _p(z.buf), _p(stats), _p(beta.p32), _p(out.buf), R, Cc, eps, act, leak)
     if act != K.ACT_NONE:
         out.mask = (out, act, leak)
+        if act in (K.ACT_RELU, K.ACT_LRELU):
+            _decision("act", out)
 
     def bw(gouts):
         (go,) = gouts
@@ -423,6 +475,9 @@ def activation(x, act, leak=0.0):
     out = Tensor(empty(x.shape, BF16))
     launch("b200_affine_act", _p(x.buf), int(x.f32), _p(out.buf), 0, x.numel, 1.0, 0.0, act, leak)
     out.mask = (out, act, leak)
+    out.logical_c = x.logical_c
+    if act in (K.ACT_RELU, K.ACT_LRELU):
+        _decision("act", out)
 
     def bw(gouts):
         go = gouts[0]
@@ -449,14 +504,73 @@ def affine(x, mul, add, out_f32=False):
 
 def reshape(x, shape):
     shape = tuple(shape)
+    last = shape[-1]
+    if x.logical_c is not None and last != x.shape[-1]:
+        # the zero channel padding must not be mixed into the data when the last dim is re-cut
+        # (models/gan.py:284: the critic's c3 output -> rows of 4*4*4L, any latent_size)
+        x = unpad_channels(x)
     if -1 in shape:
         known = -int(math.prod(shape))
+        if known <= 0 or x.numel % known:
+            raise K.B200Error("reshape: cannot infer -1 in %s from %d elements" % (shape, x.numel))
         shape = tuple(x.numel // known if d == -1 else d for d in shape)
-    assert int(math.prod(shape)) == x.numel, (shape, x.shape)
+    if int(math.prod(shape)) != x.numel:
+        raise K.B200Error("reshape: %s -> %s changes the element count" % (x.shape, shape))
     out = Tensor(x.buf, shape, mask=x.mask)
+    if last == x.shape[-1]:
+        out.logical_c = x.logical_c
 
     def bw(gouts):
         return [reshape(gouts[0], x.shape)]     # through the op so second-order tapes stay connected
+
+    _record([x], [out], bw)
+    return out
+
+
+def _slice(src, src_ld, src_off, dst, dst_ld, dst_off, rows, cols, mask=None):
+    launch("b200_slice_cols", _p(src), src_ld, src_off, _p(dst), dst_ld, dst_off, rows, cols,
+           None if mask is None else _p(mask[0].buf), 0 if mask is None else mask[1], 0.0 if mask is None else mask[2])
+
+
+def unpad_channels(x):
+    """[..., C_physical] -> [..., C_logical]: drop the zero channels a layer added (ops/layers.py)."""
+    cl, cp = x.logical_c, x.shape[-1]
+    rows = x.numel // cp
+    if x.f32:
+        raise K.B200Error("unpad_channels expects a bf16 tensor")
+    out = Tensor(empty(x.shape[:-1] + (cl,), BF16))
+    _slice(x.buf, cp, 0, out.buf, cl, 0, rows, cl)
+    if x.mask is not None and x.mask[0] is x:
+        out.mask = (out, x.mask[1], x.mask[2])          # same activation values, own storage
+
+    def bw(gouts):
+        go = _as_bf16(gouts[0])
+        gx = Tensor(empty(x.shape, BF16))
+        launch("b200_fill_f32", _p(gx.buf), gx.numel // 2, 0.0)       # bf16 zeros, two per fp32 word
+        _slice(go.buf, cl, 0, gx.buf, cp, 0, rows, cl)
+        gx.logical_c = cl
+        return [gx]
+
+    _record([x], [out], bw)
+    return out
+
+
+def pad_channels(x, cp):
+    """[..., C] -> [..., cp] with zero channels appended (the inverse of unpad_channels): gives a dense layer whose
+    input width is not a multiple of 8 (e.g. latent_size 50) the 16-byte rows TMA needs."""
+    c = x.shape[-1]
+    rows = x.numel // c
+    xb = _as_bf16(x)
+    out = Tensor(empty(x.shape[:-1] + (cp,), BF16))
+    launch("b200_fill_f32", _p(out.buf), out.numel // 2, 0.0)
+    _slice(xb.buf, c, 0, out.buf, cp, 0, rows, c)
+    out.logical_c = c
+
+    def bw(gouts):
+        go = _as_bf16(gouts[0])
+        gx = Tensor(empty(x.shape, BF16), mask=x.mask)
+        _slice(go.buf, cp, 0, gx.buf, c, 0, rows, c, x.mask)
+        return [gx]
 
     _record([x], [out], bw)
     return out
@@ -470,16 +584,33 @@ def add_grads(a, b):
 
 
 def concat_channels(xs):
-    """NHWC channel concat (pix2pix skip connections).  Copy through torch (plumbing, not math)."""
-    out = Tensor(torch.cat([t.torch() for t in xs], dim=-1).contiguous())
+    """NHWC channel concat (tf.concat(axis=1) of the NCHW reference: pix2pix skip connections and the PatchGAN's
+    rgb+depth input, hem/models/pix2pix.py:210-222,250): every piece is copied into its column slice of the
+    output; the backward reads the slice back and applies the piece's activation gradient in the same pass."""
+    for t in xs:
+        if t.logical_c is not None or t.f32:
+            raise K.B200Error("concat_channels: pieces must be unpadded bf16 tensors")
     sizes = [t.shape[-1] for t in xs]
+    ctot = sum(sizes)
+    rows = xs[0].numel // sizes[0]
+    out = Tensor(empty(xs[0].shape[:-1] + (ctot,), BF16))
+    o = 0
+    for t, c in zip(xs, sizes):
+        if t.numel // c != rows:
+            raise K.B200Error("concat_channels: pieces disagree on the leading dims")
+        _slice(t.buf, c, 0, out.buf, ctot, o, rows, c)
+        o += c
 
     def bw(gouts):
-        go = gouts[0].torch()
+        go = _as_bf16(gouts[0])
         outs, o = [], 0
         for t, c in zip(xs, sizes):
-            piece = Tensor(go[..., o:o + c].contiguous())
-            outs.append(maskmul(piece, t.mask) if t.mask is not None else piece)
+            if t.requires_grad:
+                piece = Tensor(empty(t.shape, BF16), mask=t.mask)
+                _slice(go.buf, ctot, o, piece.buf, c, 0, rows, c, t.mask)
+                outs.append(piece)
+            else:
+                outs.append(None)
             o += c
         return outs
 
@@ -597,15 +728,20 @@ def eltloss(a, b, kind, label=0.0, scale=1.0):
     out = Tensor(empty((1,), F32))
     launch("b200_fill_f32", _p(out.buf), 1, 0.0)
     launch("b200_eltloss", _p(a.buf), int(a.f32), None if b is None else _p(b.buf), a.numel, kind, label, scale, 0.0,
-           _p(out.buf), None, 0)
+           _p(out.buf), None, 0, 0, 0.0)
+    if kind == 0:
+        _decision("l1", a, b)
 
     def bw(gouts):
         seed = gouts[0]
         mult = seed[1] if isinstance(seed, tuple) else 1.0      # True = seed 1.0; ("scaled", s) = seed s
         g = Tensor(empty(a.shape, F32 if a.f32 else BF16))
+        # a = act(raw) produced by the layer itself: dl/d(raw) = dl/da * act'(a) in one pass, in fp32 (the two
+        # factors of the Bernoulli loss behind a sigmoid are ~1/(1-a) and ~(1-a): they must not be rounded apart)
+        own = a.mask is not None and a.mask[0] is a
         launch("b200_eltloss", _p(a.buf), int(a.f32), None if b is None else _p(b.buf), a.numel, kind, label, 0.0,
-               scale * mult, None, _p(g.buf), int(a.f32))
-        if a.mask is not None:
+               scale * mult, None, _p(g.buf), int(a.f32), a.mask[1] if own else 0, a.mask[2] if own else 0.0)
+        if a.mask is not None and not own:
             g = maskmul_any(g, a.mask)
         return [g]
 
@@ -658,24 +794,26 @@ def backward(seeds, wrt=(), create_graph=False, accumulate=True):
         if t.node is not None:
             nodes[t.node.seq] = t.node
 
-    for t, g in seeds:
-        push(t, True if g is None else g)
-    with recording(create_graph):
-        while nodes:
-            seq = max(nodes)
-            node = nodes.pop(seq)
-            gouts = []
-            for o in node.outputs:
-                ent = grads.pop(id(o), None) if not any(o is w for w in wrt) else grads.get(id(o))
-                gouts.append(None if ent is None else ent[1])
-            if all(g is None for g in gouts):
-                continue
-            S.active = node.active      # the variables that were trainable when the node was recorded
-            gins = node.bw(gouts)
-            for inp, gi in zip(node.inputs, gins):
-                if gi is not None and inp.requires_grad:
-                    push(inp, gi)
-    S.accumulate, S.active = prev_acc, prev_active
+    try:
+        for t, g in seeds:
+            push(t, True if g is None else g)
+        with recording(create_graph):
+            while nodes:
+                seq = max(nodes)
+                node = nodes.pop(seq)
+                gouts = []
+                for o in node.outputs:
+                    ent = grads.pop(id(o), None) if not any(o is w for w in wrt) else grads.get(id(o))
+                    gouts.append(None if ent is None else ent[1])
+                if all(g is None for g in gouts):
+                    continue
+                S.active = node.active      # the variables that were trainable when the node was recorded
+                gins = node.bw(gouts)
+                for inp, gi in zip(node.inputs, gins):
+                    if gi is not None and inp.requires_grad:
+                        push(inp, gi)
+    finally:
+        S.accumulate, S.active = prev_acc, prev_active     # an exception in a rule must not corrupt the tape state
     return [grads[id(w)][1] if id(w) in grads else None for w in wrt]
 
 

@@ -106,5 +106,6 @@ def decoder(x, latent_size, sizes, C=3, reuse=False, final=tanh):
         x = deconv2d(x, 256, 256, 5, 2, name='dc1', output_shape=(sizes[3], sizes[3]))
         x = deconv2d(x, 256, 128, 5, 2, name='dc2', output_shape=(sizes[2], sizes[2]))
         x = deconv2d(x, 128, 64, 5, 2, name='dc3', output_shape=(sizes[1], sizes[1]))
-        x = deconv2d(x, 64, C, 5, 2, name='dc4', activation=final, output_shape=(sizes[0], sizes[0]))
+        with E.f32_outputs():       # the reconstruction feeds the loss directly: keep it in fp32
+            x = deconv2d(x, 64, C, 5, 2, name='dc4', activation=final, output_shape=(sizes[0], sizes[0]))
     return x

@@ -114,18 +114,28 @@ def _finish(h, use_batch_norm, activation, fused):
 def dense(x, input_size, output_size, init=xavier_initializer, use_batch_norm=False, activation=None,
           reuse=False, name=None):
     """ops/layers.py:27-62 — act(BN(x W + b)), W [input_size, output_size]."""
-    W, b = _variables(name, (input_size, output_size), (output_size,), init)
-    act, leak, ok = _fusable(activation)
-    fuse = ok and not use_batch_norm
+    assert _logical_c(x) == input_size, "dense %s: input has %d features, input_size=%d" % (name, _logical_c(x), input_size)
     M = x.shape[0]
     if output_size == 1:
+        if x.logical_c is not None:
+            x = E.unpad_channels(x)
+        W, b = _variables(name, (input_size, 1), (1,), init)
+        act, leak, ok = _fusable(activation)
+        fuse = ok and not use_batch_norm
         h = E.dense_n1(x, W, b, act if fuse else K.ACT_NONE, leak)
         h = E.reshape(h, (M, 1))
     else:
-        g = E.conv_geom(M, 1, 1, input_size, output_size, 1, 1)
-        h = E.conv_like('fprop', E.reshape(x, (M, 1, 1, input_size)), W, g, bias=b,
-                        act=act if fuse else K.ACT_NONE, leak=leak)
-        h = E.reshape(h, (M, output_size))
+        if x.logical_c is None and input_size % 8:
+            x = E.pad_channels(x, (input_size + 15) // 16 * 16)       # e.g. latent_size 50: rows of 16-byte multiples
+        cin, cout = x.shape[-1], output_size
+        W, b = _variables(name, (input_size, output_size), (output_size,), init, (cin, cout), (cout,))
+        act, leak, ok = _fusable(activation)
+        fuse = ok and not use_batch_norm
+        g = E.conv_geom(M, 1, 1, cin, cout, 1, 1)
+        g.logical = (input_size, output_size)
+        xin = E.reshape(x, (M, 1, 1, cin))
+        h = E.conv_like('fprop', xin, W, g, bias=b, act=act if fuse else K.ACT_NONE, leak=leak)
+        h = _mark(E.reshape(h, (M, cout)), output_size)
     return _finish(h, use_batch_norm, activation, fuse)
 
 
@@ -171,6 +181,4 @@ def deconv2d(x, input_size, output_size, filter_size=3, stride=2, init=xavier_in
 @add_arg_scope
 def flatten(x, name=None):
     """ops/layers.py:152-166 — [B, -1]."""
-    if x.logical_c is not None:
-        raise K.B200Error("flatten of a channel-padded tensor (set B200GAN_CHANNEL_PAD=0 for this model)")
-    return E.reshape(x, (x.shape[0], -1))
+    return E.reshape(x, (x.shape[0], -1))          # (engine.reshape strips zero channel padding first)

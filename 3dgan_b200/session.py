@@ -203,6 +203,9 @@ class Session:
                 self.begin_step()
                 out = fn()
             ent.update(state="graph", graph=g, out=out, launches=E.S.launches - launches0)
+            # the engine was bound to the capture stream: rebind it to the current stream so that eager launches
+            # after this point (store.load -> refresh_transposed, tests) stay ordered with torch ops
+            E.begin(self.device)
             # capture does not execute: replay once so this call has the step's effect
             g.replay()
             return out

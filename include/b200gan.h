@@ -103,6 +103,10 @@ int b200_fill_f32(float* out, long long n, float v, b200_stream s);
 int b200_interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, b200_stream s);
                                                                      /* x + alpha (g - x), models/gan.py:224-226 */
 int b200_rowscale(const void* in, const float* s_row, float mul, float add, void* out, int B, int D, b200_stream s);
+int b200_slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off,
+                    long long rows, int cols, const void* mask, int mask_kind, float leak, b200_stream s);
+                                                                     /* out[r, out_off+c] = in[r, in_off+c] * act'(mask[r,c]), bf16, row strides in elements:
+                                                                        channel concat (tf.concat axis=1, hem/models/pix2pix.py:210-222) and its gradient */
 int b200_transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, b200_stream s);
 int b200_colsum(const void* x, const float* wrow, float* out, long long R, int C, float alpha, b200_stream s);
                                                                      /* out[c] += alpha sum_r wrow[r] x[r,c]: bias / fc2 weight grads */
@@ -110,7 +114,8 @@ int b200_reduce_sum(const void* x, int x_f32, long long n, float* out, float alp
 int b200_wgan_loss(const float* sums, int B, int use_gp, float lambda, float* out4, b200_stream s);
                                                                      /* models/gan.py:194-205,229-230 */
 int b200_eltloss(const void* a, int a_f32, const void* b, long long n, int kind, float label, float scale,
-                 float gscale, float* out_sum, void* grad, int grad_f32, b200_stream s);
+                 float gscale, float* out_sum, void* grad, int grad_f32, int mask_kind, float leak, b200_stream s);
+                                                                     /* grad = gscale * dl/da * act'(a), act = mask_kind: the activation that produced a (0: none) */
                                                                      /* models/cnn.py:77, vae.py:76-83, gan.py:193-194, pix2pix.py:283-299 */
 /* ---- noise (tf.random_normal / tf.random_uniform, models/gan.py:224,246; models/vae.py:127) */
 int b200_philox(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* dev_draw_counter,

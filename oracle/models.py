@@ -234,7 +234,7 @@ def ae_decoder(p, z, sizes, final_act):
     for i in range(1, 5):
         out = sizes[4 - i]
         x = T.deconv2d(x, p["decoder/vars/dc%d/weights" % i], p["decoder/vars/dc%d/bias" % i], 2, None,
-                       final_act if i == 4 else "relu", out_hw=(out, out))
+                       final_act if i == 4 else "relu", out_hw=(out, out), store_out=(i != 4))
     return x
 
 
@@ -244,7 +244,7 @@ def cnn_losses(p, x01, sizes):
     e = ae_encoder(p, x, "cnn")
     z = T.dense(e.reshape(e.shape[0], -1), p["latent/vars/d1/weights"], p["latent/vars/d1/bias"])
     d = ae_decoder(p, z, sizes, "tanh")
-    return {"loss": torch.mean(torch.abs(x - d))}, d
+    return {"loss": T.l1_mean(d, x)}, d
 
 
 def vae_losses(p, x01, eps, sizes):

@@ -82,7 +82,7 @@ def losses(p, x01, y01, add_l1=False):
     g01 = T.stored((g + 1) * 0.5)
     yy = T.stored((y + 1) * 0.5)
     g_fake = T.sigmoid_ce(df, torch.ones_like(df)).mean()
-    l1 = (yy - g01).abs().mean()
+    l1 = T.l1_mean(g01, yy)
     g_total = g_fake + 10.0 * l1 if add_l1 else g_fake
     d_real = T.sigmoid_ce(dr, torch.ones_like(dr)).mean()
     d_fake = T.sigmoid_ce(df, torch.zeros_like(df)).mean()

@@ -49,6 +49,82 @@ def stored(t):
     return _RoundBF16.apply(t) if _STORE_BF16 else t
 
 
+# --------------------------------------------------------------------------- decision injection
+class inject_decisions:
+    """Context: the oracle takes every DISCONTINUOUS decision of the graph — the relu / lrelu masks
+    (ops/activations.py:28) and the sign of the L1 residual (models/cnn.py:77) — from a
+    queue recorded by the implementation under test instead of from its own pre-activations; all
+    arithmetic stays plain fp32 (no storage emulation).
+
+    Why: d relu/dx jumps at 0, so a pre-activation that differs by one bf16 ulp between the two sides
+    flips the unit and changes its gradient by O(1); that noise (a few % per ReLU layer) hides real
+    errors of the same size.  With the decisions pinned, the two sides evaluate the SAME piecewise-
+    linear function and gradients must agree to bf16 rounding.  The queue is audited while it is
+    consumed: `stats` records, per decision, the fraction of units whose injected decision differs from
+    the oracle's own and how large the oracle's pre-activation is at those units relative to the layer
+    rms — an implementation whose masks are wrong (not merely rounded differently) shows up there.
+    """
+
+    def __init__(self, decisions):
+        self.queue = list(decisions)
+        self.stats = []
+
+    def __enter__(self):
+        global _INJECT
+        self.prev, _INJECT = _INJECT, self
+        return self
+
+    def __exit__(self, *a):
+        global _INJECT
+        _INJECT = self.prev
+
+    def pop(self, kind, like):
+        """Next recorded decision as a float tensor shaped like `like`: +1 / 0 for an activation mask
+        (unit passes / is cut), +1 / 0 / -1 for an L1 residual sign.  `like` is the oracle's own
+        pre-activation (residual); the audit compares its sign with the recorded decision."""
+        if not self.queue:
+            raise AssertionError("decision queue exhausted at a %s of shape %s" % (kind, tuple(like.shape)))
+        k, m = self.queue.pop(0)
+        if k != kind or m.numel() != like.numel():
+            raise AssertionError("decision queue out of step: got %s %s, oracle is at %s %s"
+                                 % (k, tuple(m.shape), kind, tuple(like.shape)))
+        m = m.reshape(like.shape).to(like.dtype)
+        v = like.detach()
+        own = (v > 0).to(like.dtype) if kind == "act" else torch.sign(v)
+        flip = m != own
+        rms = float(v.pow(2).mean().sqrt())
+        at = float(v[flip].abs().mean()) if bool(flip.any()) else 0.0
+        self.stats.append({"kind": kind, "shape": tuple(like.shape), "flip_frac": float(flip.float().mean()),
+                           "flip_mag_over_rms": at / max(rms, 1e-30)})
+        return m
+
+
+_INJECT = None
+
+
+class record_decisions(inject_decisions):
+    """Context: run the oracle on its own decisions and append them to `self.queue` in the format
+    `inject_decisions` consumes (used to test the injection machinery against itself)."""
+
+    def __init__(self):
+        inject_decisions.__init__(self, [])
+
+    def pop(self, kind, like):
+        v = like.detach()
+        m = (v > 0).to(like.dtype) if kind == "act" else torch.sign(v)
+        self.queue.append((kind, m.clone()))
+        return m
+
+
+def l1_mean(a, b):
+    """mean(|a - b|) — models/cnn.py:77, hem/models/pix2pix.py:286.  Under `inject_decisions` the sign
+    of the residual is the recorded one (the loss stays piecewise linear in `a`)."""
+    r = a - b
+    if _INJECT is None:
+        return torch.mean(torch.abs(r))
+    return torch.mean(r * _INJECT.pop("l1", r))
+
+
 # --------------------------------------------------------------------------- padding
 def same_pad(in_size, k, s):
     """TF 'SAME' padding (A.1): out = ceil(in/s); pad_total = max((out-1)s+k-in, 0);
@@ -97,7 +173,16 @@ def conv2d_transpose_same(x, K, out_hw, stride):
 def lrelu(x, leak=0.2):
     """ops/activations.py:28 — tf.maximum(leak*x, x).  TF's Maximum gradient routes to the
     first argument where leak*x >= x, i.e. slope = leak for x <= 0 (A.5)."""
+    if _INJECT is not None:
+        pos = _INJECT.pop("act", x)
+        return x * (pos + (1 - pos) * leak)
     return _LReLU.apply(x, leak)
+
+
+def relu(x):
+    if _INJECT is not None:
+        return x * _INJECT.pop("act", x)
+    return torch.relu(x)
 
 
 class _LReLU(torch.autograd.Function):
@@ -117,7 +202,7 @@ class _LReLU(torch.autograd.Function):
 ACTIVATIONS = {
     None: lambda t: t,
     "none": lambda t: t,
-    "relu": torch.relu,
+    "relu": relu,
     "lrelu": lrelu,
     "tanh": torch.tanh,
     "sigmoid": torch.sigmoid,
@@ -165,15 +250,17 @@ def conv2d(x, K, b, stride, beta=None, activation=None):
     return stored(ACTIVATIONS[activation](h))
 
 
-def deconv2d(x, K, b, stride=2, beta=None, activation=None, out_hw=None):
+def deconv2d(x, K, b, stride=2, beta=None, activation=None, out_hw=None, store_out=True):
     """ops/layers.py:111-148: act(BN(conv2d_transpose_SAME(x,K) + b)); output is 2x the input
-    (ops/layers.py:141) unless out_hw is given (hem/ops/layers.py:185-187)."""
+    (ops/layers.py:141) unless out_hw is given (hem/ops/layers.py:185-187).  store_out=False: the CUDA
+    path keeps this output in fp32 (the autoencoders' loss heads), so storage emulation leaves it alone."""
     if out_hw is None:
         out_hw = (x.shape[1] * 2, x.shape[2] * 2)
     h = conv2d_transpose_same(x, K, out_hw, stride) + b
     if beta is not None:
         h = batch_norm_train(stored(h), beta)
-    return stored(ACTIVATIONS[activation](h))
+    out = ACTIVATIONS[activation](h)
+    return stored(out) if store_out else out
 
 
 # --------------------------------------------------------------------------- initialisers

@@ -282,3 +282,37 @@ def test_deferred_update_runs_inline_without_a_device():
     sess.overlap_updates = False
     sess.defer_update(lambda: calls.append("inline"))
     assert calls == ["exchange", "inline"]
+
+
+def test_latent_size_whose_channel_padding_meets_a_reshape():
+    """latent_size=50: the critic's c3 output has 200 channels stored as 208; the reshape to rows of 4*4*4L
+    (models/gan.py:284) must strip the padding, not mix zero channels into the rows (B=100 used to yield 104
+    rows silently).  The reference accepts any latent_size."""
+    sess = S.Session()
+    x = S.Input(100, (32, 32, 3), slots=6)
+    train = gan_model.gan(x, _args(B=100, Lz=50))
+    E.S.dry = True
+    try:
+        sess.store.begin_pass()
+        names = []
+        orig = E.launch
+
+        def rec(name, *a, **k):
+            names.append(name)
+            return 0
+        E.launch = rec
+        try:
+            gl, dl = train.tower(x.next(), "d")
+        finally:
+            E.launch = orig
+    finally:
+        E.S.dry = False
+    assert "b200_slice_cols" in names                      # the un-padding copy ran before each fc2
+    t = E.Tensor(torch.empty((100, 4, 4, 208), dtype=torch.bfloat16, device="meta")); t.logical_c = 200
+    E.S.dry = True
+    try:
+        assert E.reshape(t, (-1, 4 * 4 * 200)).shape == (100, 3200)
+        with pytest.raises(b200gan._capi.B200Error):
+            E.reshape(E.Tensor(torch.empty((100, 3200), device="meta")), (-1, 3000))
+    finally:
+        E.S.dry = False

@@ -28,6 +28,9 @@ CONV_CASES = [
     (8, 32, 32, 3, 200, 5, 2),               # small-channel path (IWGAN c1 / dc-last)
     (4, 28, 28, 1, 64, 5, 2),                # MNIST-shaped first conv
     (2, 16, 16, 4, 64, 4, 2),                # pix2pix PatchGAN first conv (rgb+depth)
+    (512, 16, 16, 208, 400, 5, 2),           # bench.py's c2 exactly (B=512, padded 200 -> 208): 2-CTA schedules, stream-K
+    (512, 8, 8, 400, 800, 5, 2),             # bench.py's c3 exactly
+    (512, 32, 32, 3, 208, 5, 2),             # bench.py's c1 / last deconv exactly
 ]
 
 

@@ -6,17 +6,31 @@ from tests import parity as P
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("H,C,L,B", [(32, 3, 16, 8), (32, 3, 200, 32), (64, 3, 16, 4), (32, 3, 16, 64)])
+@pytest.mark.parametrize("H,C,L,B", [(32, 3, 16, 8), (32, 3, 200, 32), (64, 3, 16, 4), (32, 3, 16, 64),
+                                     (32, 3, 50, 20)])       # latent 50: z padded 50 -> 64, c3 200 -> 208 un-padded at the reshape
 def test_iwgan_step_matches_oracle(H, C, L, B):
+    """fp32 oracle on the CUDA path's linear piece (decision injection): <= 3e-2 on every variable."""
     res = P.iwgan_step_parity(H=H, C=C, L=L, B=B, verbose=True)
+    assert res["ok"], res
+
+
+def test_iwgan_headline_config_step_matches_oracle():
+    """BASELINE configs[1] exactly as bench.py runs it: 32x32x3, latent 200, batch 512 — the tile counts, stream-K
+    ranges and 2-CTA schedules of the benchmark (the CPU oracle needs ~1 min for its double backward)."""
+    res = P.iwgan_step_parity(H=32, C=3, L=200, B=512, verbose=True)
+    assert res["ok"], res
+
+
+def test_iwgan_step_matches_bf16_storage_oracle():
+    """Secondary check, round 1's method: the oracle rounds stored activations to bf16 and uses its OWN masks."""
+    res = P.iwgan_step_parity(H=32, C=3, L=200, B=32, verbose=True, mode="emulate")
     assert res["ok"], res
 
 
 def test_iwgan_reference_native_64x64_L200_step_matches_oracle():
     """The reference's own default shape (64x64x3, latent 200): its 100-channel deconv only runs because the
-    layer API pads channel counts to multiples of 16.  The generator has one more BN+ReLU stage than at 32x32,
-    so the bf16 mask-flip noise of the earliest generator layers is larger (measured 4.3e-2; critic <= 1.6e-2)."""
-    res = P.iwgan_step_parity(H=64, C=3, L=200, B=16, verbose=True, grad_tol=6e-2)
+    layer API pads channel counts to multiples of 16."""
+    res = P.iwgan_step_parity(H=64, C=3, L=200, B=16, verbose=True)
     assert res["ok"], res
 
 
@@ -74,15 +88,29 @@ def test_cuda_graph_replay_equals_eager():
 @pytest.mark.parametrize("model,H,C,L,B", [("cnn", 28, 1, 16, 8), ("cnn", 28, 1, 200, 64), ("cnn", 64, 3, 32, 4),
                                            ("vae", 32, 3, 16, 64), ("vae", 32, 3, 200, 32)])
 def test_autoencoder_step_matches_oracle(model, H, C, L, B):
-    """cnn AE (BASELINE configs[0] shape 28x28x1 B64) and VAE (configs[3] shape 32x32x3)."""
+    """cnn AE (BASELINE configs[0] shape 28x28x1 B64) and VAE (configs[3] shape 32x32x3): every variable's
+    gradient within 3e-2 of the fp32 oracle evaluated on the CUDA path's masks (audited)."""
     res = P.ae_step_parity(model=model, H=H, C=C, L=L, B=B, verbose=True)
+    assert res["ok"], res
+
+
+def test_vae_baseline_config_step_matches_oracle():
+    """BASELINE configs[3] at its own batch: 32x32x3, B=256, latent 200."""
+    res = P.ae_step_parity(model="vae", H=32, C=3, L=200, B=256, verbose=True)
+    assert res["ok"], res
+
+
+@pytest.mark.parametrize("model,H,C,L,B", [("cnn", 28, 1, 16, 8), ("vae", 32, 3, 16, 64)])
+def test_autoencoder_step_matches_bf16_storage_oracle(model, H, C, L, B):
+    """Secondary (round 1's method, loose: cosine >= 0.98, relative L2 <= 0.2): own masks, bf16 storage emulation."""
+    res = P.ae_step_parity(model=model, H=H, C=C, L=L, B=B, verbose=True, mode="emulate")
     assert res["ok"], res
 
 
 @pytest.mark.parametrize("model", ["wgan", "gan"])
 def test_gan_wgan_step_matches_oracle(model):
     """Batch-norm critic with unshared betas for D(real)/D(fake) (SURVEY App. C #5), sigmoid + log losses."""
-    res = P.iwgan_step_parity(H=32, C=3, L=16, B=32, model=model, verbose=True, grad_tol=5e-2)
+    res = P.iwgan_step_parity(H=32, C=3, L=16, B=32, model=model, verbose=True)
     assert res["ok"], res
 
 
@@ -96,7 +124,7 @@ def test_smooth_activation_chain_gradients_are_tight():
 def test_pix2pix_step_matches_oracle():
     """BASELINE configs[4] shape (256x256 rgb + depth) at batch 2, --add_l1: U-Net generator with skip
     concatenations, PatchGAN discriminator (512 -> 1 head), sigmoid-CE + L1 losses."""
-    res = P.pix2pix_step_parity(B=4, verbose=True, grad_tol=0.3, cos_tol=0.95)
+    res = P.pix2pix_step_parity(B=4, verbose=True)
     assert res["ok"], res
 
 

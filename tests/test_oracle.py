@@ -129,3 +129,54 @@ def test_models_run_at_reference_native_and_baseline_shapes():
     # VAE differentiates the reconstruction term only (models/vae.py:41): the KL head d2 still gets a
     # gradient through z = mu + sigma*eps, but nothing flows from the KL term itself
     assert float(r["grads"]["latent/vars/d2/weights"].abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------ decision injection
+def _tiny_iwgan(seed=0, B=4, L=8):
+    gs, ds = OM.gan_param_specs("iwgan", 32, 3, L)
+    p = OM.init_params(OrderedDict(list(gs.items()) + list(ds.items())), seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    return p, torch.rand(B, 32, 32, 3, generator=g), torch.randn(B, L, generator=g), torch.rand(B, 1, generator=g), L
+
+
+def test_injecting_the_oracles_own_decisions_reproduces_it():
+    """inject_decisions with the decisions the fp32 oracle takes itself must give the fp32 oracle back,
+    first- and second-order (IWGAN gradient penalty), with an all-zero audit."""
+    p, x01, z, alpha, L = _tiny_iwgan()
+    plain = OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+    with OT.record_decisions() as rec:
+        OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+    assert len(rec.queue) == 3 + 3 * 3          # generator fc1, dc1, dc2 (BN+relu) and 3 critic passes x 3 lrelu
+    with OT.inject_decisions(rec.queue) as inj:
+        got = OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+    assert not inj.queue and all(st["flip_frac"] == 0.0 for st in inj.stats)
+    assert abs(float(got["d_loss"]) - float(plain["d_loss"])) < 1e-6
+    for k in plain["grads"]:
+        assert torch.allclose(got["grads"][k], plain["grads"][k], rtol=1e-4, atol=1e-7), k
+
+
+def test_injection_audit_flags_wrong_masks_and_queue_mismatch():
+    p, x01, z, alpha, L = _tiny_iwgan()
+    with OT.record_decisions() as rec:
+        OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+    bad = [(k, m.clone()) for k, m in rec.queue]
+    bad[4] = ("act", 1 - bad[4][1])                                   # one layer's mask inverted
+    with OT.inject_decisions(bad) as inj:
+        OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+    assert inj.stats[4]["flip_frac"] == 1.0 and inj.stats[4]["flip_mag_over_rms"] > 0.5
+    with pytest.raises(AssertionError):
+        with OT.inject_decisions(rec.queue[:-1]):                     # one decision short
+            OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+    with pytest.raises(AssertionError):
+        with OT.inject_decisions([("l1", rec.queue[0][1])] + rec.queue[1:]):
+            OM.gan_grads(p, x01, z, alpha, "iwgan", 32, 3, L)
+
+
+def test_l1_sign_injection_matches_abs():
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(5, 7, generator=g, requires_grad=True)
+    b = torch.randn(5, 7, generator=g)
+    ref = torch.autograd.grad(OT.l1_mean(a, b), a)[0]
+    with OT.inject_decisions([("l1", torch.sign(a.detach() - b))]):
+        got = torch.autograd.grad(OT.l1_mean(a, b), a)[0]
+    assert torch.equal(ref, got)
