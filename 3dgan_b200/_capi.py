@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B200GAN_LIB") or os.path.join(_HERE, "lib", "libb200gan.so")
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID = range(5)
-OPT_ADAM, OPT_RMSPROP, OPT_SGD, OPT_MOMENTUM = range(4)
+OPT_ADAM, OPT_RMSPROP, OPT_SGD, OPT_MOMENTUM, OPT_ADAGRAD, OPT_ADADELTA, OPT_FTRL, OPT_CENTERED_RMSPROP = range(8)
 
 
 class ConvGeom(C.Structure):
@@ -21,6 +21,11 @@ class Epilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int), ("leak", C.c_float), ("mask_src", C.c_void_p),
                 ("mask_kind", C.c_int), ("out_f32", C.c_int), ("accumulate", C.c_int),
                 ("mask_bits", C.c_void_p), ("bits_out", C.c_void_p), ("bits_pitch", C.c_int)]
+
+
+class TransposeEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("tile_begin", C.c_longlong), ("T", C.c_int), ("A", C.c_int),
+                ("B", C.c_int), ("reserved", C.c_int)]
 
 
 class B200Error(RuntimeError):
@@ -57,7 +62,8 @@ SIGNATURES = {
     "b200_wgan_loss": [_P, _I, _I, _F, _P, _P],
     "b200_eltloss": [_P, _I, _P, _LL, _I, _F, _F, _F, _P, _P, _I, _I, _F, _P],
     "b200_philox": [_P, _I, _LL, _ULL, _P, _U, _I, _P],
-    "b200_optim_step": [_P, _P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _F, _P, _P],
+    "b200_optim_step": [_P, _P, _P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _F, _I, _P, _P],
+    "b200_transpose_batch": [_P, _I, _LL, _P],
     "b200_device_check": [],
     "b200_abi_version": [],
 }

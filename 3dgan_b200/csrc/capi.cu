@@ -691,9 +691,9 @@ extern "C" int b200_bn_bwd(const void* g, const void* z, const float* stats, flo
 extern "C" int b200_maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, b200_stream s) {
   WRAP(maskmul(g, a, out, n, kind, leak, (cudaStream_t)s), "maskmul");
 }
-extern "C" int b200_affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add,
+extern "C" int b200_affine_act(const void* in, int in_type, void* out, int out_f32, long long n, float mul, float add,
                                int act, float leak, b200_stream s) {
-  WRAP(affine_act(in, in_f32, out, out_f32, n, mul, add, act, leak, (cudaStream_t)s), "affine_act");
+  WRAP(affine_act(in, in_type, out, out_f32, n, mul, add, act, leak, (cudaStream_t)s), "affine_act");
 }
 extern "C" int b200_axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb,
                           void* out, int out_f32, long long n, b200_stream s) {
@@ -741,9 +741,14 @@ extern "C" int b200_philox(void* out, int out_f32, long long n, unsigned long lo
                            unsigned long long* dev_draw_counter, unsigned int stream_id, int normal, b200_stream s) {
   WRAP(philox_fill(out, out_f32, n, seed, dev_draw_counter, stream_id, normal, (cudaStream_t)s), "philox");
 }
-extern "C" int b200_optim_step(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, int kind,
-                               float lr, float b1, float b2, float eps, float grad_scale, float clip, int* dev_step,
-                               b200_stream s) {
-  WRAP(optim_step(p, m, v, g, p_bf16, n, kind, lr, b1, b2, eps, grad_scale, clip, dev_step, (cudaStream_t)s),
-       "optim_step");
+extern "C" int b200_optim_step(float* p, float* m, float* v, float* slot3, float* g, void* p_bf16, long long n, int kind,
+                               float lr, float b1, float b2, float eps, float grad_scale, float clip, int zero_grad,
+                               int* dev_step, b200_stream s) {
+  WRAP(optim_step(p, m, v, slot3, g, p_bf16, n, kind, lr, b1, b2, eps, grad_scale, clip, zero_grad, dev_step,
+                  (cudaStream_t)s), "optim_step");
+}
+extern "C" int b200_transpose_batch(const b200_transpose_entry* dev_table, int count, long long total_tiles,
+                                    b200_stream s) {
+  static_assert(sizeof(b200_transpose_entry) == sizeof(TransposeEntry), "table entry layout");
+  WRAP(transpose_batch(dev_table, count, total_tiles, (cudaStream_t)s), "transpose_batch");
 }

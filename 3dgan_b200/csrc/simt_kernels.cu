@@ -489,23 +489,32 @@ int maskmul(const void* g, const void* a, void* out, long long n, int kind, floa
   return 0;
 }
 
-// out = act(in * mul + add) elementwise; fp32 or bf16 in, bf16 or fp32 out
+// out = act(in * mul + add) elementwise; fp32, bf16 or uint8 in, bf16 or fp32 out.  With uint8 input this is the
+// input stage of the reference's pipeline fused into the model's first op: data.py:21-22,29 casts the decoded
+// image bytes to float32 and divides by 255, models/gan.py:50 / cnn.py:31 rescale to [-1,1] -- here the bytes go
+// host -> device as they are (a quarter of the fp32 traffic) and are normalised in the same pass (the caller
+// folds the 1/255 into mul).
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(uint8_t v) { return (float)v; }
+__device__ __forceinline__ void from_f32(float& o, float v) { o = v; }
+__device__ __forceinline__ void from_f32(bf16& o, float v) { o = __float2bfloat16(v); }
 template <typename TI, typename TO>
 __global__ void affine_act_kernel(const TI* __restrict__ in, TO* out, long long n, float mul, float add, int act,
                                   float leak) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float v = (float)in[i] * mul + add;
-    out[i] = (TO)act_fwd(v, act, leak);
-  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    from_f32(out[i], act_fwd(fmaf(to_f32(in[i]), mul, add), act, leak));
 }
-int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
+int affine_act(const void* in, int in_type, void* out, int out_f32, long long n, float mul, float add, int act,
                float leak, cudaStream_t st) {
   const int grid = stride_grid(n, 256, 4);
-  if (in_f32 && out_f32) affine_act_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, n, mul, add, act, leak);
-  else if (in_f32) affine_act_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)in, (bf16*)out, n, mul, add, act, leak);
-  else if (out_f32) affine_act_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)in, (float*)out, n, mul, add, act, leak);
-  else affine_act_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)in, (bf16*)out, n, mul, add, act, leak);
+#define AFF(TI, TO) affine_act_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, (TO*)out, n, mul, add, act, leak)
+  if (in_type == 2) { if (out_f32) AFF(uint8_t, float); else AFF(uint8_t, bf16); }
+  else if (in_type == 1) { if (out_f32) AFF(float, float); else AFF(float, bf16); }
+  else if (in_type == 0) { if (out_f32) AFF(bf16, float); else AFF(bf16, bf16); }
+  else return -1;
+#undef AFF
   return 0;
 }
 
@@ -1186,48 +1195,143 @@ int philox_fill(void* out, int out_f32, long long n, unsigned long long seed, un
 
 // =============================================================================================
 // Fused optimizer update over a flat fp32 parameter bucket (util.py:150-183 -> tf.train.*Optimizer)
-// 28 B/param: read g,p,m,v; write p,m,v; + 2 B for the bf16 compute copy.
+// One pass: read g,p,m,v (16-byte accesses), write p,m,v, the bf16 compute copy, and zeros into g (the next run's
+// gradient accumulation starts from a clean bucket without a separate fill): 32 B/param + 2 B for the bf16 copy.
 // =============================================================================================
-// kind 0 Adam (TF epsilon-hat form, A.4), 1 RMSProp (ms init 1.0, A.4), 2 SGD, 3 Momentum
-__global__ void optim_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                             const float* __restrict__ g, bf16* __restrict__ p16, long long n, int kind, float lr,
-                             float b1, float b2, float eps, float gscale, float clip, int* step) {
-  float lr_t = lr;
-  if (kind == 0) {
-    const float t = (float)(*step + 1);
-    lr_t = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+// kind 0 Adam (TF epsilon-hat form, A.4), 1 RMSProp (ms init 1.0, A.4), 2 SGD, 3 Momentum,
+//      4 Adagrad == ProximalAdagrad with l1 = l2 = 0 (accumulator init 0.1), 5 Adadelta (rho 0.95, eps 1e-8),
+//      6 FTRL (lr_power -0.5, accumulator init 0.1, l1 = l2 = 0), 7 centered RMSProp (third slot = mean gradient)
+struct OptimScalars { float lr, lr_t, b1, b2, eps, gscale, clip; int kind; };
+
+__device__ __forceinline__ void optim_one(const OptimScalars& o, float gi, float& pi, float& mi, float& vi, float& si) {
+  gi *= o.gscale;
+  if (o.clip > 0.f) pi = fminf(fmaxf(pi, -o.clip), o.clip);     // WGAN: clip BEFORE the update (models/gan.py:142-148)
+  switch (o.kind) {
+    case 0: {
+      mi = o.b1 * mi + (1.f - o.b1) * gi;
+      vi = o.b2 * vi + (1.f - o.b2) * gi * gi;
+      pi -= o.lr_t * mi / (sqrtf(vi) + o.eps);
+    } break;
+    case 1: {                                                   // b1 = decay, b2 = momentum
+      vi = o.b1 * vi + (1.f - o.b1) * gi * gi;
+      mi = o.b2 * mi + o.lr * gi * rsqrtf(vi + o.eps);
+      pi -= mi;
+    } break;
+    case 2: pi -= o.lr * gi; break;
+    case 3: {                                                   // b1 = momentum
+      mi = o.b1 * mi + gi;
+      pi -= o.lr * mi;
+    } break;
+    case 4: {                                                   // v = accumulator (init 0.1)
+      vi += gi * gi;
+      pi -= o.lr * gi * rsqrtf(vi);
+    } break;
+    case 5: {                                                   // v = accum, m = accum_update, b1 = rho
+      vi = o.b1 * vi + (1.f - o.b1) * gi * gi;
+      const float upd = sqrtf(mi + o.eps) * rsqrtf(vi + o.eps) * gi;
+      mi = o.b1 * mi + (1.f - o.b1) * upd * upd;
+      pi -= o.lr * upd;
+    } break;
+    case 6: {                                                   // v = accum (init 0.1), m = linear
+      const float na = vi + gi * gi;
+      mi += gi - (sqrtf(na) - sqrtf(vi)) / o.lr * pi;
+      pi = -mi / (sqrtf(na) / o.lr);
+      vi = na;
+    } break;
+    default: {                                                  // 7: b1 = decay, b2 = momentum, s = mean gradient
+      si = o.b1 * si + (1.f - o.b1) * gi;
+      vi = o.b1 * vi + (1.f - o.b1) * gi * gi;
+      mi = o.b2 * mi + o.lr * gi * rsqrtf(vi - si * si + o.eps);
+      pi -= mi;
+    } break;
   }
+}
+
+__global__ void optim_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float* __restrict__ s3,
+                             float* __restrict__ g, bf16* __restrict__ p16, long long n, OptimScalars o, int zero_grad,
+                             const int* __restrict__ step) {
+  if (o.kind == 0) {
+    const float t = (float)(*step + 1);
+    o.lr_t = o.lr * sqrtf(1.f - powf(o.b2, t)) / (1.f - powf(o.b1, t));
+  }
+  const bool slots = o.kind != 2, third = o.kind == 7;
+  const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * gscale;
-    float pi = p[i];
-    if (clip > 0.f) pi = fminf(fmaxf(pi, -clip), clip);     // WGAN: clip BEFORE the update (models/gan.py:142-148)
-    if (kind == 0) {
-      const float mi = b1 * m[i] + (1.f - b1) * gi;
-      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-      m[i] = mi; v[i] = vi;
-      pi -= lr_t * mi / (sqrtf(vi) + eps);
-    } else if (kind == 1) {                                  // b1 = decay, b2 = momentum
-      const float ms = b1 * v[i] + (1.f - b1) * gi * gi;
-      const float mom = b2 * m[i] + lr * gi * rsqrtf(ms + eps);
-      v[i] = ms; m[i] = mom;
-      pi -= mom;
-    } else if (kind == 2) {
-      pi -= lr * gi;
-    } else {                                                 // b1 = momentum
-      const float acc = b1 * m[i] + gi;
-      m[i] = acc;
-      pi -= lr * acc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<const float4*>(p)[i];
+    float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = m4, s4 = m4;
+    if (slots) { m4 = reinterpret_cast<const float4*>(m)[i]; v4 = reinterpret_cast<const float4*>(v)[i]; }
+    if (third) s4 = reinterpret_cast<const float4*>(s3)[i];
+    optim_one(o, g4.x, p4.x, m4.x, v4.x, s4.x);
+    optim_one(o, g4.y, p4.y, m4.y, v4.y, s4.y);
+    optim_one(o, g4.z, p4.z, m4.z, v4.z, s4.z);
+    optim_one(o, g4.w, p4.w, m4.w, v4.w, s4.w);
+    reinterpret_cast<float4*>(p)[i] = p4;
+    if (slots) { reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4; }
+    if (third) reinterpret_cast<float4*>(s3)[i] = s4;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p16) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(p4.x, p4.y), hi = __floats2bfloat162_rn(p4.z, p4.w);
+      reinterpret_cast<uint2*>(p16)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
     }
+  }
+  // tail (n not a multiple of 4; the engine's buckets are 64-element aligned, so this is for other callers)
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pi = p[i], mi = slots ? m[i] : 0.f, vi = slots ? v[i] : 0.f, si = third ? s3[i] : 0.f;
+    optim_one(o, g[i], pi, mi, vi, si);
     p[i] = pi;
+    if (slots) { m[i] = mi; v[i] = vi; }
+    if (third) s3[i] = si;
+    if (zero_grad) g[i] = 0.f;
     if (p16) p16[i] = __float2bfloat16(pi);
   }
 }
 __global__ void step_bump_kernel(int* step) { *step += 1; }
-int optim_step(float* p, float* m, float* v, const float* g, void* p16, long long n, int kind, float lr, float b1,
-               float b2, float eps, float gscale, float clip, int* step, cudaStream_t st) {
-  optim_kernel<<<stride_grid(n, 256, 4), 256, 0, st>>>(p, m, v, g, (bf16*)p16, n, kind, lr, b1, b2, eps, gscale, clip, step);
+int optim_step(float* p, float* m, float* v, float* s3, float* g, void* p16, long long n, int kind, float lr, float b1,
+               float b2, float eps, float gscale, float clip, int zero_grad, int* step, cudaStream_t st) {
+  if (kind < 0 || kind > 7 || (kind == 7 && !s3)) return -1;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v) |
+                       reinterpret_cast<uintptr_t>(s3) | reinterpret_cast<uintptr_t>(g);
+  if ((al & 15) || (reinterpret_cast<uintptr_t>(p16) & 7)) return -1;
+  OptimScalars o{lr, lr, b1, b2, eps, gscale, clip, kind};
+  optim_kernel<<<stride_grid(n >> 2, 256, 2), 256, 0, st>>>(p, m, v, s3, g, (bf16*)p16, n, o, zero_grad, step);
   step_bump_kernel<<<1, 1, 0, st>>>(step);
+  return 0;
+}
+
+// Re-layout of every K-major weight copy of one optimizer group in ONE launch: entry e describes a [T][A][B] bf16
+// block of the group's compute copy and the [T][B][A] destination (transposed per filter tap); the 32x32 tiles of
+// all entries are numbered consecutively (tile_begin) and a block finds its entry by scanning the short table.
+__global__ void transpose_batch_kernel(const TransposeEntry* __restrict__ tab, int count) {
+  __shared__ float tile[32][33];
+  __shared__ TransposeEntry e;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int k = 0;
+    while (k + 1 < count && (long long)blockIdx.x >= tab[k + 1].tile_begin) ++k;
+    e = tab[k];
+  }
+  __syncthreads();
+  const int tb = (e.B + 31) / 32, ta = (e.A + 31) / 32;
+  int t = (int)((long long)blockIdx.x - e.tile_begin);
+  const int bx = t % tb; t /= tb;
+  const int by = t % ta; t /= ta;
+  const bf16* in = reinterpret_cast<const bf16*>(e.in) + (long long)t * e.A * e.B;
+  bf16* out = reinterpret_cast<bf16*>(e.out) + (long long)t * e.A * e.B;
+  const int a0 = by * 32, b0 = bx * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int a = a0 + i, b = b0 + threadIdx.x;
+    if (a < e.A && b < e.B) tile[i][threadIdx.x] = __bfloat162float(in[(long long)a * e.B + b]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int b = b0 + i, a = a0 + threadIdx.x;
+    if (a < e.A && b < e.B) out[(long long)b * e.A + a] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+int transpose_batch(const void* table, int count, long long total_tiles, cudaStream_t st) {
+  if (count <= 0 || total_tiles <= 0 || total_tiles > 0x7fffffffLL) return -1;
+  transpose_batch_kernel<<<(int)total_tiles, dim3(32, 8), 0, st>>>((const TransposeEntry*)table, count);
   return 0;
 }
 

@@ -29,7 +29,7 @@ int smallout_dgrad(const void* dy, const void* w, const SmallConvArgs& a, cudaSt
 int smallout_wgrad(const void* x, const void* dy, float* dw, const SmallConvArgs& a, float alpha, cudaStream_t st);
 
 int maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, cudaStream_t st);
-int affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
+int affine_act(const void* in, int in_type, void* out, int out_f32, long long n, float mul, float add, int act,
                float leak, cudaStream_t st);
 int axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
           int out_f32, long long n, cudaStream_t st);
@@ -56,7 +56,10 @@ int eltloss(const void* a, int a_f32, const void* b, long long n, int kind, floa
             float* out_sum, void* grad, int grad_f32, int mask_kind, float leak, cudaStream_t st);
 int philox_fill(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* draw,
                 unsigned int stream_id, int normal, cudaStream_t st);
-int optim_step(float* p, float* m, float* v, const float* g, void* p16, long long n, int kind, float lr, float b1,
-               float b2, float eps, float gscale, float clip, int* step, cudaStream_t st);
+int optim_step(float* p, float* m, float* v, float* s3, float* g, void* p16, long long n, int kind, float lr, float b1,
+               float b2, float eps, float gscale, float clip, int zero_grad, int* step, cudaStream_t st);
+// one entry of b200_transpose_batch's device table (5 x 8 bytes; mirrored by b200_transpose_entry in b200gan.h)
+struct TransposeEntry { const void* in; void* out; long long tile_begin; int T, A; int B, pad_; };
+int transpose_batch(const void* table, int count, long long total_tiles, cudaStream_t st);
 
 }  // namespace b200

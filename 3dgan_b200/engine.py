@@ -256,11 +256,14 @@ class Param:
         return self.p16_t
 
     def refresh_transposed(self):
+        """This variable alone (lazy creation, stand-alone test Params); groups refresh all of theirs in one launch."""
         if self.p16_t is None:
             return
         a, b = self.shape[-2], self.shape[-1]
         t = self.numel // (a * b)
         launch("b200_transpose_to_bf16", _p(self.p32), 1, _p(self.p16_t), t, a, b)
+        if self.group is not None:
+            self.group._t_table = None
 
 
 def _act_code(act):
@@ -488,8 +491,12 @@ def activation(x, act, leak=0.0):
 
 
 def affine(x, mul, add, out_f32=False):
-    """out = x*mul + add (e.g. the [0,1] -> [-1,1] rescale, models/gan.py:50)."""
+    """out = x*mul + add (e.g. the [0,1] -> [-1,1] rescale, models/gan.py:50).  A uint8 input is an image batch as
+    decoded (data.py:14-22): its /255 normalisation is folded into this pass."""
     out = Tensor(empty(x.shape, F32 if out_f32 else BF16))
+    if x.buf.dtype == torch.uint8:
+        launch("b200_affine_act", _p(x.buf), 2, _p(out.buf), int(out_f32), x.numel, mul / 255.0, add, 0, 0.0)
+        return out                                   # an input batch: no gradient flows back to it
     launch("b200_affine_act", _p(x.buf), int(x.f32), _p(out.buf), int(out_f32), x.numel, mul, add, 0, 0.0)
 
     def bw(gouts):

@@ -56,8 +56,7 @@ def _default_training(sess, x, args, tower, name_losses):
         (group,) = store.groups
 
     def iteration():
-        x.reset()
-        group.zero_grad()
+        x.reset()                                     # (the gradient bucket is zero: apply_gradients resets it)
         out = tower(x.next())
         E.backward([((out[0] if isinstance(out, tuple) else out), None)])
         group.apply_gradients(sess.all_reduce_grads(group), 0.0)

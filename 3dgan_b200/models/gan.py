@@ -73,8 +73,7 @@ def gan(x, args):
             pending[0] = False
 
     def before_critic_d():
-        finish_pending()
-        d_group.zero_grad()
+        finish_pending()          # (every gradient bucket is zero here: apply_gradients resets it in the same pass)
 
     def d_run():
         g_loss, d_loss = tower(x.next(), 'd', before_critic_d)
@@ -89,14 +88,12 @@ def gan(x, args):
         return g_loss, d_loss
 
     def g_run():
-        g_group.zero_grad()
         g_loss, d_loss = tower(x.next(), 'g', finish_pending)
         E.backward([(g_loss, None)])
         g_group.apply_gradients(sess.all_reduce_grads(g_group), clip)
         return g_loss, d_loss
 
     def gan_run():                                                    # _train_gan: one run, both updates
-        g_group.zero_grad(); d_group.zero_grad()
         gl, dl = tower(x.next(), 'dg')                                # same forward for both (App. C #7)
         E.backward([(dl, None)], accumulate=store.collection('discriminator'))
         E.backward([(gl, None)], accumulate=store.collection('generator'))

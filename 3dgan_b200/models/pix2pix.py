@@ -72,9 +72,7 @@ class pix2pix:
 
     # ------------------------------------------------------------------ training (pix2pix.py:151-156)
     def _run(self, mode):
-        grp = {'d': self.d_group, 'g': self.g_group}.get(mode)
-        if grp is not None:
-            grp.zero_grad()
+        grp = {'d': self.d_group, 'g': self.g_group}.get(mode)      # (its gradient bucket is zero: see apply_gradients)
         ls = self.tower(self.x_in.next(), self.y_in.next(), mode)
         if grp is not None:
             E.backward([(ls['d_total'] if mode == 'd' else ls['g_total'], None)])

@@ -26,15 +26,19 @@ class Input:
     [B,H,W,C] float32 batch in [0,1] per `next()`.  Batches are fed by the caller (`feed`) into a
     static device ring so that a captured CUDA graph always reads the same addresses."""
 
-    def __init__(self, batch_size, shape, slots=1, device=None):
+    def __init__(self, batch_size, shape, slots=1, device=None, dtype=torch.float32):
+        """dtype float32: batches already normalised to [0,1] (what the reference's `x` tensor holds);
+        dtype uint8: image bytes as decoded — the /255 of data.py:21-22,29 then runs on the device, fused into the
+        model's first op (engine.affine), and a batch costs a quarter of the host->device traffic."""
         self.batch_size, self.shape, self.slots = batch_size, tuple(shape), slots
         self.device = device
+        self.dtype = dtype
         self.ring = None
         self.cursor = 0
 
     def materialize(self, device):
         self.device = device
-        self.ring = torch.zeros((self.slots, self.batch_size) + self.shape, dtype=torch.float32, device=device)
+        self.ring = torch.zeros((self.slots, self.batch_size) + self.shape, dtype=self.dtype, device=device)
 
     def feed(self, slot, host_or_device_batch, non_blocking=True):
         self.ring[slot].copy_(host_or_device_batch, non_blocking=non_blocking)
@@ -67,7 +71,7 @@ class Input:
 
     def next(self):
         if E.S.dry:
-            return E.Tensor(torch.empty((self.batch_size,) + self.shape, dtype=torch.float32, device="meta"))
+            return E.Tensor(torch.empty((self.batch_size,) + self.shape, dtype=self.dtype, device="meta"))
         t = E.Tensor(self.ring[self.cursor % self.slots])
         self.cursor += 1
         return t

@@ -137,6 +137,13 @@ def zeros_initializer():
 _ALIGN = 64     # elements; keeps every view 16-byte aligned in fp32 and bf16
 
 
+# optimizer name -> (kernel kind, initial value of the `v` slot).  TF defaults: RMSProp's mean square starts
+# at 1.0; Adagrad / ProximalAdagrad / FTRL accumulators at 0.1.
+_OPTIMIZERS = {"adam": (K.OPT_ADAM, 0.0), "rmsprop": (K.OPT_RMSPROP, 1.0), "sgd": (K.OPT_SGD, 0.0),
+               "momentum": (K.OPT_MOMENTUM, 0.0), "adagrad": (K.OPT_ADAGRAD, 0.1), "padagrad": (K.OPT_ADAGRAD, 0.1),
+               "adadelta": (K.OPT_ADADELTA, 0.0), "ftrl": (K.OPT_FTRL, 0.1)}
+
+
 class Group:
     """One optimizer instance's variables as flat buckets: p32 | g32 | m | v (fp32) and p16 (bf16)."""
 
@@ -147,12 +154,15 @@ class Group:
             p.offset = off
             off += (p.numel + _ALIGN - 1) // _ALIGN * _ALIGN
         self.size = off
+        self.kind, v0 = _OPTIMIZERS[cfg["optimizer"]]
+        if self.kind == K.OPT_RMSPROP and cfg.get("centered"):
+            self.kind = K.OPT_CENTERED_RMSPROP
         self.p32 = torch.zeros(off, dtype=torch.float32, device=device)
         self.g32 = torch.zeros(off, dtype=torch.float32, device=device)
         self.m = torch.zeros(off, dtype=torch.float32, device=device)
-        # RMSProp's mean-square slot starts at 1.0
-        self.v = torch.full((off,), 1.0 if cfg["optimizer"] == "rmsprop" else 0.0, dtype=torch.float32,
-                            device=device)
+        self.v = torch.full((off,), v0, dtype=torch.float32, device=device)
+        # centered RMSProp keeps a third slot (the mean gradient)
+        self.s3 = torch.zeros(off, dtype=torch.float32, device=device) if self.kind == K.OPT_CENTERED_RMSPROP else None
         self.p16 = torch.zeros(off, dtype=torch.bfloat16, device=device)
         self.step = torch.zeros(1, dtype=torch.int32, device=device)
         for p in self.params:
@@ -161,44 +171,80 @@ class Group:
             p.p32.copy_(host_values[p.name].reshape(-1))
             if p.need_t:
                 p.p16_t = torch.zeros(p.numel, dtype=torch.bfloat16, device=device)
+        self._t_table = None
         self.sync_compute_copies()
+
+    # ---- optimizer slots by their TF names (checkpoints: `<var>/Adam`, `<var>/Adam_1`, `<var>/RMSProp`, ...)
+    def slot_names(self):
+        # TF-1.x names slot variables `<var>/<OptimizerName>[_k]` in creation order (rms, [mg,] momentum for RMSProp)
+        return {K.OPT_ADAM: ("Adam", "Adam_1"), K.OPT_RMSPROP: ("RMSProp_1", "RMSProp"),
+                K.OPT_CENTERED_RMSPROP: ("RMSProp_2", "RMSProp", "RMSProp_1"), K.OPT_SGD: (),
+                K.OPT_MOMENTUM: ("Momentum",), K.OPT_ADAGRAD: (None, "Adagrad"),
+                K.OPT_ADADELTA: ("Adadelta_1", "Adadelta"), K.OPT_FTRL: ("Ftrl_1", "Ftrl")}[self.kind]
+
+    def slots(self):
+        """[(tf slot name, flat buffer)] of the slots this optimizer uses (m, v, third)."""
+        bufs = (self.m, self.v, self.s3)
+        return [(n, b) for n, b in zip(self.slot_names(), bufs) if n is not None]
 
     def sync_compute_copies(self):
         self.p16.copy_(self.p32)
         if self.p32.is_cuda:
-            for p in self.params:
-                p.refresh_transposed()
+            self.refresh_transposed()
+
+    def refresh_transposed(self):
+        """Rebuild every per-tap transposed bf16 weight copy of the group (the K-major fprop operand) from the bf16
+        compute copy: one launch over a device-resident table of (source, destination, T, A, B)."""
+        need = [p for p in self.params if p.p16_t is not None]
+        if not need or E.S.dry:
+            return
+        if self._t_table is None or self._t_table[2] != [id(p.p16_t) for p in need]:
+            import ctypes as C
+            ents = (K.TransposeEntry * len(need))()
+            tiles = 0
+            for e, p in zip(ents, need):
+                a, b = p.shape[-2], p.shape[-1]
+                t = p.numel // (a * b)
+                e.src, e.dst, e.tile_begin, e.T, e.A, e.B = p.p16.data_ptr(), p.p16_t.data_ptr(), tiles, t, a, b
+                tiles += t * ((a + 31) // 32) * ((b + 31) // 32)
+            host = torch.frombuffer(bytearray(bytes(ents)), dtype=torch.uint8).clone()
+            self._t_table = (host.to(self.p32.device), tiles, [id(p.p16_t) for p in need], len(need))
+        tab, tiles, _, n = self._t_table
+        E.launch("b200_transpose_batch", E._p(tab), n, tiles)
 
     def zero_grad(self):
         E.launch("b200_fill_f32", E._p(self.g32), self.size, 0.0)
 
     def apply_gradients(self, grad_scale=1.0, clip=0.0):
-        """opt.apply_gradients (models/gan.py:80-81): fused update + bf16 copy, then re-layout the
-        transposed weight copies the K-major fprop operand reads."""
+        """opt.apply_gradients (models/gan.py:80-81): one fused pass updates p / slots / the bf16 copy and resets
+        the gradient bucket to zero for the next run; then the transposed weight copies the K-major fprop operand
+        reads are re-laid out in one launch."""
         c = self.cfg
-        kind = {"adam": K.OPT_ADAM, "rmsprop": K.OPT_RMSPROP, "sgd": K.OPT_SGD, "momentum": K.OPT_MOMENTUM}[
-            c["optimizer"]]
+        kind = self.kind
         if kind == K.OPT_ADAM:
             b1, b2, eps = c["beta1"], c["beta2"], 1e-8
-        elif kind == K.OPT_RMSPROP:
+        elif kind in (K.OPT_RMSPROP, K.OPT_CENTERED_RMSPROP):
             b1, b2, eps = c["decay"], c["momentum"], 1e-10
         elif kind == K.OPT_MOMENTUM:
             b1, b2, eps = c["momentum"], 0.0, 0.0
+        elif kind == K.OPT_ADADELTA:
+            b1, b2, eps = 0.95, 0.0, 1e-8
         else:
             b1 = b2 = eps = 0.0
-        E.launch("b200_optim_step", E._p(self.p32), E._p(self.m), E._p(self.v), E._p(self.g32), E._p(self.p16),
-                 self.size, kind, c["lr"], b1, b2, eps, grad_scale, clip, E._p(self.step), n=2)
-        for p in self.params:
-            p.refresh_transposed()
+        E.launch("b200_optim_step", E._p(self.p32), E._p(self.m), E._p(self.v), E._p(self.s3), E._p(self.g32),
+                 E._p(self.p16), self.size, kind, c["lr"], b1, b2, eps, grad_scale, clip, 1, E._p(self.step), n=2)
+        self.refresh_transposed()
 
 
 def optimizer_cfg(args):
     """init_optimizer(args) (util.py:150-183): the hyper-parameters of one optimizer instance."""
     name = args.optimizer
-    if name not in ("adam", "rmsprop", "sgd", "momentum"):
-        raise K.B200Error("optimizer '%s' is not on the accelerated path (adam, rmsprop, sgd, momentum)" % name)
-    if name == "rmsprop" and getattr(args, "centered", False):
-        raise K.B200Error("centered RMSProp is not on the accelerated path")
+    if name == "pgd":
+        raise K.B200Error("optimizer 'pgd': the reference's init_optimizer builds it without returning it "
+                          "(util.py:171-172), so no reference run can use it")
+    if name not in _OPTIMIZERS:
+        raise K.B200Error("unknown optimizer '%s' (util.py:150-183 has: %s)" % (name, ", ".join(sorted(_OPTIMIZERS))))
     return {"optimizer": name, "lr": float(args.lr), "beta1": float(getattr(args, "beta1", 0.9)),
             "beta2": float(getattr(args, "beta2", 0.999)), "decay": float(getattr(args, "decay", 0.9)),
-            "momentum": float(getattr(args, "momentum", 0.0))}
+            "momentum": float(getattr(args, "momentum", 0.0)),
+            "centered": bool(getattr(args, "centered", False)) and name == "rmsprop"}

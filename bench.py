@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — IWGAN 32x32x3 training throughput (BASELINE.json metric) on N B200s of one node.
+"""bench.py — training throughput of the 3dgan hot path on N B200s of one node (BASELINE.json metric).
 
-A "step" is one `train_func` call of the reference (train.py:307): n_disc_train(5) critic updates + 1
-generator update (+ the d_loss report), each on a fresh batch of 512 images per GPU
-(BASELINE configs[1]; weak scaling = the reference's per-tower batch semantics).
+A "step" is one `train_func` call of the reference (train.py:307).  Workloads (`--workload`, default iwgan32 =
+BASELINE configs[1], the headline):
 
-  python bench.py [--gpus N --steps K --warmup W]            this repo's CUDA path
-  python bench.py --impl reference [...]                     CPU restatement of the reference (oracle)
+  iwgan32     Improved WGAN 32x32x3, B=512/GPU, latent 200, Adam 1e-4 (0.5, 0.9): 5 critic + 1 generator update
+  iwgan64     the reference-native 64x64x3 shape of the same model (models/gan.py hard-codes it), B=512/GPU
+  vae32       models/vae.py on 32x32x3, B=256/GPU, latent 200 (BASELINE configs[3])
+  cnn28       models/cnn.py on 28x28x1, B=64 (BASELINE configs[0], the reference's CPU-runnable case)
+  pix2pix256  hem/models/pix2pix.py on 256x256 rgb+depth pairs, B=16/GPU (BASELINE configs[4]): D, G, losses run
 
-Prints ONE JSON line (see the task contract): value = images/s with inputs resident in HBM, device
-timed, max over ranks; e2e = same through the public API with pinned-host batches copied in (Input.prefetch /
-commit: the next step's H2D copy overlaps this step's compute) and losses read back every step; roofline = the dominant kernel family (tcgen05 implicit GEMM) timed live with
-CUDA events per launch; cpu_baseline = the oracle on this box's host cores (bounded sample).
+  python bench.py [--workload W --gpus N --steps K --warmup W]       this repo's CUDA path
+  python bench.py --impl reference [...]                             CPU restatement of the reference (oracle)
+
+Prints ONE JSON line: value = images/s with inputs resident in HBM, device timed, max over ranks; e2e = the same
+through the public feed API with pinned-host uint8 batches copied in every step (Input.prefetch / commit: the next
+step's H2D copy overlaps this step's compute) and the losses read back every step; roofline = the dominant kernel
+family (tcgen05 implicit GEMM) timed live with CUDA events per launch against the measured burst bf16 peak;
+cpu_baseline = the oracle on this box's host cores (bounded sample, actual batch stated).
 """
 import argparse
 import json
@@ -25,8 +31,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "IWGAN 32x32x3 train images/sec"
 UNIT = "images/s"
+
+WORKLOADS = {
+    "iwgan32": dict(family="gan", model="iwgan", size=32, ch=3, batch=512, latent=200, n_disc=5,
+                    opt=dict(optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.9),
+                    metric="IWGAN 32x32x3 train images/sec",
+                    what="BASELINE configs[1]: 5 critic + 1 generator update per step"),
+    "iwgan64": dict(family="gan", model="iwgan", size=64, ch=3, batch=512, latent=200, n_disc=5,
+                    opt=dict(optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.9),
+                    metric="IWGAN 64x64x3 train images/sec",
+                    what="reference-native shape (models/gan.py:241-286): 5 critic + 1 generator update per step"),
+    "vae32": dict(family="ae", model="vae", size=32, ch=3, batch=256, latent=200, n_disc=0,
+                  opt=dict(optimizer="adam", lr=1e-3, beta1=0.9, beta2=0.999),
+                  metric="VAE 32x32x3 train images/sec", what="BASELINE configs[3]: one update per step"),
+    "cnn28": dict(family="ae", model="cnn", size=28, ch=1, batch=64, latent=200, n_disc=0,
+                  opt=dict(optimizer="adam", lr=1e-3, beta1=0.9, beta2=0.999),
+                  metric="CNN autoencoder 28x28x1 train images/sec", what="BASELINE configs[0]: one update per step"),
+    "pix2pix256": dict(family="pix2pix", model="pix2pix", size=256, ch=3, batch=16, latent=0, n_disc=1,
+                       opt=dict(optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.999),
+                       metric="pix2pix 256x256 train image pairs/sec",
+                       what="BASELINE configs[4]: D update, G update and the losses-only run per step"),
+}
 
 
 def parse():
@@ -35,21 +61,32 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--latent", type=int, default=200)
-    ap.add_argument("--size", type=int, default=32)
-    ap.add_argument("--n_disc_train", type=int, default=5)
+    ap.add_argument("--workload", default="iwgan32", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--latent", type=int, default=None)
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--n_disc_train", type=int, default=None)
+    ap.add_argument("--ref-batch", type=int, default=None, help="batch of the CPU reference's bounded sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-launch GEMM table (json) here")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    if a.size is not None and a.workload == "iwgan32" and a.size == 64:
+        w = dict(WORKLOADS["iwgan64"])               # round-1 spelling: --size 64
+    for key, val in (("batch", a.batch), ("latent", a.latent), ("size", a.size), ("n_disc", a.n_disc_train)):
+        if val is not None:
+            w[key] = val
+    a.w = w
+    return a
 
 
-def workload(a):
-    return {"workload": "iwgan_%dx%dx3_b%d_L%d (BASELINE configs[1]: 5 critic + 1 generator update per step)"
-                        % (a.size, a.size, a.batch, a.latent),
-            "batch_per_gpu": a.batch, "latent_size": a.latent, "n_disc_train": a.n_disc_train,
-            "optimizer": "adam lr=1e-4 beta=(0.5,0.9)"}
+def config_of(w):
+    o = w["opt"]
+    return {"workload": "%s_%dx%dx%d_b%d%s (%s)" % (w["model"], w["size"], w["size"], w["ch"], w["batch"],
+                                                   "_L%d" % w["latent"] if w["latent"] else "", w["what"]),
+            "batch_per_gpu": w["batch"], "latent_size": w["latent"], "n_disc_train": w["n_disc"],
+            "optimizer": "%s lr=%g beta=(%g,%g)" % (o["optimizer"], o["lr"], o["beta1"], o["beta2"])}
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -95,52 +132,114 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def cpu_reference(a, steps, warmup, sample_batch):
-    """The reference's CPU path restated (oracle.models.GanTrainer): same graph, schedule, optimizer and
-    synthetic inputs; one tower; all host threads.  Each step is a bounded sample (a smaller batch)."""
+def cpu_reference(w, steps, warmup, sample_batch):
+    """The reference's CPU path restated (oracle/): same graph, schedule, optimizer and synthetic inputs; one
+    tower; all host threads.  Each step is one full train_func-equivalent at batch `sample_batch`.
+    Returns (images/s, ms per step, cores)."""
     import torch
     from oracle import models as OM
+    from oracle import tf_ops as OT
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    tr = OM.GanTrainer("iwgan", a.size, 3, a.latent, sample_batch, lr=1e-4, beta1=0.5, beta2=0.9,
-                       n_disc=a.n_disc_train, seed=0)
+    o, H, C, L, B = w["opt"], w["size"], w["ch"], w["latent"], sample_batch
     gen = torch.Generator().manual_seed(1234)
-    nb = lambda: torch.rand(sample_batch, a.size, a.size, 3, generator=gen)
-    nn = lambda: (torch.randn(sample_batch, a.latent, generator=gen), torch.rand(sample_batch, 1, generator=gen))
+    if w["family"] == "gan":
+        tr = OM.GanTrainer(w["model"], H, C, L, B, lr=o["lr"], beta1=o["beta1"], beta2=o["beta2"], n_disc=w["n_disc"], seed=0)
+        nb = lambda: torch.rand(B, H, H, C, generator=gen)
+        nn = lambda: (torch.randn(B, L, generator=gen), torch.rand(B, 1, generator=gen))
+        step = lambda: tr.iteration(nb, nn)
+    elif w["family"] == "ae":
+        specs, sizes = OM.ae_param_specs(w["model"], H, C, L)
+        p = OM.init_params(specs, 0)
+        opt = OM.AdamState(p, list(p), o["lr"], o["beta1"], o["beta2"])
+
+        def step():
+            r = OM.ae_grads(p, torch.rand(B, H, H, C, generator=gen), torch.randn(B, L, generator=gen), w["model"], sizes)
+            opt.apply(p, r["grads"])
+    else:
+        from collections import OrderedDict
+        from oracle import pix2pix as OP
+        gs, ds = OP.param_specs()
+        p = OP.init_params(OrderedDict(list(gs.items()) + list(ds.items())), 0)
+        g_opt = OM.AdamState(p, list(gs), o["lr"], o["beta1"], o["beta2"])
+        d_opt = OM.AdamState(p, list(ds), o["lr"], o["beta1"], o["beta2"])
+        pair = lambda: (torch.rand(B, H, H, 3, generator=gen), torch.rand(B, H, H, 1, generator=gen))
+
+        def step():                                  # hem/models/pix2pix.py:151-156: D run, G run, losses-only run
+            d_opt.apply(p, OP.grads(p, *pair(), False)["grads"])
+            g_opt.apply(p, OP.grads(p, *pair(), False)["grads"])
+            with torch.no_grad():
+                OP.losses(p, *pair(), False)
     for _ in range(warmup):
-        tr.iteration(nb, nn)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        tr.iteration(nb, nn)
+        step()
     dt = time.perf_counter() - t0
-    return sample_batch * steps / dt, dt / steps * 1e3, cores
+    return B * steps / dt, dt / steps * 1e3, cores
+
+
+def ref_sample_batch(a):
+    if a.ref_batch:
+        return a.ref_batch
+    return {"iwgan32": 32, "iwgan64": 8, "vae32": 256, "cnn28": 64, "pix2pix256": 2}.get(a.workload, 32)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 32
-    v, ms, cores = cpu_reference(a, a.steps, a.warmup, sample)
-    cfg = workload(a)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+    w = a.w
+    sample = min(ref_sample_batch(a), w["batch"])
+    v, ms, cores = cpu_reference(w, a.steps, a.warmup, sample)
+    cfg = config_of(w)
+    # the line's config names the workload of the b200 arm; what this arm actually ran per step is stated next to it
+    cfg.update(batch_per_step_run_here=sample, same_config=(sample == w["batch"]))
+    line = {"impl": "reference", "metric": w["metric"], "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "every step = one full iteration (5 critic + 1 generator) at batch %d "
-                                       "instead of %d; torch-CPU restatement of the TF graph (TF not installable)"
-                                       % (sample, a.batch)},
+                             "sample": "every step = one full train_func-equivalent at batch %d (the b200 arm runs %d "
+                                       "per GPU); one CPU process on rank 0 whatever --gpus says; torch-CPU "
+                                       "restatement of the TF graph (TF is not installable here)" % (sample, w["batch"])},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------- our arm
+class Job:
+    """One workload on this rank: model + inputs + the step function the public API exposes."""
+
+    def __init__(self, w, sess):
+        import torch
+        from b200gan import session as S
+        from b200gan.models import MODEL_FUNCS, pix2pix
+        self.w, self.sess = w, sess
+        o, B, H, C = w["opt"], w["batch"], w["size"], w["ch"]
+        args = argparse.Namespace(model=w["model"], batch_size=B, latent_size=w["latent"], n_disc_train=w["n_disc"],
+                                  batch_norm_gen=False, batch_norm_disc=False, add_l1=False, dropout=0, noise=[], **o)
+        u8 = torch.uint8
+        if w["family"] == "pix2pix":
+            self.runs = w["n_disc"] + 2
+            self.inputs = [S.Input(B, (H, H, 3), slots=self.runs, dtype=u8), S.Input(B, (H, H, 1), slots=self.runs, dtype=u8)]
+            model = pix2pix(tuple(self.inputs), args)
+            self.iteration, self.key = model.iteration, "pix2pix_iteration"
+        else:
+            self.runs = MODEL_FUNCS[w["model"]][1](args)
+            self.inputs = [S.Input(B, (H, H, C), slots=self.runs, dtype=u8)]
+            train = MODEL_FUNCS[w["model"]][0](self.inputs[0], args)
+            self.iteration, self.key = train.iteration, w["model"] + "_iteration"
+        self.h2d = sum(i.ring.numel() * i.ring.element_size() for i in self.inputs)
+
+    def step(self):
+        return self.sess.run(self.key, self.iteration)
+
+
 def run_b200(a):
     import torch
     import b200gan  # noqa: F401
     from b200gan import engine as E
     from b200gan import session as S
-    from b200gan.models import gan as gan_model
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU fallback")
@@ -149,21 +248,20 @@ def run_b200(a):
     def mark(msg):
         if verbose:
             print("[bench rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+    w = a.w
     sess = S.Session(seed=0, noise_seed=1234)
     world, rank = sess.world, sess.rank
     if world > 1:
         sess.init_distributed("nccl")
-    args = argparse.Namespace(model="iwgan", batch_size=a.batch, latent_size=a.latent, n_disc_train=a.n_disc_train,
-                              optimizer="adam", lr=1e-4, beta1=0.5, beta2=0.9)
-    runs = a.n_disc_train + 1
-    x = S.Input(a.batch, (a.size, a.size, 3), slots=runs)
-    train = gan_model.gan(x, args)
+    job = Job(w, sess)
     mark("model built")
 
-    # synthetic data: two sets of `runs` device-resident batches (fresh batch per sess.run-equivalent)
+    # synthetic data: image bytes (uint8, as decoded: data.py:14-22); two sets of device-resident batches for the
+    # `value` leg and two pinned-host sets for the end-to-end leg (a fresh batch per sess.run-equivalent)
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    pool = torch.rand((2, runs, a.batch, a.size, a.size, 3), generator=gen, device="cuda")
-    host = torch.rand((2, runs, a.batch, a.size, a.size, 3)).pin_memory()
+    pools = [torch.randint(0, 256, (2,) + tuple(i.ring.shape), generator=gen, device="cuda", dtype=torch.uint8)
+             for i in job.inputs]
+    hosts = [torch.randint(0, 256, (2,) + tuple(i.ring.shape), dtype=torch.uint8).pin_memory() for i in job.inputs]
 
     def barrier():
         if world > 1:
@@ -171,19 +269,23 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     def step_resident(i):
-        x.ring.copy_(pool[i & 1])
-        return sess.run("gan_iteration", train.iteration)
+        for inp, pool in zip(job.inputs, pools):
+            inp.ring.copy_(pool[i & 1])
+        return job.step()
 
     def step_e2e(i):
         # the public feed API: this step's batches were prefetched (pinned host -> device on a copy stream)
         # during the previous step; the next step's copy starts before this step's losses are read back
-        x.commit()
-        out = sess.run("gan_iteration", train.iteration)
+        for inp in job.inputs:
+            inp.commit()
+        out = job.step()
         if i + 1 < a.steps:
-            x.prefetch(host[(i + 1) & 1])
+            for inp, host in zip(job.inputs, hosts):
+                inp.prefetch(host[(i + 1) & 1])
         return {k: float(v.item()) for k, v in out.items()}
 
-    for i in range(max(a.warmup, 3)):
+    warm = max(a.warmup, 3)
+    for i in range(warm):
         out = step_resident(i)
         if verbose:
             mark("warmup step %d %s" % (i, {k: float(v.item()) for k, v in out.items()}))
@@ -205,43 +307,47 @@ def run_b200(a):
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms = float(t.item())
-    value = a.batch * world * a.steps / (ms * 1e-3)
+    value = w["batch"] * world * a.steps / (ms * 1e-3)
 
     # ---- end to end: pinned host batches in, losses out, every step
     barrier()
     t0 = time.perf_counter()
     last = None
-    x.prefetch(host[0])                 # inside the timed region: every step's H2D copy is timed
+    for inp, host in zip(job.inputs, hosts):
+        inp.prefetch(host[0])           # inside the timed region: every step's H2D copy is timed
     for i in range(a.steps):
         last = step_e2e(i)
-        if os.environ.get("B200GAN_BENCH_VERBOSE"):
+        if verbose:
             print("e2e step", i, last, file=sys.stderr, flush=True)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = a.batch * world * a.steps / float(t.item())
+    e2e_value = w["batch"] * world * a.steps / float(t.item())
     clk.__exit__(None, None, None)
-    h2d = runs * a.batch * a.size * a.size * 3 * 4
-    d2h = 8
+    d2h = 4 * len(last)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+    line = {"metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warm,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload(a), l2="working set per step (activations+weights, >1 GB) exceeds the 126 MB L2",
+            "dtype": "bf16", "data": "synthetic (uint8 image bytes, normalised on the device)",
+            "config": dict(config_of(w),
+                           l2="inputs are rewritten every step and the step's working set (activations + weights + "
+                              "optimizer state) exceeds the 126 MB L2" if w["batch"] * w["size"] ** 2 >= 64 * 28 * 28 * 8
+                              else "working set may fit the 126 MB L2: a latency-bound workload, not an HBM claim",
                            parallelism="dp%d" % world, cuda_graph=bool(sess.use_graphs)),
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": job.h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "losses": last}
 
     if rank == 0 and not a.no_roofline:
-        line["roofline"] = roofline(sess, train, x, pool, a, line["ms_per_step"])
+        line["roofline"] = roofline(sess, job, pools, a, line["ms_per_step"])
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v, _, cores = cpu_reference(a, 2, 1, 32)
+        sample = min(ref_sample_batch(a), w["batch"])
+        v, _, cores = cpu_reference(w, 2, 1, sample)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "2 timed iterations (after 1 warm-up) at batch 32 instead of %d, "
-                                          "torch-CPU restatement of the reference graph" % a.batch}
+                                "sample": "2 timed steps (after 1 warm-up) at batch %d (this arm: %d), torch-CPU "
+                                          "restatement of the reference graph" % (sample, w["batch"])}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -255,30 +361,31 @@ def run_b200(a):
         os._exit(0)
 
 
-def roofline(sess, train, x, pool, a, step_ms):
-    """Dominant kernel family = the tcgen05 implicit-GEMM launches (conv fprop/dgrad/wgrad).  One extra
+def roofline(sess, job, pools, a, step_ms):
+    """Dominant kernel family = the tcgen05 implicit-GEMM launches (conv fprop/dgrad/wgrad, dense).  One extra
     step is run eagerly with a CUDA-event pair around every such launch on the launching stream;
     achieved = sum(algorithmic FLOPs) / sum(durations) over those launches."""
     import torch
     from b200gan import engine as E
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, src = 1590.0, "fallback"
+    burst, sustained, src = 1590.0, None, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
-        peak, src = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0))), "measured (sustained: timed inside a long step)"
+        burst, sustained = float(pk.get("bf16_tflops", burst)), pk.get("bf16_tflops_sustained")
+        src = "MEASURED_PEAKS.json bf16_tflops (burst: the timed region is well under a second at boost clocks)"
     prev, prev_dist = sess.use_graphs, sess.dist
     sess.use_graphs, sess.dist = False, None        # rank-0-only pass: no collective inside
     E.S.profile = []
-    x.ring.copy_(pool[0])
+    for inp, pool in zip(job.inputs, pools):
+        inp.ring.copy_(pool[0])
     it0, it1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # eager launches are host-bound: park the GPU behind a ~0.2 s spin kernel so the whole iteration is
-    # queued before it starts and the per-launch events see back-to-back execution (as in the graph replay)
+    # eager launches are host-bound: park the GPU behind a spin kernel so the whole iteration is queued before
+    # it starts and the per-launch events see back-to-back execution (as in the graph replay)
     torch.cuda._sleep(int(4e8))
     it0.record()
-    sess.run("profile", train.iteration)
+    sess.run("profile", job.iteration)
     it1.record()
     torch.cuda.synchronize()
-    iter_ms = it0.elapsed_time(it1)
     recs, E.S.profile = E.S.profile, None
     sess.use_graphs, sess.dist = prev, prev_dist
     rows = {}
@@ -297,31 +404,40 @@ def roofline(sess, train, x, pool, a, step_ms):
         json.dump(rows, open(a.profile_out, "w"), indent=1)
     n_tc = sum(r["launches"] for t_, r in rows.items() if t_.startswith("tc:"))
     achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": ncu_traffic_bytes(), "peak_source": src,
-            "kernel": "tapgemm2sm_kernel+wgrad2sm_kernel (tcgen05 cta_group::2 implicit GEMM: conv fprop/dgrad/wgrad, dense)",
-            "launches": n_tc, "flops_per_launch_avg": tot_f / max(n_tc, 1), "ms_per_launch_avg": tot_ms / max(n_tc, 1),
-            "step_share": tot_ms / step_ms if step_ms > 0 else None,
-            "note": "achieved = sum(2*N*Ho*Wo*k*k*Cin*Cout over the launches) / sum(CUDA-event durations), one eager "
-                    "iteration; step_share = those durations / the graph-replayed ms_per_step; traffic = mean dram read+write bytes per launch of the profiled c2/c3 launches "
-                    "(profiles/r1_ncu_kernels.csv)"}
+    traffic, traffic_src = ncu_traffic_bytes()
+    out = {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst,
+           "traffic": traffic, "traffic_source": traffic_src, "peak_source": src,
+           "kernel": "tapgemm2sm_kernel+wgrad2sm_kernel (tcgen05 cta_group::2 implicit GEMM: conv fprop/dgrad/wgrad, dense)",
+           "launches": n_tc, "flops_per_launch_avg": tot_f / max(n_tc, 1), "ms_per_launch_avg": tot_ms / max(n_tc, 1),
+           "step_share": tot_ms / step_ms if step_ms > 0 else None,
+           "note": "achieved = sum(2*N*Ho*Wo*k*k*Cin*Cout, logical channels, over the launches) / sum(CUDA-event "
+                   "durations), one eager iteration; step_share = those durations / the graph-replayed ms_per_step"}
+    if sustained:
+        out["peak_sustained"] = float(sustained)
+        out["frac_of_sustained"] = achieved / float(sustained)
+    return out
 
 
 def ncu_traffic_bytes():
-    """Mean DRAM bytes (read+write) per launch of the tcgen05 kernels in the committed ncu --set full capture."""
+    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
+    round (profiles/): measured under ncu on the same shapes, NOT in this run — the JSON says so."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_ncu_kernels.csv")
-    if not os.path.exists(path):
-        return None
-    rows = list(csv.reader(open(path)))
-    hdr = rows[1]
-    try:
-        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-    except ValueError:
-        return None
-    vals = [(float(r[ri]) + float(r[wi])) * 1e6 for r in rows[3:] if r and ("tapgemm" in r[0] or "wgrad" in r[0])
-            and float(r[hdr.index("gpu__time_duration.sum")]) > 100.0]
-    return sum(vals) / len(vals) if vals else None
+    for fn in ("r2_ncu_kernels.csv", "r1_ncu_kernels.csv"):
+        path = os.path.join(ROOT, "profiles", fn)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr = rows[1]
+        try:
+            ri, wi, ti = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        except ValueError:
+            continue
+        vals = [(float(r[ri]) + float(r[wi])) * 1e6 for r in rows[3:] if r and ("tapgemm" in r[0] or "wgrad" in r[0])
+                and float(r[ti]) > 100.0]
+        if vals:
+            return sum(vals) / len(vals), "profiles/%s: mean over the c2/c3 fprop, dgrad and wgrad launches of one " \
+                                          "ncu --set full capture (separate run, cold cache)" % fn
+    return None, None
 
 
 if __name__ == "__main__":

@@ -93,8 +93,11 @@ int b200_bn_bwd(const void* g, const void* z, const float* stats, float* bsum /*
 
 /* ---- elementwise / reductions */
 int b200_maskmul(const void* g, const void* a, void* out, long long n, int kind, float leak, b200_stream s);
-int b200_affine_act(const void* in, int in_f32, void* out, int out_f32, long long n, float mul, float add, int act,
-                    float leak, b200_stream s);                      /* out = act(in*mul+add); x -> 2(x-0.5), models/gan.py:50 */
+int b200_affine_act(const void* in, int in_type /*0 bf16, 1 fp32, 2 uint8*/, void* out, int out_f32, long long n,
+                    float mul, float add, int act, float leak, b200_stream s);
+                                                                     /* out = act(in*mul+add); x -> 2(x-0.5), models/gan.py:50.  in_type 2 = the input stage:
+                                                                        image bytes as decoded (data.py:14-22,29: cast to float32, / 255) are normalised here,
+                                                                        the caller folds 1/255 into mul */
 int b200_axpby(const void* a, int a_f32, float sa, const float* dev_sa, const void* b, int b_f32, float sb, void* out,
                int out_f32, long long n, b200_stream s);             /* out = a*sa*(*dev_sa) + b*sb */
 int b200_mul_add(const void* a, const void* b, const void* c, void* out, long long n, b200_stream s);
@@ -120,9 +123,31 @@ int b200_eltloss(const void* a, int a_f32, const void* b, long long n, int kind,
 /* ---- noise (tf.random_normal / tf.random_uniform, models/gan.py:224,246; models/vae.py:127) */
 int b200_philox(void* out, int out_f32, long long n, unsigned long long seed, unsigned long long* dev_draw_counter,
                 unsigned int stream_id, int normal, b200_stream s);
-/* ---- optimizer (util.py:150-183; tf.train.AdamOptimizer / RMSProp / SGD / Momentum), WGAN clip fused (gan.py:142) */
-int b200_optim_step(float* p, float* m, float* v, const float* g, void* p_bf16, long long n, int kind, float lr,
-                    float b1, float b2, float eps, float grad_scale, float clip, int* dev_step, b200_stream s);
+/* ---- optimizer (util.py:150-183: every branch of init_optimizer), WGAN clip fused (gan.py:142).  One pass over the flat
+ * bucket: p, slots and the bf16 compute copy are updated, and with zero_grad != 0 the gradient is reset to zero for the
+ * next run.  kind / (b1, b2, eps) / slots (m, v, slot3):
+ *   ADAM     (beta1, beta2, 1e-8)  m, v             tf.train.AdamOptimizer, lr_t = lr sqrt(1-b2^t)/(1-b1^t), t = *dev_step+1
+ *   RMSPROP  (decay, momentum, 1e-10)  m = mom, v = ms (init 1)        CENTERED_RMSPROP: + slot3 = mean gradient
+ *   SGD      -                      MOMENTUM (momentum)  m
+ *   ADAGRAD  v = accumulator (init 0.1); also ProximalAdagrad with l1 = l2 = 0
+ *   ADADELTA (rho 0.95, -, 1e-8)  v = accum, m = accum_update
+ *   FTRL     lr_power -0.5, l1 = l2 = 0: v = accum (init 0.1), m = linear
+ * *dev_step is incremented after the update. */
+enum { B200_OPT_ADAGRAD = 4, B200_OPT_ADADELTA = 5, B200_OPT_FTRL = 6, B200_OPT_CENTERED_RMSPROP = 7 };
+int b200_optim_step(float* p, float* m, float* v, float* slot3, float* g, void* p_bf16, long long n, int kind, float lr,
+                    float b1, float b2, float eps, float grad_scale, float clip, int zero_grad, int* dev_step,
+                    b200_stream s);
+/* Per-tap transposed bf16 copies ([T][A][B] -> [T][B][A]) of several weights in one launch: the K-major fprop operand
+ * of every conv of an optimizer group, refreshed after its update.  dev_table: `count` entries in device memory;
+ * tile_begin = number of 32x32 tiles (T * ceil(A/32) * ceil(B/32)) of the entries before this one. */
+typedef struct {
+  const void* in;        /* bf16 [T][A][B] */
+  void* out;             /* bf16 [T][B][A] */
+  long long tile_begin;
+  int T, A;
+  int B, reserved;
+} b200_transpose_entry;
+int b200_transpose_batch(const b200_transpose_entry* dev_table, int count, long long total_tiles, b200_stream s);
 
 #ifdef __cplusplus
 }

@@ -298,6 +298,39 @@ def rmsprop_step(p, g, ms, mom, lr, decay=0.9, momentum=0.01, eps=1e-10):
     p.sub_(mom)
 
 
+def centered_rmsprop_step(p, g, ms, mg, mom, lr, decay=0.9, momentum=0.01, eps=1e-10):
+    """tf.train.RMSPropOptimizer(centered=True) (util.py:160-163 with --centered): mg = mean gradient;
+    the denominator is sqrt(ms - mg^2 + eps).  In place."""
+    ms.mul_(decay).addcmul_(g, g, value=1 - decay)
+    mg.mul_(decay).add_(g, alpha=1 - decay)
+    mom.mul_(momentum).add_(lr * g / torch.sqrt(ms - mg * mg + eps))
+    p.sub_(mom)
+
+
+def adagrad_step(p, g, accum, lr):
+    """tf.train.AdagradOptimizer (util.py:166-167), accumulator init 0.1; tf.train.ProximalAdagradOptimizer
+    (util.py:173-174) with its default l1 = l2 = 0 is the same update.  In place."""
+    accum.addcmul_(g, g)
+    p.sub_(lr * g / accum.sqrt())
+
+
+def adadelta_step(p, g, accum, accum_update, lr, rho=0.95, eps=1e-8):
+    """tf.train.AdadeltaOptimizer(lr) (util.py:164-165), rho 0.95, epsilon 1e-8 (ApplyAdadelta).  In place."""
+    accum.mul_(rho).addcmul_(g, g, value=1 - rho)
+    upd = torch.sqrt(accum_update + eps) / torch.sqrt(accum + eps) * g
+    accum_update.mul_(rho).addcmul_(upd, upd, value=1 - rho)
+    p.sub_(lr * upd)
+
+
+def ftrl_step(p, g, accum, linear, lr):
+    """tf.train.FtrlOptimizer(lr) (util.py:182-183): learning_rate_power -0.5, accumulator init 0.1,
+    l1 = l2 = 0 (ApplyFtrl).  In place."""
+    new_accum = accum + g * g
+    linear.add_(g - (new_accum.sqrt() - accum.sqrt()) / lr * p)
+    p.copy_(-linear / (new_accum.sqrt() / lr))
+    accum.copy_(new_accum)
+
+
 def sgd_step(p, g, lr):
     p.sub_(lr * g)
 

@@ -109,35 +109,73 @@ def test_batch_norm_fwd_bwd(R, C):
 
 
 def test_optimizers_match_tf_formulas():
+    """Every branch of init_optimizer (util.py:150-183) through the fused update kernel vs the restated TF formulas;
+    also the bf16 compute copy, the step counter and the in-pass gradient reset."""
     from oracle import tf_ops as OT
     E.begin()
     g = torch.Generator().manual_seed(7)
-    n = 1000
-    for kind, name in ((K.OPT_ADAM, "adam"), (K.OPT_RMSPROP, "rmsprop"), (K.OPT_SGD, "sgd"), (K.OPT_MOMENTUM, "momentum")):
-        p = torch.randn(n, generator=g); m = torch.zeros(n); v = torch.ones(n) if name == "rmsprop" else torch.zeros(n)
-        dp, dm, dv = p.cuda(), m.cuda(), v.cuda()
-        p16 = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
-        step = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for t in range(1, 4):
-            gr = torch.randn(n, generator=g)
-            if name == "adam":
-                OT.adam_step(p, gr, m, v, t, 1e-3, 0.5, 0.9)
-                args = (1e-3, 0.5, 0.9, 1e-8)
-            elif name == "rmsprop":
-                OT.rmsprop_step(p, gr, v, m, 1e-3, 0.9, 0.01)
-                args = (1e-3, 0.9, 0.01, 1e-10)
-            elif name == "sgd":
-                OT.sgd_step(p, gr, 1e-2)
-                args = (1e-2, 0.0, 0.0, 0.0)
-            else:
-                OT.momentum_step(p, gr, m, 1e-2, 0.9)
-                args = (1e-2, 0.9, 0.0, 0.0)
-            E.launch("b200_optim_step", E._p(dp), E._p(dm), E._p(dv), E._p(gr.cuda()), E._p(p16), n, kind, *args,
-                     1.0, 0.0, E._p(step))
+    n = 1000 + 64 * 3            # vector body + nothing left over (buckets are 64-aligned) ...
+    cases = [(K.OPT_ADAM, "adam", 0.0), (K.OPT_RMSPROP, "rmsprop", 1.0), (K.OPT_SGD, "sgd", 0.0),
+             (K.OPT_MOMENTUM, "momentum", 0.0), (K.OPT_ADAGRAD, "adagrad", 0.1), (K.OPT_ADADELTA, "adadelta", 0.0),
+             (K.OPT_FTRL, "ftrl", 0.1), (K.OPT_CENTERED_RMSPROP, "centered", 1.0)]
+    for n in (1192, 1001):       # ... and a ragged length for the scalar tail
+        for kind, name, v0 in cases:
+            p = torch.randn(n, generator=g); m = torch.zeros(n); v = torch.full((n,), v0); s3 = torch.zeros(n)
+            dp, dm, dv, ds = p.cuda(), m.cuda(), v.cuda(), s3.cuda()
+            p16 = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+            step = torch.zeros(1, dtype=torch.int32, device="cuda")
+            for t in range(1, 4):
+                gr = torch.randn(n, generator=g)
+                if name == "adam":
+                    OT.adam_step(p, gr, m, v, t, 1e-3, 0.5, 0.9); args = (1e-3, 0.5, 0.9, 1e-8)
+                elif name == "rmsprop":
+                    OT.rmsprop_step(p, gr, v, m, 1e-3, 0.9, 0.01); args = (1e-3, 0.9, 0.01, 1e-10)
+                elif name == "centered":
+                    OT.centered_rmsprop_step(p, gr, v, s3, m, 1e-3, 0.9, 0.01); args = (1e-3, 0.9, 0.01, 1e-10)
+                elif name == "sgd":
+                    OT.sgd_step(p, gr, 1e-2); args = (1e-2, 0.0, 0.0, 0.0)
+                elif name == "momentum":
+                    OT.momentum_step(p, gr, m, 1e-2, 0.9); args = (1e-2, 0.9, 0.0, 0.0)
+                elif name == "adagrad":
+                    OT.adagrad_step(p, gr, v, 1e-2); args = (1e-2, 0.0, 0.0, 0.0)
+                elif name == "adadelta":
+                    OT.adadelta_step(p, gr, v, m, 1.0); args = (1.0, 0.95, 0.0, 1e-8)
+                else:
+                    OT.ftrl_step(p, gr, v, m, 1e-2); args = (1e-2, 0.0, 0.0, 0.0)
+                dg = gr.cuda()
+                E.launch("b200_optim_step", E._p(dp), E._p(dm), E._p(dv), E._p(ds), E._p(dg), E._p(p16), n, kind, *args,
+                         1.0, 0.0, 1, E._p(step))
+                torch.cuda.synchronize()
+                assert float(dg.abs().max()) == 0.0, name                 # gradient reset in the same pass
+            assert torch.allclose(dp.cpu(), p, rtol=3e-5, atol=2e-6), (name, n)
+            assert int(step.item()) == 3
+            assert torch.equal(p16.cpu(), dp.cpu().to(torch.bfloat16))
+
+
+def test_transpose_batch_matches_per_tensor_transposes():
+    """The one-launch re-layout of a group's K-major weight copies (b200_transpose_batch) == per-tap transposes."""
+    import argparse
+    from b200gan import session as S
+    from b200gan.models import gan as gan_model
+    sess = S.Session(seed=0)
+    x_in = S.Input(4, (32, 32, 3), slots=2)
+    args = argparse.Namespace(model="iwgan", batch_size=4, latent_size=24, n_disc_train=1, optimizer="adam", lr=1e-4,
+                              beta1=0.5, beta2=0.9)
+    gan_model.gan(x_in, args)
+    sess.begin_step()
+    n = 0
+    for grp in sess.store.groups:
+        grp.p16.copy_(torch.randn(grp.size, device="cuda"))
+        grp.refresh_transposed()
         torch.cuda.synchronize()
-        assert torch.allclose(dp.cpu(), p, rtol=2e-5, atol=1e-6), name
-        assert int(step.item()) == 3
-        assert torch.equal(p16.cpu(), dp.cpu().to(torch.bfloat16))
+        for p in grp.params:
+            if p.p16_t is None:
+                continue
+            a, b = p.shape[-2], p.shape[-1]
+            want = p.p16.reshape(-1, a, b).transpose(1, 2).contiguous().reshape(-1)
+            assert torch.equal(p.p16_t, want), p.name
+            n += 1
+    assert n >= 3
 
 
 def test_philox_moments_and_counter():

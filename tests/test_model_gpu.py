@@ -189,3 +189,26 @@ def test_train_cli_runs_wgan_rmsprop_epoch(tmp_path):
     assert "discriminator/vars/c2/weights" in ck and "generator/BatchNorm/beta" in ck
     # WGAN: parameters were clipped to +-0.01 before each update, so they sit within clip + one step
     assert float(ck["discriminator/vars/c2/weights"].abs().max()) < 0.011
+
+
+def test_uint8_input_stage_equals_normalised_float_input():
+    """Input(dtype=uint8): the /255 of data.py:21-22,29 fused into the model's first op on the device gives the
+    same step as feeding the normalised float32 batch (the reference's `x`)."""
+    import argparse
+    import torch
+    from b200gan import session as S
+    from b200gan.models import gan as gan_model
+    gen = torch.Generator().manual_seed(11)
+    raw = torch.randint(0, 256, (3, 16, 32, 32, 3), generator=gen, dtype=torch.uint8)
+    outs = []
+    for dtype in (torch.float32, torch.uint8):
+        args = argparse.Namespace(model="iwgan", batch_size=16, latent_size=16, n_disc_train=2, optimizer="adam",
+                                  lr=1e-4, beta1=0.5, beta2=0.9)
+        sess = S.Session(seed=0, noise_seed=7)
+        sess.use_graphs = False
+        x_in = S.Input(16, (32, 32, 3), slots=3, dtype=dtype)
+        train = gan_model.gan(x_in, args)
+        x_in.ring.copy_(raw.cuda() if dtype == torch.uint8 else (raw.float() / 255.0).cuda())
+        outs.append(train(sess, args))
+    for k in outs[0]:
+        assert abs(outs[0][k] - outs[1][k]) <= 2e-3 * max(1.0, abs(outs[0][k])), outs
