@@ -541,22 +541,26 @@ def _slice(src, src_ld, src_off, dst, dst_ld, dst_off, rows, cols, mask=None):
 
 def unpad_channels(x):
     """[..., C_physical] -> [..., C_logical]: drop the zero channels a layer added (ops/layers.py)."""
-    cl, cp = x.logical_c, x.shape[-1]
-    rows = x.numel // cp
-    if x.f32:
-        raise K.B200Error("unpad_channels expects a bf16 tensor")
-    out = Tensor(empty(x.shape[:-1] + (cl,), BF16))
-    _slice(x.buf, cp, 0, out.buf, cl, 0, rows, cl)
+    cl = x.logical_c
+    out = take_channels(x, cl)
     if x.mask is not None and x.mask[0] is x:
         out.mask = (out, x.mask[1], x.mask[2])          # same activation values, own storage
+    return out
+
+
+def take_channels(x, c, mask=None):
+    """out = x[..., :c] * act'(mask): leading channel slice (un-padding), with the activation gradient of the
+    tensor the result is a gradient FOR fused in.  Its backward zero-pads again (both directions are recorded
+    ops, so the gradient-penalty's second-order sweep passes through them)."""
+    cp = x.shape[-1]
+    rows = x.numel // cp
+    xb = _as_bf16(x)
+    out = Tensor(empty(x.shape[:-1] + (c,), BF16), mask=mask)
+    _slice(xb.buf, cp, 0, out.buf, c, 0, rows, c, mask)
 
     def bw(gouts):
-        go = _as_bf16(gouts[0])
-        gx = Tensor(empty(x.shape, BF16))
-        launch("b200_fill_f32", _p(gx.buf), gx.numel // 2, 0.0)       # bf16 zeros, two per fp32 word
-        _slice(go.buf, cl, 0, gx.buf, cp, 0, rows, cl)
-        gx.logical_c = cl
-        return [gx]
+        gx = pad_channels(gouts[0], cp)
+        return [maskmul(gx, x.mask) if (x.mask is not None and x.mask[0] is not x) else gx]
 
     _record([x], [out], bw)
     return out
@@ -564,20 +568,18 @@ def unpad_channels(x):
 
 def pad_channels(x, cp):
     """[..., C] -> [..., cp] with zero channels appended (the inverse of unpad_channels): gives a dense layer whose
-    input width is not a multiple of 8 (e.g. latent_size 50) the 16-byte rows TMA needs."""
+    input width is not a multiple of 8 (e.g. latent_size 50) the 16-byte rows TMA needs, and is the backward of
+    take_channels."""
     c = x.shape[-1]
     rows = x.numel // c
     xb = _as_bf16(x)
     out = Tensor(empty(x.shape[:-1] + (cp,), BF16))
-    launch("b200_fill_f32", _p(out.buf), out.numel // 2, 0.0)
+    launch("b200_fill_f32", _p(out.buf), out.numel // 2, 0.0)        # bf16 zeros, two per fp32 word
     _slice(xb.buf, c, 0, out.buf, cp, 0, rows, c)
     out.logical_c = c
 
     def bw(gouts):
-        go = _as_bf16(gouts[0])
-        gx = Tensor(empty(x.shape, BF16), mask=x.mask)
-        _slice(go.buf, cp, 0, gx.buf, c, 0, rows, c, x.mask)
-        return [gx]
+        return [take_channels(gouts[0], c, x.mask)]
 
     _record([x], [out], bw)
     return out

@@ -122,9 +122,16 @@ def test_smooth_activation_chain_gradients_are_tight():
 
 
 def test_pix2pix_step_matches_oracle():
-    """BASELINE configs[4] shape (256x256 rgb + depth) at batch 2, --add_l1: U-Net generator with skip
-    concatenations, PatchGAN discriminator (512 -> 1 head), sigmoid-CE + L1 losses."""
-    res = P.pix2pix_step_parity(B=4, verbose=True)
+    """BASELINE configs[4] exactly (256x256 rgb + depth, batch 16), --add_l1: U-Net generator with skip
+    concatenations, PatchGAN discriminator (512 -> 1 head), sigmoid-CE + L1 losses; 3e-2 on every variable."""
+    res = P.pix2pix_step_parity(B=16, verbose=True)
+    assert res["ok"], res
+
+
+def test_pix2pix_small_batch_step_matches_oracle():
+    """Batch 4: the decoder's first batch norms see 16-64 samples per channel, which amplifies bf16 storage noise
+    (measured 1e-1 at the deepest encoder layer; see iwgan_step_parity's note): looser bar, same injected oracle."""
+    res = P.pix2pix_step_parity(B=4, verbose=True, grad_tol=0.15, cos_tol=0.985)
     assert res["ok"], res
 
 
