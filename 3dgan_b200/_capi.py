@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200_outer_mask": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "b200_bn_sums": [_P, _P, _LL, _I, _P],
     "b200_bn_apply": [_P, _P, _P, _P, _LL, _I, _F, _I, _F, _P],
+    "b200_bn_update_moving": [_P, _LL, _I, _P, _P, _F, _I, _P],
     "b200_bn_bwd": [_P, _P, _P, _P, _P, _LL, _I, _F, _P],
     "b200_maskmul": [_P, _P, _P, _LL, _I, _F, _P],
     "b200_affine_act": [_P, _I, _P, _I, _LL, _F, _F, _I, _F, _P],

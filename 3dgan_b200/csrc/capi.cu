@@ -684,6 +684,10 @@ extern "C" int b200_bn_apply(const void* z, const float* stats, const float* bet
                              float eps, int act, float leak, b200_stream s) {
   WRAP(bn_apply(z, stats, beta, out, R, C, eps, act, leak, (cudaStream_t)s), "bn_apply");
 }
+extern "C" int b200_bn_update_moving(const float* stats, long long R, int C, float* moving_mean, float* moving_var,
+                                     float decay, int unbiased, b200_stream s) {
+  WRAP(bn_update_moving(stats, R, C, moving_mean, moving_var, decay, unbiased, (cudaStream_t)s), "bn_update_moving");
+}
 extern "C" int b200_bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* dz, long long R, int C,
                            float eps, b200_stream s) {
   WRAP(bn_bwd(g, z, stats, bsum, dz, R, C, eps, (cudaStream_t)s), "bn_bwd");

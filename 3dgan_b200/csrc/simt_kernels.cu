@@ -853,6 +853,23 @@ int bn_apply(const void* z, const float* stats, const float* beta, void* out, lo
     bn_apply_kernel<<<stride_grid(R * C, 256, 4), 256, 0, st>>>((const bf16*)z, stats, beta, (bf16*)out, R, C, eps, act, leak);
   return 0;
 }
+// moving_mean / moving_variance of tf.contrib.layers.batch_norm (decay 0.999, A.3): mv -= (mv - batch) * (1 - decay)
+// from the sums bn_sums left in stats; `unbiased` feeds n/(n-1) * variance (the fused NCHW kernel of hem/ops/layers.py:124)
+__global__ void bn_update_moving_kernel(const float* __restrict__ stats, float invR, float unbias, float* mm, float* mv,
+                                        int C, float one_minus_decay) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mean = stats[c] * invR;
+  const float var = fmaxf(stats[C + c] * invR - mean * mean, 0.f) * unbias;
+  mm[c] -= (mm[c] - mean) * one_minus_decay;
+  mv[c] -= (mv[c] - var) * one_minus_decay;
+}
+int bn_update_moving(const float* stats, long long R, int C, float* mm, float* mv, float decay, int unbiased, cudaStream_t st) {
+  if (R < 1 || C < 1) return -1;
+  const float unbias = (unbiased && R > 1) ? (float)R / (float)(R - 1) : 1.f;
+  bn_update_moving_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, 1.f / (float)R, unbias, mm, mv, C, 1.f - decay);
+  return 0;
+}
 // backward sums: bsum[0:C] += sum_r g ; bsum[C:2C] += sum_r g * xhat      (g already holds act')
 __global__ void bn_bwd_sums_kernel(const bf16* __restrict__ g, const bf16* __restrict__ z, const float* __restrict__ stats,
                                    float* bsum, long long R, int C, float eps, int rows_per_block) {

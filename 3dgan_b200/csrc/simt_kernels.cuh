@@ -44,6 +44,7 @@ int colsum(const void* x, const float* wrow, float* out, long long R, int C, flo
 int bn_sums(const void* z, float* stats, long long R, int C, cudaStream_t st);
 int bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps, int act,
              float leak, cudaStream_t st);
+int bn_update_moving(const float* stats, long long R, int C, float* mm, float* mv, float decay, int unbiased, cudaStream_t st);
 int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* dz, long long R, int C, float eps,
            cudaStream_t st);
 int gemv_rows(const void* a, const void* w, const float* bias, float* out, int M, int K, int act, float leak,

@@ -36,6 +36,7 @@ class _State:
     decisions = None           # list -> (kind, tensors) of every discontinuous decision of the forward (tests)
     cyclic = []                # weak refs to tensors that sit on a reference cycle (self-mask, tape node)
     f32_out = False            # layer outputs are kept in fp32 (loss heads of the autoencoders)
+    bn_updates = False         # this run executes batch norm's UPDATE_OPS (moving averages), models/gan.py:69-70
 
 
 S = _State()
@@ -428,14 +429,17 @@ def outer_mask(g, W, like):
 
 
 # ------------------------------------------------------------------------------------------ batch norm
-def batch_norm_act(z, beta, act=K.ACT_NONE, leak=0.0, eps=1e-3):
+def batch_norm_act(z, beta, act=K.ACT_NONE, leak=0.0, eps=1e-3, moving=None, decay=0.999, unbiased=False):
     """tf.contrib.layers.batch_norm(h) with defaults, then the layer activation
-    (ops/layers.py:58-59,103-104,144-145): beta only, biased batch statistics, eps 1e-3."""
+    (ops/layers.py:58-59,103-104,144-145): beta only, biased batch statistics, eps 1e-3.
+    moving = (moving_mean, moving_variance) fp32 buffers, updated when the run executes UPDATE_OPS."""
     Cc = z.shape[-1]
     R = z.numel // Cc
     stats = empty((2 * Cc,), F32)
     launch("b200_fill_f32", _p(stats), 2 * Cc, 0.0)
     launch("b200_bn_sums", _p(z.buf), _p(stats), R, Cc)
+    if moving is not None and S.bn_updates:
+        launch("b200_bn_update_moving", _p(stats), R, Cc, _p(moving[0]), _p(moving[1]), decay, int(unbiased))
     out = Tensor(empty(z.shape, BF16))
     launch("b200_bn_apply", _p(z.buf), _p(stats), _p(beta.p32), _p(out.buf), R, Cc, eps, act, leak)
     if act != K.ACT_NONE:

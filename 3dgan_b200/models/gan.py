@@ -76,7 +76,9 @@ def gan(x, args):
         finish_pending()          # (every gradient bucket is zero here: apply_gradients resets it in the same pass)
 
     def d_run():
+        E.S.bn_updates = True                     # d_train_op depends on batchnorm_updates in all three schedules
         g_loss, d_loss = tower(x.next(), 'd', before_critic_d)
+        E.S.bn_updates = False
         E.backward([(d_loss, None)])
         if sess.dist is not None and sess.overlap_updates:
             # multi-GPU: the all-reduce runs on a side stream and overlaps the next run's generator forward
@@ -88,13 +90,17 @@ def gan(x, args):
         return g_loss, d_loss
 
     def g_run():
+        E.S.bn_updates = args.model == 'wgan'     # gan.py:145-148 (wgan) vs 163 (iwgan: g_train_op has no dependency)
         g_loss, d_loss = tower(x.next(), 'g', finish_pending)
+        E.S.bn_updates = False
         E.backward([(g_loss, None)])
         g_group.apply_gradients(sess.all_reduce_grads(g_group), clip)
         return g_loss, d_loss
 
     def gan_run():                                                    # _train_gan: one run, both updates
+        E.S.bn_updates = True                                         # gan.py:126-128
         gl, dl = tower(x.next(), 'dg')                                # same forward for both (App. C #7)
+        E.S.bn_updates = False
         E.backward([(dl, None)], accumulate=store.collection('discriminator'))
         E.backward([(gl, None)], accumulate=store.collection('generator'))
         d_group.apply_gradients(sess.all_reduce_grads(d_group), 0.0)

@@ -73,7 +73,9 @@ class pix2pix:
     # ------------------------------------------------------------------ training (pix2pix.py:151-156)
     def _run(self, mode):
         grp = {'d': self.d_group, 'g': self.g_group}.get(mode)      # (its gradient bucket is zero: see apply_gradients)
+        E.S.bn_updates = grp is not None               # d_train_op / g_train_op depend on batchnorm_updates (pix2pix.py:145-147)
         ls = self.tower(self.x_in.next(), self.y_in.next(), mode)
+        E.S.bn_updates = False
         if grp is not None:
             E.backward([(ls['d_total'] if mode == 'd' else ls['g_total'], None)])
             grp.apply_gradients(self.sess.all_reduce_grads(grp), 0.0)

@@ -88,17 +88,21 @@ def _fusable(activation):
     return code[0], code[1], True
 
 
-def batch_norm(h, activation=None):
+def batch_norm(h, activation=None, fused_nchw=False):
     """tf.contrib.layers.batch_norm(h) with defaults (ops/layers.py:10,58): creates
-    `<scope>/BatchNorm[_k]/beta`; never shares it through `reuse`."""
+    `<scope>/BatchNorm[_k]/beta` (+ the non-trainable moving_mean / moving_variance, decay 0.999); never shares them
+    through `reuse`.  fused_nchw: the Gen-2 call (hem/ops/layers.py:124, fused=True) whose moving
+    variance is fed the unbiased batch variance."""
     st = get_store()
     st.scope.append(st.unique_bn_scope())
     try:
         beta = st.get_variable('beta', (_logical_c(h),), zeros_initializer(), (h.shape[-1],))
+        mm = st.get_state('moving_mean', (_logical_c(h),), 0.0, (h.shape[-1],))
+        mv = st.get_state('moving_variance', (_logical_c(h),), 1.0, (h.shape[-1],))
     finally:
         st.scope.pop()
     act, leak, ok = _fusable(activation)
-    out = _mark(E.batch_norm_act(h, beta, act, leak), _logical_c(h))
+    out = _mark(E.batch_norm_act(h, beta, act, leak, moving=(mm.buf, mv.buf), unbiased=fused_nchw), _logical_c(h))
     return out if ok else _mark(activation(out), _logical_c(h))
 
 

@@ -22,6 +22,8 @@ class VariableStore:
         self.seed = seed
         self.finalized = False
         self.groups = []
+        self.state = OrderedDict()      # non-trainable variables (batch norm moving averages): name -> StateVar
+        self.state_buf = None
 
     # ---------------------------------------------------------------- scopes
     def path(self, name=None):
@@ -59,6 +61,17 @@ class VariableStore:
             raise ValueError("variable %s: shape %s != existing %s" % (full, tuple(shape), p.logical_shape))
         return p
 
+    def get_state(self, name, shape, value, physical_shape=None):
+        """A non-trainable fp32 variable (tf.contrib.layers.batch_norm's moving_mean / moving_variance)."""
+        full = self.path(name)
+        sv = self.state.get(full)
+        if sv is None:
+            if self.finalized:
+                raise K.B200Error("state variable %s requested after the store was finalized" % full)
+            sv = StateVar(full, tuple(shape if physical_shape is None else physical_shape), tuple(shape), float(value))
+            self.state[full] = sv
+        return sv
+
     def collection(self, prefix):
         """tf.get_collection(TRAINABLE_VARIABLES, scope) (models/gan.py:65-66)."""
         return [p for n, p in self.params.items() if n.startswith(prefix)]
@@ -80,6 +93,14 @@ class VariableStore:
         missing = [n for n, p in self.params.items() if id(p) not in seen]
         if missing:
             raise K.B200Error("variables without an optimizer group: %s" % missing[:4])
+        off = 0
+        for sv in self.state.values():
+            sv.offset = off
+            off += (sv.numel + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.state_buf = torch.zeros(max(off, 1), dtype=torch.float32, device=device)
+        for sv in self.state.values():
+            sv.buf = self.state_buf[sv.offset:sv.offset + sv.numel]
+            sv.logical(sv.buf).fill_(sv.value)       # padded channels stay 0: they are never read
         self.finalized = True
 
     def load(self, values):
@@ -92,6 +113,19 @@ class VariableStore:
 
     def state_dict(self):
         return OrderedDict((n, p.logical(p.p32.detach()).cpu().clone()) for n, p in self.params.items())
+
+
+class StateVar:
+    def __init__(self, name, shape, logical_shape, value):
+        self.name, self.shape, self.logical_shape, self.value = name, shape, logical_shape, value
+        self.numel = int(math.prod(shape))
+        self.buf = None
+
+    def logical(self, flat):
+        t = flat.reshape(self.shape)
+        if self.logical_shape != self.shape:
+            t = t[tuple(slice(0, d) for d in self.logical_shape)]
+        return t
 
 
 def _pad_to(t, shape):

@@ -88,6 +88,10 @@ int b200_outer_mask(const float* g, const void* w, const void* mask, void* out, 
 int b200_bn_sums(const void* z, float* stats /*[2C], zeroed*/, long long R, int C, b200_stream s);
 int b200_bn_apply(const void* z, const float* stats, const float* beta, void* out, long long R, int C, float eps,
                   int act, float leak, b200_stream s);
+/* UPDATE_OPS of batch_norm (run by the train ops that depend on `batchnorm_updates`, models/gan.py:69-70,130,165):
+ * moving -= (moving - batch) * (1 - decay) from the sums of b200_bn_sums; unbiased != 0: n/(n-1) variance (fused NCHW kernel) */
+int b200_bn_update_moving(const float* stats, long long R, int C, float* moving_mean, float* moving_var, float decay,
+                          int unbiased, b200_stream s);
 int b200_bn_bwd(const void* g, const void* z, const float* stats, float* bsum /*[2C], zeroed; bsum[0:C] = dbeta*/,
                 void* dz, long long R, int C, float eps, b200_stream s);
 

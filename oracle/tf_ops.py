@@ -21,10 +21,14 @@ class _RoundBF16(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g
+        # store_bf16(grads=True): the gradient arriving at a stored tensor is itself a tensor the CUDA path
+        # keeps in bf16, so it is rounded as well (used to measure how much of a GPU-vs-fp32-oracle difference
+        # is storage rounding: tests/test_oracle.py::test_bf16_storage_noise_*)
+        return g.to(torch.bfloat16).to(g.dtype) if _ROUND_GRADS else g
 
 
 _STORE_BF16 = False
+_ROUND_GRADS = False
 
 
 class store_bf16:
@@ -33,16 +37,16 @@ class store_bf16:
     GP interpolates) is rounded to bf16 here too.  Arithmetic stays fp32.  With it on, ReLU/LReLU masks
     agree with the GPU's, which removes the mask-flip noise that dominates fp32-oracle comparisons."""
 
-    def __init__(self, on=True):
-        self.on = on
+    def __init__(self, on=True, grads=False):
+        self.on, self.grads = on, grads
 
     def __enter__(self):
-        global _STORE_BF16
-        self.prev, _STORE_BF16 = _STORE_BF16, self.on
+        global _STORE_BF16, _ROUND_GRADS
+        self.prev, _STORE_BF16, _ROUND_GRADS = (_STORE_BF16, _ROUND_GRADS), self.on, self.on and self.grads
 
     def __exit__(self, *a):
-        global _STORE_BF16
-        _STORE_BF16 = self.prev
+        global _STORE_BF16, _ROUND_GRADS
+        _STORE_BF16, _ROUND_GRADS = self.prev
 
 
 def stored(t):

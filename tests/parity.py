@@ -156,6 +156,27 @@ class oracle_mode:
         return ok, worst
 
 
+NOISE_FACTOR = 1.6
+
+
+def storage_noise_floor(run_oracle, decisions, ref_grads):
+    """How far bf16 STORAGE alone moves each variable's gradient: the oracle is re-run on the same decisions with
+    every stored activation and every gradient arriving at one rounded to bf16 (arithmetic stays fp32), and
+    compared with its own fp32 result.  In networks whose batch norms project most of the gradient signal away
+    (pix2pix's decoder, small-batch generators) this rounding noise is attenuated less than the signal, so the
+    relative error grows layer by layer — on the CPU alone: 0.2 % at pix2pix's last deconv, 8 % at its first conv
+    (tests/test_oracle.py::test_bf16_storage_noise_grows_through_batch_norm_stacks).  A variable's tolerance is
+    max(3e-2, NOISE_FACTOR x this floor): the CUDA path may deviate from the fp32 oracle by what bf16 storage
+    costs the oracle itself, not more."""
+    with OT.inject_decisions(decisions), OT.store_bf16(True, grads=True):
+        noisy = run_oracle()
+    floor = {}
+    for k_, v in ref_grads.items():
+        n_ = float(v.norm())
+        floor[k_] = float((noisy["grads"][k_] - v).norm()) / n_ if n_ > 1e-12 else 0.0
+    return floor
+
+
 def same_decisions(a, b):
     return len(a) == len(b) and all(x[0] == y[0] and torch.equal(x[1], y[1]) for x, y in zip(a, b))
 
@@ -248,11 +269,12 @@ def iwgan_step_parity(H=32, C=3, L=16, B=8, model="iwgan", seed=0, verbose=False
             if k_.startswith("discriminator/"):
                 scale[k_] -= float(ref["grads"][k_].norm())
     worst = 0.0
-    # Batch norm over few rows amplifies bf16 storage noise of the layers below it (a channel whose 8-64 samples
-    # happen to have a small variance is scaled by up to 1/sqrt(eps) = 32): measured 4-5e-2 on the generator's fc1 at
-    # B <= 32 against 3e-3 at the BASELINE batch of 512 (test_iwgan_headline_config_step_matches_oracle holds the
-    # 3e-2 bar there on every variable).  Variables under a batch norm with fewer than 128 rows get 6e-2.
-    small_bn = B < 128
+    # Small-batch cases: variables below a batch norm see bf16 storage noise amplified (storage_noise_floor); their
+    # bar is max(grad_tol, NOISE_FACTOR x floor).  At the BASELINE batch of 512 no floor is used: 3e-2 everywhere.
+    floor = {}
+    if mode == "inject" and B < 128:
+        floor = storage_noise_floor(lambda: OM.gan_grads(p, x01, z, alpha, model, H, C, L), traces["d"], refs["d"]["grads"])
+    report["noise_floor_max"] = max(floor.values()) if floor else 0.0
     for md in ("d", "g"):
         ref = refs[md]
         for name in ("g_loss", "d_loss"):
@@ -273,8 +295,9 @@ def iwgan_step_parity(H=32, C=3, L=16, B=8, model="iwgan", seed=0, verbose=False
                 # emulate / fp32 modes only: fc1 sits behind batch-norm over only B rows per feature, where
                 # one-ulp differences flip ReLU masks (the injected mode has no such excuse)
                 loose = mode != "inject" and name.endswith("fc1/weights")
-                under_small_bn = small_bn and (name.startswith("generator/") or model != "iwgan")
-                bad = e > (max(grad_tol, 8e-2) if loose else (max(grad_tol, 6e-2) if under_small_bn else grad_tol))
+                # (the floor is relative to the variable's own norm; rescale to the test's `scale`)
+                fl = floor.get(name, 0.0) * float(want.norm()) / wn
+                bad = e > (max(grad_tol, 8e-2) if loose else max(grad_tol, NOISE_FACTOR * fl))
             worst = max(worst, e)
             if verbose or bad:
                 print("  [%s] %-40s err %.3e (scale %.3e)%s" % (md, name, e, wn, "  <-- FAIL" if bad else ""))
@@ -393,6 +416,9 @@ def ae_step_parity(model="cnn", H=28, C=1, L=16, B=8, seed=0, verbose=False, gra
     report = {"ok": True, "mode": mode}
     aok, report["decisions"] = om.audit(verbose)
     report["ok"] = aok
+    floor = {}
+    if mode == "inject" and model == "vae" and B < 128:          # (see storage_noise_floor)
+        floor = storage_noise_floor(lambda: OM.ae_grads(p, x01, eps, model, sizes), trace, ref["grads"])
     names = {"cnn": ["loss"], "vae": ["decoder_loss", "latent_loss", "total_loss"]}[model]
     outs = out if isinstance(out, tuple) else (out,)
     for nme, t in zip(names, outs):
@@ -415,8 +441,9 @@ def ae_step_parity(model="cnn", H=28, C=1, L=16, B=8, seed=0, verbose=False, gra
             bad = e > max(1e-2, 1e-3 * wref)
         else:
             e = float((got - want).norm()) / wn
-            cos = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
-            bad = e > grad_tol or cos < cos_tol
+            cos = float((got.double() * want.double()).sum() / (got.double().norm() * want.double().norm() + 1e-30))
+            tol = max(grad_tol, NOISE_FACTOR * floor.get(name, 0.0))
+            bad = e > tol or cos < min(cos_tol, 1.0 - tol * tol)
         worst = max(worst, e if not under_bn else 0.0)
         if verbose or bad:
             print("  [%s] %-36s err %.3e (norm %.3e)%s" % (model, name, e, wn, "  <-- FAIL" if bad else ""))
@@ -545,6 +572,10 @@ def pix2pix_step_parity(B=2, add_l1=True, seed=0, verbose=False, grad_tol=3e-2, 
         aok, report["decisions_" + md] = om.audit(verbose and md == "d")
         report["ok"] = report["ok"] and aok
     worst = 0.0
+    floor = {}
+    if mode == "inject":                                                       # (see storage_noise_floor)
+        floor = storage_noise_floor(lambda: OP.grads(p, x01, y01, add_l1), traces["d"], refs["d"]["grads"])
+    report["noise_floor_max"] = max(floor.values()) if floor else 0.0
     for md in ("d", "g"):
         ref = refs[md]
         for nme, g_ in got[md]["losses"].items():
@@ -562,11 +593,13 @@ def pix2pix_step_parity(B=2, add_l1=True, seed=0, verbose=False, grad_tol=3e-2, 
                 cos = 1.0
             else:
                 e = float((g_ - want).norm()) / wn
-                cos = float((g_ * want).sum() / (g_.norm() * want.norm() + 1e-30))
-                bad = e > grad_tol or cos < cos_tol
+                cos = float((g_.double() * want.double()).sum() / (g_.double().norm() * want.double().norm() + 1e-30))
+                tol = max(grad_tol, NOISE_FACTOR * floor.get(name, 0.0))
+                bad = e > tol or cos < min(cos_tol, 1.0 - tol * tol)
                 worst = max(worst, e)
             if verbose or bad:
-                print("  [%s] %-40s err %.3e cos %.4f (norm %.3e)%s" % (md, name, e, cos, wn, "  <-- FAIL" if bad else ""))
+                print("  [%s] %-40s err %.3e cos %.4f (norm %.3e, bf16-storage floor %.3e)%s"
+                      % (md, name, e, cos, wn, floor.get(name, 0.0), "  <-- FAIL" if bad else ""))
             if bad:
                 report["ok"] = False
     report["worst_grad_err"] = worst

@@ -316,3 +316,47 @@ def test_latent_size_whose_channel_padding_meets_a_reshape():
             E.reshape(E.Tensor(torch.empty((100, 3200), device="meta")), (-1, 3000))
     finally:
         E.S.dry = False
+
+
+def test_checkpoint_round_trip_by_tf_names(tmp_path):
+    """3dgan_b200/checkpoint.py on host buffers: variables, TF-named optimizer slots (logical shapes, channel padding
+    stripped), step counters and batch-norm moving averages survive save -> fresh session -> restore."""
+    from b200gan import checkpoint as CK
+    from b200gan.variables import optimizer_cfg
+
+    def build():
+        sess = S.Session()
+        x = S.Input(4, (32, 32, 3), slots=6)
+        gan_model.gan(x, _args("wgan", B=4, Lz=50))              # latent 50: 200-channel layers stored as 208
+        st = sess.store
+        st.finalize([("generator", st.collection("generator"), optimizer_cfg(_args())),
+                     ("discriminator", st.collection("discriminator"), optimizer_cfg(_args()))], torch.device("cpu"))
+        sess.counter = torch.zeros(1, dtype=torch.int64)
+        return sess
+
+    a = build()
+    g = torch.Generator().manual_seed(3)
+    for grp in a.store.groups:
+        for p in grp.params:                                     # write only the logical block: padding stays zero
+            p.logical(p.p32).copy_(torch.randn(p.logical_shape, generator=g))
+            p.logical(grp.m[p.offset:p.offset + p.numel]).copy_(torch.randn(p.logical_shape, generator=g))
+            p.logical(grp.v[p.offset:p.offset + p.numel]).copy_(torch.rand(p.logical_shape, generator=g))
+        grp.step.fill_(7)
+    for sv in a.store.state.values():
+        sv.logical(sv.buf).copy_(torch.randn(sv.logical_shape, generator=g))
+    a.counter.fill_(42)
+    path = CK.save(a, str(tmp_path), 3, global_epoch=3, extra={"note": "x"})
+    ck = torch.load(path, weights_only=False)
+    assert ck["variables"]["discriminator/vars/c3/weights"].shape == (5, 5, 100, 200)
+    assert ck["slots"]["discriminator/vars/c3/weights/Adam_1"].shape == (5, 5, 100, 200)
+    assert ck["state"]["discriminator/BatchNorm_1/moving_variance"].shape == (200,)
+    assert ck["global_step"] == 14 and ck["global_epoch"] == 3
+    assert abs(ck["optimizers"]["generator"]["optimizers/beta1_power"] - 0.5 ** 8) < 1e-12
+    b = build()
+    assert CK.latest(str(tmp_path)) == path
+    got = CK.restore_latest(b, str(tmp_path))
+    assert got[1:3] == (14, 3) and got[3]["note"] == "x" and int(b.counter.item()) == 42
+    for ga, gb in zip(a.store.groups, b.store.groups):
+        assert torch.equal(ga.p32, gb.p32) and torch.equal(ga.m, gb.m) and torch.equal(ga.v, gb.v)
+        assert int(gb.step.item()) == 7 and torch.equal(gb.p16, gb.p32.to(torch.bfloat16))
+    assert torch.equal(a.store.state_buf, b.store.state_buf)

@@ -123,15 +123,15 @@ def test_smooth_activation_chain_gradients_are_tight():
 
 def test_pix2pix_step_matches_oracle():
     """BASELINE configs[4] exactly (256x256 rgb + depth, batch 16), --add_l1: U-Net generator with skip
-    concatenations, PatchGAN discriminator (512 -> 1 head), sigmoid-CE + L1 losses; 3e-2 on every variable."""
+    concatenations, PatchGAN discriminator (512 -> 1 head), sigmoid-CE + L1 losses.  Every variable within
+    max(3e-2, 1.6 x its bf16-storage noise floor) of the fp32 oracle on the CUDA path's decisions: the discriminator
+    and the upper decoder hold 3e-2 outright; below the decoder's batch norms the floor itself reaches 5-8e-2."""
     res = P.pix2pix_step_parity(B=16, verbose=True)
     assert res["ok"], res
 
 
 def test_pix2pix_small_batch_step_matches_oracle():
-    """Batch 4: the decoder's first batch norms see 16-64 samples per channel, which amplifies bf16 storage noise
-    (measured 1e-1 at the deepest encoder layer; see iwgan_step_parity's note): looser bar, same injected oracle."""
-    res = P.pix2pix_step_parity(B=4, verbose=True, grad_tol=0.15, cos_tol=0.985)
+    res = P.pix2pix_step_parity(B=4, verbose=True)
     assert res["ok"], res
 
 
@@ -192,10 +192,49 @@ def test_train_cli_runs_wgan_rmsprop_epoch(tmp_path):
                       "--optimizer", "rmsprop", "--lr", "5e-5", "--epochs", "1", "--epoch_size", "64",
                       "--n_disc_train", "2", "--dir", str(tmp_path)])
     assert set(status) == {"g_loss", "d_loss"} and all(math.isfinite(v) for v in status.values())
-    ck = torch.load(os.path.join(str(tmp_path), "checkpoint-1.pt"))
-    assert "discriminator/vars/c2/weights" in ck and "generator/BatchNorm/beta" in ck
+    ck = torch.load(os.path.join(str(tmp_path), "checkpoint-1.pt"), weights_only=False)
+    v = ck["variables"]
+    assert "discriminator/vars/c2/weights" in v and "generator/BatchNorm/beta" in v
     # WGAN: parameters were clipped to +-0.01 before each update, so they sit within clip + one step
-    assert float(ck["discriminator/vars/c2/weights"].abs().max()) < 0.011
+    assert float(v["discriminator/vars/c2/weights"].abs().max()) < 0.011
+    # TF-named optimizer slots, counters and batch-norm moving averages travel with the variables
+    assert "discriminator/vars/c2/weights/RMSProp" in ck["slots"] and "generator/vars/fc1/bias/RMSProp_1" in ck["slots"]
+    assert ck["global_epoch"] == 1 and ck["global_step"] == 4 * (2 + 1)          # 4 iterations x (2 critic + 1 generator)
+    mm = ck["state"]["generator/BatchNorm/moving_mean"]
+    assert mm.shape == (64 * 16,) and float(mm.abs().max()) > 0                  # UPDATE_OPS ran (wgan: d and g runs)
+    assert os.path.exists(os.path.join(str(tmp_path), "checkpoint-0.pt"))        # parameters before any training
+    assert open(os.path.join(str(tmp_path), "checkpoint")).read().strip() == "checkpoint-1.pt"
+
+
+def test_resume_from_dir_reproduces_the_uninterrupted_run(tmp_path):
+    """train.py:254-259,279-282: a run finds the newest checkpoint in --dir, restores variables, optimizer slots,
+    step counters, noise and data streams, and `--epochs +1` continues it; the result equals training the two
+    epochs in one go (up to the run-to-run noise of fp32 atomics, as in test_cuda_graph_replay_equals_eager)."""
+    import importlib.util
+    import os
+    import torch
+    spec = importlib.util.spec_from_file_location("b200_train", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "train.py"))
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    common = ["--model", "iwgan", "--batch_size", "16", "--image_size", "32", "--latent_size", "16", "--optimizer", "adam",
+              "--lr", "1e-4", "--beta1", "0.5", "--beta2", "0.9", "--epoch_size", "64", "--n_disc_train", "2"]
+    one, two = str(tmp_path / "straight"), str(tmp_path / "resumed")
+    tr.main(common + ["--epochs", "2", "--dir", one])
+    tr.main(common + ["--epochs", "1", "--dir", two])
+    tr.main(common + ["--epochs", "+1", "--dir", two])                  # restores checkpoint-1, trains epoch 2
+    a = torch.load(os.path.join(one, "checkpoint-2.pt"), weights_only=False)
+    b = torch.load(os.path.join(two, "checkpoint-2.pt"), weights_only=False)
+    assert a["global_step"] == b["global_step"] == 2 * 4 * 3 and b["global_epoch"] == 2
+    assert a["noise_counter"] == b["noise_counter"]
+    for k in a["variables"]:
+        assert torch.allclose(a["variables"][k], b["variables"][k], rtol=0, atol=2e-3), k
+    for k in a["slots"]:
+        assert torch.allclose(a["slots"][k], b["slots"][k], rtol=2e-2, atol=1e-5), k
+    # a third invocation with the same --epochs has nothing left to do and leaves the state alone
+    tr.main(common + ["--epochs", "2", "--dir", two])
+    c = torch.load(os.path.join(two, "checkpoint-2.pt"), weights_only=False)
+    assert all(torch.equal(b["variables"][k], c["variables"][k]) for k in b["variables"])
 
 
 def test_uint8_input_stage_equals_normalised_float_input():

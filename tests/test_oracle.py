@@ -180,3 +180,24 @@ def test_l1_sign_injection_matches_abs():
     with OT.inject_decisions([("l1", torch.sign(a.detach() - b))]):
         got = torch.autograd.grad(OT.l1_mean(a, b), a)[0]
     assert torch.equal(ref, got)
+
+
+def test_bf16_storage_noise_grows_through_batch_norm_stacks():
+    """Why the GPU parity bars are calibrated per variable (tests/parity.py::storage_noise_floor): on the CPU
+    alone, rounding stored activations and gradients to bf16 (same masks, fp32 arithmetic) moves pix2pix's
+    gradients by ~0.2 % at the last deconv but several % below the decoder's batch norms, which project most of
+    the gradient signal away while passing the rounding noise."""
+    from oracle import pix2pix as OP
+    gs, ds = OP.param_specs()
+    p = OP.init_params(OrderedDict(list(gs.items()) + list(ds.items())), 0)
+    g = torch.Generator().manual_seed(5)
+    x01, y01 = torch.rand(1, 256, 256, 3, generator=g), torch.rand(1, 256, 256, 1, generator=g)
+    with OT.record_decisions() as rec:
+        a = OP.grads(p, x01, y01, True)
+    with OT.inject_decisions(rec.queue), OT.store_bf16(True, grads=True):
+        b = OP.grads(p, x01, y01, True)
+    rel = lambda k: float((a["grads"][k] - b["grads"][k]).norm() / a["grads"][k].norm())
+    assert rel("generator/decoder/vars/8/weights") < 1e-2
+    assert rel("discriminator/vars/m1/weights") < 1e-2
+    assert rel("generator/enocder/vars/1/weights") > 3e-2
+    assert rel("generator/enocder/vars/1/weights") > 5 * rel("generator/decoder/vars/8/weights")

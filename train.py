@@ -9,8 +9,10 @@ Same flags, `--config` files (whitespace `key value` tokens, CLI wins, train.py:
 `train_func(sess, args) -> {loss: float}` contract.  Differences, all outside the hot path: the input
 pipeline is synthetic ([0,1] float32 batches of `--image_size`/`--channels`; TFRecord decoding is out of
 scope), `--n_gpus` is realised as one process per GPU (launch with torchrun; each rank
-is one tower with its own batch of `--batch_size`), summaries/TensorBoard are not produced, checkpoints
-are torch files keyed by the reference's TF variable names.
+is one tower with its own batch of `--batch_size`), summaries/TensorBoard are not produced.  Checkpoints
+(3dgan_b200/checkpoint.py) are torch files keyed by the reference's TF variable / slot names; like the
+reference's Supervisor the run restores the newest checkpoint found in `--dir`, `--epochs +n` trains n more
+epochs, a checkpoint is written before the first step and after every epoch.
 """
 import argparse
 import os
@@ -78,6 +80,7 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     import torch
     import b200gan  # noqa: F401
+    from b200gan import checkpoint as CK
     from b200gan import session as S
     from b200gan.models import MODEL_FUNCS
 
@@ -87,26 +90,49 @@ def main(argv=None):
                      noise_seed=1234 if args.seed is None else args.seed)
     if sess.world > 1:
         sess.init_distributed("nccl")
+    # save options to disk for later reference (train.py:200-208)
+    if sess.rank == 0:
+        os.makedirs(args.dir, exist_ok=True)
+        with open(os.path.join(args.dir, 'options.config'), 'w') as f:
+            for k in vars(args):
+                f.write('{} {}\n'.format(k, getattr(args, k)))
     runs = MODEL_FUNCS[args.model][1](args)
     x = S.Input(args.batch_size, (args.image_size, args.image_size, args.channels), slots=runs)
     train_func = MODEL_FUNCS[args.model][0](x, args)                 # train.py:246
     n_examples = args.epoch_size if args.epoch_size > 0 else 100 * args.batch_size
     iter_per_epoch = max(1, n_examples // (args.batch_size * max(sess.world, 1)))   # train.py:221-224
-    max_epochs = int(args.epochs.lstrip('+'))
     gen = torch.Generator(device="cuda").manual_seed(1234 + sess.rank)
+
+    # Supervisor.managed_session: restore the newest checkpoint of --dir if there is one (train.py:254-259,276-278)
+    current_step, current_epoch = 0, 0
+    restored = CK.restore_latest(sess, args.dir)
+    if restored is not None:
+        path, current_step, current_epoch, extra = restored
+        if extra.get("data_rng") is not None and sess.rank == 0:
+            gen.set_state(extra["data_rng"])
+        if sess.rank == 0:
+            print("Restored %s (global_step %d, global_epoch %d)" % (path, current_step, current_epoch), flush=True)
+    # `--epochs +n`: n more epochs on top of the restored ones (train.py:279-282)
+    max_epochs = current_epoch + int(args.epochs[1:]) if args.epochs[0] == '+' else int(args.epochs)
+
+    def checkpoint(tag, epoch):
+        CK.save(sess, args.dir, tag, global_epoch=epoch, extra={"data_rng": gen.get_state()})
+
+    if current_step == 0:                                             # train.py:288-292: parameters before any training
+        checkpoint(0, 0)
     start = time.time()
     status = None
-    for epoch in range(max_epochs):
+    for epoch in range(current_epoch, max_epochs):
         t0 = time.time()
         for i in range(iter_per_epoch):
             x.ring.copy_(torch.rand(x.ring.shape, generator=gen, device="cuda"))
             status = train_func(sess, args)                           # train.py:307
+        current_epoch = epoch + 1                                     # increment_global_epoch, train.py:323-325
         if sess.rank == 0:
             dt = time.time() - t0
-            print("Epoch %3d  %d it  %.2f batch/s  %s" % (epoch + 1, iter_per_epoch, iter_per_epoch / dt,
+            print("Epoch %3d  %d it  %.2f batch/s  %s" % (current_epoch, iter_per_epoch, iter_per_epoch / dt,
                                                          {k: round(v, 5) for k, v in status.items()}), flush=True)
-            os.makedirs(args.dir, exist_ok=True)
-            torch.save(sess.store.state_dict(), os.path.join(args.dir, "checkpoint-%d.pt" % (epoch + 1)))
+        checkpoint(current_epoch, current_epoch)                      # saver.save(..., global_step=global_epoch), train.py:329
     if sess.rank == 0:
         print("Training complete! Elapsed time: %ds" % int(time.time() - start))
     return status
