@@ -74,6 +74,7 @@ static int make_tmap(CUtensorMap* tm, const void* base, int rank, const long lon
   return 0;
 }
 
+static long long align256(long long v);
 static int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -106,6 +107,43 @@ static int weight_prefetch() {
 
 static bool is_small(int c) { return c <= 4; }
 
+// Split-K for tensor-core layers with few output tiles and long reductions (pix2pix's inner U-Net layers: 16..1024
+// output pixels, K = 16 taps x 512..1024 channels): without it a handful of CTAs stream the whole weight tensor.
+// Returns the number of K slices (1 = off) for the fprop (op 0) / dgrad (op 1) launch of this geometry.
+static int tc_tap_splits(const b200_conv_geom* g, int op) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("B200GAN_TAPSPLIT"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return 1;
+  const int st = g->stride, kk = g->k * g->k;
+  int bw, bh, bn;
+  long long ctas;
+  int iters;
+  if (op == 0) {
+    pick_pixel_tile(g->Wo, g->Ho, kTileM, &bw, &bh, &bn);
+    const int tiles = cdiv(g->Wo, bw) * cdiv(g->Ho, bh) * cdiv(g->N, bn);
+    const int kch = cdiv(g->Cin, kBlockK);
+    iters = kk * kch;
+    const int dual = tapgemm_dual(tiles, iters);
+    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * cdiv(g->Cout, pick_bn_tile(g->Cout));
+  } else {
+    const int ew = cdiv(g->W, st), eh = cdiv(g->H, st);
+    pick_pixel_tile(ew, eh, kTileM, &bw, &bh, &bn);
+    const int tiles = cdiv(ew, bw) * cdiv(eh, bh) * cdiv(g->N, bn);
+    const int kch = cdiv(g->Cout, kBlockK);
+    const int phases = st * st;
+    iters = std::max(1, kk / phases) * kch;                      // per phase
+    const int dual = tapgemm_dual(tiles, kch);
+    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * cdiv(g->Cin, pick_bn_tile(g->Cin)) * phases;
+  }
+  if (ctas >= 64 || iters < 16) return 1;
+  int s = (int)(160 / ctas);
+  s = std::min(s, iters / 4);
+  return std::max(s, 1);
+}
+static long long tc_out_elems(const b200_conv_geom* g, int op) {
+  return op == 0 ? (long long)g->N * g->Ho * g->Wo * g->Cout : (long long)g->N * g->H * g->W * g->Cin;
+}
+
 extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
   const int kk = g->k * g->k;
   if (is_small(g->Cin)) {
@@ -124,7 +162,7 @@ extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
 // the SIMT small-channel / small-output epilogues do not)
 extern "C" int b200_conv2d_epilogue_bits(const b200_conv_geom* g, int op, int has_workspace) {
   const int r = b200_conv2d_route(g, op);
-  if (r == 1) return op == 0 || op == 1;
+  if (r == 1) return (op == 0 || op == 1) && !(has_workspace && tc_tap_splits(g, op) > 1);
   if (r == 2) return op == 0 && has_workspace && (g->Cout % 8 == 0);
   return 0;
 }
@@ -342,12 +380,36 @@ static int small_kp(const b200_conv_geom* g) { return cdiv(g->k * g->k * g->Cin,
 static bool small_gemm_ok(const b200_conv_geom* g) { return g->Cout % 8 == 0; }
 
 extern "C" long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op) {
+  if (!is_small(g->Cin) && op != 2 && b200_conv2d_route(g, op) == 1)      // split-K partial sums: fp32 image of the output
+    return tc_tap_splits(g, op) > 1 ? align256(tc_out_elems(g, op) * 4) : 0;
   if (!is_small(g->Cin) || !small_gemm_ok(g)) return 0;
   const long long M = (long long)g->N * g->Ho * g->Wo;
   const int Kp = small_kp(g);
   if (op == 0) return align256(M * Kp * 2) + align256((long long)g->Cout * Kp * 2);
   if (op == 1) return align256(M * Kp * 4);
   return align256(M * Kp * 2);
+}
+
+// Split-K launch of a prepared tap GEMM (see tc_tap_splits): zero the fp32 workspace, let every K slice add its
+// partial tile into it, then apply the caller's epilogue in one elementwise pass.  Returns false when the launch
+// should go the normal way (no split for this geometry, or no workspace was passed).
+static bool run_split_k(TapGemmParams& p, const b200_conv_geom* g, int op, const b200_epilogue* e, void* out,
+                        void* workspace, long long workspace_bytes, cudaStream_t st) {
+  const int splits = tc_tap_splits(g, op);
+  const long long n = tc_out_elems(g, op);
+  if (splits <= 1 || !workspace || workspace_bytes < n * 4 || (e && e->accumulate)) return false;
+  cudaMemsetAsync(workspace, 0, n * 4, st);
+  p.splits = splits;
+  p.cta2 = 0;
+  p.stages = pick_stages(tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail));
+  p.out = workspace;
+  p.out_f32 = 1; p.accumulate = 2;
+  p.bias = nullptr; p.act = 0; p.mask_src = nullptr; p.mask_bits = nullptr; p.bits_out = nullptr;
+  p.tma_store = 0;
+  launch_tapgemm(p, st);
+  splitk_finalize((const float*)workspace, out, e ? e->out_f32 : 0, n, p.ncols, e ? e->bias : nullptr, e ? e->act : 0,
+                  e ? e->leak : 0.f, e ? e->mask_src : nullptr, e ? e->mask_kind : 0, st);
+  return true;
 }
 
 extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, void* y, const b200_conv_geom* g,
@@ -440,6 +502,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
                                          : tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail)),
                       std::max(2, (p.kchunks - p.merge_tail) * g->k * g->k));
   p.out = y;
+  if (run_split_k(p, g, 0, e, y, workspace, workspace_bytes, st)) return check_launch("conv2d_fprop(split-K)");
   setup_out_maps(p, e);
   launch_tapgemm(p, st);
   return check_launch("conv2d_fprop");
@@ -566,6 +629,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.stages = pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
                                 : tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail));
   p.out = dx;
+  if (run_split_k(p, g, 1, e, dx, workspace, workspace_bytes, st)) return check_launch("conv2d_dgrad(split-K)");
   setup_out_maps(p, e);
   launch_tapgemm(p, st);
   return check_launch("conv2d_dgrad");

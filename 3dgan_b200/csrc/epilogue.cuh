@@ -145,7 +145,8 @@ __device__ __noinline__ static void epilogue_store16_slow(const EpilogueArgs& e,
     else if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[o + j]), e.mask_kind, e.leak);
     if (e.out_f32) {
       float* dst = reinterpret_cast<float*>(e.out) + o + j;
-      *dst = e.accumulate ? *dst + v : v;
+      if (e.accumulate == 2) atomicAdd(dst, v);
+      else *dst = e.accumulate ? *dst + v : v;
     } else {
       reinterpret_cast<__nv_bfloat16*>(e.out)[o + j] = __float2bfloat16(v);
     }
@@ -269,6 +270,11 @@ __device__ __forceinline__ void epilogue_store16(const EpilogueArgs& e, const ui
     for (int j = 0; j < 16; j += 4) {
       if (j < nv) {
         float4 f = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (e.accumulate == 2) {                         // split-K partial tile: fire-and-forget vector reduction
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(f.x), "f"(f.y), "f"(f.z),
+                       "f"(f.w) : "memory");
+          continue;
+        }
         if (e.accumulate) {
           const float4 old = *reinterpret_cast<const float4*>(dst + j);
           f.x += old.x; f.y += old.y; f.z += old.z; f.w += old.w;

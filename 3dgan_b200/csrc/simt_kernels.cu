@@ -601,6 +601,29 @@ int rowscale(const void* in, const float* s, float mul, float add, void* out, in
   return 0;
 }
 
+// Epilogue of a split-K tap GEMM: out[i] = act(ws[i] + bias[i % C]) * act'(mask[i]) over the fp32 workspace the K
+// slices reduced into (same element order as the output tensor, channels innermost).
+template <typename TO>
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, TO* __restrict__ out, long long n, int C,
+                                       const float* __restrict__ bias, int act, float leak,
+                                       const bf16* __restrict__ mask, int mask_kind) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = ws[i];
+    if (bias) v += __ldg(bias + (int)(i % C));
+    v = act_fwd(v, act, leak);
+    if (mask) v *= act_grad_from_out(__bfloat162float(mask[i]), mask_kind, leak);
+    from_f32(out[i], v);
+  }
+}
+int splitk_finalize(const float* ws, void* out, int out_f32, long long n, int C, const float* bias, int act, float leak,
+                    const void* mask, int mask_kind, cudaStream_t st) {
+  const int grid = stride_grid(n, 256, 2);
+  if (out_f32) splitk_finalize_kernel<float><<<grid, 256, 0, st>>>(ws, (float*)out, n, C, bias, act, leak, (const bf16*)mask, mask_kind);
+  else splitk_finalize_kernel<bf16><<<grid, 256, 0, st>>>(ws, (bf16*)out, n, C, bias, act, leak, (const bf16*)mask, mask_kind);
+  return 0;
+}
+
 // out[r, out_off + c] = in[r, in_off + c] * act'(mask[r, c])  for c < cols: column-slice copy between row-major bf16
 // matrices with different row strides.  Channel concatenation (pix2pix skip connections, hem/models/pix2pix.py:
 // 210-222) writes each piece into its slice of the concat buffer; its backward reads the slice back and applies
@@ -1320,35 +1343,58 @@ int optim_step(float* p, float* m, float* v, float* s3, float* g, void* p16, lon
 // Re-layout of every K-major weight copy of one optimizer group in ONE launch: entry e describes a [T][A][B] bf16
 // block of the group's compute copy and the [T][B][A] destination (transposed per filter tap); the 32x32 tiles of
 // all entries are numbered consecutively (tile_begin) and a block finds its entry by scanning the short table.
-__global__ void transpose_batch_kernel(const TransposeEntry* __restrict__ tab, int count) {
-  __shared__ float tile[32][33];
+__global__ void __launch_bounds__(256) transpose_batch_kernel(const TransposeEntry* __restrict__ tab, int count) {
+  // 64 x 64 tiles, 16-byte global accesses on both sides; the tile is transposed on its way into shared memory
+  __shared__ bf16 sm[64][66];                 // sm[b][a]; 66: rows 4-byte aligned, bank = (b + a/2) % 32
   __shared__ TransposeEntry e;
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
+  if (threadIdx.x == 0) {
     int k = 0;
     while (k + 1 < count && (long long)blockIdx.x >= tab[k + 1].tile_begin) ++k;
     e = tab[k];
   }
   __syncthreads();
-  const int tb = (e.B + 31) / 32, ta = (e.A + 31) / 32;
+  const int A = e.A, B = e.B;
+  const int tb = (B + 63) / 64, ta = (A + 63) / 64;
   int t = (int)((long long)blockIdx.x - e.tile_begin);
   const int bx = t % tb; t /= tb;
   const int by = t % ta; t /= ta;
-  const bf16* in = reinterpret_cast<const bf16*>(e.in) + (long long)t * e.A * e.B;
-  bf16* out = reinterpret_cast<bf16*>(e.out) + (long long)t * e.A * e.B;
-  const int a0 = by * 32, b0 = bx * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int a = a0 + i, b = b0 + threadIdx.x;
-    if (a < e.A && b < e.B) tile[i][threadIdx.x] = __bfloat162float(in[(long long)a * e.B + b]);
+  const bf16* in = reinterpret_cast<const bf16*>(e.in) + (long long)t * A * B;
+  bf16* out = reinterpret_cast<bf16*>(e.out) + (long long)t * A * B;
+  const int a0 = by * 64, b0 = bx * 64;
+  const int lane8 = (threadIdx.x & 7) * 8, row = threadIdx.x >> 3;          // 8 vectors per 64-wide row, 32 rows per pass
+  const bool vin = (B & 7) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+  const bool vout = (A & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int a = a0 + row + 32 * i, b = b0 + lane8;
+    if (a < A) {
+      if (vin && b + 8 <= B) {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + (long long)a * B + b);
+        const bf16* vp = reinterpret_cast<const bf16*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sm[lane8 + j][row + 32 * i] = vp[j];
+      } else {
+        for (int j = 0; j < 8 && b + j < B; ++j) sm[lane8 + j][row + 32 * i] = in[(long long)a * B + b + j];
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int b = b0 + i, a = a0 + threadIdx.x;
-    if (a < e.A && b < e.B) out[(long long)b * e.A + a] = __float2bfloat16(tile[threadIdx.x][i]);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int b = b0 + row + 32 * i, a = a0 + lane8;
+    if (b < B) {
+      if (vout && a + 8 <= A) {
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(&sm[row + 32 * i][lane8]);
+        *reinterpret_cast<uint4*>(out + (long long)b * A + a) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+      } else {
+        for (int j = 0; j < 8 && a + j < A; ++j) out[(long long)b * A + a + j] = sm[row + 32 * i][lane8 + j];
+      }
+    }
   }
 }
 int transpose_batch(const void* table, int count, long long total_tiles, cudaStream_t st) {
   if (count <= 0 || total_tiles <= 0 || total_tiles > 0x7fffffffLL) return -1;
-  transpose_batch_kernel<<<(int)total_tiles, dim3(32, 8), 0, st>>>((const TransposeEntry*)table, count);
+  transpose_batch_kernel<<<(int)total_tiles, 256, 0, st>>>((const TransposeEntry*)table, count);
   return 0;
 }
 

@@ -37,6 +37,8 @@ int mul_add(const void* a, const void* b, const void* c, void* out, long long n,
 int fill_f32(float* out, long long n, float v, cudaStream_t st);
 int interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, cudaStream_t st);
 int rowscale(const void* in, const float* s, float mul, float add, void* out, int B, int D, cudaStream_t st);
+int splitk_finalize(const float* ws, void* out, int out_f32, long long n, int C, const float* bias, int act, float leak,
+                    const void* mask, int mask_kind, cudaStream_t st);
 int slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off, long long rows,
                int cols, const void* mask, int mask_kind, float leak, cudaStream_t st);
 int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B, cudaStream_t st);

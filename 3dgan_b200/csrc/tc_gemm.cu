@@ -67,8 +67,13 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   const int stage_bytes = a_bytes + b_bytes + tail_area;
   PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
 
-  // CTA -> p.dual consecutive pixel tiles (first pixel of each), phase, N offset
-  const int phase = blockIdx.z;
+  // CTA -> p.dual consecutive pixel tiles (first pixel of each), phase, N offset.  p.splits > 1 (layers with only a
+  // few output tiles but long reductions: the 1x1 .. 8x8 maps of pix2pix's U-Net, hem/models/pix2pix.py:187-227):
+  // blockIdx.z also carries a K split -- each CTA runs a slice of the phase's (tap, K chunk) sequence and adds its
+  // partial tile into an fp32 workspace with red.global.add; a finalize kernel applies the epilogue.
+  const int nsplit = p.splits > 1 ? p.splits : 1;
+  const int phase = blockIdx.z % p.nphases;
+  const int split = blockIdx.z / p.nphases;
   int pw0[2], ph0[2], pn0[2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -85,7 +90,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
   const int tap_begin = p.phase_tap_begin[phase];
   const int ntaps = p.phase_tap_begin[phase + 1] - tap_begin;
   const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;     // pipeline iterations per tap
-  const int iters = ntaps * kloops;
+  const int iters_all = ntaps * kloops;
+  const int it_begin = (int)((long long)iters_all * split / nsplit);
+  const int it_end = (int)((long long)iters_all * (split + 1) / nsplit);
+  const int iters = it_end - it_begin;
 
   const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
   if (tr && threadIdx.x == 0) ps->trace[0] = clock64();
@@ -145,18 +153,24 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
           if (++pkc == p.kchunks) { pkc = 0; ++ptp; }
         }
       };
-      for (int i = 0; i < p.l2_prefetch; ++i) prefetch_next();
-      for (int tp = 0; tp < ntaps; ++tp) {
-        const int tap = tap_begin + tp;
-        int c0[5], c1[5];
+      const bool l2pf = p.l2_prefetch && nsplit == 1;
+      if (l2pf) for (int i = 0; i < p.l2_prefetch; ++i) prefetch_next();
+      int tp = it_begin / kloops, kc = it_begin - tp * kloops;
+      int c0[5], c1[5], brow = 0;
+      bool new_tap = true;
+      {
+        for (int it = it_begin; it < it_end; ++it) {
+          if (new_tap) {
+            const int tap = tap_begin + tp;
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-          c0[d + 1] = base[0][d + 1] + p.tap_a_off[tap][d];
-          c1[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
-        }
-        const int brow = p.tap_b_row[tap] + n0;
-        for (int kc = 0; kc < kloops; ++kc) {
-          if (p.l2_prefetch) prefetch_next();
+            for (int d = 0; d < 4; ++d) {
+              c0[d + 1] = base[0][d + 1] + p.tap_a_off[tap][d];
+              c1[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
+            }
+            brow = p.tap_b_row[tap] + n0;
+            new_tap = false;
+          }
+          if (l2pf) prefetch_next();
           mbar_wait(empty0 + 8 * s, par ^ 1);
           const uint32_t full = full0 + 8 * s;
           const uint32_t a_dst = smem0 + s * stage_bytes;
@@ -204,6 +218,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
             }
           }
           if (++s == p.stages) { s = 0; par ^= 1; }
+          if (++kc == kloops) { kc = 0; ++tp; new_tap = true; }
         }
       }
     }
@@ -222,7 +237,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
       const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       const bool dual = p.dual == 2;
-      int s = 0, kc = 0;
+      int s = 0, kc = it_begin % kloops;
       uint32_t par = 0, acc = 0;
       if (tr) ps->trace[1] = clock64();
       for (int it = 0; it < iters; ++it) {
@@ -790,11 +805,12 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     if (trace_env < 0) trace_env = env_int("B200GAN_GEMM_TRACE", 0);
     q.trace = trace_env;
     q.cluster_y = (cy_env == 2 && p.dual == 2 && ntile_y >= 2) ? 2 : 1;
-    dim3 grid((tiles + 1) / 2 * 2, (ntile_y + q.cluster_y - 1) / q.cluster_y * q.cluster_y, p.nphases);
+    const int nsplit = p.splits > 1 ? p.splits : 1;
+    dim3 grid((tiles + 1) / 2 * 2, (ntile_y + q.cluster_y - 1) / q.cluster_y * q.cluster_y, p.nphases * nsplit);
     if (simple) launch_clustered(tapgemm_kernel<2, true>, q, grid, smem, 2, stream, q.cluster_y);
     else launch_clustered(tapgemm_kernel<2, false>, q, grid, smem, 2, stream, q.cluster_y);
   } else {
-    dim3 grid(tiles, ntile_y, p.nphases);
+    dim3 grid(tiles, ntile_y, p.nphases * (p.splits > 1 ? p.splits : 1));
     if (simple) launch_clustered(tapgemm_kernel<1, true>, p, grid, smem, 1, stream);
     else launch_clustered(tapgemm_kernel<1, false>, p, grid, smem, 1, stream);
   }

@@ -58,9 +58,11 @@ struct TapGemmParams {
   int tma_store;                      // 1: the epilogue stages its tiles in the (idle) pipeline smem and bulk-stores them
   int stage_pitch;                    // bytes per staged row = bn_tile * element size
   int cluster_y;                      // set by launch_tapgemm: 2 -> 2x2 clusters, the N-tile pair also shares A
+  int splits;                         // > 1: split-K over blockIdx.z (1-CTA kernel only); the epilogue must be the
+                                      // atomic fp32 accumulate (accumulate == 2) into a zeroed workspace
   void* out;
   int out_f32;                        // 0: bf16, 1: fp32
-  int accumulate;                     // fp32 only: out += result
+  int accumulate;                     // fp32 only: 1: out += result (one writer); 2: red.global.add (split-K partials)
   const float* bias;                  // [ncols] or null
   int act;
   float leak;

@@ -84,9 +84,10 @@ SMALL_CHANNEL_GEMM = True      # False: image-side layers use the SIMT kernels (
 
 
 def _workspace(g, op):
-    """Scratch for the small-channel im2col/col2im route (torch tensor as a byte buffer)."""
-    n = K.workspace_bytes(g, op) if SMALL_CHANNEL_GEMM else 0
-    if n == 0:
+    """Scratch the call asks for (torch tensor as a byte buffer): im2col / col2im of the small-channel route, or the
+    fp32 partial-sum image of a split-K launch (tensor-core layers with few output tiles)."""
+    n = K.workspace_bytes(g, op)
+    if n == 0 or (not SMALL_CHANNEL_GEMM and K.route(g, op) == 2):
         return None, 0
     return empty((n,), torch.uint8), n
 
@@ -335,7 +336,7 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
         tag, fl = _conv_tag("fprop", g) if S.profile is not None else (None, 0)
         launch("b200_conv2d_fprop", _p(x.buf), _p(W.p16), _p(wt), _p(out.buf), C.byref(g), C.byref(e), _p(ws), wsb,
                flops=fl, tag=tag)
-        if ws is not None:
+        if ws is not None and wt is None:
             x.im2col = (_geom_key(g), ws)       # the filter gradient of this layer reads the same im2col
     else:
         tag, fl = _conv_tag("dgrad", g) if S.profile is not None else (None, 0)

@@ -240,7 +240,7 @@ class Group:
                 a, b = p.shape[-2], p.shape[-1]
                 t = p.numel // (a * b)
                 e.src, e.dst, e.tile_begin, e.T, e.A, e.B = p.p16.data_ptr(), p.p16_t.data_ptr(), tiles, t, a, b
-                tiles += t * ((a + 31) // 32) * ((b + 31) // 32)
+                tiles += t * ((a + 63) // 64) * ((b + 63) // 64)
             host = torch.frombuffer(bytearray(bytes(ents)), dtype=torch.uint8).clone()
             self._t_table = (host.to(self.p32.device), tiles, [id(p.p16_t) for p in need], len(need))
         tab, tiles, _, n = self._t_table

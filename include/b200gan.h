@@ -143,7 +143,7 @@ int b200_optim_step(float* p, float* m, float* v, float* slot3, float* g, void* 
                     b200_stream s);
 /* Per-tap transposed bf16 copies ([T][A][B] -> [T][B][A]) of several weights in one launch: the K-major fprop operand
  * of every conv of an optimizer group, refreshed after its update.  dev_table: `count` entries in device memory;
- * tile_begin = number of 32x32 tiles (T * ceil(A/32) * ceil(B/32)) of the entries before this one. */
+ * tile_begin = number of 64x64 tiles (T * ceil(A/64) * ceil(B/64)) of the entries before this one. */
 typedef struct {
   const void* in;        /* bf16 [T][A][B] */
   void* out;             /* bf16 [T][B][A] */

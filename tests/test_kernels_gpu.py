@@ -28,6 +28,11 @@ CONV_CASES = [
     (8, 32, 32, 3, 200, 5, 2),               # small-channel path (IWGAN c1 / dc-last)
     (4, 28, 28, 1, 64, 5, 2),                # MNIST-shaped first conv
     (2, 16, 16, 4, 64, 4, 2),                # pix2pix PatchGAN first conv (rgb+depth)
+    (16, 2, 2, 512, 512, 4, 2),              # pix2pix e8 / d1: 16 output pixels, K = 16 x 512 -> split-K over taps
+    (16, 4, 4, 512, 512, 4, 2),              # pix2pix e7 / d2
+    (16, 16, 16, 512, 512, 4, 2),            # pix2pix e5: 1024 output pixels, split-K
+    (16, 4, 4, 1024, 512, 4, 2),             # d2's conv geometry with the concatenated 1024 channels (dgrad splits)
+    (3, 8, 8, 136, 72, 5, 2),                # split-K with ragged K chunk, ragged N and a partial tile
     (512, 16, 16, 208, 400, 5, 2),           # bench.py's c2 exactly (B=512, padded 200 -> 208): 2-CTA schedules, stream-K
     (512, 8, 8, 400, 800, 5, 2),             # bench.py's c3 exactly
     (512, 32, 32, 3, 208, 5, 2),             # bench.py's c1 / last deconv exactly
@@ -55,6 +60,8 @@ def test_small_channel_simt_fallback(case):
 
 def test_conv_dgrad_fused_mask():
     res = P.conv_case(4, 16, 16, 200, 400, 5, 2, with_mask=True)
+    assert res["dgrad"] < TOL["dgrad"], res
+    res = P.conv_case(16, 4, 4, 512, 512, 4, 2, with_mask=True)          # split-K: the mask is applied by the finalize pass
     assert res["dgrad"] < TOL["dgrad"], res
     res = P.conv_case(4, 32, 32, 3, 200, 5, 2, with_mask=True)
     assert res["dgrad"] < TOL["dgrad"], res

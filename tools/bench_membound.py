@@ -103,7 +103,7 @@ def main():
     off = 0
     for e, (t, aa, bb) in zip(ents, ((25, 208, 400), (25, 400, 800))):
         e.src, e.dst, e.tile_begin, e.T, e.A, e.B = src.data_ptr() + off * 2, dst.data_ptr() + off * 2, tiles, t, aa, bb
-        tiles += t * ((aa + 31) // 32) * ((bb + 31) // 32)
+        tiles += t * ((aa + 63) // 64) * ((bb + 63) // 64)
         off += t * aa * bb
     tab = torch.frombuffer(bytearray(bytes(ents)), dtype=torch.uint8).clone().to(dev)
     timed("transpose_batch", "c2+c3 taps (10.08 M)", off * 4, lambda: L("b200_transpose_batch", P(tab), 2, tiles), "1 read + 1 write (bf16)")
