@@ -65,6 +65,13 @@ SIGNATURES = {
     "b200_philox": [_P, _I, _LL, _ULL, _P, _U, _I, _P],
     "b200_optim_step": [_P, _P, _P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _F, _I, _P, _P],
     "b200_transpose_batch": [_P, _I, _LL, _P],
+    "b200_nccl_load": [C.c_char_p],
+    "b200_nccl_version": [],
+    "b200_nccl_unique_id": [_P],
+    "b200_nccl_init": [_P, _I, _I, C.POINTER(C.c_void_p)],
+    "b200_nccl_allreduce_f32": [_P, _P, _LL, _P],
+    "b200_nccl_broadcast_f32": [_P, _P, _LL, _I, _P],
+    "b200_nccl_destroy": [_P],
     "b200_device_check": [],
     "b200_abi_version": [],
 }
@@ -86,6 +93,8 @@ def lib():
         L.b200_conv2d_workspace_bytes.restype = C.c_longlong
         L.b200_last_error.restype = C.c_char_p
         L.b200_last_error.argtypes = []
+        L.b200_nccl_last_error.restype = C.c_char_p
+        L.b200_nccl_last_error.argtypes = []
         _lib = L
     return _lib
 
@@ -94,8 +103,21 @@ def call(name, *args):
     L = lib()
     rc = getattr(L, name)(*args)
     if rc != 0:
-        raise B200Error("%s failed (%d): %s" % (name, rc, L.b200_last_error().decode()))
+        err = L.b200_nccl_last_error() if name.startswith("b200_nccl_") else L.b200_last_error()
+        raise B200Error("%s failed (%d): %s" % (name, rc, err.decode()))
     return rc
+
+
+def nccl_library_path():
+    """The libnccl torch itself uses (the nvidia-nccl wheel), so that one NCCL build serves the whole process."""
+    import glob
+    import importlib.util
+    spec = importlib.util.find_spec("nvidia")
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        hits = sorted(glob.glob(os.path.join(base, "nccl", "lib", "libnccl.so*")))
+        if hits:
+            return hits[0]
+    return None
 
 
 def workspace_bytes(geom, op):

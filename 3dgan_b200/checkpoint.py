@@ -22,6 +22,7 @@ from collections import OrderedDict
 import torch
 
 from . import _capi as K
+from . import engine as E
 
 FORMAT = "b200gan-checkpoint-v1"
 INDEX = "checkpoint"
@@ -93,8 +94,10 @@ def save(sess, directory, tag, global_epoch=0, extra=None):
     """Write `<directory>/checkpoint-<tag>.pt` and point the index file at it.  With several ranks: batch norm moving
     averages are taken from the LAST rank (the reference runs the last tower's UPDATE_OPS, models/gan.py:69-70);
     rank 0 writes."""
-    if sess.dist is not None and sess.store.state_buf is not None:
-        sess.dist.broadcast(sess.store.state_buf, src=sess.world - 1)
+    if sess.world > 1 and sess.store.state_buf is not None and sess.store.state:
+        if sess.cuda:
+            E.begin(sess.device)
+        sess.broadcast(sess.store.state_buf, sess.world - 1)
     if sess.rank != 0:
         return None
     os.makedirs(directory, exist_ok=True)

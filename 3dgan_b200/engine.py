@@ -35,6 +35,7 @@ class _State:
     profile = None             # list -> per-launch CUDA-event records of the conv-family launches
     decisions = None           # list -> (kind, tensors) of every discontinuous decision of the forward (tests)
     cyclic = []                # weak refs to tensors that sit on a reference cycle (self-mask, tape node)
+    touched = {}               # id -> Param recorded on the tape since the last sweep that consumed them
     f32_out = False            # layer outputs are kept in fp32 (loss heads of the autoencoders)
     bn_updates = False         # this run executes batch norm's UPDATE_OPS (moving averages), models/gan.py:69-70
 
@@ -56,6 +57,7 @@ def begin(device=None):
 
 
 def release_tape():
+    S.touched = {}
     live, S.cyclic = S.cyclic, []
     for r in live:
         t = r()
@@ -81,13 +83,14 @@ def launch(name, *args, n=1, flops=0, tag=None):
 # relu/lrelu outputs also get a 1-bit/element sign map that the gradient epilogues read (B200GAN_SIGN_BITS=0: off)
 SIGN_BITMAPS = os.environ.get("B200GAN_SIGN_BITS", "1") != "0"
 SMALL_CHANNEL_GEMM = True      # False: image-side layers use the SIMT kernels (no workspace)
+TAP_SPLIT = True               # False: never hand a split-K workspace to the tensor-core launches
 
 
 def _workspace(g, op):
     """Scratch the call asks for (torch tensor as a byte buffer): im2col / col2im of the small-channel route, or the
     fp32 partial-sum image of a split-K launch (tensor-core layers with few output tiles)."""
     n = K.workspace_bytes(g, op)
-    if n == 0 or (not SMALL_CHANNEL_GEMM and K.route(g, op) == 2):
+    if n == 0 or not (SMALL_CHANNEL_GEMM if K.route(g, op) == 2 else TAP_SPLIT):
         return None, 0
     return empty((n,), torch.uint8), n
 
@@ -202,7 +205,7 @@ class Node:
     __slots__ = ("seq", "inputs", "outputs", "bw", "active")
 
 
-def _record(inputs, outputs, bw, uses_active_param=False):
+def _record(inputs, outputs, bw, uses_active_param=False, params=()):
     if not S.recording:
         return
     if not (uses_active_param or any(t.requires_grad for t in inputs)):
@@ -210,6 +213,12 @@ def _record(inputs, outputs, bw, uses_active_param=False):
     n = Node()
     S.seq += 1
     n.seq, n.inputs, n.outputs, n.bw, n.active = S.seq, list(inputs), list(outputs), bw, S.active
+    for p in params:
+        # earliest tape position that uses this variable: once a reverse sweep has passed it, the variable's
+        # gradient is final (Session.Exchange starts its all-reduce there, under the rest of the backward)
+        if p is not None and p.active and id(p) not in S.touched:
+            p.first_seq = n.seq
+            S.touched[id(p)] = p
     for o in outputs:
         o.requires_grad = True
         o.node = n
@@ -228,6 +237,7 @@ class Param:
         self.p32 = self.g32 = self.p16 = self.p16_t = None
         self.group = None
         self.need_t = False
+        self.first_seq = None
 
     @property
     def active(self):
@@ -373,7 +383,7 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
             launch("b200_colsum", _p(go.buf), None, _p(bias.g32), go.numel // c, c, 1.0)
         return [gx]
 
-    _record([x], [out], bw, W.active or (bias is not None and bias.active))
+    _record([x], [out], bw, W.active or (bias is not None and bias.active), params=(W, bias))
     return out
 
 
@@ -403,7 +413,7 @@ def dense_n1(x, W, bias, act=K.ACT_NONE, leak=0.0):
             launch("b200_reduce_sum", _p(go.buf), 1, M, _p(bias.g32), 1.0, 0)
         return [gx]
 
-    _record([x], [out], bw, W.active or bias.active)
+    _record([x], [out], bw, W.active or bias.active, params=(W, bias))
     return out
 
 
@@ -425,7 +435,7 @@ def outer_mask(g, W, like):
             launch("b200_gemv_rows", _p(c.buf), _p(W.p16), None, _p(gg.buf), M, Kd, 0, 0.0)
         return [gg]
 
-    _record([g], [out], bw, W.active)
+    _record([g], [out], bw, W.active, params=(W,))
     return out
 
 
@@ -461,7 +471,7 @@ def batch_norm_act(z, beta, act=K.ACT_NONE, leak=0.0, eps=1e-3, moving=None, dec
             dz = maskmul(dz, z.mask)
         return [dz]
 
-    _record([z], [out], bw, beta.active)
+    _record([z], [out], bw, beta.active, params=(beta,))
     return out
 
 
@@ -785,16 +795,22 @@ def random_fill(shape, normal, seed, counter, stream_id, f32=True):
 
 
 # ------------------------------------------------------------------------------------------ backward pass
-def backward(seeds, wrt=(), create_graph=False, accumulate=True):
+def backward(seeds, wrt=(), create_graph=False, accumulate=True, on_ready=None):
     """Reverse sweep.  seeds: list of (tensor, grad Tensor | None); None = seed 1.0 on a scalar loss.
     With accumulate=True (or a list of Params) parameter gradients are added into those Params' g32 views;
-    tf.gradients(ys, xs)-style calls (models/gan.py:228) pass accumulate=False and read `wrt`."""
+    tf.gradients(ys, xs)-style calls (models/gan.py:228) pass accumulate=False and read `wrt`.
+    on_ready(param): called as soon as the sweep has passed the earliest tape node that uses `param`, i.e. when
+    its gradient is final (every variable recorded since the last consuming sweep is reported, the rest at the end)."""
     grads = {}
     nodes = {}
     if accumulate not in (True, False):
         accumulate = frozenset(id(p) for p in accumulate)
     prev_acc, S.accumulate = S.accumulate, accumulate
     prev_active = S.active
+    waiting = []
+    if on_ready is not None and accumulate is not False:
+        waiting = sorted((p for p in S.touched.values() if accumulate is True or id(p) in accumulate),
+                         key=lambda p: -p.first_seq)
 
     def push(t, g):
         if t.node is None and not any(t is w for w in wrt):
@@ -814,6 +830,9 @@ def backward(seeds, wrt=(), create_graph=False, accumulate=True):
         with recording(create_graph):
             while nodes:
                 seq = max(nodes)
+                while waiting and waiting[0].first_seq > seq:
+                    S.touched.pop(id(waiting[0]), None)
+                    on_ready(waiting.pop(0))
                 node = nodes.pop(seq)
                 gouts = []
                 for o in node.outputs:
@@ -826,6 +845,13 @@ def backward(seeds, wrt=(), create_graph=False, accumulate=True):
                 for inp, gi in zip(node.inputs, gins):
                     if gi is not None and inp.requires_grad:
                         push(inp, gi)
+            S.active = prev_active
+            for p in waiting:
+                S.touched.pop(id(p), None)
+                on_ready(p)
+            if accumulate is not False and on_ready is None:      # this sweep consumed their gradients all the same
+                for k_ in [k_ for k_, p in S.touched.items() if accumulate is True or k_ in accumulate]:
+                    del S.touched[k_]
     finally:
         S.accumulate, S.active = prev_acc, prev_active     # an exception in a rule must not corrupt the tape state
     return [grads[id(w)][1] if id(w) in grads else None for w in wrt]

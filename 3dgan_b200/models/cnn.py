@@ -55,11 +55,15 @@ def _default_training(sess, x, args, tower, name_losses):
         store.finalize([('all', params, optimizer_cfg(args))], sess.device)
         (group,) = store.groups
 
+    ex = sess.exchange(group) if sess.cuda else None
+
     def iteration():
         x.reset()                                     # (the gradient bucket is zero: apply_gradients resets it)
         out = tower(x.next())
-        E.backward([((out[0] if isinstance(out, tuple) else out), None)])
-        group.apply_gradients(sess.all_reduce_grads(group), 0.0)
+        ex.begin()
+        E.backward([((out[0] if isinstance(out, tuple) else out), None)], on_ready=ex.on_ready)
+        ex.finish()
+        group.apply_gradients(ex.join(), 0.0)
         return {k: v.buf for k, v in name_losses(out).items()}
 
     def helper(sess_, args_):

@@ -64,12 +64,13 @@ def gan(x, args):
     clip = 0.01 if args.model == 'wgan' else 0.0                      # gan.py:142-143
 
     pending = [False]                             # a critic exchange is in flight on the side stream
+    ex_d = sess.exchange(d_group) if sess.cuda else None
+    ex_g = sess.exchange(g_group) if sess.cuda else None
 
     def finish_pending():
         """Join the deferred gradient exchange of the previous critic run and apply its update."""
         if pending[0]:
-            sess.join_updates()
-            d_group.apply_gradients(1.0 / sess.world, clip)
+            d_group.apply_gradients(ex_d.join(), clip)
             pending[0] = False
 
     def before_critic_d():
@@ -79,32 +80,39 @@ def gan(x, args):
         E.S.bn_updates = True                     # d_train_op depends on batchnorm_updates in all three schedules
         g_loss, d_loss = tower(x.next(), 'd', before_critic_d)
         E.S.bn_updates = False
-        E.backward([(d_loss, None)])
-        if sess.dist is not None and sess.overlap_updates:
-            # multi-GPU: the all-reduce runs on a side stream and overlaps the next run's generator forward
-            # (which reads no critic variable); the update itself is applied when that run reaches the critic
-            sess.defer_update(lambda: sess.all_reduce_grads(d_group))
+        # average_gradients: buckets of the critic's gradient go out as the sweep finishes them (c3 + fc2 first)
+        ex_d.begin()
+        E.backward([(d_loss, None)], on_ready=ex_d.on_ready)
+        ex_d.finish()
+        if ex_d.active and sess.overlap_updates:
+            # multi-GPU: the tail of the exchange also overlaps the next run's generator forward (which reads no
+            # critic variable); the update itself is applied when that run reaches the critic
             pending[0] = True
         else:
-            d_group.apply_gradients(sess.all_reduce_grads(d_group), clip)
+            d_group.apply_gradients(ex_d.join(), clip)
         return g_loss, d_loss
 
     def g_run():
         E.S.bn_updates = args.model == 'wgan'     # gan.py:145-148 (wgan) vs 163 (iwgan: g_train_op has no dependency)
         g_loss, d_loss = tower(x.next(), 'g', finish_pending)
         E.S.bn_updates = False
-        E.backward([(g_loss, None)])
-        g_group.apply_gradients(sess.all_reduce_grads(g_group), clip)
+        ex_g.begin()
+        E.backward([(g_loss, None)], on_ready=ex_g.on_ready)
+        ex_g.finish()
+        g_group.apply_gradients(ex_g.join(), clip)
         return g_loss, d_loss
 
     def gan_run():                                                    # _train_gan: one run, both updates
         E.S.bn_updates = True                                         # gan.py:126-128
         gl, dl = tower(x.next(), 'dg')                                # same forward for both (App. C #7)
         E.S.bn_updates = False
-        E.backward([(dl, None)], accumulate=store.collection('discriminator'))
-        E.backward([(gl, None)], accumulate=store.collection('generator'))
-        d_group.apply_gradients(sess.all_reduce_grads(d_group), 0.0)
-        g_group.apply_gradients(sess.all_reduce_grads(g_group), 0.0)
+        ex_d.begin(); ex_g.begin()
+        E.backward([(dl, None)], accumulate=store.collection('discriminator'), on_ready=ex_d.on_ready)
+        ex_d.finish()
+        E.backward([(gl, None)], accumulate=store.collection('generator'), on_ready=ex_g.on_ready)
+        ex_g.finish()
+        d_group.apply_gradients(ex_d.join(), 0.0)
+        g_group.apply_gradients(ex_g.join(), 0.0)
         return gl, dl
 
     def iteration():

@@ -77,8 +77,11 @@ class pix2pix:
         ls = self.tower(self.x_in.next(), self.y_in.next(), mode)
         E.S.bn_updates = False
         if grp is not None:
-            E.backward([(ls['d_total'] if mode == 'd' else ls['g_total'], None)])
-            grp.apply_gradients(self.sess.all_reduce_grads(grp), 0.0)
+            ex = self.sess.exchange(grp)                 # buckets go out under the rest of the backward (229 MB/step)
+            ex.begin()
+            E.backward([(ls['d_total'] if mode == 'd' else ls['g_total'], None)], on_ready=ex.on_ready)
+            ex.finish()
+            grp.apply_gradients(ex.join(), 0.0)
         return ls
 
     def iteration(self):

@@ -97,6 +97,9 @@ class Session:
         self.graphs = {}
         self.use_graphs = os.environ.get("B200GAN_CUDA_GRAPHS", "1") != "0"
         self.dist = None
+        self.comm = None                                # b200_nccl_* communicator (ctypes void*), data plane
+        self.muted = False                              # True: no collectives (rank-local profiling passes)
+        self._exchanges = {}
         # gradient exchange + optimizer update of one run overlap the start of the next run (side stream)
         self.overlap_updates = os.environ.get("B200GAN_OVERLAP_UPDATE", "1") != "0"
         self._side = None
@@ -139,20 +142,63 @@ class Session:
 
     # ---------------------------------------------------------------- data parallel
     def init_distributed(self, backend="nccl"):
+        """One process per GPU = one tower (util.py:54-77).  torch.distributed is the control plane (rendezvous,
+        barriers, the bench's max-over-ranks); the gradient exchange itself goes through the C ABI's b200_nccl_*
+        entry points on a communicator of our own (CPU-only runs / the gloo tests fall back to torch's all_reduce)."""
         import torch.distributed as dist
         if self.world > 1 and not dist.is_initialized():
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world,
                                     device_id=self.device if backend == "nccl" else None)
         self.dist = dist if self.world > 1 else None
+        if self.dist is not None and self.cuda and os.environ.get("B200GAN_NCCL_ABI", "1") != "0":
+            import ctypes
+            from . import _capi as K
+            path = K.nccl_library_path()
+            K.call("b200_nccl_load", path.encode() if path else None)
+            uid = ctypes.create_string_buffer(128)
+            if self.rank == 0:
+                K.call("b200_nccl_unique_id", uid)
+            t = torch.tensor(list(uid.raw), dtype=torch.uint8, device=self.device if backend == "nccl" else "cpu")
+            dist.broadcast(t, 0)
+            raw = bytes(t.cpu().tolist())
+            comm = ctypes.c_void_p()
+            K.call("b200_nccl_init", raw, self.rank, self.world, ctypes.byref(comm))
+            self.comm = comm
+
+    def all_reduce(self, flat):
+        """In-place sum over ranks of a contiguous fp32 slice, asynchronous on the engine's current stream."""
+        if self.muted:
+            return
+        if self.comm is not None:
+            E.launch("b200_nccl_allreduce_f32", self.comm, E._p(flat), flat.numel())
+        elif self.dist is not None:
+            self.dist.all_reduce(flat)
+
+    def broadcast(self, flat, src):
+        if self.comm is not None:
+            E.launch("b200_nccl_broadcast_f32", self.comm, E._p(flat), flat.numel(), src)
+        elif self.dist is not None:
+            self.dist.broadcast(flat, src)
 
     def all_reduce_grads(self, group):
         """average_gradients (util.py:118-147): sum over ranks here, the 1/n is folded into the
         optimizer kernel's grad_scale."""
-        if self.dist is not None:
-            self.dist.all_reduce(group.g32)
+        self.all_reduce(group.g32)
         return 1.0 / self.world
 
+    def exchange(self, group):
+        """The bucketed, overlapped form of all_reduce_grads for one optimizer group (one Exchange per group)."""
+        ex = self._exchanges.get(id(group))
+        if ex is None:
+            ex = self._exchanges[id(group)] = Exchange(self, group)
+        return ex
+
     # ---------------------------------------------------------------- overlapped parameter updates
+    def side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def defer_update(self, fn):
         """Run `fn` (the gradient all-reduce of one optimizer group: it touches only that group's gradient
         bucket and allocates nothing) on a side stream, ordered after everything issued so far.  The caller
@@ -164,19 +210,18 @@ class Session:
             fn()
             return
         import ctypes
-        if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+        side = self.side_stream()
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(main)
-        self._side.wait_event(fork)
+        side.wait_event(fork)
         prev = E.S.stream
-        E.S.stream = ctypes.c_void_p(self._side.cuda_stream)
+        E.S.stream = ctypes.c_void_p(side.cuda_stream)
         try:
-            with torch.cuda.stream(self._side):
+            with torch.cuda.stream(side):
                 fn()
                 self._join_event = torch.cuda.Event()
-                self._join_event.record(self._side)
+                self._join_event.record(side)
         finally:
             E.S.stream = prev
 
@@ -216,3 +261,84 @@ class Session:
         ent["graph"].replay()
         E.S.launches += ent["launches"]
         return ent["out"]
+
+
+class Exchange:
+    """average_gradients (util.py:118-147) for one optimizer group, overlapped with the backward pass.
+
+    The group's flat fp32 gradient bucket is cut into buckets of >= `bucket_bytes` walking the variables in REVERSE
+    creation order — the order in which a reverse sweep finishes them (the last layers first).  `on_ready(param)`
+    (engine.backward calls it the moment a variable's gradient is final) starts a bucket's all-reduce on a side
+    stream as soon as all of its variables are final, so the exchange of the deep layers (IWGAN critic: c3 + fc2 =
+    33 MB of the 40 MB) runs under the remaining backward of the shallow ones; `finish()` sends what is left and
+    `join()` makes the main stream wait for the side stream before the optimizer reads the bucket.  With one rank
+    everything is a no-op.  Inside a CUDA-graph capture the fork / join events become graph edges."""
+
+    def __init__(self, sess, group, bucket_bytes=None):
+        self.sess, self.group = sess, group
+        if bucket_bytes is None:
+            bucket_bytes = int(os.environ.get("B200GAN_BUCKET_MB", "8")) << 20
+        self.buckets = []                        # [lo, hi, set(param ids)] element ranges of the flat bucket
+        hi, ids, lo = group.size, set(), group.size
+        for p in reversed(group.params):
+            lo = p.offset
+            ids.add(id(p))
+            if (hi - lo) * 4 >= bucket_bytes:
+                self.buckets.append((lo, hi, ids))
+                hi, ids = lo, set()
+        if ids:
+            self.buckets.append((0, hi, ids))
+        self.begin()
+
+    @property
+    def active(self):
+        s = self.sess
+        return (s.dist is not None or s.comm is not None) and not s.muted
+
+    def begin(self):
+        self.ready, self.next = set(), 0
+        self._event = None
+
+    def on_ready(self, param):
+        if not self.active or E.S.dry:
+            return
+        self.ready.add(id(param))
+        while self.next < len(self.buckets) and self.buckets[self.next][2] <= self.ready:
+            self._fire(self.buckets[self.next])
+            self.next += 1
+
+    def finish(self):
+        """Send every bucket that has not gone yet (variables the sweep never reported included)."""
+        if not self.active or E.S.dry:
+            return
+        while self.next < len(self.buckets):
+            self._fire(self.buckets[self.next])
+            self.next += 1
+
+    def _fire(self, bucket):
+        import ctypes
+        lo, hi, _ = bucket
+        sess = self.sess
+        if not sess.cuda or not sess.overlap_updates:
+            sess.all_reduce(self.group.g32[lo:hi])
+            return
+        side, main = sess.side_stream(), torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        prev = E.S.stream
+        E.S.stream = ctypes.c_void_p(side.cuda_stream)
+        try:
+            with torch.cuda.stream(side):
+                sess.all_reduce(self.group.g32[lo:hi])
+                self._event = torch.cuda.Event()
+                self._event.record(side)
+        finally:
+            E.S.stream = prev
+
+    def join(self):
+        """Main stream waits for the exchange; returns the optimizer's grad_scale (the 1/n of the average)."""
+        if self._event is not None:
+            torch.cuda.current_stream().wait_event(self._event)
+            self._event = None
+        return 1.0 / self.sess.world

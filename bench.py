@@ -373,8 +373,8 @@ def roofline(sess, job, pools, a, step_ms):
         pk = json.load(open(peaks_path))
         burst, sustained = float(pk.get("bf16_tflops", burst)), pk.get("bf16_tflops_sustained")
         src = "MEASURED_PEAKS.json bf16_tflops (burst: the timed region is well under a second at boost clocks)"
-    prev, prev_dist = sess.use_graphs, sess.dist
-    sess.use_graphs, sess.dist = False, None        # rank-0-only pass: no collective inside
+    prev, prev_muted = sess.use_graphs, sess.muted
+    sess.use_graphs, sess.muted = False, True       # rank-0-only pass: no collective inside
     E.S.profile = []
     for inp, pool in zip(job.inputs, pools):
         inp.ring.copy_(pool[0])
@@ -387,7 +387,7 @@ def roofline(sess, job, pools, a, step_ms):
     it1.record()
     torch.cuda.synchronize()
     recs, E.S.profile = E.S.profile, None
-    sess.use_graphs, sess.dist = prev, prev_dist
+    sess.use_graphs, sess.muted = prev, prev_muted
     rows = {}
     tot_f = tot_ms = 0.0
     for name, flops, e0, e1, tag in recs:

@@ -153,6 +153,21 @@ typedef struct {
 } b200_transpose_entry;
 int b200_transpose_batch(const b200_transpose_entry* dev_table, int count, long long total_tiles, b200_stream s);
 
+/* ---- data-parallel exchange: average_gradients (util.py:118-147) as an NCCL all-reduce over NVLink.
+ * One process per GPU = one tower (util.py:54-77).  libnccl is loaded at run time (b200_nccl_load: explicit path, else
+ * "libnccl.so.2"); rank 0 creates the 128-byte unique id, the host exchanges it by any means (the Python host uses its
+ * torch.distributed rendezvous), every rank calls b200_nccl_init.  The collectives are in place, asynchronous on the
+ * given stream and may be captured in a CUDA graph; the 1/n of the average is folded into b200_optim_step's grad_scale.
+ * Errors: negative return, text in b200_nccl_last_error(). */
+const char* b200_nccl_last_error(void);
+int b200_nccl_load(const char* libnccl_path /* may be NULL */);
+int b200_nccl_version(void);
+int b200_nccl_unique_id(void* out128);
+int b200_nccl_init(const void* id128, int rank, int world, void** comm_out);
+int b200_nccl_allreduce_f32(void* comm, float* buf, long long n, b200_stream s);          /* buf = sum over ranks */
+int b200_nccl_broadcast_f32(void* comm, float* buf, long long n, int root, b200_stream s);
+int b200_nccl_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

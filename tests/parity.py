@@ -236,10 +236,11 @@ def iwgan_step_parity(H=32, C=3, L=16, B=8, model="iwgan", seed=0, verbose=False
                              if n_.startswith(prefix)}}
     report = {"ok": True, "mode": mode}
     # The critic run and the generator run repeat the same forward.  Batch-norm statistics are reduced with fp32
-    # atomics, so the two passes may round a handful of near-zero units to different sides: each run is compared
-    # with the oracle on ITS OWN decisions, and the two traces may differ in at most 0.1 % of the units.
+    # atomics (and small layers run split-K with fp32 atomics), so the two passes may round a few near-zero units to
+    # different sides: each run is compared with the oracle on ITS OWN decisions, and the two traces may differ in
+    # at most 1 % of a layer's units.
     report["decisions_d_vs_g"] = decisions_diff(traces["d"], traces["g"])
-    if report["decisions_d_vs_g"] > 1e-3:
+    if report["decisions_d_vs_g"] > 1e-2:
         report["ok"] = False
     # ---- oracle
     refs = {}
@@ -559,8 +560,8 @@ def pix2pix_step_parity(B=2, add_l1=True, seed=0, verbose=False, grad_tol=3e-2, 
                    "grads": {n_: prm.logical(prm.g32).float().cpu().clone() for n_, prm in sess.store.params.items()
                              if n_.startswith(prefix)}}
     report = {"ok": True, "mode": mode}
-    report["decisions_d_vs_g"] = decisions_diff(traces["d"], traces["g"])     # (see iwgan_step_parity)
-    if report["decisions_d_vs_g"] > 1e-3:
+    report["decisions_d_vs_g"] = decisions_diff(traces["d"], traces["g"])     # (see iwgan_step_parity; split-K atomics too)
+    if report["decisions_d_vs_g"] > 1e-2:
         report["ok"] = False
     refs = {}
     for md in ("d", "g"):

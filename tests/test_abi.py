@@ -23,7 +23,18 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_binding_table_matches_header():
-    assert set(_capi.SIGNATURES) | {"b200_last_error"} == set(declared_symbols())
+    assert set(_capi.SIGNATURES) | {"b200_last_error", "b200_nccl_last_error"} == set(declared_symbols())
+
+
+def test_nccl_entry_points_load_the_library_and_fail_loudly_without_a_communicator():
+    """b200_nccl_* (SURVEY 8b): libnccl is resolved at run time; no communicator -> error text, never a silent no-op."""
+    L = _capi.lib()
+    path = _capi.nccl_library_path()
+    assert path and os.path.exists(path)
+    assert L.b200_nccl_load(path.encode()) == 0
+    assert L.b200_nccl_version() >= 20000
+    assert L.b200_nccl_allreduce_f32(None, None, 16, None) != 0
+    assert b"communicator" in L.b200_nccl_last_error()
 
 
 def test_no_device_fails_loudly():

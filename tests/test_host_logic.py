@@ -155,14 +155,33 @@ def _dp_worker(rank, world, port, out):
         g32 = torch.arange(8, dtype=torch.float32) * (rank + 1)
     scale = sess.all_reduce_grads(G)
     avg = G.g32 * scale
+    # Session.Exchange: buckets cut in reverse creation order, each sent once all of its variables are final
+    class Prm:
+        def __init__(self, off, n):
+            self.offset, self.numel = off, n
+
+    class Grp:
+        params = [Prm(0, 64), Prm(64, 192), Prm(256, 64), Prm(320, 704)]
+        size = 1024
+        g32 = torch.arange(1024, dtype=torch.float32) * (rank + 1)
+    ex = S.Exchange(sess, Grp, bucket_bytes=1024)             # >= 256 elements per bucket
+    bounds = [(lo, hi) for lo, hi, _ in ex.buckets]
+    ex.begin()
+    sent = []
+    for prm in reversed(Grp.params):
+        ex.on_ready(prm)
+        sent.append(ex.next)
+    ex.finish()
+    ex_scale = ex.join()
+    ex_ok = bool(torch.equal(Grp.g32 * ex_scale, torch.arange(1024, dtype=torch.float32) * 1.5))
     # ops.input.batch_slice: tower r takes rows [r*B, (r+1)*B)
     from b200gan.ops.input import batch_slice
     glob = E.Tensor(torch.arange(4 * world, dtype=torch.float32).reshape(4 * world, 1))
     sl = batch_slice(glob, 4, rank).torch().flatten().tolist()
     if rank == 0:
-        out.put((avg.tolist(), scale, sl))
+        out.put((avg.tolist(), scale, sl, bounds, sent, ex_ok))
     else:
-        out.put((None, scale, sl))
+        out.put((None, scale, sl, bounds, sent, ex_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -187,6 +206,10 @@ def test_data_parallel_exchange_is_tower_mean_gloo_world2():
     assert all(abs(r[1] - 0.5) < 1e-9 for r in res)
     slices = sorted(r[2] for r in res)
     assert slices == [[0.0, 1.0, 2.0, 3.0], [4.0, 5.0, 6.0, 7.0]]
+    for r in res:
+        assert r[3] == [(320, 1024), (64, 320), (0, 64)]      # last variables first; the small tail is its own bucket
+        assert r[4] == [1, 1, 2, 3]                            # a bucket leaves when its LAST variable is final
+        assert r[5]                                            # every element exchanged exactly once: tower mean
 
 
 def test_pix2pix_build_pass_matches_reference_variables():

@@ -227,6 +227,7 @@ def test_sign_bitmaps_match_value_masks():
     chain = [(32, 3, 200), (16, 200, 400), (8, 400, 800)]          # IWGAN critic c1, c2, c3
     x = P.dev(torch.randn(N, 32, 32, 3, generator=g))
     acts = []
+    E.TAP_SPLIT = False            # (at this tiny batch the launches would otherwise take the split-K route: no bitmaps)
     for (H, Cin, Cout) in chain:
         geom = E.conv_geom(N, H, H, Cin, Cout, 5, 2)
         Wp = P.make_param(torch.randn(5, 5, Cin, Cout, generator=g) * (0.3 / math.sqrt(25 * Cin)) * 5)
@@ -256,3 +257,4 @@ def test_sign_bitmaps_match_value_masks():
         y.bits = saved
         torch.cuda.synchronize()
         assert torch.equal(f_bits.torch(), f_vals.torch())
+    E.TAP_SPLIT = True
