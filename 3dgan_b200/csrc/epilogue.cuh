@@ -65,6 +65,11 @@ struct EpilogueArgs {
   // epilogue (L1 is almost all shared memory here, so they usually went to L2)
   uint32_t bias_smem;
   int bias_col0;
+  // stream-K fixup (tapgemm2sm_sk_kernel): `partial_n` fp32 partial accumulator images of this row, `partial_stride`
+  // elements apart, indexed by the column offset inside the tile; added to the accumulators before the epilogue
+  const float* partial_row;
+  int partial_n;
+  long long partial_stride;
 };
 
 // Epilogue warps are idle during the main loop: pull the mask rows they will need into L2 meanwhile.
@@ -304,6 +309,36 @@ inline bool epilogue_is_simple(int act, const void* mask_src, const void* mask_b
 
 // One output row's chunks c0, c0+step, ... of an accumulator row in TMEM: the TMEM load and the side loads
 // of chunk i+1 are issued before chunk i is processed.
+// accumulators += the other contributors' partial sums of the same 16 columns (L2 loads: they were written by other SMs)
+__device__ __forceinline__ void epilogue_add_partials(const EpilogueArgs& e, uint32_t* v, int c) {
+  for (int k = 0; k < e.partial_n; ++k) {
+    const float4* src = reinterpret_cast<const float4*>(e.partial_row + (long long)k * e.partial_stride + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 f = __ldcg(src + j);
+      v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + f.x);
+      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + f.y);
+      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + f.z);
+      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + f.w);
+    }
+  }
+}
+
+// stream-K contributor: the raw accumulator row goes to the partial-sum workspace (fp32, 64 bytes per chunk)
+__device__ __forceinline__ void epilogue_dump_row(uint32_t trow, float* drow, int c_first, int c_step, int c_end) {
+#pragma unroll 1
+  for (int c = c_first; c < c_end; c += c_step) {
+    uint32_t v[16];
+    tmem_ld16(trow + c, v);
+    tmem_ld_wait16(v);
+    float4* dst = reinterpret_cast<float4*>(drow + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3])));
+  }
+}
+
 template <bool kSimple>
 __device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t trow, long long off, bool row_ok,
                                              int n0, int c_first, int c_step, int c_end) {
@@ -326,7 +361,10 @@ __device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t tro
         tmem_ld16(trow + c1, vn);
         nxt = epilogue_load_side(e, off, n0 + c1, row_ok, bits_row);
       }
-      if (row_ok) epilogue_store16<kSimple>(e, vc, off, n0 + c, &cur, bits_row);
+      if (row_ok) {
+        if (e.partial_n) epilogue_add_partials(e, vc, c);
+        epilogue_store16<kSimple>(e, vc, off, n0 + c, &cur, bits_row);
+      }
     }
   } else {
     // general epilogues (fp32 out, value masks, tanh/sigmoid) keep one accumulator buffer: fewer registers
@@ -336,7 +374,10 @@ __device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t tro
       tmem_ld16(trow + c, v);
       const ChunkSide cur = epilogue_load_side(e, off, n0 + c, row_ok, bits_row);
       tmem_ld_wait16(v);
-      if (row_ok) epilogue_store16<kSimple>(e, v, off, n0 + c, &cur, bits_row);
+      if (row_ok) {
+        if (e.partial_n) epilogue_add_partials(e, v, c);
+        epilogue_store16<kSimple>(e, v, off, n0 + c, &cur, bits_row);
+      }
     }
   }
 }

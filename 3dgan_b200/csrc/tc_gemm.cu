@@ -17,14 +17,26 @@ namespace {
 constexpr int kMaxThreads = 64 + 32 * 16;   // warp0 TMA, warp1 MMA, then 4..16 epilogue warps (launch parameter)
 constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KiB: 128 rows x 128 B
 
+// one contiguous piece of a CTA pair's stream-K range that lies inside a single (phase, N tile, pixel group) item
+struct SkSeg {
+  int phase, ntile, group;     // the item
+  int it0, len;                // K-iterations [it0, it0 + len) of the item's (tap, K chunk) sequence
+  int finishing;               // 1: contains the item's last iteration -> this pair runs the item's epilogue
+  int first_pair;              // finishing && it0 > 0: partials of pairs [first_pair, own pair) must be added
+  int pad_;
+};
+constexpr int kMaxSkSegs = 12;
+
 struct PipeSmem {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full;
   uint64_t tmem_empty;
   uint32_t tmem_base;
+  int nseg;                    // stream-K: segments of this pair, in processing order
   long long trace[6];          // B200GAN_GEMM_TRACE: clock stamps of CTA (0,0,0) (debug)
   alignas(16) float bias[256]; // this N tile's bias row (epilogue)
+  SkSeg segs[kMaxSkSegs];
 };
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm_kernel(const __grid_co
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
     ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
     ea.bias_smem = 0; ea.bias_col0 = n0;
+    ea.partial_row = nullptr; ea.partial_n = 0; ea.partial_stride = 0;
     if (p.bias) {
       for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += (int)blockDim.x - 64)
         ps->bias[i] = (n0 + i < p.ncols) ? __ldg(p.bias + n0 + i) : 0.f;
@@ -601,6 +614,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
     ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
     ea.bias_smem = 0; ea.bias_col0 = n0;
+    ea.partial_row = nullptr; ea.partial_n = 0; ea.partial_stride = 0;
     if (p.bias) {
       for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += (int)blockDim.x - 64)
         ps->bias[i] = (n0 + i < p.ncols) ? __ldg(p.bias + n0 + i) : 0.f;
@@ -660,6 +674,330 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();       // the pair's MMAs / barrier traffic are finished in both CTAs
+  if (warp == 1) tmem_dealloc_2sm<2 * kTmemCols>(tmem);
+}
+
+// =============================================================================================
+// Tap GEMM, 2-CTA form, persistent stream-K schedule
+// =============================================================================================
+// The plain 2-CTA kernel launches one cluster per item = (phase, N tile, group of 4 pixel tiles): IWGAN's c2 / c3 have
+// 128 / 64 equal items for the 74 cluster slots of a B200, so 14 % of the machine idles in the last wave and every
+// CTA pays its own prologue (barrier init, TMEM allocation, pipeline fill).  Here 74 persistent pairs each take an
+// equal contiguous range of the linearised (item, K-iteration) space, as wgrad2sm_kernel does.  A range cuts items:
+//   * a piece that ends before its item does ("contributor") dumps its fp32 accumulators to a workspace region and
+//     raises a flag;
+//   * the piece that contains the item's last iteration ("finisher") adds the contributors' partials to its
+//     accumulators and runs the normal fused epilogue.
+// Inside a range only the LAST piece can be a contributor and only the FIRST can be a finisher with contributors; the
+// contributor piece is processed first, so every flag a finisher waits for was raised long before (no pair ever
+// depends on work that is scheduled after a wait), and the TMA ring keeps streaming across piece boundaries.
+template <bool kSimple>
+__global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __grid_constant__ TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pair = blockIdx.x >> 1;
+
+  const int half_rows = p.bn_tile / 2;
+  const int b_bytes = half_rows * kBlockK * 2;
+  const int a_bytes = 2 * kABytes;
+  const int tail_area = p.merge_tail ? (2 * kTileM + half_rows) * 32 : 0;
+  const int stage_bytes = a_bytes + b_bytes + tail_area;
+  PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
+  const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;
+  const int tail_row_bytes = p.tail_mode == 1 ? 32 : 64;
+
+  if (threadIdx.x == 0) {
+    // this pair's pieces, in processing order (identical in both CTAs)
+    const long long rb = (long long)pair * p.sk_range;
+    const long long re = min(rb + p.sk_range, p.sk_total);
+    SkSeg tmp[kMaxSkSegs];
+    int n = 0;
+    for (long long pos = rb; pos < re && n < kMaxSkSegs;) {
+      int ph = 0;
+      while (ph + 1 < p.nphases && pos >= p.sk_phase_base[ph + 1]) ++ph;
+      const int len_p = (p.phase_tap_begin[ph + 1] - p.phase_tap_begin[ph]) * kloops;
+      const long long rel = pos - p.sk_phase_base[ph];
+      const int item = (int)(rel / len_p);
+      SkSeg g;
+      g.phase = ph;
+      g.ntile = item / p.sk_groups;
+      g.group = item - g.ntile * p.sk_groups;
+      g.it0 = (int)(rel - (long long)item * len_p);
+      g.len = (int)min((long long)(len_p - g.it0), re - pos);
+      g.finishing = (g.it0 + g.len == len_p) ? 1 : 0;
+      g.first_pair = (int)((pos - g.it0) / p.sk_range);
+      g.pad_ = 0;
+      tmp[n++] = g;
+      pos += g.len;
+    }
+    int k = 0;
+    if (n > 0 && !tmp[n - 1].finishing) ps->segs[k++] = tmp[n - 1];      // the contributor piece goes first
+    for (int j = 0; j < n - (n > 0 && !tmp[n - 1].finishing ? 1 : 0); ++j) ps->segs[k++] = tmp[j];
+    ps->nseg = n;
+  }
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ps->tmem_full), 1);
+    mbar_init(smem_u32(&ps->tmem_empty), 2 * ((blockDim.x >> 5) - 2));     // the epilogue warps of BOTH CTAs
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+  const int nseg = ps->nseg;
+
+  // first pixel of the CTA's two tiles of a group, per piece
+  auto tile_origin = [&](const SkSeg& g, int i, int& pw0, int& ph0, int& pn0) {
+    int t = g.group * 4 + (int)crank * 2 + i;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    pw0 = tw * p.bw; ph0 = th * p.bh; pn0 = t * p.bn;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ TMA producer (both CTAs)
+      int s = 0;
+      uint32_t par = 0;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      const uint32_t smem0 = smem_u32(smem);
+      const int a_tile = kABytes, t_tile = kTileM * 32;
+      for (int k = 0; k < nseg; ++k) {
+        const SkSeg g = ps->segs[k];
+        int base[2][5];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          int pw0, ph0, pn0;
+          tile_origin(g, i, pw0, ph0, pn0);
+          base[i][0] = 0;
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            base[i][d + 1] = pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
+        }
+        const int tap_begin = p.phase_tap_begin[g.phase];
+        const int n0 = g.ntile * p.bn_tile;
+        int tp = g.it0 / kloops, kc = g.it0 - tp * kloops;
+        int c0[5], c1[5], brow = 0;
+        bool new_tap = true;
+        for (int it = 0; it < g.len; ++it) {
+          if (new_tap) {
+            const int tap = tap_begin + tp;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              c0[d + 1] = base[0][d + 1] + p.tap_a_off[tap][d];
+              c1[d + 1] = base[1][d + 1] + p.tap_a_off[tap][d];
+            }
+            brow = p.tap_b_row[tap] + n0 + (int)crank * half_rows;
+            new_tap = false;
+          }
+          mbar_wait(empty0 + 8 * s, par ^ 1);
+          const uint32_t full = full0 + 8 * s;
+          const uint32_t a_dst = smem0 + s * stage_bytes;
+          const bool with_tail = p.merge_tail && kc == kloops - 1;
+          const bool tail = !p.merge_tail && p.tail_mode != 0 && kc == p.kchunks - 1;
+          c0[0] = kc * kBlockK;
+          c1[0] = kc * kBlockK;
+          if (tail) {
+            const int n_tile = kTileM * tail_row_bytes;
+            if (leader) mbar_arrive_expect_tx(full, 2 * (2 * n_tile + half_rows * tail_row_bytes));
+            tma_load_nd_2sm(p.a_rank, a_dst, &p.tmA_tail, full, c0);
+            tma_load_nd_2sm(p.a_rank, a_dst + n_tile, &p.tmA_tail, full, c1);
+            tma_load_2d_2sm(a_dst + 2 * n_tile, &p.tmB_tail, full, kc * kBlockK, brow);
+          } else {
+            if (leader) mbar_arrive_expect_tx(full, 2 * (a_bytes + b_bytes + (with_tail ? tail_area : 0)));
+            tma_load_nd_2sm(p.a_rank, a_dst, &p.tmA, full, c0);
+            tma_load_nd_2sm(p.a_rank, a_dst + a_tile, &p.tmA, full, c1);
+            tma_load_2d_2sm(a_dst + 2 * a_tile, &p.tmB, full, kc * kBlockK, brow);
+            if (with_tail) {
+              const uint32_t t_dst = a_dst + a_bytes + b_bytes;
+              c0[0] = (kc + 1) * kBlockK;
+              c1[0] = (kc + 1) * kBlockK;
+              tma_load_nd_2sm(p.a_rank, t_dst, &p.tmA_tail, full, c0);
+              tma_load_nd_2sm(p.a_rank, t_dst + t_tile, &p.tmA_tail, full, c1);
+              tma_load_2d_2sm(t_dst + 2 * t_tile, &p.tmB_tail, full, (kc + 1) * kBlockK, brow);
+            }
+          }
+          if (++s == p.stages) { s = 0; par ^= 1; }
+          if (++kc == kloops) { kc = 0; ++tp; new_tap = true; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+      const uint32_t idesc = make_idesc_bf16(2 * kTileM, p.bn_tile, 0, 0);
+      const int tail_steps = (p.k_total - (p.kchunks - 1) * kBlockK + 15) / 16;
+      const uint32_t smem0 = smem_u32(smem);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem0, 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem0 + a_bytes, 16, 1024);
+      const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
+      const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
+      int s = 0;
+      uint32_t par = 0, seg_par = 0;
+      for (int k = 0; k < nseg; ++k) {
+        const SkSeg g = ps->segs[k];
+        if (k > 0) {
+          mbar_wait(smem_u32(&ps->tmem_empty), seg_par);       // both CTAs' epilogues have drained the accumulators
+          tc_fence_after();
+          seg_par ^= 1;
+        }
+        int kc = g.it0 % kloops;
+        uint32_t acc = 0;
+        for (int it = 0; it < g.len; ++it) {
+          mbar_wait(full0 + 8 * s, par);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
+          const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
+          if (!p.merge_tail && p.tail_mode != 0 && kc == p.kchunks - 1) {
+            const uint32_t base = smem0 + s * stage_bytes;
+            const uint32_t n_tile = kTileM * tail_row_bytes;
+            const uint32_t layout = p.tail_mode == 1 ? 6u : 4u;
+            const uint32_t sbo = 8 * tail_row_bytes;
+            const uint64_t ta0 = make_smem_desc(base, 16, sbo, layout);
+            const uint64_t ta1 = make_smem_desc(base + n_tile, 16, sbo, layout);
+            const uint64_t tb = make_smem_desc(base + 2 * n_tile, 16, sbo, layout);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (q < tail_steps) {
+                umma_bf16_2sm(tmem, ta0 + 2 * q, tb + 2 * q, idesc, acc);
+                umma_bf16_2sm(tmem + kTmemCols, ta1 + 2 * q, tb + 2 * q, idesc, acc);
+                acc = 1;
+              }
+            }
+          } else {
+            const int nsteps = (p.merge_tail || kc != p.kchunks - 1 || p.tail_mode == 0) ? kBlockK / 16 : tail_steps;
+#pragma unroll
+            for (int q = 0; q < kBlockK / 16; ++q) {
+              if (q < nsteps) {
+                umma_bf16_2sm(tmem, adesc + 2 * q, bdesc + 2 * q, idesc, acc);
+                umma_bf16_2sm(tmem + kTmemCols, adesc + (kABytes >> 4) + 2 * q, bdesc + 2 * q, idesc, acc);
+                acc = 1;
+              }
+            }
+            if (p.merge_tail && kc == kloops - 1) {
+              const uint32_t tb0 = smem0 + s * stage_bytes + a_bytes + b_bytes;
+              const uint32_t t_tile = kTileM * 32;
+              const uint64_t tbd = make_smem_desc(tb0 + 2 * t_tile, 16, 256, 6);
+              umma_bf16_2sm(tmem, make_smem_desc(tb0, 16, 256, 6), tbd, idesc, 1);
+              umma_bf16_2sm(tmem + kTmemCols, make_smem_desc(tb0 + t_tile, 16, 256, 6), tbd, idesc, 1);
+            }
+          }
+          umma_commit_2sm(empty0 + 8 * s, (uint16_t)0x3);
+          if (++kc == kloops) kc = 0;
+          if (++s == p.stages) { s = 0; par ^= 1; }
+        }
+        umma_commit_2sm(smem_u32(&ps->tmem_full), (uint16_t)0x3);
+      }
+    }
+    __syncwarp();
+  } else {
+    // -------------------------------------------------------------------- epilogue warps (each CTA: its own rows)
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int ncg = ((int)(blockDim.x >> 5) - 2) >> 2;
+    const int nepi = (int)blockDim.x - 64;
+    const int r = q * 32 + lane;
+    const int iw = r % p.bw;
+    const int ih = (r / p.bw) % p.bh;
+    const int in = r / (p.bw * p.bh);
+    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    EpilogueArgs ea;
+    ea.bias = p.bias; ea.act = p.act; ea.leak = p.leak; ea.mask_src = p.mask_src;
+    ea.mask_kind = p.mask_kind; ea.alpha = p.alpha; ea.out = p.out; ea.out_f32 = p.out_f32;
+    ea.accumulate = p.accumulate; ea.ncols = p.ncols; ea.pipelined = p.epi_pipe;
+    ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
+    ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
+    ea.bias_smem = 0; ea.bias_col0 = 0;
+    ea.partial_row = nullptr; ea.partial_n = 0; ea.partial_stride = 2 * p.sk_region;     // next pair, same CTA rank
+    float* my_region = p.sk_partial + ((long long)pair * 2 + crank) * p.sk_region;
+    uint32_t full_par = 0;
+    int bias_ntile = -1;
+    for (int k = 0; k < nseg; ++k) {
+      const SkSeg g = ps->segs[k];
+      const int n0 = g.ntile * p.bn_tile;
+      const int ext_w = p.phase_ext_w[g.phase], ext_h = p.phase_ext_h[g.phase];
+      bool row_ok[2];
+      long long off[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int pw0, ph0, pn0;
+        tile_origin(g, i, pw0, ph0, pn0);
+        const int pw = pw0 + iw, ph = ph0 + ih, pn = pn0 + in;
+        const bool tile_ok = g.group * 4 + (int)crank * 2 + i < total_tiles;
+        row_ok[i] = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
+        off[i] = p.phase_o_off[g.phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh + (long long)pw * p.o_sw;
+        if (g.finishing && row_ok[i] && cg == 0) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
+      }
+      if (g.finishing && p.bias && g.ntile != bias_ntile) {
+        named_barrier(2, nepi);                                  // everyone is done with the previous bias row
+        for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += nepi)
+          ps->bias[i] = (n0 + i < p.ncols) ? __ldg(p.bias + n0 + i) : 0.f;
+        named_barrier(2, nepi);
+        bias_ntile = g.ntile;
+      }
+      ea.bias_smem = p.bias ? smem_u32(&ps->bias[0]) : 0u;
+      ea.bias_col0 = n0;
+      ea.partial_n = 0;
+      if (g.finishing && g.it0 > 0) {
+        // wait for the contributors (they ran their piece first: the flags are up unless something is badly off)
+        if (threadIdx.x == 64) {
+          for (int c = g.first_pair; c < pair; ++c) {
+            volatile int* f = p.sk_flags + c * 2 + crank;
+            uint32_t spin = 0;
+            while (*f == 0) { if (++spin > (1u << 26)) __trap(); }
+            *f = 0;                                              // consumed: the next launch starts from zero
+          }
+          __threadfence();
+        }
+        named_barrier(3, nepi);
+        ea.partial_n = pair - g.first_pair;
+      }
+      mbar_wait(smem_u32(&ps->tmem_full), full_par);
+      full_par ^= 1;
+      tc_fence_after();
+      const int c_end = g.finishing ? min(p.bn_tile, p.ncols - n0) : p.bn_tile;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+        if (g.finishing) {
+          ea.partial_row = p.sk_partial + ((long long)g.first_pair * 2 + crank) * p.sk_region +
+                           (long long)(i * kTileM + r) * p.bn_tile;
+          epilogue_row<kSimple>(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, c_end);
+        } else {
+          epilogue_dump_row(trow, my_region + (long long)(i * kTileM + r) * p.bn_tile, cg * 16, ncg * 16, c_end);
+        }
+      }
+      tc_fence_before();
+      if (!g.finishing) {
+        __threadfence();                                         // partials visible device-wide ...
+        named_barrier(3, nepi);
+        if (threadIdx.x == 64) {                                 // ... before the flag goes up
+          volatile int* f = p.sk_flags + pair * 2 + crank;
+          *f = 1;
+          __threadfence();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&ps->tmem_empty), 0);    // on the leader's barrier
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
   if (warp == 1) tmem_dealloc_2sm<2 * kTmemCols>(tmem);
 }
 
@@ -766,7 +1104,78 @@ int tapgemm_stage_bytes_2sm(int bn_tile, int merge_tail) {
   return 2 * kABytes + (bn_tile / 2) * kBlockK * 2 + (merge_tail ? (2 * kTileM + bn_tile / 2) * 32 : 0);
 }
 
+// Library-owned scratch of the stream-K schedule: one region of fp32 partial accumulators per CTA (2 tiles x 128 rows
+// x up to 256 columns) and one flag per CTA.  Allocated once per process on first use (never during a stream capture:
+// such a launch falls back to the plain 2-CTA kernel); launches that use it are ordered by the stream they share.
+struct SkScratch { float* partial; int* flags; int pairs; int device; };
+static bool sk_scratch(SkScratch* out, cudaStream_t stream) {
+  static SkScratch sc = {nullptr, nullptr, 0, -1};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (sc.partial && sc.device == dev) { *out = sc; return true; }
+  if (sc.partial) return false;                       // a second device in one process: not supported by this scratch
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return false; }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int pairs = sms / 2;
+  float* part = nullptr;
+  int* flags = nullptr;
+  if (cudaMalloc(&part, (size_t)pairs * 2 * 2 * kTileM * kTmemCols * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&flags, (size_t)pairs * 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaMemset(flags, 0, (size_t)pairs * 2 * sizeof(int));
+  sc = {part, flags, pairs, dev};
+  *out = sc;
+  return true;
+}
+
+// Decide and launch the stream-K form (see tapgemm2sm_sk_kernel).  Returns false when the plain kernel should run.
+static bool launch_tapgemm_sk(const TapGemmParams& p0, cudaStream_t stream) {
+  static int enabled = -1;
+  if (enabled < 0) enabled = env_int("B200GAN_STREAMK", 1);
+  if (!enabled) return false;
+  const int total_tiles = p0.tiles_w * p0.tiles_h * p0.tiles_n;
+  const int groups = (total_tiles + 3) / 4;
+  const int ny = (p0.ncols + p0.bn_tile - 1) / p0.bn_tile;
+  const int kloops = p0.merge_tail ? p0.kchunks - 1 : p0.kchunks;
+  SkScratch sc;
+  TapGemmParams p = p0;
+  long long total = 0;
+  int min_len = 1 << 30;
+  for (int ph = 0; ph < p.nphases; ++ph) {
+    const int len = (p.phase_tap_begin[ph + 1] - p.phase_tap_begin[ph]) * kloops;
+    p.sk_phase_base[ph] = total;
+    total += (long long)groups * ny * len;
+    min_len = len < min_len ? len : min_len;
+  }
+  p.sk_phase_base[p.nphases] = total;
+  const long long items = (long long)groups * ny * p.nphases;
+  if (min_len < 8 || items < 16) return false;
+  if (!sk_scratch(&sc, stream)) return false;
+  const int pairs = sc.pairs;
+  if (items % pairs == 0 && p.nphases == 1) return false;          // whole waves already: nothing to gain
+  const long long range = (total + pairs - 1) / pairs;
+  if (range < 24 || range / min_len + 3 > kMaxSkSegs) return false;
+  p.sk = 1; p.sk_groups = groups; p.sk_ny = ny; p.sk_total = total; p.sk_range = range;
+  p.sk_partial = sc.partial; p.sk_flags = sc.flags; p.sk_region = 2LL * kTileM * p.bn_tile;
+  p.tma_store = 0;
+  const size_t smem = (size_t)p.stages * tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail) + sizeof(PipeSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(tapgemm2sm_sk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(tapgemm2sm_sk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    configured = true;
+  }
+  const int npairs = (int)((total + range - 1) / range);
+  if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
+    launch_clustered(tapgemm2sm_sk_kernel<true>, p, dim3(2 * npairs), smem, 2, stream);
+  else
+    launch_clustered(tapgemm2sm_sk_kernel<false>, p, dim3(2 * npairs), smem, 2, stream);
+  return true;
+}
+
 void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
+  if (p.cta2 && launch_tapgemm_sk(p, stream)) return;
   if (p.cta2) {
     const size_t smem2 = (size_t)p.stages * tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail) + sizeof(PipeSmem) + 1024;
     static bool configured2 = false;
@@ -948,6 +1357,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
     ea.mask_bits = p.mask_bits; ea.bits_out = p.bits_out; ea.bits_pitch = p.bits_pitch; ea.row_elems = p.row_elems;
     ea.stage_row = 0; ea.stage_bits = 0; ea.stage_col0 = 0;
     ea.bias_smem = 0; ea.bias_col0 = 0;
+    ea.partial_row = nullptr; ea.partial_n = 0; ea.partial_stride = 0;
     if (p.bias) {
       for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += (int)blockDim.x - 64)
         ps->bias[i] = (i < p.ncols) ? __ldg(p.bias + i) : 0.f;

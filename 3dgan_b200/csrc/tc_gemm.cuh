@@ -60,6 +60,15 @@ struct TapGemmParams {
   int cluster_y;                      // set by launch_tapgemm: 2 -> 2x2 clusters, the N-tile pair also shares A
   int splits;                         // > 1: split-K over blockIdx.z (1-CTA kernel only); the epilogue must be the
                                       // atomic fp32 accumulate (accumulate == 2) into a zeroed workspace
+  // stream-K persistent form of the 2-CTA kernel (tapgemm2sm_sk_kernel), set by launch_tapgemm:
+  int sk;                             // 1: this launch is stream-K
+  int sk_groups;                      // pixel-tile groups (4 tiles = one CTA pair) per (phase, N tile)
+  int sk_ny;                          // N tiles
+  long long sk_total, sk_range;       // total (item, K-iteration) positions; positions per CTA pair
+  long long sk_phase_base[kMaxPhases + 1];   // first position of each phase's items
+  float* sk_partial;                  // [pair][cta][2 tiles][128 rows][bn_tile] fp32 partial accumulators
+  int* sk_flags;                      // [pair][cta] 1 = that CTA's partial is published (reset by the consumer)
+  long long sk_region;                // floats per CTA region = 2 * 128 * bn_tile
   void* out;
   int out_f32;                        // 0: bf16, 1: fp32
   int accumulate;                     // fp32 only: 1: out += result (one writer); 2: red.global.add (split-K partials)

@@ -110,6 +110,8 @@ def _conv_tag(op, g):
 
 
 def empty(shape, dtype=BF16):
+    if not S.dry and S.device is None:
+        raise K.B200Error("engine.begin() has not bound a CUDA device / stream yet (Session.begin_step does it)")
     return torch.empty(shape, dtype=dtype, device="meta" if S.dry else S.device)
 
 

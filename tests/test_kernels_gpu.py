@@ -33,6 +33,9 @@ CONV_CASES = [
     (16, 16, 16, 512, 512, 4, 2),            # pix2pix e5: 1024 output pixels, split-K
     (16, 4, 4, 1024, 512, 4, 2),             # d2's conv geometry with the concatenated 1024 channels (dgrad splits)
     (3, 8, 8, 136, 72, 5, 2),                # split-K with ragged K chunk, ragged N and a partial tile
+    (128, 16, 16, 208, 400, 5, 2),           # stream-K schedule: 32 items over 74 CTA pairs, ~3 pieces per item
+    (96, 8, 8, 400, 800, 5, 2),              # stream-K with a 32-wide K tail (not merged) and 4 N tiles
+    (40, 32, 32, 64, 128, 4, 2),             # stream-K on a pix2pix mid layer (k4 s2, short items)
     (512, 16, 16, 208, 400, 5, 2),           # bench.py's c2 exactly (B=512, padded 200 -> 208): 2-CTA schedules, stream-K
     (512, 8, 8, 400, 800, 5, 2),             # bench.py's c3 exactly
     (512, 32, 32, 3, 208, 5, 2),             # bench.py's c1 / last deconv exactly
@@ -62,6 +65,8 @@ def test_conv_dgrad_fused_mask():
     res = P.conv_case(4, 16, 16, 200, 400, 5, 2, with_mask=True)
     assert res["dgrad"] < TOL["dgrad"], res
     res = P.conv_case(16, 4, 4, 512, 512, 4, 2, with_mask=True)          # split-K: the mask is applied by the finalize pass
+    assert res["dgrad"] < TOL["dgrad"], res
+    res = P.conv_case(128, 16, 16, 208, 400, 5, 2, with_mask=True)       # stream-K finisher applies the fused mask
     assert res["dgrad"] < TOL["dgrad"], res
     res = P.conv_case(4, 32, 32, 3, 200, 5, 2, with_mask=True)
     assert res["dgrad"] < TOL["dgrad"], res
@@ -222,6 +227,7 @@ def test_sign_bitmaps_match_value_masks():
     """relu/lrelu epilogues also write a 1-bit/element sign map; a gradient epilogue masked through the
     bitmap must equal the one masked through the stored activation, bit for bit."""
     import numpy as np
+    E.begin()
     g = torch.Generator().manual_seed(3)
     N = 6
     chain = [(32, 3, 200), (16, 200, 400), (8, 400, 800)]          # IWGAN critic c1, c2, c3
