@@ -131,8 +131,9 @@ static int tc_tap_splits(const b200_conv_geom* g, int op) {
     const int tiles = cdiv(ew, bw) * cdiv(eh, bh) * cdiv(g->N, bn);
     const int kch = cdiv(g->Cout, kBlockK);
     const int phases = st * st;
+    const int min_taps = std::max(1, (g->k / st) * (g->k / st));   // taps of the lightest output parity
     iters = std::max(1, kk / phases) * kch;                      // per phase
-    const int dual = tapgemm_dual(tiles, kch);
+    const int dual = tapgemm_dual(tiles, min_taps * kch);
     ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * cdiv(g->Cin, pick_bn_tile(g->Cin)) * phases;
   }
   if (ctas >= 64 || iters < 16) return 1;
@@ -623,7 +624,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.tiles_w = cdiv(ext_w0, p.bw); p.tiles_h = cdiv(ext_h0, p.bh); p.tiles_n = cdiv(g->N, p.bn);
   p.ext_n = g->N;
   p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
-  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks);
+  // two pixel tiles per CTA (and with them the 2-CTA kernels) whenever the lightest phase still has a real K loop
+  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, phs[np - 1].nt * p.kchunks);
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
   p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
   p.stages = pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)

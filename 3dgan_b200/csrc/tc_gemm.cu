@@ -17,27 +17,29 @@ namespace {
 constexpr int kMaxThreads = 64 + 32 * 16;   // warp0 TMA, warp1 MMA, then 4..16 epilogue warps (launch parameter)
 constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KiB: 128 rows x 128 B
 
-// one contiguous piece of a CTA pair's stream-K range that lies inside a single (phase, N tile, pixel group) item
+// one contiguous piece of a CTA pair's range that lies inside a single (phase, N tile, pixel group) item
 struct SkSeg {
-  int phase, ntile, group;     // the item
-  int it0, len;                // K-iterations [it0, it0 + len) of the item's (tap, K chunk) sequence
-  int finishing;               // 1: contains the item's last iteration -> this pair runs the item's epilogue
-  int first_pair;              // finishing && it0 > 0: partials of pairs [first_pair, own pair) must be added
-  int pad_;
+  uint16_t ntile, it0, len, first_pair;   // K-iterations [it0, it0 + len) of the item's (tap, K chunk) sequence;
+                                          // finishing && it0 > 0: partials of pairs [first_pair, own) must be added
+  uint32_t group;                         // pixel-tile group of the item
+  uint8_t phase, finishing, pad_[2];      // finishing: contains the item's last iteration -> runs the item's epilogue
 };
-constexpr int kMaxSkSegs = 12;
+constexpr int kMaxSkSegs = 44;
 
 struct PipeSmem {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full;
   uint64_t tmem_empty;
+  uint64_t acc_full[2];        // persistent kernel: one pair of barriers per TMEM accumulator buffer
+  uint64_t acc_empty[2];
   uint32_t tmem_base;
-  int nseg;                    // stream-K: segments of this pair, in processing order
+  int nseg;                    // persistent kernel: pieces of this pair, in processing order
   long long trace[6];          // B200GAN_GEMM_TRACE: clock stamps of CTA (0,0,0) (debug)
   alignas(16) float bias[256]; // this N tile's bias row (epilogue)
   SkSeg segs[kMaxSkSegs];
 };
+static_assert(sizeof(PipeSmem) <= 2048, "PipeSmem must fit the slack pick_stages leaves");
 
 __device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
   uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -678,19 +680,22 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
 }
 
 // =============================================================================================
-// Tap GEMM, 2-CTA form, persistent stream-K schedule
+// Tap GEMM, 2-CTA form, persistent schedule (whole items, or stream-K pieces)
 // =============================================================================================
-// The plain 2-CTA kernel launches one cluster per item = (phase, N tile, group of 4 pixel tiles): IWGAN's c2 / c3 have
-// 128 / 64 equal items for the 74 cluster slots of a B200, so 14 % of the machine idles in the last wave and every
-// CTA pays its own prologue (barrier init, TMEM allocation, pipeline fill).  Here 74 persistent pairs each take an
-// equal contiguous range of the linearised (item, K-iteration) space, as wgrad2sm_kernel does.  A range cuts items:
-//   * a piece that ends before its item does ("contributor") dumps its fp32 accumulators to a workspace region and
-//     raises a flag;
-//   * the piece that contains the item's last iteration ("finisher") adds the contributors' partials to its
-//     accumulators and runs the normal fused epilogue.
-// Inside a range only the LAST piece can be a contributor and only the FIRST can be a finisher with contributors; the
-// contributor piece is processed first, so every flag a finisher waits for was raised long before (no pair ever
-// depends on work that is scheduled after a wait), and the TMA ring keeps streaming across piece boundaries.
+// The plain 2-CTA kernel launches one cluster per item = (phase, N tile, group of 4 pixel tiles) and every CTA pays
+// its own prologue (barrier init, TMEM allocation, cluster sync, pipeline fill) and an epilogue nothing overlaps.
+// For items of 8-32 K-iterations (pix2pix's 64..256-channel k4 layers, the autoencoders) that fixed cost is 3-4x
+// the MMA time.  Here 74 persistent pairs each walk a contiguous range of the linearised (item, K-iteration) space
+// (as wgrad2sm_kernel does) while the TMA ring streams across item boundaries, and
+//   * p.sk_snap = 1 (the default use): range boundaries are snapped to item boundaries, so every piece is a whole
+//     item; with N tiles <= 128 columns the two pixel tiles of an item take 256 TMEM columns and the accumulators
+//     are DOUBLE-BUFFERED: the epilogue of item i overlaps the MMAs of item i+1;
+//   * p.sk_snap = 0 (stream-K proper, B200GAN_STREAMK=1): ranges are equal and cut items.  A piece that ends before
+//     its item does ("contributor") dumps its fp32 accumulators to a workspace region and raises a flag; the piece
+//     with the item's last iteration ("finisher") adds the contributors' partials and runs the fused epilogue.  Only
+//     the LAST piece of a range can be a contributor and only the FIRST a finisher with contributors; the contributor
+//     piece is processed first, so every flag a finisher waits for was raised long before.  Measured on IWGAN's
+//     75-150-iteration items: slower than the plain kernel (profiles/r2_streamk_ab.txt), hence opt-in.
 template <bool kSimple>
 __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -709,34 +714,51 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
   PipeSmem* ps = reinterpret_cast<PipeSmem*>(smem + (size_t)p.stages * stage_bytes);
   const int kloops = p.merge_tail ? p.kchunks - 1 : p.kchunks;
   const int tail_row_bytes = p.tail_mode == 1 ? 32 : 64;
+  // accumulator buffers: N tile <= 128 -> buffer b at columns [256 b, 256 b + 256), tile i at +128 i
+  const int nbuf = p.bn_tile <= 128 ? 2 : 1;
+  const uint32_t tile_cols = nbuf == 2 ? 128u : (uint32_t)kTmemCols;
 
   if (threadIdx.x == 0) {
     // this pair's pieces, in processing order (identical in both CTAs)
-    const long long rb = (long long)pair * p.sk_range;
-    const long long re = min(rb + p.sk_range, p.sk_total);
-    SkSeg tmp[kMaxSkSegs];
-    int n = 0;
-    for (long long pos = rb; pos < re && n < kMaxSkSegs;) {
+    auto phase_of = [&](long long pos) {
       int ph = 0;
       while (ph + 1 < p.nphases && pos >= p.sk_phase_base[ph + 1]) ++ph;
-      const int len_p = (p.phase_tap_begin[ph + 1] - p.phase_tap_begin[ph]) * kloops;
+      return ph;
+    };
+    auto len_of = [&](int ph) { return (p.phase_tap_begin[ph + 1] - p.phase_tap_begin[ph]) * kloops; };
+    auto snap = [&](long long pos) {            // floor to the start of the item that contains pos
+      if (pos >= p.sk_total) return p.sk_total;
+      const int ph = phase_of(pos);
+      const long long rel = pos - p.sk_phase_base[ph];
+      return pos - rel % len_of(ph);
+    };
+    long long rb = (long long)pair * p.sk_range;
+    long long re = min(rb + p.sk_range, p.sk_total);
+    if (p.sk_snap) { rb = snap(rb); re = snap(re); }
+    int n = 0;
+    for (long long pos = rb; pos < re && n < kMaxSkSegs;) {
+      const int ph = phase_of(pos);
+      const int len_p = len_of(ph);
       const long long rel = pos - p.sk_phase_base[ph];
       const int item = (int)(rel / len_p);
       SkSeg g;
-      g.phase = ph;
-      g.ntile = item / p.sk_groups;
-      g.group = item - g.ntile * p.sk_groups;
-      g.it0 = (int)(rel - (long long)item * len_p);
-      g.len = (int)min((long long)(len_p - g.it0), re - pos);
+      g.phase = (uint8_t)ph;
+      g.ntile = (uint16_t)(item / p.sk_groups);
+      g.group = (uint32_t)(item - (int)g.ntile * p.sk_groups);
+      g.it0 = (uint16_t)(rel - (long long)item * len_p);
+      g.len = (uint16_t)min((long long)(len_p - g.it0), re - pos);
       g.finishing = (g.it0 + g.len == len_p) ? 1 : 0;
-      g.first_pair = (int)((pos - g.it0) / p.sk_range);
-      g.pad_ = 0;
-      tmp[n++] = g;
+      g.first_pair = (uint16_t)((pos - g.it0) / p.sk_range);
+      g.pad_[0] = g.pad_[1] = 0;
+      ps->segs[n++] = g;
       pos += g.len;
     }
-    int k = 0;
-    if (n > 0 && !tmp[n - 1].finishing) ps->segs[k++] = tmp[n - 1];      // the contributor piece goes first
-    for (int j = 0; j < n - (n > 0 && !tmp[n - 1].finishing ? 1 : 0); ++j) ps->segs[k++] = tmp[j];
+    // a contributor piece (necessarily the last one) is processed first: rotate it to the front
+    if (n > 1 && !ps->segs[n - 1].finishing) {
+      const SkSeg last = ps->segs[n - 1];
+      for (int j = n - 1; j > 0; --j) ps->segs[j] = ps->segs[j - 1];
+      ps->segs[0] = last;
+    }
     ps->nseg = n;
   }
   if (warp == 0 && elect_one()) {
@@ -746,8 +768,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
       mbar_init(smem_u32(&ps->full[s]), 1);
       mbar_init(smem_u32(&ps->empty[s]), 1);
     }
-    mbar_init(smem_u32(&ps->tmem_full), 1);
-    mbar_init(smem_u32(&ps->tmem_empty), 2 * ((blockDim.x >> 5) - 2));     // the epilogue warps of BOTH CTAs
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&ps->acc_full[b]), 1);
+      mbar_init(smem_u32(&ps->acc_empty[b]), 2 * ((blockDim.x >> 5) - 2));   // the epilogue warps of BOTH CTAs
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<2 * kTmemCols>(smem_u32(&ps->tmem_base));
@@ -760,7 +784,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
 
   // first pixel of the CTA's two tiles of a group, per piece
   auto tile_origin = [&](const SkSeg& g, int i, int& pw0, int& ph0, int& pn0) {
-    int t = g.group * 4 + (int)crank * 2 + i;
+    int t = (int)g.group * 4 + (int)crank * 2 + i;
     const int tw = t % p.tiles_w; t /= p.tiles_w;
     const int th = t % p.tiles_h; t /= p.tiles_h;
     pw0 = tw * p.bw; ph0 = th * p.bh; pn0 = t * p.bn;
@@ -787,11 +811,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
             base[i][d + 1] = pw0 * p.a_mul[0][d] + ph0 * p.a_mul[1][d] + pn0 * p.a_mul[2][d];
         }
         const int tap_begin = p.phase_tap_begin[g.phase];
-        const int n0 = g.ntile * p.bn_tile;
-        int tp = g.it0 / kloops, kc = g.it0 - tp * kloops;
+        const int n0 = (int)g.ntile * p.bn_tile;
+        int tp = (int)g.it0 / kloops, kc = (int)g.it0 - tp * kloops;
         int c0[5], c1[5], brow = 0;
         bool new_tap = true;
-        for (int it = 0; it < g.len; ++it) {
+        for (int it = 0; it < (int)g.len; ++it) {
           if (new_tap) {
             const int tap = tap_begin + tp;
 #pragma unroll
@@ -846,17 +870,19 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
       const uint32_t desc_step = (uint32_t)stage_bytes >> 4;
       const uint32_t full0 = smem_u32(&ps->full[0]), empty0 = smem_u32(&ps->empty[0]);
       int s = 0;
-      uint32_t par = 0, seg_par = 0;
+      uint32_t par = 0;
       for (int k = 0; k < nseg; ++k) {
         const SkSeg g = ps->segs[k];
-        if (k > 0) {
-          mbar_wait(smem_u32(&ps->tmem_empty), seg_par);       // both CTAs' epilogues have drained the accumulators
+        const int buf = k % nbuf;
+        if (k >= nbuf) {
+          // both CTAs' epilogues have drained this buffer's previous accumulators
+          mbar_wait(smem_u32(&ps->acc_empty[buf]), (uint32_t)((k / nbuf - 1) & 1));
           tc_fence_after();
-          seg_par ^= 1;
         }
-        int kc = g.it0 % kloops;
+        const uint32_t d0 = tmem + (uint32_t)buf * kTmemCols, d1 = d0 + tile_cols;
+        int kc = (int)g.it0 % kloops;
         uint32_t acc = 0;
-        for (int it = 0; it < g.len; ++it) {
+        for (int it = 0; it < (int)g.len; ++it) {
           mbar_wait(full0 + 8 * s, par);
           tc_fence_after();
           const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
@@ -872,8 +898,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               if (q < tail_steps) {
-                umma_bf16_2sm(tmem, ta0 + 2 * q, tb + 2 * q, idesc, acc);
-                umma_bf16_2sm(tmem + kTmemCols, ta1 + 2 * q, tb + 2 * q, idesc, acc);
+                umma_bf16_2sm(d0, ta0 + 2 * q, tb + 2 * q, idesc, acc);
+                umma_bf16_2sm(d1, ta1 + 2 * q, tb + 2 * q, idesc, acc);
                 acc = 1;
               }
             }
@@ -882,8 +908,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
 #pragma unroll
             for (int q = 0; q < kBlockK / 16; ++q) {
               if (q < nsteps) {
-                umma_bf16_2sm(tmem, adesc + 2 * q, bdesc + 2 * q, idesc, acc);
-                umma_bf16_2sm(tmem + kTmemCols, adesc + (kABytes >> 4) + 2 * q, bdesc + 2 * q, idesc, acc);
+                umma_bf16_2sm(d0, adesc + 2 * q, bdesc + 2 * q, idesc, acc);
+                umma_bf16_2sm(d1, adesc + (kABytes >> 4) + 2 * q, bdesc + 2 * q, idesc, acc);
                 acc = 1;
               }
             }
@@ -891,15 +917,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
               const uint32_t tb0 = smem0 + s * stage_bytes + a_bytes + b_bytes;
               const uint32_t t_tile = kTileM * 32;
               const uint64_t tbd = make_smem_desc(tb0 + 2 * t_tile, 16, 256, 6);
-              umma_bf16_2sm(tmem, make_smem_desc(tb0, 16, 256, 6), tbd, idesc, 1);
-              umma_bf16_2sm(tmem + kTmemCols, make_smem_desc(tb0 + t_tile, 16, 256, 6), tbd, idesc, 1);
+              umma_bf16_2sm(d0, make_smem_desc(tb0, 16, 256, 6), tbd, idesc, 1);
+              umma_bf16_2sm(d1, make_smem_desc(tb0 + t_tile, 16, 256, 6), tbd, idesc, 1);
             }
           }
           umma_commit_2sm(empty0 + 8 * s, (uint16_t)0x3);
           if (++kc == kloops) kc = 0;
           if (++s == p.stages) { s = 0; par ^= 1; }
         }
-        umma_commit_2sm(smem_u32(&ps->tmem_full), (uint16_t)0x3);
+        umma_commit_2sm(smem_u32(&ps->acc_full[buf]), (uint16_t)0x3);
       }
     }
     __syncwarp();
@@ -923,11 +949,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
     ea.bias_smem = 0; ea.bias_col0 = 0;
     ea.partial_row = nullptr; ea.partial_n = 0; ea.partial_stride = 2 * p.sk_region;     // next pair, same CTA rank
     float* my_region = p.sk_partial + ((long long)pair * 2 + crank) * p.sk_region;
-    uint32_t full_par = 0;
     int bias_ntile = -1;
     for (int k = 0; k < nseg; ++k) {
       const SkSeg g = ps->segs[k];
-      const int n0 = g.ntile * p.bn_tile;
+      const int buf = k % nbuf;
+      const int n0 = (int)g.ntile * p.bn_tile;
       const int ext_w = p.phase_ext_w[g.phase], ext_h = p.phase_ext_h[g.phase];
       bool row_ok[2];
       long long off[2];
@@ -936,17 +962,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
         int pw0, ph0, pn0;
         tile_origin(g, i, pw0, ph0, pn0);
         const int pw = pw0 + iw, ph = ph0 + ih, pn = pn0 + in;
-        const bool tile_ok = g.group * 4 + (int)crank * 2 + i < total_tiles;
+        const bool tile_ok = (int)g.group * 4 + (int)crank * 2 + i < total_tiles;
         row_ok[i] = tile_ok && pw < ext_w && ph < ext_h && pn < p.ext_n;
         off[i] = p.phase_o_off[g.phase] + (long long)pn * p.o_sn + (long long)ph * p.o_sh + (long long)pw * p.o_sw;
         if (g.finishing && row_ok[i] && cg == 0) epilogue_prefetch_mask(ea, off[i], n0, p.bn_tile);
       }
-      if (g.finishing && p.bias && g.ntile != bias_ntile) {
+      if (g.finishing && p.bias && (int)g.ntile != bias_ntile) {
         named_barrier(2, nepi);                                  // everyone is done with the previous bias row
         for (int i = (int)threadIdx.x - 64; i < p.bn_tile; i += nepi)
           ps->bias[i] = (n0 + i < p.ncols) ? __ldg(p.bias + n0 + i) : 0.f;
         named_barrier(2, nepi);
-        bias_ntile = g.ntile;
+        bias_ntile = (int)g.ntile;
       }
       ea.bias_smem = p.bias ? smem_u32(&ps->bias[0]) : 0u;
       ea.bias_col0 = n0;
@@ -954,7 +980,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
       if (g.finishing && g.it0 > 0) {
         // wait for the contributors (they ran their piece first: the flags are up unless something is badly off)
         if (threadIdx.x == 64) {
-          for (int c = g.first_pair; c < pair; ++c) {
+          for (int c = (int)g.first_pair; c < pair; ++c) {
             volatile int* f = p.sk_flags + c * 2 + crank;
             uint32_t spin = 0;
             while (*f == 0) { if (++spin > (1u << 26)) __trap(); }
@@ -963,15 +989,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
           __threadfence();
         }
         named_barrier(3, nepi);
-        ea.partial_n = pair - g.first_pair;
+        ea.partial_n = pair - (int)g.first_pair;
       }
-      mbar_wait(smem_u32(&ps->tmem_full), full_par);
-      full_par ^= 1;
+      mbar_wait(smem_u32(&ps->acc_full[buf]), (uint32_t)((k / nbuf) & 1));
       tc_fence_after();
       const int c_end = g.finishing ? min(p.bn_tile, p.ncols - n0) : p.bn_tile;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kTmemCols + (uint32_t)i * tile_cols;
         if (g.finishing) {
           ea.partial_row = p.sk_partial + ((long long)g.first_pair * 2 + crank) * p.sk_region +
                            (long long)(i * kTileM + r) * p.bn_tile;
@@ -991,7 +1016,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_sk_kernel(const __g
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(smem_u32(&ps->tmem_empty), 0);    // on the leader's barrier
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&ps->acc_empty[buf]), 0);    // on the leader's barrier
     }
   }
 
@@ -1129,35 +1154,55 @@ static bool sk_scratch(SkScratch* out, cudaStream_t stream) {
   return true;
 }
 
-// Decide and launch the stream-K form (see tapgemm2sm_sk_kernel).  Returns false when the plain kernel should run.
+// Decide and launch the persistent form (see tapgemm2sm_sk_kernel).  Returns false when the plain kernel should run.
+//   * items of <= 64 K-iterations with N tiles <= 128: whole-item ranges + double-buffered accumulators (default on,
+//     B200GAN_PERSIST=0 disables);
+//   * B200GAN_STREAMK=1: stream-K proper for everything else that does not fill whole waves (opt-in, see the kernel).
 static bool launch_tapgemm_sk(const TapGemmParams& p0, cudaStream_t stream) {
-  static int enabled = -1;
-  if (enabled < 0) enabled = env_int("B200GAN_STREAMK", 1);
-  if (!enabled) return false;
+  static int streamk = -1, persist = -1;
+  if (streamk < 0) { streamk = env_int("B200GAN_STREAMK", 0); persist = env_int("B200GAN_PERSIST", 1); }
+  if (!streamk && !persist) return false;
   const int total_tiles = p0.tiles_w * p0.tiles_h * p0.tiles_n;
   const int groups = (total_tiles + 3) / 4;
   const int ny = (p0.ncols + p0.bn_tile - 1) / p0.bn_tile;
   const int kloops = p0.merge_tail ? p0.kchunks - 1 : p0.kchunks;
+  if (groups > 60000 || ny > 60000) return false;
   SkScratch sc;
   TapGemmParams p = p0;
   long long total = 0;
-  int min_len = 1 << 30;
+  int min_len = 1 << 30, max_len = 0;
   for (int ph = 0; ph < p.nphases; ++ph) {
     const int len = (p.phase_tap_begin[ph + 1] - p.phase_tap_begin[ph]) * kloops;
     p.sk_phase_base[ph] = total;
     total += (long long)groups * ny * len;
     min_len = len < min_len ? len : min_len;
+    max_len = len > max_len ? len : max_len;
   }
   p.sk_phase_base[p.nphases] = total;
   const long long items = (long long)groups * ny * p.nphases;
-  if (min_len < 8 || items < 16) return false;
-  if (!sk_scratch(&sc, stream)) return false;
-  const int pairs = sc.pairs;
-  if (items % pairs == 0 && p.nphases == 1) return false;          // whole waves already: nothing to gain
+  if (min_len < 1 || max_len > 60000) return false;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static int pairs_env = -1;
+  if (pairs_env < 0) pairs_env = env_int("B200GAN_SK_PAIRS", 0);
+  const int pairs = (pairs_env > 0 && pairs_env < sms / 2) ? pairs_env : sms / 2;
   const long long range = (total + pairs - 1) / pairs;
-  if (range < 24 || range / min_len + 3 > kMaxSkSegs) return false;
+  const bool whole_items = persist && p.bn_tile <= 128 && max_len <= 64 && items >= pairs + pairs / 2 &&
+                           range / min_len + 3 <= kMaxSkSegs;
+  if (whole_items) {
+    p.sk_snap = 1;
+    p.sk_partial = nullptr; p.sk_flags = nullptr;
+  } else {
+    if (!streamk || min_len < 8 || items < 16) return false;
+    if (items % pairs == 0 && p.nphases == 1) return false;          // whole waves already: nothing to gain
+    if (range < 24 || range / min_len + 3 > kMaxSkSegs) return false;
+    if (!sk_scratch(&sc, stream) || pairs > sc.pairs) return false;
+    p.sk_snap = 0;
+    p.sk_partial = sc.partial; p.sk_flags = sc.flags;
+  }
   p.sk = 1; p.sk_groups = groups; p.sk_ny = ny; p.sk_total = total; p.sk_range = range;
-  p.sk_partial = sc.partial; p.sk_flags = sc.flags; p.sk_region = 2LL * kTileM * p.bn_tile;
+  p.sk_region = 2LL * kTileM * p.bn_tile;
   p.tma_store = 0;
   const size_t smem = (size_t)p.stages * tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail) + sizeof(PipeSmem) + 1024;
   static bool configured = false;

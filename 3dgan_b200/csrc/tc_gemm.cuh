@@ -61,7 +61,8 @@ struct TapGemmParams {
   int splits;                         // > 1: split-K over blockIdx.z (1-CTA kernel only); the epilogue must be the
                                       // atomic fp32 accumulate (accumulate == 2) into a zeroed workspace
   // stream-K persistent form of the 2-CTA kernel (tapgemm2sm_sk_kernel), set by launch_tapgemm:
-  int sk;                             // 1: this launch is stream-K
+  int sk;                             // 1: this launch runs the persistent kernel
+  int sk_snap;                        // 1: range boundaries snapped to item boundaries (whole items, no partial sums)
   int sk_groups;                      // pixel-tile groups (4 tiles = one CTA pair) per (phase, N tile)
   int sk_ny;                          // N tiles
   long long sk_total, sk_range;       // total (item, K-iteration) positions; positions per CTA pair

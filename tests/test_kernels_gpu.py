@@ -36,6 +36,9 @@ CONV_CASES = [
     (128, 16, 16, 208, 400, 5, 2),           # stream-K schedule: 32 items over 74 CTA pairs, ~3 pieces per item
     (96, 8, 8, 400, 800, 5, 2),              # stream-K with a 32-wide K tail (not merged) and 4 N tiles
     (40, 32, 32, 64, 128, 4, 2),             # stream-K on a pix2pix mid layer (k4 s2, short items)
+    (16, 128, 128, 64, 128, 4, 2),           # pix2pix e2 / d7: persistent 2-CTA kernel, whole items, double-buffered TMEM
+    (8, 64, 64, 128, 256, 4, 2),             # pix2pix e3 / d6 (dgrad: N tile 128; fprop: N tile 256 -> plain kernel)
+    (256, 16, 16, 64, 128, 5, 2),            # VAE c2 / dc3 at its BASELINE batch: persistent, ragged phases (9/6/6/4 taps)
     (512, 16, 16, 208, 400, 5, 2),           # bench.py's c2 exactly (B=512, padded 200 -> 208): 2-CTA schedules, stream-K
     (512, 8, 8, 400, 800, 5, 2),             # bench.py's c3 exactly
     (512, 32, 32, 3, 208, 5, 2),             # bench.py's c1 / last deconv exactly

@@ -52,6 +52,8 @@ CASES = [
 ]
 if os.environ.get("WAVE_CASES") == "step":
     CASES = [(512, 16, 200, 400, 5), (512, 8, 400, 800, 5)]
+if os.environ.get("WAVE_CASES") == "ab":
+    CASES = [(512, 16, 208, 400, 5), (592, 16, 208, 400, 5), (512, 8, 400, 800, 5), (592, 8, 400, 800, 5)]
 if os.environ.get("WAVE_CASES") == "cin":
     CASES = [(296, 16, c, 400, 5) for c in (192, 200, 208, 224, 256, 264, 320, 328, 336)]
 for (N, H, Cin, Cout, k) in CASES:
