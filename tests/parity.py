@@ -173,7 +173,7 @@ def storage_noise_floor(run_oracle, decisions, ref_grads):
     floor = {}
     for k_, v in ref_grads.items():
         n_ = float(v.norm())
-        floor[k_] = float((noisy["grads"][k_] - v).norm()) / n_ if n_ > 1e-12 else 0.0
+        floor[k_] = float((noisy["grads"][k_] - v).norm()) / n_ if n_ > 1e-6 else 0.0     # (analytically-zero gradients: no floor)
     return floor
 
 
