@@ -56,6 +56,12 @@ SIGNATURES = {
     "b200_fill_f32": [_P, _LL, _F, _P],
     "b200_interp": [_P, _P, _P, _P, _I, _I, _P],
     "b200_rowscale": [_P, _P, _F, _F, _P, _I, _I, _P],
+    "b200_dropout": [_P, _P, _P, _LL, _F, _P],
+    "b200_instnorm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "b200_instnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "b200_layout_convert": [_P, _I, _P, _I, _I, _I, _I, _F, _F, _P],
+    "b200_summary_stats": [_P, _I, _LL, _P, _P, _I, _P],
+    "b200_montage": [_P, _I, _P, _I, _I, _I, _I, _I, _F, _F, _P],
     "b200_slice_cols": [_P, _LL, _I, _P, _LL, _I, _LL, _I, _P, _I, _F, _P],
     "b200_transpose_to_bf16": [_P, _I, _P, _I, _I, _I, _P],
     "b200_colsum": [_P, _P, _P, _LL, _I, _F, _P],

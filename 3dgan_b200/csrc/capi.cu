@@ -782,6 +782,29 @@ extern "C" int b200_rowscale(const void* in, const float* s_row, float mul, floa
                              b200_stream s) {
   WRAP(rowscale(in, s_row, mul, add, out, B, D, (cudaStream_t)s), "rowscale");
 }
+extern "C" int b200_dropout(const void* in, const float* u, void* out, long long n, float keep_prob, b200_stream s) {
+  WRAP(dropout_apply(in, u, out, n, keep_prob, (cudaStream_t)s), "dropout");
+}
+extern "C" int b200_instnorm_fwd(const void* x, const float* scale, const float* shift, void* out, float* stats, int N,
+                                 int HW, int C, float eps, b200_stream s) {
+  WRAP(instnorm_fwd(x, scale, shift, out, stats, N, HW, C, eps, (cudaStream_t)s), "instnorm_fwd");
+}
+extern "C" int b200_instnorm_bwd(const void* g, const void* x, const float* stats, const float* scale, void* dx,
+                                 float* dscale, float* dshift, int N, int HW, int C, b200_stream s) {
+  WRAP(instnorm_bwd(g, x, stats, scale, dx, dscale, dshift, N, HW, C, (cudaStream_t)s), "instnorm_bwd");
+}
+extern "C" int b200_layout_convert(const void* in, int in_type, void* out, int to_nchw, int N, int C, int HW, float mul,
+                                   float add, b200_stream s) {
+  WRAP(layout_convert(in, in_type, out, to_nchw, N, C, HW, mul, add, (cudaStream_t)s), "layout_convert");
+}
+extern "C" int b200_summary_stats(const void* x, int x_type, long long n, float* out5, unsigned int* counts, int nb,
+                                  b200_stream s) {
+  WRAP(summary_stats(x, x_type, n, out5, counts, nb, (cudaStream_t)s), "summary_stats");
+}
+extern "C" int b200_montage(const void* x, int x_type, float* out, int m, int n, int H, int W, int C, float mul, float add,
+                            b200_stream s) {
+  WRAP(montage(x, x_type, out, m, n, H, W, C, mul, add, (cudaStream_t)s), "montage");
+}
 extern "C" int b200_slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off,
                                long long rows, int cols, const void* mask, int mask_kind, float leak, b200_stream s) {
   WRAP(slice_cols(in, in_ld, in_off, out, out_ld, out_off, rows, cols, mask, mask_kind, leak, (cudaStream_t)s),

@@ -22,6 +22,7 @@ static int num_sms() {
   }
   return g_num_sms;
 }
+static int std_max(int a, int b) { return a > b ? a : b; }
 static int stride_grid(long long n, int threads, int per_thread = 1) {
   long long need = (n + (long long)threads * per_thread - 1) / ((long long)threads * per_thread);
   long long cap = (long long)num_sms() * 8;
@@ -692,6 +693,235 @@ int transpose_to_bf16(const void* in, int in_f32, void* out, int T, int A, int B
   dim3 grid((B + 31) / 32, (A + 31) / 32, T), block(32, 8);
   if (in_f32) transpose_kernel<float><<<grid, block, 0, st>>>((const float*)in, (bf16*)out, A, B);
   else transpose_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)in, (bf16*)out, A, B);
+  return 0;
+}
+
+// =============================================================================================
+// Gen-2 layer options (hem/ops/layers.py): dropout, instance norm; input layout; summaries
+// =============================================================================================
+// tf.nn.dropout(h, keep_prob) (hem/ops/layers.py:64,132,208): out = in * [u >= 1 - keep] / keep with u ~ U[0,1) drawn by
+// the caller (b200_philox); the backward applies the same kernel to the gradient with the same u.
+__global__ void dropout_kernel(const bf16* __restrict__ in, const float* __restrict__ u, bf16* out, long long n, float keep) {
+  const float inv = 1.f / keep, thr = 1.f - keep;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = __float2bfloat16(u[i] >= thr ? __bfloat162float(in[i]) * inv : 0.f);
+}
+int dropout_apply(const void* in, const float* u, void* out, long long n, float keep, cudaStream_t st) {
+  if (!(keep > 0.f) || keep > 1.f) return -1;
+  dropout_kernel<<<stride_grid(n, 256, 4), 256, 0, st>>>((const bf16*)in, u, (bf16*)out, n, keep);
+  return 0;
+}
+
+// hem.instance_norm (hem/ops/images.py:73-89): per sample and channel, moments over H x W, eps 1e-3, then
+// scale[c] * xhat + shift[c].  NHWC here.  One block per (sample, 32-channel slab): 32 x 8 threads, rows strided by 8.
+// stats[n][2C] keeps (mean, rstd) for the backward.
+__global__ void instnorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    bf16* out, float* stats, int HW, int C, float eps) {
+  __shared__ float red[2][8][33];
+  const int n = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const bf16* xs = x + (long long)n * HW * C;
+  float s = 0.f, q = 0.f;
+  if (c < C)
+    for (int r = ty; r < HW; r += 8) { const float v = __bfloat162float(xs[(long long)r * C + c]); s += v; q = fmaf(v, v, q); }
+  red[0][ty][tx] = s; red[1][ty][tx] = q;
+  __syncthreads();
+  float mean = 0.f, rstd = 0.f;
+  if (c < C) {
+    s = q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s += red[0][j][tx]; q += red[1][j][tx]; }
+    mean = s / HW;
+    rstd = rsqrtf(fmaxf(q / HW - mean * mean, 0.f) + eps);
+    if (ty == 0) { stats[(long long)n * 2 * C + c] = mean; stats[(long long)n * 2 * C + C + c] = rstd; }
+    const float a = scale[c] * rstd, b = shift[c] - mean * a;
+    bf16* os = out + (long long)n * HW * C;
+    for (int r = ty; r < HW; r += 8)
+      os[(long long)r * C + c] = __float2bfloat16(fmaf(__bfloat162float(xs[(long long)r * C + c]), a, b));
+  }
+}
+// dx = scale*rstd * (g - mean(g) - xhat * mean(g*xhat));  dscale[c] += sum g*xhat;  dshift[c] += sum g
+__global__ void instnorm_bwd_kernel(const bf16* __restrict__ g, const bf16* __restrict__ x, const float* __restrict__ stats,
+                                    const float* __restrict__ scale, bf16* dx, float* dscale, float* dshift, int HW, int C) {
+  __shared__ float red[2][8][33];
+  const int n = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long base = (long long)n * HW * C;
+  float mean = 0.f, rstd = 0.f, s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    mean = stats[(long long)n * 2 * C + c]; rstd = stats[(long long)n * 2 * C + C + c];
+    for (int r = ty; r < HW; r += 8) {
+      const float gv = __bfloat162float(g[base + (long long)r * C + c]);
+      const float xh = (__bfloat162float(x[base + (long long)r * C + c]) - mean) * rstd;
+      s1 += gv; s2 = fmaf(gv, xh, s2);
+    }
+  }
+  red[0][ty][tx] = s1; red[1][ty][tx] = s2;
+  __syncthreads();
+  if (c < C) {
+    s1 = s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += red[0][j][tx]; s2 += red[1][j][tx]; }
+    if (ty == 0) { atomicAdd(dshift + c, s1); atomicAdd(dscale + c, s2); }
+    const float a = scale[c] * rstd, m1 = s1 / HW, m2 = s2 / HW;
+    for (int r = ty; r < HW; r += 8) {
+      const float gv = __bfloat162float(g[base + (long long)r * C + c]);
+      const float xh = (__bfloat162float(x[base + (long long)r * C + c]) - mean) * rstd;
+      dx[base + (long long)r * C + c] = __float2bfloat16(a * (gv - m1 - xh * m2));
+    }
+  }
+}
+int instnorm_fwd(const void* x, const float* scale, const float* shift, void* out, float* stats, int N, int HW, int C,
+                 float eps, cudaStream_t st) {
+  if (N < 1 || HW < 1 || C < 1) return -1;
+  instnorm_fwd_kernel<<<dim3((C + 31) / 32, N), 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, stats, HW, C, eps);
+  return 0;
+}
+int instnorm_bwd(const void* g, const void* x, const float* stats, const float* scale, void* dx, float* dscale,
+                 float* dshift, int N, int HW, int C, cudaStream_t st) {
+  if (N < 1 || HW < 1 || C < 1) return -1;
+  instnorm_bwd_kernel<<<dim3((C + 31) / 32, N), 256, 0, st>>>((const bf16*)g, (const bf16*)x, stats, scale, (bf16*)dx,
+                                                              dscale, dshift, HW, C);
+  return 0;
+}
+
+// Input stage for NCHW sources (the Gen-2 pipeline yields NCHW, hem/ops/layers.py:117-119): out NHWC bf16 =
+// in[n][c][h][w] * mul + add, in: uint8 (caller folds 1/255 into mul) | fp32 | bf16.  And the way back for samples.
+template <typename TI>
+__global__ void nchw_to_nhwc_kernel(const TI* __restrict__ in, bf16* __restrict__ out, int C, int HW, float mul, float add) {
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * C * HW;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = fmaf(to_f32(in[base + (long long)c * HW + p]), mul, add);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) out[base + (long long)p * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+template <typename TI>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ in, float* __restrict__ out, int C, int HW, float mul, float add) {
+  __shared__ float tile[32][33];
+  const long long base = (long long)blockIdx.z * C * HW;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < HW) tile[i][threadIdx.x] = fmaf(to_f32(in[base + (long long)p * C + c]), mul, add);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[base + (long long)c * HW + p] = tile[threadIdx.x][i];
+  }
+}
+int layout_convert(const void* in, int in_type, void* out, int to_nchw, int N, int C, int HW, float mul, float add,
+                   cudaStream_t st) {
+  if (N < 1 || C < 1 || HW < 1 || N > 65535) return -1;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  if (!to_nchw) {
+    if (in_type == 2) nchw_to_nhwc_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)in, (bf16*)out, C, HW, mul, add);
+    else if (in_type == 1) nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>((const float*)in, (bf16*)out, C, HW, mul, add);
+    else if (in_type == 0) nchw_to_nhwc_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)in, (bf16*)out, C, HW, mul, add);
+    else return -1;
+  } else {
+    if (in_type == 1) nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)in, (float*)out, C, HW, mul, add);
+    else if (in_type == 0) nhwc_to_nchw_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)in, (float*)out, C, HW, mul, add);
+    else return -1;
+  }
+  return 0;
+}
+
+// Summaries after the step (ops/summaries.py:13-40): what tf.summary.histogram / tf.nn.zero_fraction need of a tensor in
+// one pass -- out5 = {min, max, sum, sum of squares, number of zeros}; counts[nb] (optional) = TensorBoard's default
+// exponential buckets: index 0 holds v <= -1e-12*1.1^(nb/2-1) ... middle = [-1e-12, 1e-12), growth 1.1 on both sides.
+template <typename TI>
+__global__ void summary_kernel(const TI* __restrict__ x, long long n, float* out5, unsigned int* counts, int nb) {
+  float mn = 3.4e38f, mx = -3.4e38f, s = 0.f, q = 0.f, z = 0.f;
+  const int half = nb / 2;
+  const float inv_log = 1.f / logf(1.1f);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float v = to_f32(x[i]);
+    mn = fminf(mn, v); mx = fmaxf(mx, v); s += v; q = fmaf(v, v, q); z += (v == 0.f) ? 1.f : 0.f;
+    if (counts) {
+      const float a = fabsf(v);
+      int k = a < 1e-12f ? 0 : min(half - 1, 1 + (int)floorf(logf(a * 1e12f) * inv_log));
+      atomicAdd(counts + (v < 0.f ? half - 1 - k : half + k), 1u);
+    }
+  }
+  __shared__ float red[5][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); z += __shfl_xor_sync(0xffffffffu, z, o);
+  }
+  if (lane == 0) { red[0][w] = mn; red[1][w] = mx; red[2][w] = s; red[3][w] = q; red[4][w] = z; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int j = 1; j < nw; ++j) {
+      mn = fminf(mn, red[0][j]); mx = fmaxf(mx, red[1][j]); s += red[2][j]; q += red[3][j]; z += red[4][j];
+    }
+    // float atomic min / max through the ordered-int trick (values are finite)
+    atomicMin(reinterpret_cast<int*>(out5), mn >= 0.f ? __float_as_int(mn) : (int)(0x80000000u - (unsigned)__float_as_int(mn)));
+    atomicMax(reinterpret_cast<int*>(out5) + 1, mx >= 0.f ? __float_as_int(mx) : (int)(0x80000000u - (unsigned)__float_as_int(mx)));
+    atomicAdd(out5 + 2, s); atomicAdd(out5 + 3, q); atomicAdd(out5 + 4, z);
+  }
+}
+__global__ void summary_init_kernel(float* out5, unsigned int* counts, int nb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    reinterpret_cast<int*>(out5)[0] = 0x7f7fffff;          // ordered-int encoding of +FLT_MAX
+    reinterpret_cast<int*>(out5)[1] = (int)(0x80000000u - 0xff7fffffu);   // of -FLT_MAX
+    out5[2] = out5[3] = out5[4] = 0.f;
+  }
+  if (counts && i < nb) counts[i] = 0u;
+}
+__global__ void summary_fix_kernel(float* out5) {          // decode the ordered ints back to floats
+  for (int k = 0; k < 2; ++k) {
+    const int e = reinterpret_cast<int*>(out5)[k];
+    out5[k] = e >= 0 ? __int_as_float(e) : __int_as_float((int)(0x80000000u - (unsigned)e));
+  }
+}
+int summary_stats(const void* x, int x_type, long long n, float* out5, unsigned int* counts, int nb, cudaStream_t st) {
+  if (n < 1 || (counts && (nb < 4 || (nb & 1)))) return -1;
+  summary_init_kernel<<<(std_max(nb, 1) + 255) / 256, 256, 0, st>>>(out5, counts, counts ? nb : 0);
+  int grid = stride_grid(n, 256, 8);
+  if (grid > num_sms() * 4) grid = num_sms() * 4;
+  if (x_type == 1) summary_kernel<float><<<grid, 256, 0, st>>>((const float*)x, n, out5, counts, nb);
+  else if (x_type == 0) summary_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, n, out5, counts, nb);
+  else return -1;
+  summary_fix_kernel<<<1, 1, 0, st>>>(out5);
+  return 0;
+}
+
+// montage_summary (ops/summaries.py:95-124): images [B, H, W, C] -> one [m*H, n*W, C] grid image; image j goes to
+// row block j % m, column block j / m (tf.split along the batch into n groups, concatenated side by side).
+template <typename TI>
+__global__ void montage_kernel(const TI* __restrict__ x, float* __restrict__ out, int m, int n, int H, int W, int C,
+                               float mul, float add) {
+  const long long total = (long long)m * n * H * W * C;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int gx = (int)(t % ((long long)n * W)); t /= (long long)n * W;
+    const int gy = (int)t;
+    const int j = (gx / W) * m + gy / H;
+    out[i] = fmaf(to_f32(x[(((long long)j * H + gy % H) * W + gx % W) * C + c]), mul, add);
+  }
+}
+int montage(const void* x, int x_type, float* out, int m, int n, int H, int W, int C, float mul, float add, cudaStream_t st) {
+  if (m < 1 || n < 1 || H < 1 || W < 1 || C < 1) return -1;
+  const int grid = stride_grid((long long)m * n * H * W * C, 256, 4);
+  if (x_type == 1) montage_kernel<float><<<grid, 256, 0, st>>>((const float*)x, out, m, n, H, W, C, mul, add);
+  else if (x_type == 0) montage_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, out, m, n, H, W, C, mul, add);
+  else return -1;
   return 0;
 }
 

@@ -37,6 +37,15 @@ int mul_add(const void* a, const void* b, const void* c, void* out, long long n,
 int fill_f32(float* out, long long n, float v, cudaStream_t st);
 int interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, cudaStream_t st);
 int rowscale(const void* in, const float* s, float mul, float add, void* out, int B, int D, cudaStream_t st);
+int dropout_apply(const void* in, const float* u, void* out, long long n, float keep, cudaStream_t st);
+int instnorm_fwd(const void* x, const float* scale, const float* shift, void* out, float* stats, int N, int HW, int C,
+                 float eps, cudaStream_t st);
+int instnorm_bwd(const void* g, const void* x, const float* stats, const float* scale, void* dx, float* dscale,
+                 float* dshift, int N, int HW, int C, cudaStream_t st);
+int layout_convert(const void* in, int in_type, void* out, int to_nchw, int N, int C, int HW, float mul, float add,
+                   cudaStream_t st);
+int summary_stats(const void* x, int x_type, long long n, float* out5, unsigned int* counts, int nb, cudaStream_t st);
+int montage(const void* x, int x_type, float* out, int m, int n, int H, int W, int C, float mul, float add, cudaStream_t st);
 int splitk_finalize(const float* ws, void* out, int out_f32, long long n, int C, const float* bias, int act, float leak,
                     const void* mask, int mask_kind, cudaStream_t st);
 int slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off, long long rows,

@@ -163,7 +163,7 @@ class recording:
 # ------------------------------------------------------------------------------------------ tensors
 class Tensor:
     __slots__ = ("buf", "shape", "requires_grad", "_mask", "node", "grad_f32", "im2col", "bits", "logical_c",
-                 "__weakref__")
+                 "layout", "__weakref__")
 
     def __init__(self, buf, shape=None, requires_grad=False, mask=None):
         self.buf = buf
@@ -175,6 +175,7 @@ class Tensor:
         self.im2col = None         # (geometry key, workspace) left by a small-channel fprop of this tensor
         self.bits = None           # int16 [rows, ceil(C/16)] sign bitmap written by the producing relu/lrelu epilogue
         self.logical_c = None      # channels that carry data when the last dim is zero-padded (ops/layers.py)
+        self.layout = "NHWC"       # "NCHW": an input batch as the Gen-2 pipeline yields it (converted by the first op)
 
     @property
     def mask(self):
@@ -311,12 +312,20 @@ def same_pad(size, k, s):
     return out, total // 2
 
 
-def conv_geom(N, H, W, Cin, Cout, k, stride):
-    """TF SAME geometry of conv [N,H,W,Cin] -> [N,ceil(H/s),ceil(W/s),Cout]."""
+def conv_geom(N, H, W, Cin, Cout, k, stride, padding='SAME'):
+    """TF geometry of conv [N,H,W,Cin] -> [N,Ho,Wo,Cout]: SAME (Ho = ceil(H/s), the smaller half of the
+    padding first) or VALID (no padding, Ho = (H - k) // s + 1; hem/ops/layers.py:118 `padding=padding`)."""
     g = K.ConvGeom()
     g.N, g.H, g.W, g.Cin, g.Cout, g.k, g.stride = N, H, W, Cin, Cout, k, stride
-    g.Ho, g.pad_t = same_pad(H, k, stride)
-    g.Wo, g.pad_l = same_pad(W, k, stride)
+    if padding == 'SAME':
+        g.Ho, g.pad_t = same_pad(H, k, stride)
+        g.Wo, g.pad_l = same_pad(W, k, stride)
+    elif padding == 'VALID':
+        if H < k or W < k:
+            raise K.B200Error("VALID convolution: the %dx%d filter does not fit a %dx%d input" % (k, k, H, W))
+        g.Ho, g.Wo, g.pad_t, g.pad_l = (H - k) // stride + 1, (W - k) // stride + 1, 0, 0
+    else:
+        raise K.B200Error("padding must be 'SAME' or 'VALID'")
     return g
 
 
@@ -510,6 +519,15 @@ def activation(x, act, leak=0.0):
 def affine(x, mul, add, out_f32=False):
     """out = x*mul + add (e.g. the [0,1] -> [-1,1] rescale, models/gan.py:50).  A uint8 input is an image batch as
     decoded (data.py:14-22): its /255 normalisation is folded into this pass."""
+    if x.layout == "NCHW":
+        # an input batch in the reference's Gen-2 layout (hem/ops/layers.py:117-119): transposed to the kernels' NHWC in
+        # the same pass that rescales (and, for image bytes, normalises) it
+        n, c, h, w = x.shape
+        out = Tensor(empty((n, h, w, c), BF16))
+        u8 = x.buf.dtype == torch.uint8
+        launch("b200_layout_convert", _p(x.buf), 2 if u8 else int(x.f32), _p(out.buf), 0, n, c, h * w,
+               mul / 255.0 if u8 else mul, add)
+        return out
     out = Tensor(empty(x.shape, F32 if out_f32 else BF16))
     if x.buf.dtype == torch.uint8:
         launch("b200_affine_act", _p(x.buf), 2, _p(out.buf), int(out_f32), x.numel, mul / 255.0, add, 0, 0.0)
@@ -599,6 +617,73 @@ def pad_channels(x, cp):
         return [take_channels(gouts[0], c, x.mask)]
 
     _record([x], [out], bw)
+    return out
+
+
+def to_nchw(x, mul=1.0, add=0.0):
+    """NHWC activation -> fp32 NCHW copy (samples / summaries handed back in the reference's Gen-2 layout)."""
+    n, h, w, c = x.shape
+    out = Tensor(empty((n, c, h, w), F32))
+    out.layout = "NCHW"
+    launch("b200_layout_convert", _p(x.buf), int(x.f32), _p(out.buf), 1, n, c, h * w, mul, add)
+    return out
+
+
+def add(a, b):
+    """a + b (the shortcut of hem.residual, hem/ops/layers.py:304)."""
+    out = Tensor(empty(a.shape, BF16))
+    launch("b200_axpby", _p(a.buf), int(a.f32), 1.0, None, _p(b.buf), int(b.f32), 1.0, _p(out.buf), 0, a.numel)
+    out.logical_c = a.logical_c
+
+    def bw(gouts):
+        go = gouts[0]
+        return [maskmul(go, t.mask) if (t.requires_grad and t.mask is not None) else go for t in (a, b)]
+
+    _record([a, b], [out], bw)
+    return out
+
+
+def dropout(x, keep_prob, u):
+    """tf.nn.dropout(h, keep_prob) (hem/ops/layers.py:64,132,208; the reference passes its `dropout` value as
+    keep_prob): out = x * [u >= 1 - keep] / keep, u ~ U[0,1) fp32 drawn by the caller (Session.random_uniform)."""
+    xb = _as_bf16(x)
+    out = Tensor(empty(x.shape, BF16))
+    out.logical_c = x.logical_c
+    launch("b200_dropout", _p(xb.buf), _p(u.buf), _p(out.buf), x.numel, float(keep_prob))
+
+    def bw(gouts):
+        go = _as_bf16(gouts[0])
+        gx = Tensor(empty(x.shape, BF16))
+        launch("b200_dropout", _p(go.buf), _p(u.buf), _p(gx.buf), x.numel, float(keep_prob))
+        return [maskmul(gx, x.mask) if x.mask is not None else gx]
+
+    _record([x], [out], bw)
+    return out
+
+
+def instance_norm(x, scale, shift, eps=1e-3):
+    """hem.instance_norm (hem/ops/images.py:73-89): per sample and channel, moments over H x W; scale * xhat + shift."""
+    n, h, w, c = x.shape
+    xb = _as_bf16(x)
+    stats = empty((n, 2 * c), F32)
+    out = Tensor(empty(x.shape, BF16))
+    out.logical_c = x.logical_c
+    launch("b200_instnorm_fwd", _p(xb.buf), _p(scale.p32), _p(shift.p32), _p(out.buf), _p(stats), n, h * w, c, eps)
+
+    def bw(gouts):
+        go = _as_bf16(gouts[0])
+        dx = Tensor(empty(x.shape, BF16))
+        both = scale.accum and shift.accum
+        ds = scale.g32 if both else empty((c,), F32)
+        dh = shift.g32 if both else empty((c,), F32)
+        if not both:
+            launch("b200_fill_f32", _p(ds), c, 0.0)
+            launch("b200_fill_f32", _p(dh), c, 0.0)
+        launch("b200_instnorm_bwd", _p(go.buf), _p(xb.buf), _p(stats), _p(scale.p32), _p(dx.buf), _p(ds), _p(dh),
+               n, h * w, c)
+        return [maskmul(dx, x.mask) if x.mask is not None else dx]
+
+    _record([x], [out], bw, scale.active or shift.active, params=(scale, shift))
     return out
 
 

@@ -1,10 +1,13 @@
-"""The reference's Gen-2 layer API (hem/ops/layers.py:23-356, hem/ops/activations.py, hem/ops/images.py:53-70,
-hem/ops/losses.py:10-15) with the same signatures.
+"""The reference's Gen-2 layer API (hem/ops/layers.py:23-356, hem/ops/activations.py, hem/ops/images.py:53-89,
+hem/ops/losses.py:10-15) with the same signatures and op order:
 
-The reference runs these layers in NCHW (`data_format='NCHW'`, hem/ops/layers.py:117-119); the tensors here
-are the engine's NHWC buffers, so "axis=1" channel concatenations of the reference become
-`engine.concat_channels`.  Math is identical (fused batch-norm = same batch statistics, beta only).
-Kwargs that no in-scope model uses (batch-renorm, instance-norm, dropout, VALID padding, `residual`) raise.
+    conv / matmul + bias -> [instance norm] -> [batch norm (fused NCHW statistics)] -> activation -> [dropout]
+
+The reference runs these layers in NCHW (`data_format='NCHW'`, hem/ops/layers.py:117-119); activations here are the
+engine's NHWC buffers, so its "axis=1" channel concatenations become `engine.concat_channels`, and an NCHW input batch
+(session.Input(layout="NCHW"), as the Gen-2 pipeline yields it) is transposed by the first op that touches it
+(`rescale`).  `hem.reshape` takes the NHWC shape the reference's own helper takes (hem/ops/layers.py:343-356).
+Not on the accelerated path: `use_batch_renorm` (raises).
 """
 from .. import _capi as K
 from .. import engine as E
@@ -14,22 +17,21 @@ from ..ops.arg_scope import add_arg_scope
 from ..variables import xavier_initializer
 
 
-def _unsupported(use_batch_renorm, use_instance_norm, dropout, padding):
-    if use_batch_renorm or use_instance_norm:
-        raise K.B200Error("batch-renorm / instance-norm are outside the accelerated path (SURVEY §2 row 8)")
-    if dropout and dropout > 0:
-        raise K.B200Error("dropout is outside the accelerated path (default 0, hem/models/pix2pix.py:49-52)")
-    if padding != 'SAME':
-        raise K.B200Error("only SAME padding is on the accelerated path")
+def _opts(use_batch_renorm, use_instance_norm, dropout, padding, reuse):
+    if use_batch_renorm:
+        raise K.B200Error("batch renormalisation (renorm=True, hem/ops/layers.py:62,124) is not on the accelerated path")
+    if padding not in ('SAME', 'VALID'):
+        raise K.B200Error("padding must be 'SAME' or 'VALID'")
+    return _L._Opts(instance_norm=bool(use_instance_norm), dropout=dropout or 0, padding=padding, fused_nchw=True,
+                    reuse=reuse)
 
 
 @add_arg_scope
 def dense(x, input_size, output_size, init=xavier_initializer, use_batch_norm=False, use_batch_renorm=False,
           activation=None, reuse=False, dropout=0, name=None):
-    """hem/ops/layers.py:23-67."""
-    _unsupported(use_batch_renorm, False, dropout, 'SAME')
-    return _L.dense._arg_scope_target(x, input_size, output_size, init=init, use_batch_norm=use_batch_norm,
-                                      activation=activation, reuse=reuse, name=name)
+    """hem/ops/layers.py:23-67 (`dropout` is the keep probability, as the reference passes it to tf.nn.dropout)."""
+    return _L._dense(x, input_size, output_size, init, use_batch_norm, activation, name,
+                     _opts(use_batch_renorm, False, dropout, 'SAME', reuse))
 
 
 @add_arg_scope
@@ -37,23 +39,39 @@ def conv2d(x, input_size, output_size, filter_size=3, stride=1, init=xavier_init
            use_batch_renorm=False, use_instance_norm=False, activation=None, reuse=False, dropout=0, padding='SAME',
            name=None):
     """hem/ops/layers.py:71-135."""
-    _unsupported(use_batch_renorm, use_instance_norm, dropout, padding)
-    return _L.conv2d._arg_scope_target(x, input_size, output_size, filter_size, stride, init=init,
-                                       use_batch_norm=use_batch_norm, activation=activation, reuse=reuse, name=name)
+    return _L._conv2d(x, input_size, output_size, filter_size, stride, init, use_batch_norm, activation, name,
+                      _opts(use_batch_renorm, use_instance_norm, dropout, padding, reuse))
 
 
 @add_arg_scope
 def deconv2d(x, input_size, output_size, filter_size=3, stride=2, init=xavier_initializer, output_shape=None,
              use_batch_norm=False, use_batch_renorm=False, use_instance_norm=False, activation=None, reuse=False,
              dropout=0, padding='SAME', name=None):
-    """hem/ops/layers.py:139-211."""
-    _unsupported(use_batch_renorm, use_instance_norm, dropout, padding)
-    return _L.deconv2d._arg_scope_target(x, input_size, output_size, filter_size, stride, init=init,
-                                         use_batch_norm=use_batch_norm, activation=activation, reuse=reuse, name=name,
-                                         output_shape=output_shape)
+    """hem/ops/layers.py:139-211.  output_shape: (H, W) of the result (the reference passes the full NCHW shape
+    tensor; only its spatial part is free)."""
+    if output_shape is not None and len(output_shape) == 4:
+        output_shape = tuple(output_shape[2:])                    # [N, C, H, W] as the reference builds it
+    return _L._deconv2d(x, input_size, output_size, filter_size, stride, init, use_batch_norm, activation, name,
+                        output_shape, _opts(use_batch_renorm, use_instance_norm, dropout, padding, reuse))
+
+
+@add_arg_scope
+def residual(x, input_size, output_size, filter_size=3, stride=1, init=xavier_initializer, use_batch_norm=False,
+             use_batch_renorm=False, use_instance_norm=False, activation=None, reuse=False, dropout=0, padding='SAME',
+             name=None):
+    """hem/ops/layers.py:216-320: two convolutions with a shortcut taken after the first conv + bias."""
+    return _L._residual(x, input_size, output_size, filter_size, stride, init, use_batch_norm, activation, name,
+                        _opts(use_batch_renorm, use_instance_norm, dropout, padding, reuse))
 
 
 flatten = _L.flatten
+
+
+@add_arg_scope
+def reshape(x, shape, name=None):
+    """hem/ops/layers.py:343-356: `shape` is given in NHWC order (the reference converts it to NCHW; the engine's
+    activations already are NHWC)."""
+    return E.reshape(x, tuple(shape))
 
 
 def lrelu(x, leak=0.2, name=None):
@@ -65,9 +83,20 @@ fused_lrelu = make_lrelu
 
 
 def rescale(x, orig=(-1, 1), new=(0, 1), name=None):
-    """hem/ops/images.py:53-70: (x - orig0) * (new1-new0)/(orig1-orig0) + new0."""
+    """hem/ops/images.py:53-70: (x - orig0) * (new1-new0)/(orig1-orig0) + new0.  An NCHW / uint8 input batch is
+    transposed / normalised in the same pass (engine.affine)."""
     mul = (new[1] - new[0]) / (orig[1] - orig[0])
     return E.affine(x, mul, new[0] - orig[0] * mul)
+
+
+def instance_norm(x, reuse=False, name=None):
+    """hem/ops/images.py:73-89."""
+    return _L.instance_norm(x, name)
+
+
+def to_nchw(x):
+    """Hand an activation back in the reference's layout (fp32 [N, C, H, W])."""
+    return E.to_nchw(x)
 
 
 def rmse(x, x_hat, name='rmse'):

@@ -26,13 +26,16 @@ class Input:
     [B,H,W,C] float32 batch in [0,1] per `next()`.  Batches are fed by the caller (`feed`) into a
     static device ring so that a captured CUDA graph always reads the same addresses."""
 
-    def __init__(self, batch_size, shape, slots=1, device=None, dtype=torch.float32):
+    def __init__(self, batch_size, shape, slots=1, device=None, dtype=torch.float32, layout="NHWC"):
         """dtype float32: batches already normalised to [0,1] (what the reference's `x` tensor holds);
         dtype uint8: image bytes as decoded — the /255 of data.py:21-22,29 then runs on the device, fused into the
-        model's first op (engine.affine), and a batch costs a quarter of the host->device traffic."""
+        model's first op (engine.affine), and a batch costs a quarter of the host->device traffic.
+        layout "NCHW": `shape` is (C, H, W), batches arrive as the reference's Gen-2 pipeline lays them out
+        (hem/ops/layers.py:117-119); the model's first op (hem.rescale) transposes them on the device."""
         self.batch_size, self.shape, self.slots = batch_size, tuple(shape), slots
         self.device = device
         self.dtype = dtype
+        self.layout = layout
         self.ring = None
         self.cursor = 0
 
@@ -71,9 +74,11 @@ class Input:
 
     def next(self):
         if E.S.dry:
-            return E.Tensor(torch.empty((self.batch_size,) + self.shape, dtype=self.dtype, device="meta"))
-        t = E.Tensor(self.ring[self.cursor % self.slots])
-        self.cursor += 1
+            t = E.Tensor(torch.empty((self.batch_size,) + self.shape, dtype=self.dtype, device="meta"))
+        else:
+            t = E.Tensor(self.ring[self.cursor % self.slots])
+            self.cursor += 1
+        t.layout = self.layout
         return t
 
 

@@ -24,6 +24,8 @@ class VariableStore:
         self.groups = []
         self.state = OrderedDict()      # non-trainable variables (batch norm moving averages): name -> StateVar
         self.state_buf = None
+        self.collect = False            # True: layers register their outputs in `collections` (summary passes)
+        self.collections = {}           # 'conv_layers' | 'dense_layers' -> [(name, Tensor)]  (ops/layers.py:60,105,146)
 
     # ---------------------------------------------------------------- scopes
     def path(self, name=None):
@@ -37,6 +39,7 @@ class VariableStore:
         graph construction, so every replay of the model function must regenerate the same names."""
         self.bn_counters = {}
         self.scope = []
+        self.collections = {}
 
     def unique_bn_scope(self):
         base = self.path()
@@ -71,6 +74,12 @@ class VariableStore:
             sv = StateVar(full, tuple(shape if physical_shape is None else physical_shape), tuple(shape), float(value))
             self.state[full] = sv
         return sv
+
+    def add_to_collection(self, key, name, tensor):
+        """tf.add_to_collection('conv_layers' | 'dense_layers', h) of the layers (ops/layers.py:60,105,146): only while
+        a summary pass is collecting, so that training passes do not pin their activations."""
+        if self.collect:
+            self.collections.setdefault(key, []).append((self.path(name), tensor))
 
     def collection(self, prefix):
         """tf.get_collection(TRAINABLE_VARIABLES, scope) (models/gan.py:65-66)."""
@@ -157,6 +166,13 @@ def xavier_initializer():
 def random_normal_initializer(mean=0.0, stddev=0.02):
     def init(shape, gen):
         return (torch.randn(shape, generator=gen, dtype=torch.float64) * stddev + mean).to(torch.float32)
+
+    return init
+
+
+def ones_initializer():
+    def init(shape, gen):
+        return torch.ones(shape, dtype=torch.float32)
 
     return init
 

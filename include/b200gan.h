@@ -110,6 +110,25 @@ int b200_fill_f32(float* out, long long n, float v, b200_stream s);
 int b200_interp(const void* x, const void* g, const float* alpha, void* out, int B, int D, b200_stream s);
                                                                      /* x + alpha (g - x), models/gan.py:224-226 */
 int b200_rowscale(const void* in, const float* s_row, float mul, float add, void* out, int B, int D, b200_stream s);
+/* ---- Gen-2 layer options (hem/ops/layers.py) */
+int b200_dropout(const void* in, const float* u, void* out, long long n, float keep_prob, b200_stream s);
+                                                                     /* tf.nn.dropout(h, keep_prob) (hem/ops/layers.py:64,132,208): out = in [u >= 1-keep] / keep,
+                                                                        u ~ U[0,1) from b200_philox; the gradient goes through the same call with the same u */
+int b200_instnorm_fwd(const void* x, const float* scale, const float* shift, void* out, float* stats /*[N][2C]: mean, rstd*/,
+                      int N, int HW, int C, float eps, b200_stream s);   /* hem.instance_norm (hem/ops/images.py:73-89), NHWC */
+int b200_instnorm_bwd(const void* g, const void* x, const float* stats, const float* scale, void* dx, float* dscale,
+                      float* dshift, int N, int HW, int C, b200_stream s);   /* dscale / dshift are accumulated (+=) */
+/* ---- layout at the boundary: the Gen-2 pipeline and layers are NCHW (hem/ops/layers.py:117-119), the kernels NHWC.
+ * to_nchw = 0: out (bf16 NHWC) = in (NCHW; in_type 0 bf16, 1 fp32, 2 uint8 image bytes) * mul + add  -- the input stage;
+ * to_nchw = 1: out (fp32 NCHW) = in (NHWC bf16 | fp32) * mul + add                                   -- samples / summaries */
+int b200_layout_convert(const void* in, int in_type, void* out, int to_nchw, int N, int C, int HW, float mul, float add,
+                        b200_stream s);
+/* ---- summaries after the step (ops/summaries.py:13-40,95-124) */
+int b200_summary_stats(const void* x, int x_type, long long n, float* out5 /*min,max,sum,sumsq,zeros*/,
+                       unsigned int* counts /*[nb] or NULL: TensorBoard-style exponential buckets, growth 1.1 from 1e-12, mirrored*/,
+                       int nb, b200_stream s);                       /* tf.summary.histogram + tf.nn.zero_fraction in one pass */
+int b200_montage(const void* x, int x_type, float* out, int m, int n, int H, int W, int C, float mul, float add,
+                 b200_stream s);                                     /* montage_summary: [m*n,H,W,C] -> [m*H, n*W, C] fp32 */
 int b200_slice_cols(const void* in, long long in_ld, int in_off, void* out, long long out_ld, int out_off,
                     long long rows, int cols, const void* mask, int mask_kind, float leak, b200_stream s);
                                                                      /* out[r, out_off+c] = in[r, in_off+c] * act'(mask[r,c]), bf16, row strides in elements:

@@ -173,6 +173,24 @@ def conv2d_transpose_same(x, K, out_hw, stride):
     return y.permute(0, 2, 3, 1)
 
 
+def conv2d_valid(x, K, stride):
+    """tf.nn.conv2d(x, K, strides, 'VALID') — hem/ops/layers.py:118 with padding='VALID'."""
+    y = F.conv2d(x.permute(0, 3, 1, 2), K.permute(3, 2, 0, 1), stride=stride)
+    return y.permute(0, 2, 3, 1)
+
+
+def instance_norm(x, scale, shift, eps=1e-3):
+    """hem/ops/images.py:73-89 (NHWC here): per sample and channel moments over H, W; scale * xhat + shift."""
+    mu = x.mean(dim=(1, 2), keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=(1, 2), keepdim=True)
+    return scale * (x - mu) / torch.sqrt(var + eps) + shift
+
+
+def dropout(x, keep_prob, u):
+    """tf.nn.dropout(x, keep_prob) with its uniform draw u made explicit: x / keep * floor(keep + u)."""
+    return x / keep_prob * torch.floor(keep_prob + u)
+
+
 # --------------------------------------------------------------------------- activations
 def lrelu(x, leak=0.2):
     """ops/activations.py:28 — tf.maximum(leak*x, x).  TF's Maximum gradient routes to the
