@@ -143,6 +143,9 @@ def test_residual_block_with_instance_norm_and_dropout_matches_oracle():
     assert abs(float(loss.buf.item()) - float(ref)) < 2e-3 * abs(float(ref)) + 1e-5
     assert set(q) == set(sess.store.params)
     for (name, prm), want in zip(sess.store.params.items(), grads):
+        if name == 'net/vars/rB/bias':            # feeds an instance norm: analytically zero gradient, ours is rounding noise
+            assert float(prm.logical(prm.g32).abs().max()) < 1e-3 and float(want.abs().max()) < 1e-5
+            continue
         e = P.rel_err(prm.logical(prm.g32), want)
         print("  [residual] %-24s err %.3e" % (name, e))
         assert e < 2e-2, (name, e)
