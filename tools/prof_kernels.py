@@ -7,7 +7,8 @@ from b200gan import engine as E, _capi as K
 from tests.parity import make_param, dev
 
 # physical channel counts of the bench step (the layer API stores 200-channel layers as 208)
-CASES = [(512, 16, 16, 208, 400, 5, 2), (512, 8, 8, 400, 800, 5, 2), (512, 32, 32, 3, 208, 5, 2)]
+CASES = [(512, 16, 16, 208, 400, 5, 2), (512, 8, 8, 400, 800, 5, 2), (512, 32, 32, 3, 208, 5, 2),
+         (16, 128, 128, 64, 128, 4, 2)]          # + pix2pix e2 / d7: the persistent double-buffered 2-CTA kernel
 reps = int(os.environ.get("REPS", "1"))
 E.begin()
 for (N, H, W, Cin, Cout, k, s) in CASES:

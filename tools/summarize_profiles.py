@@ -47,9 +47,11 @@ if os.path.exists(rep):
     with open(os.path.join(out_dir, "%s_ncu_kernels.csv" % tag), "w") as f:
         w = csv.writer(f)
         w.writerow(["# ncu --set full --clock-control none, tools/prof_kernels.py: c2 (16x16x208->8x8x400, 200 logical channels), c3 (8x8x400->4x4x800), "
-                    "c1 (32x32x3->16x16x208) fprop/dgrad/wgrad at B=512"])
+                    "c1 (32x32x3->16x16x208) fprop/dgrad/wgrad at B=512; pix2pix e2/d7 (128x128x64->64x64x128 k4 s2, B=16: persistent kernel)"])
         w.writerow([hdr[i] for i in idx])
         w.writerow([units[i] for i in idx])
         for r in rows[2:]:
+            if "at::" in r[hdr.index("Kernel Name")]:
+                continue                        # torch fill / copy kernels of the test set-up, not ours
             w.writerow([r[i][:60] for i in idx])
     print("wrote ncu kernel summary")
