@@ -1,6 +1,6 @@
 // Hand-written sm_100a implicit-GEMM kernels: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) fed by TMA
-// through a multi-stage mbarrier pipeline, warp-specialised (1 TMA warp, 1 MMA warp, 4 epilogue
-// warps).  Replaces the cuDNN/cuBLAS calls TensorFlow made for the reference's
+// through a multi-stage mbarrier pipeline, warp-specialised (1 TMA warp, 1 MMA warp, 16 epilogue
+// warps: four per TMEM lane quarter).  Replaces the cuDNN/cuBLAS calls TensorFlow made for the reference's
 // tf.nn.conv2d / conv2d_transpose / matmul call sites (ops/layers.py:57,101,142;
 // hem/ops/layers.py:61,118,189) and their autodiff gradients.
 #include "tc_gemm.cuh"
