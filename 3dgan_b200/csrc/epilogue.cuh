@@ -339,11 +339,115 @@ __device__ __forceinline__ void epilogue_dump_row(uint32_t trow, float* drow, in
   }
 }
 
-template <bool kSimple>
+// ---- lean path: the staged (TMA-store) bf16 epilogue of full 16-column chunks with every option resolved at
+// compile time -- bias from shared memory, none / relu / lrelu, sign bitmap out, sign-bitmap mask in.  The general
+// epilogue_store16 spends ~95 of its ~200 instructions per chunk on run-time option checks and register copies, and
+// the epilogue warps are issue-bound (16 warps on 4 schedulers): this path is what the hot launches take.
+template <bool kBias, bool kBitsOut, bool kMaskBits>
+__device__ __forceinline__ void epilogue_chunk_lean(const EpilogueArgs& e, const uint32_t* acc, int col, float slope,
+                                                    float neg, uint32_t mbits, long long bits_row) {
+  float v[16];
+  if (kBias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 b4 = ld_shared_f4(e.bias_smem + (uint32_t)(col - e.bias_col0 + 4 * j) * 4);
+      v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b4.x;
+      v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b4.y;
+      v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b4.z;
+      v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b4.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+  if (slope != 1.f) {                       // relu (slope 0) / lrelu: max(v, slope v); uniform branch
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+  }
+  if (kBitsOut) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+    if (e.stage_bits) st_shared_u16(e.stage_bits + (((col - e.stage_col0) >> 4) << 1), (uint16_t)w);
+    else e.bits_out[bits_row + (col >> 4)] = (uint16_t)w;
+  }
+  if (kMaskBits) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = ((mbits >> j) & 1u) ? v[j] : v[j] * neg;
+  }
+  const uint32_t dst = e.stage_row + (uint32_t)(col - e.stage_col0) * 2;
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    pk[j] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  st_shared_v4(dst, pk[0], pk[1], pk[2], pk[3]);
+  st_shared_v4(dst + 16, pk[4], pk[5], pk[6], pk[7]);
+}
+
+// chunks c_first, c_first + c_step, ... < c_end of one accumulator row, two register buffers in ping-pong: the TMEM
+// load (and the mask word) of the next chunk is in flight while this one is processed, with no register copies
+template <bool kBias, bool kBitsOut, bool kMaskBits>
+__device__ __forceinline__ void epilogue_row_lean(const EpilogueArgs& e, uint32_t trow, bool row_ok, int n0, int c_first,
+                                                  int c_step, int c_end, long long bits_row) {
+  const float slope = e.act == ACT_NONE ? 1.f : (e.act == ACT_RELU ? 0.f : e.leak);
+  const float neg = e.mask_kind == ACT_LRELU ? e.leak : 0.f;
+  uint32_t va[16], vb[16], ma = 0, mb = 0;
+  int c = c_first;
+  tmem_ld16(trow + c, va);
+  if (kMaskBits && row_ok) ma = __ldg(e.mask_bits + bits_row + ((n0 + c) >> 4));
+  while (true) {
+    const int c1 = c + c_step;
+    tmem_ld_wait16(va);
+    if (c1 < c_end) {
+      tmem_ld16(trow + c1, vb);
+      if (kMaskBits && row_ok) mb = __ldg(e.mask_bits + bits_row + ((n0 + c1) >> 4));
+    }
+    if (row_ok) epilogue_chunk_lean<kBias, kBitsOut, kMaskBits>(e, va, n0 + c, slope, neg, ma, bits_row);
+    if (c1 >= c_end) break;
+    const int c2 = c1 + c_step;
+    tmem_ld_wait16(vb);
+    if (c2 < c_end) {
+      tmem_ld16(trow + c2, va);
+      if (kMaskBits && row_ok) ma = __ldg(e.mask_bits + bits_row + ((n0 + c2) >> 4));
+    }
+    if (row_ok) epilogue_chunk_lean<kBias, kBitsOut, kMaskBits>(e, vb, n0 + c1, slope, neg, mb, bits_row);
+    if (c2 >= c_end) break;
+    c = c2;
+  }
+}
+
+// kLean: bit `sel` set = instantiate the lean path for that option combination (sel = bias 4 | bits_out 2 | mask_bits 1);
+// combinations left out take the general path (a kernel with a lot of live state of its own keeps only what it needs)
+template <bool kSimple, int kLean = 0xff>
 __device__ __forceinline__ void epilogue_row(const EpilogueArgs& e, uint32_t trow, long long off, bool row_ok,
                                              int n0, int c_first, int c_step, int c_end) {
   // c_end: first column offset (relative to the tile) that must not be processed
   if (c_first >= c_end) return;
+  if (kSimple && kLean) {
+    // all chunks full, staged bf16 output, bias (if any) in shared memory, masks (if any) as bitmaps: the lean path
+    const bool lean = e.stage_row != 0 && !e.out_f32 && !e.accumulate && e.alpha == 1.f && (c_end & 15) == 0 &&
+                      (!e.bias || e.bias_smem) && (!e.mask_src || e.mask_bits) && e.partial_n == 0 &&
+                      (e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_LRELU);
+    if (lean) {
+      const long long brow = (e.mask_bits || e.bits_out) ? (off / e.row_elems) * e.bits_pitch : 0;
+      const int sel = (e.bias ? 4 : 0) | (e.bits_out ? 2 : 0) | (e.mask_bits ? 1 : 0);
+#define B200_LEAN_CASE(S, A, B, C)                                                                   \
+  if ((kLean >> S) & 1) {                                                                            \
+    if (sel == S) { epilogue_row_lean<A, B, C>(e, trow, row_ok, n0, c_first, c_step, c_end, brow); return; } \
+  }
+      B200_LEAN_CASE(0, false, false, false)
+      B200_LEAN_CASE(1, false, false, true)
+      B200_LEAN_CASE(2, false, true, false)
+      B200_LEAN_CASE(3, false, true, true)
+      B200_LEAN_CASE(4, true, false, false)
+      B200_LEAN_CASE(5, true, false, true)
+      B200_LEAN_CASE(6, true, true, false)
+      B200_LEAN_CASE(7, true, true, true)
+#undef B200_LEAN_CASE
+    }
+  }
   // word offset of this output row in the sign bitmaps (the output is dense: row = element offset / row width)
   const long long bits_row = (e.mask_bits || e.bits_out) ? (off / e.row_elems) * e.bits_pitch : 0;
   if (kSimple) {

@@ -1431,7 +1431,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) smallk_kernel(const __grid_con
         named_barrier(1, nepi);
       }
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols;
-      epilogue_row<kSimple>(ea, trow, off, row_ok, 0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols));
+      // (this persistent kernel serves the image-side GEMMs: the hot one is bias + lrelu + sign bitmap)
+      epilogue_row<kSimple, (1 << 6)>(ea, trow, off, row_ok, 0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols));
       tc_fence_before();
       __syncwarp();
       if (p.trace && blockIdx.x == 0 && threadIdx.x == 64 && tile / (int)gridDim.x < 12) ps->trace[4][tile / gridDim.x] = clock64();
