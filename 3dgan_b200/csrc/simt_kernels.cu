@@ -12,15 +12,16 @@ namespace b200 {
 
 typedef __nv_bfloat16 bf16;
 
-static int g_num_sms = 0;
-static int num_sms() {
-  if (!g_num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+static int num_sms() {                 // cached per device (a process may drive several)
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return g_num_sms;
+  return sms[dev];
 }
 static int std_max(int a, int b) { return a > b ? a : b; }
 static int stride_grid(long long n, int threads, int per_thread = 1) {

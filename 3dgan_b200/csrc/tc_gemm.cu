@@ -1031,6 +1031,29 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+// Launch configuration that must be applied once PER DEVICE (cudaFuncSetAttribute is per device; a process may drive
+// several): true the first time it is called with `flags` on the current device.
+constexpr int kMaxDevices = 64;
+static bool first_use_on_device(bool* flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+static int device_sms() {
+  static int sms[kMaxDevices] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) return 148;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  return sms[dev];
+}
+
 int gemm_threads() {
   static int v = -1;
   if (v < 0) {
@@ -1181,9 +1204,7 @@ static bool launch_tapgemm_sk(const TapGemmParams& p0, cudaStream_t stream) {
   p.sk_phase_base[p.nphases] = total;
   const long long items = (long long)groups * ny * p.nphases;
   if (min_len < 1 || max_len > 60000) return false;
-  int sms = 148, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sms();
   static int pairs_env = -1;
   if (pairs_env < 0) pairs_env = env_int("B200GAN_SK_PAIRS", 0);
   const int pairs = (pairs_env > 0 && pairs_env < sms / 2) ? pairs_env : sms / 2;
@@ -1205,11 +1226,10 @@ static bool launch_tapgemm_sk(const TapGemmParams& p0, cudaStream_t stream) {
   p.sk_region = 2LL * kTileM * p.bn_tile;
   p.tma_store = 0;
   const size_t smem = (size_t)p.stages * tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail) + sizeof(PipeSmem) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(tapgemm2sm_sk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tapgemm2sm_sk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
   }
   const int npairs = (int)((total + range - 1) / range);
   if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
@@ -1223,11 +1243,10 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   if (p.cta2 && launch_tapgemm_sk(p, stream)) return;
   if (p.cta2) {
     const size_t smem2 = (size_t)p.stages * tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail) + sizeof(PipeSmem) + 1024;
-    static bool configured2 = false;
-    if (!configured2) {
+    static bool configured2[kMaxDevices] = {false};
+    if (first_use_on_device(configured2)) {
       cudaFuncSetAttribute(tapgemm2sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       cudaFuncSetAttribute(tapgemm2sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      configured2 = true;
     }
     const int tiles2 = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
     const int ny = (p.ncols + p.bn_tile - 1) / p.bn_tile;
@@ -1240,13 +1259,12 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
   }
   const int stage_bytes = tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail);
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(tapgemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tapgemm_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tapgemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(tapgemm_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    configured = true;
   }
   const int tiles = (p.tiles_w * p.tiles_h * p.tiles_n + p.dual - 1) / p.dual;
   const int ntile_y = (p.ncols + p.bn_tile - 1) / p.bn_tile;
@@ -1481,16 +1499,12 @@ void launch_smallk(const SmallKParams& p, cudaStream_t stream) {
                        (p.bits_stage ? ((kTileM * p.bits_pitch * 2 + 127) & ~127) : 0);
   const size_t smem = (size_t)p.kchunks * p.bn_tile * kBlockK * 2 + (size_t)p.slots * p.kchunks * kABytes + stage +
                       sizeof(SmallKSmem) + 1024;
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(smallk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     cudaFuncSetAttribute(smallk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
   }
+  const int sms = device_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   static int ahead = -1;
   if (ahead < 0) ahead = env_int("B200GAN_SMALLK_AHEAD", 0);
@@ -1959,14 +1973,9 @@ int wgrad_dual(int m_tiles) {
 
 static void launch_wgrad_2sm(const WgradParams& p0, cudaStream_t stream) {
   WgradParams p = p0;
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(wgrad2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
   }
   // transposed orientation: M = Cb (dY channels, units of 512), N = Ca (X channels)
   p.bn_tile = p.bn_tile_t;
@@ -1979,6 +1988,7 @@ static void launch_wgrad_2sm(const WgradParams& p0, cudaStream_t stream) {
   p.units = ((p.Cb + 511) / 512) * p.n_tiles * p.ntaps;
   const long long total = (long long)p.units * p.total_chunks;
   long long pairs = total / 4;
+  const int sms = device_sms();
   if (pairs > sms / 2) pairs = sms / 2;
   if (pairs < 1) pairs = 1;
   p.chunks_per_cta = (int)((total + pairs - 1) / pairs);
@@ -1997,19 +2007,15 @@ void launch_wgrad(const WgradParams& p0, int /*splits_hint*/, cudaStream_t strea
   WgradParams p = p0;
   const int stage_bytes = (2 * p.dual + p.nb_boxes) * 64 * 64 * 2;
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
-  static bool configured = false;
-  static int sms = 148;
-  if (!configured) {
+  static bool configured[kMaxDevices] = {false};
+  if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
   }
   // equal share of the (unit, chunk) space per CTA, one CTA per SM; a CTA gets at least 4 chunks
   p.units = ((p.m_tiles + p.dual - 1) / p.dual) * p.n_tiles * p.ntaps;
   const long long total = (long long)p.units * p.total_chunks;
   long long ctas = total / 4;
+  const int sms = device_sms();
   if (ctas > sms) ctas = sms;
   if (ctas < 1) ctas = 1;
   p.chunks_per_cta = (int)((total + ctas - 1) / ctas);
