@@ -201,7 +201,10 @@ class Session:
     # ---------------------------------------------------------------- overlapped parameter updates
     def side_stream(self):
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            # B200GAN_SIDE_PRIORITY=1: a high-priority stream, so that the exchange's CTAs are placed as soon as SMs
+            # free up instead of queueing behind the next GEMM's grid
+            prio = -1 if os.environ.get("B200GAN_SIDE_PRIORITY", "0") != "0" else 0
+            self._side = torch.cuda.Stream(device=self.device, priority=prio)
         return self._side
 
     def defer_update(self, fn):
