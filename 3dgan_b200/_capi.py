@@ -40,6 +40,8 @@ SIGNATURES = {
     "b200_conv2d_fprop": [_P, _P, _P, _P, _GP, _EP, _P, _LL, _P],
     "b200_conv2d_dgrad": [_P, _P, _P, _GP, _EP, _P, _LL, _P],
     "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P, _LL, _I, _P],
+    "b200_conv2d_wgrad_bias": [_P, _P, _P, _P, _GP, _F, _P, _LL, _I, _P],
+    "b200_conv2d_wgrad_folds_bias": [_GP, _I],
     "b200_conv2d_workspace_bytes": [_GP, _I],
     "b200_conv2d_route": [_GP, _I],
     "b200_conv2d_epilogue_bits": [_GP, _I, _I],
@@ -133,6 +135,11 @@ def workspace_bytes(geom, op):
 def epilogue_bits(geom, op, has_workspace):
     """True when that conv call reads / writes the sign bitmaps of b200_epilogue (tensor-core epilogues)."""
     return lib().b200_conv2d_epilogue_bits(C.byref(geom), op, int(bool(has_workspace))) == 1
+
+
+def wgrad_folds_bias(geom, has_workspace):
+    """True when b200_conv2d_wgrad_bias also produces the bias gradient for this geometry (image-side layers)."""
+    return lib().b200_conv2d_wgrad_folds_bias(C.byref(geom), int(bool(has_workspace))) == 1
 
 
 def route(geom, op):

@@ -12,6 +12,7 @@
 #include "../../include/b200gan.h"
 #include "simt_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "img_conv.cuh"
 
 using namespace b200;
 
@@ -380,11 +381,24 @@ static int small_kp(const b200_conv_geom* g) { return cdiv(g->k * g->k * g->Cin,
 // the small-channel layers can run as im2col/col2im + tensor-core GEMM when the big side is TMA-aligned
 static bool small_gemm_ok(const b200_conv_geom* g) { return g->Cout % 8 == 0; }
 
+// Row-group K layout of the fused image-side kernels (img_conv.cuh): when the geometry qualifies, the fprop and wgrad
+// workspaces are [gathered rows M x k*16 bf16 | weights Cout x k*16 bf16 | filter-gradient image k*16 x Cout fp32]
+static ImgConvGeom img_geom(const b200_conv_geom* g) {
+  return ImgConvGeom{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->k, g->stride, g->pad_t, g->pad_l};
+}
+static bool img_layout(const b200_conv_geom* g) {
+  return is_small(g->Cin) && small_gemm_ok(g) && img_fprop_supported(img_geom(g), g->Cout, 1);
+}
+static long long img_ws_a(const b200_conv_geom* g) { return align256((long long)g->N * g->Ho * g->Wo * g->k * 16 * 2); }
+static long long img_ws_w(const b200_conv_geom* g) { return align256((long long)g->Cout * g->k * 16 * 2); }
+static long long img_ws_t(const b200_conv_geom* g) { return align256((long long)g->Cout * g->k * 16 * 4); }
+
 extern "C" long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op) {
   if (!is_small(g->Cin) && op != 2 && b200_conv2d_route(g, op) == 1)      // split-K partial sums: fp32 image of the output
     return tc_tap_splits(g, op) > 1 ? align256(tc_out_elems(g, op) * 4) : 0;
   if (!is_small(g->Cin) || !small_gemm_ok(g)) return 0;
   const long long M = (long long)g->N * g->Ho * g->Wo;
+  if (img_layout(g) && op != 1) return img_ws_a(g) + img_ws_w(g) + img_ws_t(g);   // [gathered rows | weights | dW image]
   const int Kp = small_kp(g);
   if (op == 0) return align256(M * Kp * 2) + align256((long long)g->Cout * Kp * 2);
   if (op == 1) return align256(M * Kp * 4);
@@ -422,6 +436,43 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     // im2col (bf16 [M,Kp]) + padded transposed filter [Cout,Kp] -> tcgen05 GEMM with the fused epilogue
     if (workspace_bytes < b200_conv2d_workspace_bytes(g, 0)) return fail("conv2d_fprop: workspace too small");
     const long long M = (long long)g->N * g->Ho * g->Wo;
+    if (img_layout(g)) {
+      // fused gather + GEMM + epilogue (img_conv.cu); general epilogues (fp32 out, value masks, tanh / sigmoid,
+      // accumulate) keep the GEMM route, fed in the same row-group layout so that the workspace always holds
+      // what the filter gradient of this layer expects
+      const ImgConvGeom ig = img_geom(g);
+      const int K16 = g->k * 16;
+      __nv_bfloat16* A16 = (__nv_bfloat16*)workspace;
+      const long long x_words = (long long)g->N * g->H * g->W * g->Cin / 2;
+      const bool epi_ok = !e || (!e->out_f32 && !e->accumulate && e->act <= ACT_LRELU && (!e->mask_src || e->mask_bits));
+      const uintptr_t al = reinterpret_cast<uintptr_t>(y) | (e ? reinterpret_cast<uintptr_t>(e->bits_out) : 0);
+      if (epi_ok && (al & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        ImgFpropParams q;
+        memset(&q, 0, sizeof q);
+        q.g = ig; q.x = (const __nv_bfloat16*)x; q.x_words = x_words; q.w = (const __nv_bfloat16*)w; q.ldw = g->Cout;
+        q.bias = e ? e->bias : nullptr; q.M = M; q.num_tiles = (int)((M + kTileM - 1) / kTileM); q.ncols = g->Cout;
+        // staged rows padded so that the row pitch in words is 4 mod 8: the 16-byte row stores are conflict free
+        int pitch = g->Cout * 2;
+        if ((pitch / 4) % 8 != 4 && pitch + 16 <= 512) pitch += 16;
+        q.stage_pitch = pitch;
+        long long dimsO[2] = {g->Cout, M}, strO[2] = {1, g->Cout};
+        int boxO[2] = {pitch / 2, kTileM}, esO[2] = {1, 1};
+        if (make_tmap(&q.tmOut, y, 2, dimsO, strO, boxO, esO, 0, 2)) return -1;
+        q.bits_out = e ? (uint16_t*)e->bits_out : nullptr;
+        q.mask_bits = e ? (const uint16_t*)e->mask_bits : nullptr;
+        q.bits_pitch = e ? e->bits_pitch : 0;
+        q.bits_stage = (q.bits_out && M % kTileM == 0 && (q.bits_pitch * kTileM * 2) % 16 == 0) ? 1 : 0;
+        q.act = e ? e->act : 0; q.leak = e ? e->leak : 0.f; q.mask_kind = e ? e->mask_kind : 0;
+        q.im2col_out = A16;
+        launch_img_fprop(q, st);
+        return check_launch("conv2d_fprop(fused gather)");
+      }
+      __nv_bfloat16* Wt16 = (__nv_bfloat16*)((char*)workspace + img_ws_a(g));
+      launch_img_im2col16((const __nv_bfloat16*)x, x_words, ig, A16, 1, st);
+      launch_img_wpad16((const __nv_bfloat16*)w, g->Cout, g->Cout, g->k, g->k * g->Cin, Wt16, st);
+      if (dense_gemm(A16, M, K16, K16, Wt16, g->Cout, K16, y, g->Cout, g->Cout, e, st)) return -1;
+      return check_launch("conv2d_fprop(gather + GEMM)");
+    }
     const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
     char* A = (char*)workspace;
     char* Wt = A + align256(M * Kp * 2);
@@ -637,15 +688,41 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   return check_launch("conv2d_dgrad");
 }
 
+extern "C" int b200_conv2d_wgrad_folds_bias(const b200_conv_geom* g, int has_workspace) {
+  return (b200_conv2d_route(g, 2) == 2 && has_workspace && img_layout(g)) ? 1 : 0;
+}
+
 extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_geom* g, float alpha,
                                  void* workspace, long long workspace_bytes, int workspace_holds_im2col,
                                  b200_stream s) {
+  return b200_conv2d_wgrad_bias(x, dy, dw, nullptr, g, alpha, workspace, workspace_bytes, workspace_holds_im2col, s);
+}
+
+extern "C" int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, float* dbias, const b200_conv_geom* g,
+                                      float alpha, void* workspace, long long workspace_bytes,
+                                      int workspace_holds_im2col, b200_stream s) {
   cudaStream_t st = (cudaStream_t)s;
   const int route = b200_conv2d_route(g, 2);
   if (route < 0) return route;
+  if (dbias && !b200_conv2d_wgrad_folds_bias(g, workspace != nullptr))
+    return fail("conv2d_wgrad_bias: this geometry does not fold the bias gradient (see b200_conv2d_wgrad_folds_bias)");
   if (route == 2 && workspace && small_gemm_ok(g)) {
     if (workspace_bytes < b200_conv2d_workspace_bytes(g, 2)) return fail("conv2d_wgrad: workspace too small");
     const long long M = (long long)g->N * g->Ho * g->Wo;
+    if (img_layout(g)) {
+      // rows gathered in the row-group layout (left by the fprop of the same input, or gathered here) x dy on the
+      // tensor cores into a k*16 x Cout fp32 image, then folded into the TF layout; the ones column of the gather
+      // makes row 15 the column sum of dy = the bias gradient
+      const int K16 = g->k * 16;
+      __nv_bfloat16* A16 = (__nv_bfloat16*)workspace;
+      float* T = (float*)((char*)workspace + img_ws_a(g) + img_ws_w(g));
+      if (!workspace_holds_im2col)
+        launch_img_im2col16((const __nv_bfloat16*)x, (long long)g->N * g->H * g->W * g->Cin / 2, img_geom(g), A16, 1, st);
+      cudaMemsetAsync(T, 0, (size_t)K16 * g->Cout * 4, st);
+      if (dense_wgrad(A16, K16, K16, dy, g->Cout, M, T, g->Cout, alpha, st)) return -1;
+      launch_img_wgrad_fold(T, g->Cout, g->k, g->k * g->Cin, dw, g->Cout, dbias, st);
+      return check_launch("conv2d_wgrad(gathered rows)");
+    }
     const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
@@ -722,7 +799,7 @@ extern "C" int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const
 // thin wrappers
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
-extern "C" int b200_abi_version(void) { return 3; }
+extern "C" int b200_abi_version(void) { return 4; }
 extern "C" int b200_device_check(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device"); }

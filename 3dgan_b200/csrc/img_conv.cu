@@ -1,0 +1,708 @@
+// Fused image-side convolution kernels (see img_conv.cuh): the window gather of a <= 4-channel input happens in
+// producer warps that write the swizzled A tiles directly, the bias rides in a spare K column, and the epilogue
+// works on packed bf16 pairs.  Replaces im2col_k5c3 + wpad_transpose + smallk_kernel for the critic's first
+// conv (models/gan.py:206 -> ops/layers.py:101) and for the input gradient of the generator's last deconv.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+
+#include "img_conv.cuh"
+#include "ptx.cuh"
+#include "tc_gemm.cuh"
+
+namespace b200 {
+
+namespace {
+
+// 20 warps (5 per scheduler: 96 registers each): warps 0-3 producers (window staging, gather of one A row = output
+// pixel per thread, thread 0 issues the MMAs), warps 4-19 epilogue (they also build the weight tile at kernel start)
+constexpr int kImgProducers = 128;
+constexpr int kImgEpiWarps = 16;
+constexpr int kImgEpiThreads = kImgEpiWarps * 32;
+constexpr int kImgFirstEpiWarp = kImgProducers / 32;
+constexpr int kImgThreads = kImgProducers + kImgEpiThreads;
+constexpr int kAChunk0 = kTileM * 128;                   // K 0..63  (filter rows 0..3): 128 rows x 128 B, SWIZZLE_128B
+constexpr int kATail = kTileM * 32;                      // K 64..79 (filter row 4):     128 rows x 32 B,  SWIZZLE_32B
+constexpr int kASlot = kAChunk0 + kATail;
+constexpr int kMaxSlots = 4;
+
+struct ImgSmem {
+  uint64_t b_ready;
+  uint64_t a_empty[kMaxSlots];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  long long trace[10][8];   // B200GAN_IMG_DBG & 16: clock stamps of CTA 0's first tiles
+};
+
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+__host__ __device__ inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// per output pixel: where its window starts and which of the 16 slots of a filter row are inside the image
+struct RowCtx {
+  int n, iy0, ix0;
+  uint32_t wm[8];          // validity of slots (2i, 2i+1) as half-word masks
+  bool ok;
+};
+
+__device__ __forceinline__ RowCtx make_row_ctx(const ImgConvGeom& g, long long pix, long long M) {
+  RowCtx rc;
+  rc.ok = pix < M;
+  const int hw = g.Ho * g.Wo;
+  const int p = rc.ok ? (int)pix : 0;
+  rc.n = p / hw;
+  const int rem = p - rc.n * hw;
+  const int oy = rem / g.Wo;
+  const int ox = rem - oy * g.Wo;
+  rc.ix0 = ox * g.stride - g.pad_l;
+  rc.iy0 = oy * g.stride - g.pad_t;
+  const int j_lo = max(0, -rc.ix0) * g.Cin;
+  const int j_hi = max(0, min(g.k, g.W - rc.ix0)) * g.Cin;
+  const uint32_t em = rc.ok ? (((1u << j_hi) - 1u) & ~((1u << j_lo) - 1u)) : 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    rc.wm[i] = (((em >> (2 * i)) & 1u) ? 0xffffu : 0u) | (((em >> (2 * i + 1)) & 1u) ? 0xffff0000u : 0u);
+  return rc;
+}
+
+// the 16 slots of filter row kh of one pixel: k*Cin contiguous input elements (2-byte aligned) fetched as aligned
+// 32-bit words (gather_load) and funnel-shifted into place (gather_finish); slot 15 |= ones_bits.  Split in two so
+// that a caller can put the loads of all filter rows in flight before it consumes the first.
+struct GroupLoad {
+  uint32_t wd[8];
+  uint32_t sh;             // 0 | 16: the window starts on an even | odd element; 32: filter row outside the image
+};
+__device__ __forceinline__ GroupLoad gather_load(const ImgConvGeom& g, const uint32_t* __restrict__ xw, int x_words,
+                                                 const RowCtx& rc, int kh) {
+  GroupLoad L;
+  const int iy = rc.iy0 + kh;
+  if (rc.ok && iy >= 0 && iy < g.H) {
+    const int e0 = ((rc.n * g.H + iy) * g.W + rc.ix0) * g.Cin;
+    const int w0 = e0 >> 1;                     // floor (e0 is negative only for the first pixel's left padding)
+    L.sh = (uint32_t)(e0 & 1) * 16u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = w0 + i;
+      L.wd[i] = (idx >= 0 && idx < x_words) ? __ldg(xw + idx) : 0u;
+    }
+  } else {
+    L.sh = 32u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) L.wd[i] = 0u;
+  }
+  return L;
+}
+__device__ __forceinline__ void gather_finish(const GroupLoad& L, const RowCtx& rc, uint32_t ones_bits, uint32_t* o) {
+  const uint32_t sh = L.sh & 31u;               // (an outside row holds zeros: any shift will do)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(L.wd[i], i < 7 ? L.wd[i + 1] : 0u, sh) & rc.wm[i];
+  o[7] |= ones_bits;
+}
+
+// ---- epilogue of one 16-column chunk: acc -> act -> sign word -> (mask) -> packed bf16 -> staged row.
+// Every option is a template parameter: the epilogue warps are issue bound (measured: 2500 of the 3000 cycles a tile's
+// epilogue takes are instruction issue, the rest TMEM read bandwidth), so nothing is decided at run time per chunk.
+template <bool kMask, bool kAct, bool kWantBits>
+__device__ __forceinline__ uint32_t img_chunk(const uint32_t* acc, float slope, float neg, uint32_t mbits, uint32_t dst) {
+  uint32_t sign_word = 0;
+  // two halves of 8 columns, each finished (packed and stored) before the next starts: keeps the live set small
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[8];
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[8 * h + j]);
+    if (kAct) {                               // relu (slope 0) / lrelu: max(v, slope v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], slope * v[j]);
+    }
+    if (kMask) {
+      if (kWantBits) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sign_word |= (v[j] > 0.f ? 1u : 0u) << (8 * h + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ((mbits >> (8 * h + j)) & 1u) ? v[j] : v[j] * neg;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    if (kWantBits && !kMask) {
+      // sign bits from the packed pairs: one compare per two elements (bf16(v) > 0 <=> v > 0 up to underflow);
+      // element 2j -> bit 2j, element 2j+1 -> bit 2j+17 of w, folded below
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&pk[j]), zero2);
+        sign_word |= m & ((1u << (8 * h + 2 * j)) | (1u << (8 * h + 2 * j + 17)));
+      }
+    }
+    st_shared_v4(dst + 16 * h, pk[0], pk[1], pk[2], pk[3]);
+  }
+  if (kWantBits && !kMask) sign_word = (sign_word & 0xffffu) | (sign_word >> 16);
+  return sign_word;
+}
+
+// this warp's chunks cg, cg+4, ... (my_n <= 4 of them) of one accumulator row, fully unrolled with two register buffers
+// in ping-pong: the TMEM load (and mask word) of the next chunk is in flight while this one is processed.  All bases
+// are for chunk cg; chunk i is 64 TMEM columns / 128 staged bytes / 4 sign words further.
+// kBits: 0 no sign words, 1 staged in shared memory, 2 stored to global memory from registers (partial tiles)
+template <bool kMask, bool kAct, int kBits>
+__device__ __forceinline__ void img_row(uint32_t trow, int my_n, uint32_t srow, uint32_t sbits, const uint16_t* mrow,
+                                        uint16_t* brow, bool row_ok, float slope, float neg) {
+  // One accumulator buffer, no lookahead: the 4 epilogue warps of a scheduler cover each other's TMEM-load latency,
+  // and a second buffer in ping-pong made ptxas spill one of them in several of the option combinations
+  // (a spilled buffer costs more than all the latency it could hide: local memory is an L2 round trip here).
+#pragma unroll 1
+  for (int i = 0; i < my_n; ++i) {
+    uint32_t v[16];
+    tmem_ld16(trow + 64 * i, v);
+    uint32_t m = 0;
+    if (kMask) m = row_ok ? (uint32_t)__ldg(mrow + 4 * i) : 0u;
+    tmem_ld_wait16(v);
+    const uint32_t sw = img_chunk<kMask, kAct, kBits != 0>(v, slope, neg, m, srow + 128 * i);
+    if (kBits == 1) st_shared_u16(sbits + 8 * i, (uint16_t)sw);
+    if (kBits == 2) { if (row_ok) brow[4 * i] = (uint16_t)sw; }
+  }
+}
+
+// ---- input window in shared memory: the padded image rows a tile needs, zero padding included, so that the gather
+// is mask free.  Row slot g holds padded row G_first + g, G = n * Hp + (iy + pad_t) with Hp = (Ho-1)*stride + k; the
+// data of a row starts at element win_off (a multiple of 8: 16-byte aligned for cp.async), the columns before /
+// after it are never written and stay zero.
+// n / d for 0 <= n < 2^31 with a host-made reciprocal (ImgFpropParams::div_*): one wide multiply instead of the
+// ~40-instruction (32-bit) or ~100-instruction (64-bit) division sequence, several of which sat on the producers'
+// critical path per tile
+__device__ __forceinline__ int fdiv(int n, ImgDiv d) { return (int)(((unsigned long long)(unsigned)n * d.mul) >> d.shr); }
+
+struct TileSpan { int g_first, n_rows; };
+__device__ __forceinline__ TileSpan tile_span(const ImgFpropParams& p, int tile) {
+  const int hw = p.g.Ho * p.g.Wo;
+  const int p0 = tile * kTileM;
+  const int p1 = min((int)p.M, p0 + kTileM) - 1;
+  const int n0 = fdiv(p0, p.div_hw), oy0 = fdiv(p0 - n0 * hw, p.div_wo);
+  const int n1 = fdiv(p1, p.div_hw), oy1 = fdiv(p1 - n1 * hw, p.div_wo);
+  TileSpan t;
+  t.g_first = n0 * p.win_hp + oy0 * p.g.stride;
+  t.n_rows = n1 * p.win_hp + oy1 * p.g.stride + p.g.k - t.g_first;
+  return t;
+}
+
+// The 128 producer threads stage a tile's window: piece q = tid + 128*i covers bytes [j*piece, +piece) of window row
+// g, (g, j) = divmod(q, pieces per row), piece = 16 (or 4) bytes.  Split in two so that the global loads of the NEXT
+// tile's window are in flight while the current tile is gathered: stage_load (global -> registers; rows outside the
+// image give zeros) and stage_store (registers -> window).  Host guarantees rows x pieces-per-row <= 128 * kWinRegs.
+constexpr int kWinRegs = 6;
+struct WinRegs { uint4 v[kWinRegs]; };
+
+__device__ __forceinline__ const char* stage_src(const ImgFpropParams& p, const TileSpan& t, int q, int total,
+                                                 int piece_bytes) {
+  if (q >= total) return nullptr;
+  const int g = fdiv(q, p.div_ppr), j = q - g * p.win_ppr;
+  const int G = t.g_first + g;
+  const int n = fdiv(G, p.div_hp);
+  const int iy = G - n * p.win_hp - p.g.pad_t;
+  if (n >= p.g.N || iy < 0 || iy >= p.g.H) return nullptr;
+  return reinterpret_cast<const char*>(p.x) + (size_t)(n * p.g.H + iy) * (p.g.W * p.g.Cin * 2) + j * piece_bytes;
+}
+__device__ __forceinline__ void stage_load(const ImgFpropParams& p, const TileSpan& t, int tid, WinRegs& R) {
+  const int total = t.n_rows * p.win_ppr;
+#pragma unroll
+  for (int i = 0; i < kWinRegs; ++i) {
+    R.v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (p.win_vec16) {
+      const char* src = stage_src(p, t, tid + kImgProducers * i, total, 16);
+      if (src) R.v[i] = __ldg(reinterpret_cast<const uint4*>(src));
+    } else {                                              // 4-byte pieces, four per register slot
+      const char* s0 = stage_src(p, t, tid + kImgProducers * (4 * i + 0), total, 4);
+      const char* s1 = stage_src(p, t, tid + kImgProducers * (4 * i + 1), total, 4);
+      const char* s2 = stage_src(p, t, tid + kImgProducers * (4 * i + 2), total, 4);
+      const char* s3 = stage_src(p, t, tid + kImgProducers * (4 * i + 3), total, 4);
+      if (s0) R.v[i].x = __ldg(reinterpret_cast<const uint32_t*>(s0));
+      if (s1) R.v[i].y = __ldg(reinterpret_cast<const uint32_t*>(s1));
+      if (s2) R.v[i].z = __ldg(reinterpret_cast<const uint32_t*>(s2));
+      if (s3) R.v[i].w = __ldg(reinterpret_cast<const uint32_t*>(s3));
+    }
+  }
+}
+__device__ __forceinline__ void stage_store1(const ImgFpropParams& p, uint32_t win, int q, int total, uint32_t v) {
+  if (q >= total) return;
+  const int g = fdiv(q, p.div_ppr), j = q - g * p.win_ppr;
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(win + (uint32_t)(g * p.win_pitch + p.win_off) * 2 + j * 4), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stage_store(const ImgFpropParams& p, const TileSpan& t, uint32_t win, int tid,
+                                            const WinRegs& R) {
+  const int total = t.n_rows * p.win_ppr;
+#pragma unroll
+  for (int i = 0; i < kWinRegs; ++i) {
+    if (p.win_vec16) {
+      const int q = tid + kImgProducers * i;
+      if (q < total) {
+        const int g = fdiv(q, p.div_ppr), j = q - g * p.win_ppr;
+        st_shared_v4(win + (uint32_t)(g * p.win_pitch + p.win_off) * 2 + j * 16, R.v[i].x, R.v[i].y, R.v[i].z, R.v[i].w);
+      }
+    } else {
+      stage_store1(p, win, tid + kImgProducers * (4 * i + 0), total, R.v[i].x);
+      stage_store1(p, win, tid + kImgProducers * (4 * i + 1), total, R.v[i].y);
+      stage_store1(p, win, tid + kImgProducers * (4 * i + 2), total, R.v[i].z);
+      stage_store1(p, win, tid + kImgProducers * (4 * i + 3), total, R.v[i].w);
+    }
+  }
+}
+// the image rows of a window are one contiguous range of x: pull the lines of a tile two steps ahead into L2 (the
+// input was usually evicted by the output stream of the previous launches, and DRAM latency under that store
+// traffic is longer than one tile)
+__device__ __forceinline__ void prefetch_window(const ImgFpropParams& p, const TileSpan& t, int tid) {
+  const int row_bytes = p.g.W * p.g.Cin * 2;
+  int n0 = fdiv(t.g_first, p.div_hp), iy0 = t.g_first - n0 * p.win_hp - p.g.pad_t;
+  const int Gl = t.g_first + t.n_rows - 1;
+  int n1 = fdiv(Gl, p.div_hp), iy1 = Gl - n1 * p.win_hp - p.g.pad_t;
+  if (iy0 < 0) iy0 = 0;
+  if (iy0 >= p.g.H) { iy0 = 0; ++n0; }
+  if (iy1 >= p.g.H) iy1 = p.g.H - 1;
+  if (iy1 < 0) { iy1 = p.g.H - 1; --n1; }
+  if (n1 >= p.g.N) { n1 = p.g.N - 1; iy1 = p.g.H - 1; }
+  const long long lo = (long long)(n0 * p.g.H + iy0) * row_bytes, hi = (long long)(n1 * p.g.H + iy1 + 1) * row_bytes;
+  const char* base = reinterpret_cast<const char*>(p.x);
+  for (long long o = (lo & ~127ll) + (long long)tid * 128; o < hi; o += kImgProducers * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+}
+
+template <int kK>
+__global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_constant__ ImgFpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long t_start = clock64();
+  constexpr int kSteps0 = kK < 4 ? kK : 4;              // 16-wide MMA K steps in the SWIZZLE_128B chunk
+  constexpr bool kTail = kK == 5;
+  const int kcin = p.g.k * p.g.Cin;
+
+  const int b0_bytes = p.ncols * 128;
+  const int bt_bytes = kTail ? align_up(p.ncols * 32, 1024) : 0;
+  const int out_bytes = align_up(kTileM * p.stage_pitch, 1024);
+  const int bits_bytes = p.bits_stage ? align_up(kTileM * p.bits_pitch * 2, 128) : 0;
+  const int win_bytes = align_up(p.win_rows * p.win_pitch * 2, 128);
+  uint8_t* smem_b0 = smem;
+  uint8_t* smem_bt = smem_b0 + b0_bytes;
+  uint8_t* smem_a = smem_bt + bt_bytes;
+  uint8_t* smem_out = smem_a + (size_t)p.slots * kASlot;
+  uint8_t* smem_bits = smem_out + 2 * out_bytes;
+  uint8_t* smem_win = smem_bits + 2 * bits_bytes;
+  ImgSmem* ps = reinterpret_cast<ImgSmem*>(smem_win + 2 * win_bytes);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmOut);
+    mbar_init(smem_u32(&ps->b_ready), kImgEpiThreads);
+    for (int s = 0; s < p.slots; ++s) mbar_init(smem_u32(&ps->a_empty[s]), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&ps->acc_full[a]), 1);
+      mbar_init(smem_u32(&ps->acc_empty[a]), kImgEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp < kImgFirstEpiWarp) {
+    // ------------------------------------------------------------------ producers: window staging, gather, MMA issue
+    const int r = threadIdx.x;                              // the A row (output pixel of the tile) of this thread
+    const uint32_t ones = 0x3F800000u;                     // bf16 1.0 in slot 15 of groups 0 / 1 (bias pair; wgrad: colsum)
+    uint32_t wm[8];                                        // slots >= k*Cin are zero
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wm[i] = (2 * i < kcin ? 0xffffu : 0u) | (2 * i + 1 < kcin ? 0xffff0000u : 0u);
+    const uint32_t win0 = smem_u32(smem_win);
+    // both windows start out zero: the padding columns are never written again
+    for (int i = threadIdx.x * 16; i < 2 * win_bytes; i += kImgProducers * 16) st_shared_v4(win0 + i, 0u, 0u, 0u, 0u);
+    named_barrier(2, kImgProducers);
+    TileSpan ts_next = tile_span(p, blockIdx.x);
+    WinRegs wr;
+    stage_load(p, ts_next, threadIdx.x, wr);
+    if ((int)(blockIdx.x + gridDim.x) < p.num_tiles) prefetch_window(p, tile_span(p, blockIdx.x + gridDim.x), threadIdx.x);
+    stage_store(p, ts_next, win0, threadIdx.x, wr);
+    named_barrier(2, kImgProducers);
+
+    const uint32_t idesc = make_idesc_bf16(kTileM, p.ncols, 0, 0);
+    const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b0), 16, 1024);
+    const uint64_t bdesct = make_smem_desc(smem_u32(smem_bt), 16, 256, 6);
+    const int hw = p.g.Ho * p.g.Wo;
+    const int off0 = p.win_off - p.g.pad_l * p.g.Cin;
+    int s = 0, it = 0, acc = 0;
+    uint32_t par = 0, accpar = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t win = win0 + (it & 1) * win_bytes;
+      const TileSpan ts = ts_next;
+      const int next = tile + gridDim.x;
+      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[6][it] = clock64();
+      if (next < p.num_tiles) {
+        ts_next = tile_span(p, next);
+        stage_load(p, ts_next, threadIdx.x, wr);
+        if (next + (int)gridDim.x < p.num_tiles) prefetch_window(p, tile_span(p, next + gridDim.x), threadIdx.x);
+      }
+      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[7][it] = clock64();
+      mbar_wait(smem_u32(&ps->a_empty[s]), par ^ 1);
+      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[0][it] = clock64();
+      const uint32_t a_addr = smem_u32(smem_a) + (uint32_t)s * kASlot;
+      {
+        const long long pix = (long long)tile * kTileM + r;
+        const bool ok = pix < p.M;
+        const int pi = ok ? (int)pix : 0;
+        const int n = fdiv(pi, p.div_hw);
+        const int rem = pi - n * hw;
+        const int oy = fdiv(rem, p.div_wo);
+        const int ox = rem - oy * p.g.Wo;
+        const int e = (n * p.win_hp + oy * p.g.stride - ts.g_first) * p.win_pitch + off0 + ox * p.g.stride * p.g.Cin;
+        const uint32_t src = win + (uint32_t)(e >> 1) * 4;
+        const uint32_t sh = (uint32_t)(e & 1) * 16u;
+        const uint32_t row_pitch = (uint32_t)p.win_pitch * 2;
+#pragma unroll
+        for (int kh = 0; kh < kK; ++kh) {
+          uint32_t wd[9], o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(src + kh * row_pitch + i * 4));
+          wd[8] = 0u;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = ok ? (__funnelshift_r(wd[i], wd[i + 1], sh) & wm[i]) : 0u;
+          if (kh < 2) o[7] |= ones;
+          if (kh < 4) {
+            const uint32_t base = a_addr + r * 128;
+            st_shared_v4(base + (((2 * kh) ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+            st_shared_v4(base + (((2 * kh + 1) ^ (r & 7)) << 4), o[4], o[5], o[6], o[7]);
+          } else {
+            const uint32_t base = a_addr + kAChunk0 + r * 32;
+            const uint32_t sw = (r >> 2) & 1;
+            st_shared_v4(base + (sw << 4), o[0], o[1], o[2], o[3]);
+            st_shared_v4(base + ((sw ^ 1) << 4), o[4], o[5], o[6], o[7]);
+          }
+          if (p.im2col_out && ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.im2col_out + (size_t)pix * (kK * 16) + kh * 16);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[8][it] = clock64();
+      fence_proxy_async_smem();                            // A rows (generic proxy) -> visible to the tensor core
+      if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((it + 1) & 1) * win_bytes, threadIdx.x, wr);
+      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[9][it] = clock64();
+      named_barrier(2, kImgProducers);
+      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[1][it] = clock64();
+      if (threadIdx.x == 0) {
+        if (it == 0) mbar_wait(smem_u32(&ps->b_ready), 0);
+        mbar_wait(smem_u32(&ps->acc_empty[acc]), accpar ^ 1);
+        tc_fence_after();
+        if ((p.dbg & 16) && blockIdx.x == 0 && it < 8) ps->trace[2][it] = clock64();
+        const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+        const uint32_t d = tmem + acc * kTmemCols;
+#pragma unroll
+        for (int ks = 0; ks < kSteps0; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc0 + 2 * ks, idesc, ks ? 1u : 0u);
+        if (kTail) umma_bf16(d, make_smem_desc(a_addr + kAChunk0, 16, 256, 6), bdesct, idesc, 1u);
+        umma_commit(smem_u32(&ps->a_empty[s]));
+        umma_commit(smem_u32(&ps->acc_full[acc]));
+      }
+      __syncwarp();
+      if (++s == p.slots) { s = 0; par ^= 1; }
+      acc ^= 1;
+      if (acc == 0) accpar ^= 1;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int et = threadIdx.x - kImgProducers;
+    // first the weights: B[n][kh*16 + j] = w[(kh*kcin + j)][n]  (K-major, swizzled like a TMA load would leave it);
+    // slot 15 of groups 0 / 1 = bias split into a bf16 high and low part (their A column is 1.0)
+    {
+      const int K16 = kK * 16;
+      const int n8s = p.ncols >> 3;
+      for (int item = et; item < n8s * K16; item += kImgEpiThreads) {
+        const int kk = item % K16, n8 = item / K16;
+        const int kh = kk >> 4, j = kk & 15;
+        uint32_t v[4] = {0u, 0u, 0u, 0u};
+        if (j < kcin) {
+          const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)(kh * kcin + j) * p.ldw + n8 * 8));
+          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else if (j == 15 && p.bias && kh < 2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t h2[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float bv = __ldg(p.bias + n8 * 8 + 2 * i + h);
+              const __nv_bfloat16 hi = __float2bfloat16(bv);
+              const __nv_bfloat16 val = kh == 0 ? hi : __float2bfloat16(bv - __bfloat162float(hi));
+              h2[h] = (uint32_t)__bfloat16_as_ushort(val);
+            }
+            v[i] = h2[0] | (h2[1] << 16);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = n8 * 8 + i;
+          const uint16_t val = (uint16_t)((i & 1) ? (v[i >> 1] >> 16) : (v[i >> 1] & 0xffffu));
+          uint32_t dst;
+          if (kh < 4) dst = smem_u32(smem_b0) + n * 128 + ((((kk >> 3)) ^ (n & 7)) << 4) + (kk & 7) * 2;
+          else dst = smem_u32(smem_bt) + n * 32 + (((((kk - 64) >> 3)) ^ ((n >> 2) & 1)) << 4) + (kk & 7) * 2;
+          st_shared_u16(dst, val);
+        }
+      }
+      fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core's reads
+      mbar_arrive(smem_u32(&ps->b_ready));
+    }
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read
+    const int cg = (warp - kImgFirstEpiWarp) >> 2;
+    const int r = q * 32 + lane;
+    const int nchunks = p.ncols >> 4;
+    const bool issuer = et == 0;
+    const int my_n = cg < nchunks ? (nchunks - cg + 3) >> 2 : 0;
+    const int bits_mode = p.bits_out ? (p.bits_stage ? 1 : 2) : 0;
+    const float slope = p.act == ACT_NONE ? 1.f : (p.act == ACT_RELU ? 0.f : p.leak);
+    const float neg = p.mask_kind == ACT_LRELU ? p.leak : 0.f;
+    int acc = 0, so = 0, ti = 0;
+    uint32_t accpar = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const long long row = (long long)tile * kTileM + r;
+      const bool row_ok = row < p.M;
+      mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
+      tc_fence_after();
+      if ((p.dbg & 16) && blockIdx.x == 0 && issuer && ti < 8) ps->trace[3][ti] = clock64();
+      if (issuer) bulk_wait_read1();                       // the store that last used this stage has read it
+      named_barrier(1, kImgEpiThreads);
+      // bases of this warp's first chunk (cg): TMEM column, staged row, staged / global sign words, mask words
+      const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + acc * kTmemCols + cg * 16;
+      const uint32_t srow = smem_u32(smem_out) + so * out_bytes + r * p.stage_pitch + cg * 32;
+      const uint32_t sbits = smem_u32(smem_bits) + so * bits_bytes + r * p.bits_pitch * 2 + cg * 2;
+      const uint16_t* mrow = p.mask_bits ? p.mask_bits + (row_ok ? row : 0) * p.bits_pitch + cg : nullptr;
+      uint16_t* brow = p.bits_out ? p.bits_out + (row_ok ? row : 0) * p.bits_pitch + cg : nullptr;
+#define IMG_ROW(M_, A_, B_) img_row<M_, A_, B_>(trow, my_n, srow, sbits, mrow, brow, row_ok, slope, neg)
+      if (p.dbg & 8) {
+      } else if (p.mask_bits) {
+        if (bits_mode == 0) IMG_ROW(true, true, 0); else if (bits_mode == 1) IMG_ROW(true, true, 1); else IMG_ROW(true, true, 2);
+      } else if (p.act != ACT_NONE) {
+        if (bits_mode == 0) IMG_ROW(false, true, 0); else if (bits_mode == 1) IMG_ROW(false, true, 1); else IMG_ROW(false, true, 2);
+      } else {
+        if (bits_mode == 0) IMG_ROW(false, false, 0); else if (bits_mode == 1) IMG_ROW(false, false, 1); else IMG_ROW(false, false, 2);
+      }
+#undef IMG_ROW
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[acc]));
+      if ((p.dbg & 16) && blockIdx.x == 0 && issuer && ti < 8) ps->trace[4][ti] = clock64();
+      fence_proxy_async_smem();                            // staged rows (generic proxy) -> visible to the bulk copy engine
+      named_barrier(1, kImgEpiThreads);
+      if (issuer && !(p.dbg & 4)) {
+        tma_store_2d(&p.tmOut, smem_u32(smem_out) + so * out_bytes, 0, tile * kTileM);
+        if (p.bits_stage)
+          bulk_store_1d(p.bits_out + (size_t)tile * kTileM * p.bits_pitch, smem_u32(smem_bits) + so * bits_bytes,
+                        (uint32_t)(kTileM * p.bits_pitch * 2));
+        bulk_commit();
+      }
+      if ((p.dbg & 16) && blockIdx.x == 0 && issuer && ti < 8) ps->trace[5][ti] = clock64();
+      so ^= 1;
+      acc ^= 1;
+      if (acc == 0) accpar ^= 1;
+    }
+    if (issuer) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if ((p.dbg & 16) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = ps->trace[0][0];
+    printf("kernel start->first gather %lld\n", t0 - t_start);
+    for (int i = 0; i < 7; ++i)
+      printf("tile %d: stage %lld..%lld gather %lld..%lld fence+cpwait ..%lld barrier ..%lld  mma %lld  epi %lld..%lld store_issued %lld\n", i,
+             ps->trace[6][i] - t0, ps->trace[7][i] - t0, ps->trace[0][i] - t0, ps->trace[8][i] - t0, ps->trace[9][i] - t0,
+             ps->trace[1][i] - t0, ps->trace[2][i] - t0, ps->trace[3][i] - t0, ps->trace[4][i] - t0, ps->trace[5][i] - t0);
+    printf("end %lld\n", clock64() - t0);
+  }
+  if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem);
+}
+
+// standalone gather (same K layout): one thread per output pixel
+template <int kK>
+__global__ void __launch_bounds__(256) img_im2col16_kernel(const __nv_bfloat16* __restrict__ x, int x_words,
+                                                           ImgConvGeom g, long long M, __nv_bfloat16* __restrict__ out,
+                                                           uint32_t ones) {
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= M) return;
+  const RowCtx rc = make_row_ctx(g, pix, M);
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+#pragma unroll
+  for (int kh = 0; kh < kK; ++kh) {
+    uint32_t o[8];
+    const GroupLoad L = gather_load(g, xw, x_words, rc, kh);
+    gather_finish(L, rc, kh < 2 ? ones : 0u, o);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pix * (kK * 16) + kh * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+
+// weights in the same K layout for the GEMM route (general epilogues): Wt[n][kh*16 + j] = w[kh*kcin + j][n], pads zero
+__global__ void img_wpad16_kernel(const __nv_bfloat16* __restrict__ w, int ldw, int ncols, int k, int kcin,
+                                  __nv_bfloat16* __restrict__ wt) {
+  const int Kp = k * 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncols * Kp) return;
+  const int n = i % ncols, kk = i / ncols;
+  const int kh = kk >> 4, j = kk & 15;
+  wt[(size_t)n * Kp + kk] = j < kcin ? w[(size_t)(kh * kcin + j) * ldw + n] : __float2bfloat16(0.f);
+}
+
+// filter gradient computed in the row-group layout -> the TF layout: dw[kh*kcin + j][n] += t[kh*16 + j][n];
+// row 15 (the ones column of the gather) is the column sum of dy = the bias gradient
+__global__ void img_wgrad_fold_kernel(const float* __restrict__ t, int ncols, int k, int kcin, float* __restrict__ dw,
+                                      int ldo, float* __restrict__ dbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncols * k * 16) return;
+  const int n = i % ncols, kk = i / ncols;
+  const int kh = kk >> 4, j = kk & 15;
+  const float v = t[(size_t)kk * ncols + n];
+  if (j < kcin) dw[(size_t)(kh * kcin + j) * ldo + n] += v;
+  else if (kk == 15 && dbias) dbias[n] += v;
+}
+
+constexpr int kMaxDev = 64;
+bool first_use(bool* flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+int dev_sms() {
+  static int sms[kMaxDev] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return 148;
+  if (!sms[dev]) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
+  }
+  return sms[dev];
+}
+
+}  // namespace
+
+size_t img_fprop_smem(const ImgFpropParams& p) {
+  const int bt = p.g.k == 5 ? align_up(p.ncols * 32, 1024) : 0;
+  return (size_t)p.ncols * 128 + bt + (size_t)p.slots * kASlot + 2 * (size_t)align_up(kTileM * p.stage_pitch, 1024) +
+         2 * (size_t)(p.bits_stage ? align_up(kTileM * p.bits_pitch * 2, 128) : 0) +
+         2 * (size_t)align_up(p.win_rows * p.win_pitch * 2, 128) + sizeof(ImgSmem) + 1024;
+}
+
+static ImgDiv make_div(int d) {
+  int L = 0;
+  while ((1ll << L) < d) ++L;
+  ImgDiv r;
+  r.shr = 31 + L;
+  r.mul = (uint32_t)(((1ull << r.shr) + d - 1) / d);       // ceil(2^(31+L) / d) < 2^32: exact quotients for n < 2^31
+  return r;
+}
+
+// window layout for a geometry (see stage_window): padded-row pitch, data offset, padded rows per image and the
+// largest number of padded rows one 128-pixel tile spans
+static void img_window(const ImgConvGeom& g, int* pitch, int* off, int* hp, int* rows) {
+  *off = align_up(g.pad_l * g.Cin, 8);
+  const int reach = *off - g.pad_l * g.Cin + (g.Wo - 1) * g.stride * g.Cin + 18;   // last element a gather may touch
+  *pitch = align_up(std::max(reach, *off + g.W * g.Cin), 8);
+  *hp = (g.Ho - 1) * g.stride + g.k;
+  static thread_local ImgConvGeom cg = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static thread_local int crows = 0;
+  if (memcmp(&cg, &g, sizeof g) != 0) {
+    const long long M = (long long)g.N * g.Ho * g.Wo;
+    const int hw = g.Ho * g.Wo;
+    int best = 0;
+    for (long long p0 = 0; p0 < M; p0 += kTileM) {
+      const long long p1 = std::min(M, p0 + kTileM) - 1;
+      const int n0 = (int)(p0 / hw), oy0 = (int)(p0 % hw) / g.Wo, n1 = (int)(p1 / hw), oy1 = (int)(p1 % hw) / g.Wo;
+      best = std::max(best, (n1 - n0) * *hp + (oy1 - oy0) * g.stride + g.k);
+      if (p0 / kTileM > 4096 && (p0 % hw) == 0) break;         // the pattern repeats once a tile starts an image
+    }
+    cg = g; crows = best;
+  }
+  *rows = crows;
+}
+
+bool img_fprop_supported(const ImgConvGeom& g, int ncols, int has_bias) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("B200GAN_NO_IMGFUSE"); off = e ? atoi(e) : 0; }
+  if (off) return false;
+  if (g.k < 3 || g.k > 5 || g.k * g.Cin > 15) return false;
+  (void)has_bias;                                            // k >= 3: groups 0 and 1 both exist for the bias pair
+  if (ncols % 16 || ncols < 16 || ncols > 256) return false;
+  const long long numel = (long long)g.N * g.H * g.W * g.Cin;
+  if ((g.W * g.Cin) & 1 || numel >= (1ll << 31)) return false;     // image rows are copied as 4-byte words
+  if ((long long)g.N * g.Ho * g.Wo >= (1ll << 31) - 256) return false;
+  // worst-case shared memory: two A slots, padded output stage, staged sign words, both input windows
+  ImgFpropParams q;
+  memset(&q, 0, sizeof q);
+  q.g = g; q.ncols = ncols; q.slots = 2; q.stage_pitch = ncols * 2 + 16; q.bits_stage = 1; q.bits_pitch = ncols / 16;
+  img_window(g, &q.win_pitch, &q.win_off, &q.win_hp, &q.win_rows);
+  // the window is staged through registers (kWinRegs pieces per producer thread)
+  const int rb = g.W * g.Cin * 2;
+  if (q.win_rows * (rb / (rb % 16 == 0 ? 16 : 4)) > kImgProducers * kWinRegs * (rb % 16 == 0 ? 1 : 4)) return false;
+  return img_fprop_smem(q) <= 227 * 1024;
+}
+
+void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
+  ImgFpropParams p = p0;
+  img_window(p.g, &p.win_pitch, &p.win_off, &p.win_hp, &p.win_rows);
+  p.div_hw = make_div(p.g.Ho * p.g.Wo); p.div_wo = make_div(p.g.Wo); p.div_hp = make_div(p.win_hp);
+  p.win_vec16 = ((p.g.W * p.g.Cin * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) ? 1 : 0;
+  p.win_ppr = p.g.W * p.g.Cin * 2 / (p.win_vec16 ? 16 : 4);
+  p.div_ppr = make_div(p.win_ppr);
+  p.slots = kMaxSlots;
+  while (p.slots > 2 && img_fprop_smem(p) > 227 * 1024) --p.slots;
+  const size_t smem = img_fprop_smem(p);
+  static bool configured[kMaxDev] = {false};
+  if (first_use(configured)) {
+    cudaFuncSetAttribute(img_fprop_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(img_fprop_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(img_fprop_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  const int sms = dev_sms();
+  const int grid = p.num_tiles < sms ? p.num_tiles : sms;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("B200GAN_IMG_DBG"); dbg = e ? atoi(e) : 0; }
+  p.dbg = dbg;
+  if (dbg & 1) p.im2col_out = nullptr;
+  if (p.g.k == 5) img_fprop_kernel<5><<<grid, kImgThreads, smem, stream>>>(p);
+  else if (p.g.k == 4) img_fprop_kernel<4><<<grid, kImgThreads, smem, stream>>>(p);
+  else img_fprop_kernel<3><<<grid, kImgThreads, smem, stream>>>(p);
+}
+
+void launch_img_im2col16(const __nv_bfloat16* x, long long x_words, const ImgConvGeom& g, __nv_bfloat16* out, int ones,
+                         cudaStream_t stream) {
+  const long long M = (long long)g.N * g.Ho * g.Wo;
+  const int grid = (int)((M + 255) / 256);
+  const uint32_t ob = ones ? 0x3F800000u : 0u;
+  if (g.k == 5) img_im2col16_kernel<5><<<grid, 256, 0, stream>>>(x, (int)x_words, g, M, out, ob);
+  else if (g.k == 4) img_im2col16_kernel<4><<<grid, 256, 0, stream>>>(x, (int)x_words, g, M, out, ob);
+  else img_im2col16_kernel<3><<<grid, 256, 0, stream>>>(x, (int)x_words, g, M, out, ob);
+}
+
+void launch_img_wpad16(const __nv_bfloat16* w, int ldw, int ncols, int k, int kcin, __nv_bfloat16* wt,
+                       cudaStream_t stream) {
+  const int n = ncols * k * 16;
+  img_wpad16_kernel<<<(n + 255) / 256, 256, 0, stream>>>(w, ldw, ncols, k, kcin, wt);
+}
+
+void launch_img_wgrad_fold(const float* t, int ncols, int k, int kcin, float* dw, int ldo, float* dbias,
+                           cudaStream_t stream) {
+  const int n = ncols * k * 16;
+  img_wgrad_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(t, ncols, k, kcin, dw, ldo, dbias);
+}
+
+}  // namespace b200

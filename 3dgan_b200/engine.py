@@ -387,6 +387,13 @@ def conv_like(direction, x, W, geom, bias=None, act=K.ACT_NONE, leak=0.0, out_ma
                 ws, wsb, ready = cached[1], cached[1].numel(), 1
             else:
                 (ws, wsb), ready = _workspace(g, 2), 0
+            # image-side layers: the gathered rows carry a ones column, so the same pass yields the bias gradient
+            fold = (bias is not None and bias.accum and direction == "fprop" and ws is not None
+                    and K.wgrad_folds_bias(g, True))
+            if fold:
+                launch("b200_conv2d_wgrad_bias", _p(a_.buf), _p(b_.buf), _p(W.g32), _p(bias.g32), C.byref(g), 1.0,
+                       _p(ws), wsb, ready, flops=fl, tag=tag)
+                return [gx]
             launch("b200_conv2d_wgrad", _p(a_.buf), _p(b_.buf), _p(W.g32), C.byref(g), 1.0, _p(ws), wsb, ready,
                    flops=fl, tag=tag)
         if bias is not None and bias.accum:

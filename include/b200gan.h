@@ -68,6 +68,12 @@ int b200_conv2d_wgrad(const void* x, const void* dy, float* dw, const b200_conv_
                       void* workspace, long long workspace_bytes, int workspace_holds_im2col, b200_stream s);
 /* workspace_holds_im2col: pass 1 with the workspace a previous b200_conv2d_fprop of the SAME x and geometry
  * used (its first bytes are im2col(x)); the small-channel wgrad then skips recomputing it. */
+/* Same, and dbias[Cout] += column sums of dy (the bias gradient TF autodiff emits for ops/layers.py:101-105) in the
+ * same pass: the gathered rows of the image-side route carry a ones column.  Only geometries for which
+ * b200_conv2d_wgrad_folds_bias(g, workspace != NULL) returns 1 accept dbias != NULL. */
+int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, float* dbias, const b200_conv_geom* g, float alpha,
+                           void* workspace, long long workspace_bytes, int workspace_holds_im2col, b200_stream s);
+int b200_conv2d_wgrad_folds_bias(const b200_conv_geom* g, int has_workspace);
 /* scratch the call needs (0 for the direct tensor-core route).  Small-channel (image-side, Cin <= 4) layers
  * run as im2col / col2im + the same tcgen05 GEMM when a workspace of this size is passed; with
  * workspace == NULL they fall back to the coalesced SIMT kernels. */

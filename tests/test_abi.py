@@ -93,4 +93,4 @@ def test_epilogue_bits_query_is_host_only_logic():
     g = _capi.ConvGeom(N=8, H=32, W=32, Cin=3, Ho=16, Wo=16, Cout=208, k=5, stride=2, pad_t=1, pad_l=1)
     assert _capi.epilogue_bits(g, 0, True) and not _capi.epilogue_bits(g, 0, False)  # image side: GEMM route only
     assert not _capi.epilogue_bits(g, 1, True)                                         # col2im epilogue: no bitmaps
-    assert _capi.abi_version() == 3 if hasattr(_capi, "abi_version") else True
+    assert _capi.abi_version() == 4 if hasattr(_capi, "abi_version") else True

@@ -73,7 +73,9 @@ def test_critic_step_kernel_schedule():
         E.S.dry = False
     n_f = calls.count("b200_conv2d_fprop")
     n_d = calls.count("b200_conv2d_dgrad")
-    n_w = calls.count("b200_conv2d_wgrad")
+    # (image-side c1: the real / fake filter gradients also yield the bias gradient -- b200_conv2d_wgrad_bias)
+    n_w = calls.count("b200_conv2d_wgrad") + calls.count("b200_conv2d_wgrad_bias")
+    assert calls.count("b200_conv2d_wgrad_bias") == 2, calls
     # fprop: G (fc1) + 3 critic passes x 3 convs + second-order 3  = 1 + 9 + 3
     assert n_f == 13, calls
     # dgrad: G's 3 deconvs + first-order GP chain (3) + real and fake paths (c3, c2 each)

@@ -64,6 +64,62 @@ def test_small_channel_simt_fallback(case):
         assert err < TOL[op], (case, res)
 
 
+IMG_CASES = [
+    # N, H, W, Cin, Cout, k, stride            fused image-side route (img_conv.cu): gather in the producer warps
+    (8, 32, 32, 3, 208, 5, 2),                 # IWGAN c1 at the padded channel count, whole tiles
+    (3, 20, 20, 3, 64, 5, 2),                  # M = 300: partial last tile, sign words stored from registers
+    (2, 64, 64, 3, 64, 4, 2),                  # pix2pix first conv (k4: one 128-byte K chunk, no tail)
+    (5, 12, 12, 3, 32, 3, 1),                  # k3 s1
+    (4, 28, 28, 1, 64, 5, 2),                  # MNIST first conv (Cin 1: odd / even window starts)
+    (2, 18, 18, 2, 48, 5, 2),                  # Cin 2
+    (300, 32, 32, 3, 208, 5, 2),               # more tiles than SMs: the A ring and both accumulators wrap
+]
+
+
+@pytest.mark.parametrize("case", IMG_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_image_side_fused(case):
+    """Fused gather fprop (bias in the spare K column, packed epilogue, sign words) and the filter gradient on the
+    gathered rows with the bias gradient folded in, vs the oracle; then the same with a sign-bitmap mask."""
+    from oracle import tf_ops as OT
+    N, H, W, Cin, Cout, k, s = case
+    E.begin()
+    g = torch.Generator().manual_seed(11)
+    geom = E.conv_geom(N, H, W, Cin, Cout, k, s)
+    assert K.wgrad_folds_bias(geom, True), "case is meant for the fused route"
+    x = P.bf16_round(torch.randn(N, H, W, Cin, generator=g))
+    Wt = P.bf16_round(torch.randn(k, k, Cin, Cout, generator=g) / (k * (Cin ** 0.5)))
+    b = torch.randn(Cout, generator=g) * 0.3
+    Wp, bp = P.make_param(Wt, "w"), P.make_param(b, "b")
+    pre_ref = OT.conv2d(x, Wt, b, s, None, None)
+    y_ref = torch.where(pre_ref > 0, pre_ref, 0.2 * pre_ref)
+    go = P.bf16_round(torch.randn(N, geom.Ho, geom.Wo, Cout, generator=g))
+    with E.recording(True, active=[Wp, bp]):
+        xt = P.dev(x)
+        y = E.conv_like("fprop", xt, Wp, geom, bias=bp, act=K.ACT_LRELU, leak=0.2)
+        torch.cuda.synchronize()
+        yv = y.torch().float().cpu()
+        assert P.rel_err(yv, y_ref) < 6e-3
+        if y.bits is not None:
+            # bit j of word (row, c/16) = out[row, c + j] > 0
+            words = y.bits.cpu().to(torch.int32) & 0xffff
+            got = torch.stack([(words >> j) & 1 for j in range(16)], dim=-1).reshape(words.shape[0], -1)[:, :Cout]
+            assert torch.equal(got.bool(), (yv.reshape(-1, Cout) > 0))
+        E.backward([(y, P.dev(go))], wrt=[])
+    torch.cuda.synchronize()
+    xr, Wr, br = x.clone(), Wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    gw_ref, gb_ref = torch.autograd.grad(OT.conv2d(xr, Wr, br, s, None, None), [Wr, br], go)
+    assert P.rel_err(Wp.g32.reshape(Wt.shape), gw_ref) < 2e-3
+    assert P.rel_err(bp.g32, gb_ref) < 2e-3
+    # no bias, no activation, output multiplied by lrelu'(a) read from a's sign bitmap
+    a_prev = E.conv_like("fprop", P.dev(x), Wp, geom, bias=bp, act=K.ACT_LRELU, leak=0.2)
+    if a_prev.bits is not None:
+        x2 = P.bf16_round(torch.randn(N, H, W, Cin, generator=g))
+        z = E.conv_like("fprop", P.dev(x2), Wp, geom, out_mask=a_prev.mask)
+        torch.cuda.synchronize()
+        z_ref = OT.conv2d_same(x2, Wt, s) * P.act_grad_from_out(a_prev.torch().float().cpu(), K.ACT_LRELU)
+        assert P.rel_err(z.torch().float(), z_ref) < 6e-3
+
+
 def test_conv_dgrad_fused_mask():
     res = P.conv_case(4, 16, 16, 200, 400, 5, 2, with_mask=True)
     assert res["dgrad"] < TOL["dgrad"], res

@@ -29,7 +29,7 @@ def timed(fn, reps=5, inner=10):
     ts.sort()
     return ts[len(ts) // 2]
 
-N, H, Cin, Cout, k = 512, 32, 3, 200, 5
+N, H, Cin, Cout, k = 512, 32, 3, int(os.environ.get("COUT", "208")), 5
 g = torch.Generator().manual_seed(0)
 geom = E.conv_geom(N, H, H, Cin, Cout, k, 2)
 x = dev(torch.randn(N, H, H, Cin, generator=g)); dy = dev(torch.randn(N, geom.Ho, geom.Wo, Cout, generator=g))
