@@ -570,6 +570,21 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
     if (workspace_bytes < b200_conv2d_workspace_bytes(g, 1)) return fail("conv2d_dgrad: workspace too small");
     if (e && e->accumulate) return fail("small-channel dgrad: accumulate unsupported");
     const long long M = (long long)g->N * g->Ho * g->Wo;
+    if (img_dgrad_supported(img_geom(g), g->Cout) && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+      // fused: tensor-core GEMM per image, the col2im gather reads its fp32 image from shared memory (img_conv.cu)
+      ImgDgradParams q;
+      memset(&q, 0, sizeof q);
+      q.g = img_geom(g); q.cout = g->Cout; q.w = (const __nv_bfloat16*)w; q.ldw = g->Cout;
+      long long dimsA[2] = {g->Cout, M}, strA[2] = {1, g->Cout};
+      int boxA[2] = {64, kTileM}, boxT[2] = {16, kTileM}, es[2] = {1, 1};
+      if (make_tmap(&q.tmA, dy, 2, dimsA, strA, boxA, es)) return -1;
+      if (g->Cout % 64 && make_tmap(&q.tmA_tail, dy, 2, dimsA, strA, boxT, es, 32)) return -1;
+      q.bias = e ? e->bias : nullptr; q.act = e ? e->act : 0; q.leak = e ? e->leak : 0.f;
+      q.mask_src = e ? (const __nv_bfloat16*)e->mask_src : nullptr; q.mask_kind = e ? e->mask_kind : 0;
+      q.out = dx; q.out_f32 = e ? e->out_f32 : 0;
+      launch_img_dgrad(q, st);
+      return check_launch("conv2d_dgrad(fused col2im)");
+    }
     const int Kp = small_kp(g), kk = g->k * g->k * g->Cin;
     b200_epilogue te;
     memset(&te, 0, sizeof te);
@@ -718,8 +733,10 @@ extern "C" int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, 
       float* T = (float*)((char*)workspace + img_ws_a(g) + img_ws_w(g));
       if (!workspace_holds_im2col)
         launch_img_im2col16((const __nv_bfloat16*)x, (long long)g->N * g->H * g->W * g->Cin / 2, img_geom(g), A16, 1, st);
-      cudaMemsetAsync(T, 0, (size_t)K16 * g->Cout * 4, st);
+      if (cudaMemsetAsync(T, 0, (size_t)K16 * g->Cout * 4, st) != cudaSuccess) return check_launch("conv2d_wgrad(memset)");
+      if (check_launch("conv2d_wgrad(gather)")) return -1;
       if (dense_wgrad(A16, K16, K16, dy, g->Cout, M, T, g->Cout, alpha, st)) return -1;
+      if (check_launch("conv2d_wgrad(GEMM on gathered rows)")) return -1;
       launch_img_wgrad_fold(T, g->Cout, g->k, g->k * g->Cin, dw, g->Cout, dbias, st);
       return check_launch("conv2d_wgrad(gathered rows)");
     }

@@ -11,6 +11,7 @@
 #include "img_conv.cuh"
 #include "ptx.cuh"
 #include "tc_gemm.cuh"
+#include "epilogue.cuh"
 
 namespace b200 {
 
@@ -267,9 +268,9 @@ __device__ __forceinline__ void prefetch_window(const ImgFpropParams& p, const T
   if (iy1 >= p.g.H) iy1 = p.g.H - 1;
   if (iy1 < 0) { iy1 = p.g.H - 1; --n1; }
   if (n1 >= p.g.N) { n1 = p.g.N - 1; iy1 = p.g.H - 1; }
-  const long long lo = (long long)(n0 * p.g.H + iy0) * row_bytes, hi = (long long)(n1 * p.g.H + iy1 + 1) * row_bytes;
+  const uint32_t lo = (uint32_t)(n0 * p.g.H + iy0) * row_bytes, hi = (uint32_t)(n1 * p.g.H + iy1 + 1) * row_bytes;
   const char* base = reinterpret_cast<const char*>(p.x);
-  for (long long o = (lo & ~127ll) + (long long)tid * 128; o < hi; o += kImgProducers * 128)
+  for (uint32_t o = (lo & ~127u) + (uint32_t)tid * 128u; o < hi; o += 32u * 128u)
     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
 }
 
@@ -297,6 +298,14 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
   uint8_t* smem_win = smem_bits + 2 * bits_bytes;
   ImgSmem* ps = reinterpret_cast<ImgSmem*>(smem_win + 2 * win_bytes);
 
+  // producers: the first window's global loads go out before any setup (DRAM latency under the prologue)
+  TileSpan ts_next = tile_span(p, blockIdx.x);
+  WinRegs wr;
+  if (warp < kImgFirstEpiWarp) {
+    stage_load(p, ts_next, threadIdx.x, wr);
+    // both windows start out zero: the padding columns are never written again
+    for (int i = threadIdx.x * 16; i < 2 * win_bytes; i += kImgProducers * 16) st_shared_v4(smem_u32(smem_win) + i, 0u, 0u, 0u, 0u);
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmOut);
     mbar_init(smem_u32(&ps->b_ready), kImgEpiThreads);
@@ -320,17 +329,16 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
     uint32_t wm[8];                                        // slots >= k*Cin are zero
 #pragma unroll
     for (int i = 0; i < 8; ++i) wm[i] = (2 * i < kcin ? 0xffffu : 0u) | (2 * i + 1 < kcin ? 0xffff0000u : 0u);
+    const bool full14 = kcin >= 14;
     const uint32_t win0 = smem_u32(smem_win);
-    // both windows start out zero: the padding columns are never written again
-    for (int i = threadIdx.x * 16; i < 2 * win_bytes; i += kImgProducers * 16) st_shared_v4(win0 + i, 0u, 0u, 0u, 0u);
+    // tile spans run two tiles ahead: ts_next (staged into registers now) and ts_next2 (its lines pulled into L2)
+    TileSpan ts_next2 = ts_next;
+    if ((int)(blockIdx.x + gridDim.x) < p.num_tiles) {
+      ts_next2 = tile_span(p, blockIdx.x + gridDim.x);
+      if (warp == 3) prefetch_window(p, ts_next2, lane);
+    }
+    stage_store(p, ts_next, win0, threadIdx.x, wr);       // (zeroed before the CTA barrier above)
     named_barrier(2, kImgProducers);
-    TileSpan ts_next = tile_span(p, blockIdx.x);
-    WinRegs wr;
-    stage_load(p, ts_next, threadIdx.x, wr);
-    if ((int)(blockIdx.x + gridDim.x) < p.num_tiles) prefetch_window(p, tile_span(p, blockIdx.x + gridDim.x), threadIdx.x);
-    stage_store(p, ts_next, win0, threadIdx.x, wr);
-    named_barrier(2, kImgProducers);
-
     const uint32_t idesc = make_idesc_bf16(kTileM, p.ncols, 0, 0);
     const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b0), 16, 1024);
     const uint64_t bdesct = make_smem_desc(smem_u32(smem_bt), 16, 256, 6);
@@ -344,9 +352,12 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
       const int next = tile + gridDim.x;
       if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[6][it] = clock64();
       if (next < p.num_tiles) {
-        ts_next = tile_span(p, next);
+        ts_next = ts_next2;
         stage_load(p, ts_next, threadIdx.x, wr);
-        if (next + (int)gridDim.x < p.num_tiles) prefetch_window(p, tile_span(p, next + gridDim.x), threadIdx.x);
+        if (next + (int)gridDim.x < p.num_tiles) {
+          ts_next2 = tile_span(p, next + gridDim.x);
+          if (warp == 3) prefetch_window(p, ts_next2, lane);
+        }
       }
       if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[7][it] = clock64();
       mbar_wait(smem_u32(&ps->a_empty[s]), par ^ 1);
@@ -372,7 +383,11 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(src + kh * row_pitch + i * 4));
           wd[8] = 0u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = ok ? (__funnelshift_r(wd[i], wd[i + 1], sh) & wm[i]) : 0u;
+          for (int i = 0; i < 8; ++i) {
+            o[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
+            if (i == 7 || !full14) o[i] &= wm[i];         // k*Cin >= 14: only the last word holds empty slots
+            if (!ok) o[i] = 0u;
+          }
           if (kh < 2) o[7] |= ones;
           if (kh < 4) {
             const uint32_t base = a_addr + r * 128;
@@ -525,6 +540,214 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
     printf("end %lld\n", clock64() - t0);
   }
   if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem);
+}
+
+// =============================================================================================
+// Fused image-side dgrad (see ImgDgradParams)
+// =============================================================================================
+constexpr int kDgThreads = 64 + 512;                     // warp 0 TMA producer, warp 1 MMA issuer, 16 epilogue warps
+constexpr int kDgEpiThreads = 512;
+constexpr int kTPitch = 84;                              // fp32 words per row of T in shared memory (4 x odd: the
+                                                         // per-row 16-byte stores of a warp are conflict free)
+struct DgSmem {
+  uint64_t full[8], empty[8];
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t b_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kDgThreads, 1) img_dgrad_kernel(const __grid_constant__ ImgDgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int K16 = p.g.k * 16;                             // MMA N: the row-group layout of the filter taps
+  const int kcin = p.g.k * p.g.Cin;
+  const int nchunks = p.kfull + (p.ktail ? 1 : 0);        // K chunks (over Cout) per tile
+  const int b_chunk = K16 * 128;
+  uint8_t* smem_b = smem;                                 // kfull chunks [K16 rows][64 cout] SW128, then the tail [K16][16] SW32
+  uint8_t* smem_bt = smem_b + (size_t)p.kfull * b_chunk;
+  uint8_t* smem_a = smem_bt + (p.ktail ? align_up(K16 * 32, 1024) : 0);
+  uint8_t* smem_t = smem_a + (size_t)p.stages * kAChunk0;
+  DgSmem* ps = reinterpret_cast<DgSmem*>(smem_t + (size_t)p.tiles_per_image * kTileM * kTPitch * 4);
+  const int n_images = p.g.N;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmA);
+    if (p.ktail) tma_prefetch_desc(&p.tmA_tail);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&ps->acc_full[a]), 1);
+      mbar_init(smem_u32(&ps->acc_empty[a]), 16);
+    }
+    mbar_init(smem_u32(&ps->b_ready), kDgEpiThreads);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ TMA producer: dy tiles, chunk by chunk
+      int s = 0;
+      uint32_t par = 0;
+      for (int img = blockIdx.x; img < n_images; img += gridDim.x)
+        for (int t = 0; t < p.tiles_per_image; ++t) {
+          const int row0 = (img * p.tiles_per_image + t) * kTileM;
+          for (int kc = 0; kc < nchunks; ++kc) {
+            mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
+            const uint32_t full = smem_u32(&ps->full[s]);
+            const uint32_t dst = smem_u32(smem_a) + (uint32_t)s * kAChunk0;
+            if (kc < p.kfull) {
+              mbar_arrive_expect_tx(full, kAChunk0);
+              tma_load_2d(dst, &p.tmA, full, kc * 64, row0);
+            } else {
+              mbar_arrive_expect_tx(full, kATail);
+              tma_load_2d(dst, &p.tmA_tail, full, kc * 64, row0);
+            }
+            if (++s == p.stages) { s = 0; par ^= 1; }
+          }
+        }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ MMA issuer
+      const uint32_t idesc = make_idesc_bf16(kTileM, K16, 0, 0);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b), 16, 1024);
+      const uint64_t bdesct = make_smem_desc(smem_u32(smem_bt), 16, 256, 6);
+      mbar_wait(smem_u32(&ps->b_ready), 0);
+      int s = 0, ab = 0;
+      uint32_t par = 0, abpar = 0;
+      for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
+        mbar_wait(smem_u32(&ps->acc_empty[ab]), abpar ^ 1);
+        tc_fence_after();
+        for (int t = 0; t < p.tiles_per_image; ++t) {
+          const uint32_t d = tmem + ab * kTmemCols + t * 128;
+          uint32_t accum = 0;
+          for (int kc = 0; kc < nchunks; ++kc) {
+            mbar_wait(smem_u32(&ps->full[s]), par);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a) + (uint32_t)s * kAChunk0;
+            if (kc < p.kfull) {
+              const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
+              const uint64_t bdesc = bdesc0 + (uint64_t)(((uint32_t)b_chunk >> 4) * kc);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) { umma_bf16(d, adesc + 2 * ks, bdesc + 2 * ks, idesc, accum); accum = 1; }
+            } else {
+              umma_bf16(d, make_smem_desc(a_addr, 16, 256, 6), bdesct, idesc, accum);
+              accum = 1;
+            }
+            umma_commit(smem_u32(&ps->empty[s]));
+            if (++s == p.stages) { s = 0; par ^= 1; }
+          }
+        }
+        umma_commit(smem_u32(&ps->acc_full[ab]));
+        ab ^= 1;
+        if (ab == 0) abpar ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int et = threadIdx.x - 64;
+    // the weights as the B operand: B[kh*16 + j][cout] = w[kh*kcin + j][cout] (rows of couts: K-major as they lie)
+    {
+      const int c8s = p.cout >> 3;
+      for (int item = et; item < K16 * c8s; item += kDgEpiThreads) {
+        const int c8 = item % c8s, kk = item / c8s;
+        const int kh = kk >> 4, j = kk & 15;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (j < kcin) v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)(kh * kcin + j) * p.ldw + c8 * 8));
+        const int kc = c8 >> 3, cc = c8 & 7;
+        uint32_t dst;
+        if (kc < p.kfull) dst = smem_u32(smem_b) + kc * b_chunk + kk * 128 + ((cc ^ (kk & 7)) << 4);
+        else dst = smem_u32(smem_bt) + kk * 32 + ((cc ^ ((kk >> 2) & 1)) << 4);
+        st_shared_v4(dst, v.x, v.y, v.z, v.w);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&ps->b_ready));
+    }
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int nq = K16 >> 4;                               // 16-column chunks of T
+    const int hwc = p.g.H * p.g.W * p.g.Cin;
+    const uint32_t t0 = smem_u32(smem_t);
+    int ab = 0;
+    uint32_t abpar = 0;
+    for (int img = blockIdx.x; img < n_images; img += gridDim.x) {
+      mbar_wait(smem_u32(&ps->acc_full[ab]), abpar);
+      tc_fence_after();
+      // accumulators -> T in shared memory (fp32 rows of kTPitch words)
+      for (int t = 0; t < p.tiles_per_image; ++t)
+        for (int c = cg; c < nq; c += 4) {
+          uint32_t v[16];
+          tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + ab * kTmemCols + t * 128 + c * 16, v);
+          tmem_ld_wait16(v);
+          const uint32_t dst = t0 + (uint32_t)((t * kTileM + r) * kTPitch + c * 16) * 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st_shared_v4(dst + 16 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[ab]));
+      named_barrier(1, kDgEpiThreads);
+      // every output element gathers its taps: kh = kh0 + jh*stride with kh0 = (iy + pad_t) mod stride reads output row
+      // oy0 - jh (same along x).  The loop bounds are uniform (ceil(k/stride) each way) and the loads predicated, so a
+      // warp walks <= 9 (stride 2) combinations instead of diverging over all k*k
+      const float* T = reinterpret_cast<const float*>(smem_t);
+      const size_t obase = (size_t)img * hwc;
+      const int st = p.g.stride, nj = (p.g.k + st - 1) / st;
+      const int cin = p.g.Cin;
+      for (int pix = et; pix < p.g.H * p.g.W; pix += kDgEpiThreads) {     // one input pixel (all its channels) per thread
+        const int iy = fdiv(pix, p.div_w);
+        const int ix = pix - iy * p.g.W;
+        const int ty = iy + p.g.pad_t, tx = ix + p.g.pad_l;
+        int kh0, kw0, oy0, ox0;
+        if (st == 2) { kh0 = ty & 1; kw0 = tx & 1; oy0 = ty >> 1; ox0 = tx >> 1; }
+        else if (st == 1) { kh0 = 0; kw0 = 0; oy0 = ty; ox0 = tx; }
+        else { oy0 = ty / st; kh0 = ty - oy0 * st; ox0 = tx / st; kw0 = tx - ox0 * st; }
+        const int base = (oy0 * p.g.Wo + ox0) * kTPitch + kh0 * 16 + kw0 * cin;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int jh = 0; jh < nj; ++jh) {
+          const bool vh = kh0 + jh * st < p.g.k && oy0 - jh >= 0 && oy0 - jh < p.g.Ho;
+          const int offh = jh * (st * 16 - p.g.Wo * kTPitch);
+          for (int jw = 0; jw < nj; ++jw) {
+            const bool vv = vh && kw0 + jw * st < p.g.k && ox0 - jw >= 0 && ox0 - jw < p.g.Wo;
+            const float* tp = T + (vv ? base + offh + jw * (st * cin - kTPitch) : 0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < cin) acc[c] += vv ? tp[c] : 0.f;
+          }
+        }
+        const size_t o = obase + (size_t)pix * cin;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c >= cin) break;
+          float v = acc[c];
+          if (p.bias) v += __ldg(p.bias + c);
+          v = act_fwd(v, p.act, p.leak);
+          if (p.mask_src) v *= act_grad_from_out(__bfloat162float(p.mask_src[o + c]), p.mask_kind, p.leak);
+          if (p.out_f32) reinterpret_cast<float*>(p.out)[o + c] = v;
+          else reinterpret_cast<__nv_bfloat16*>(p.out)[o + c] = __float2bfloat16(v);
+        }
+      }
+      named_barrier(1, kDgEpiThreads);                     // T is free for the next image
+      ab ^= 1;
+      if (ab == 0) abpar ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<2 * kTmemCols>(tmem);
 }
 
 // standalone gather (same K layout): one thread per output pixel
@@ -681,6 +904,40 @@ void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
   if (p.g.k == 5) img_fprop_kernel<5><<<grid, kImgThreads, smem, stream>>>(p);
   else if (p.g.k == 4) img_fprop_kernel<4><<<grid, kImgThreads, smem, stream>>>(p);
   else img_fprop_kernel<3><<<grid, kImgThreads, smem, stream>>>(p);
+}
+
+static size_t img_dgrad_smem(const ImgConvGeom& g, int cout, int stages) {
+  const int K16 = g.k * 16, kfull = cout / 64, ktail = cout % 64;
+  return (size_t)kfull * K16 * 128 + (ktail ? align_up(K16 * 32, 1024) : 0) + (size_t)stages * kAChunk0 +
+         (size_t)(g.Ho * g.Wo) * kTPitch * 4 + sizeof(DgSmem) + 1024;
+}
+
+bool img_dgrad_supported(const ImgConvGeom& g, int cout) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("B200GAN_NO_IMGFUSE"); off = e ? atoi(e) : 0; }
+  if (off) return false;
+  if (g.k < 1 || g.k > 5 || g.k * g.Cin > 15 || g.Cin > 4) return false;
+  if (g.Ho * g.Wo != 128 && g.Ho * g.Wo != 256) return false;       // one image = 1 or 2 accumulator tiles
+  if (cout % 64 != 0 && cout % 64 != 16) return false;              // K tail: none or one 16-wide SWIZZLE_32B box
+  if (cout % 8 || cout > 1024) return false;
+  if ((long long)g.N * g.H * g.W * g.Cin >= (1ll << 31) || (long long)g.N * g.Ho * g.Wo >= (1ll << 31)) return false;
+  return img_dgrad_smem(g, cout, 2) <= 227 * 1024;
+}
+
+void launch_img_dgrad(const ImgDgradParams& p0, cudaStream_t stream) {
+  ImgDgradParams p = p0;
+  p.kfull = p.cout / 64; p.ktail = p.cout % 64;
+  p.tiles_per_image = p.g.Ho * p.g.Wo / kTileM;
+  p.div_w = make_div(p.g.W);
+  p.stages = 8;
+  while (p.stages > 2 && img_dgrad_smem(p.g, p.cout, p.stages) > 227 * 1024) --p.stages;
+  const size_t smem = img_dgrad_smem(p.g, p.cout, p.stages);
+  static bool configured[kMaxDev] = {false};
+  if (first_use(configured))
+    cudaFuncSetAttribute(img_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  const int sms = dev_sms();
+  const int grid = p.g.N < sms ? p.g.N : sms;
+  img_dgrad_kernel<<<grid, kDgThreads, smem, stream>>>(p);
 }
 
 void launch_img_im2col16(const __nv_bfloat16* x, long long x_words, const ImgConvGeom& g, __nv_bfloat16* out, int ones,

@@ -45,6 +45,32 @@ struct ImgFpropParams {
   __nv_bfloat16* im2col_out;          // optional [M][k*16] copy of the gathered rows (for the later filter gradient)
 };
 
+// Fused input gradient / transposed-conv forward of an image-side layer: dx[N,H,W,Cin] = epi(conv^T(dy, W)).
+// T[pixel, kh*16 + kw*Cin + c] = sum_cout dy[pixel, cout] * w[kh,kw,c,cout] runs on the tensor cores (dy tiles by TMA,
+// the weights resident in shared memory), a whole image (1 or 2 tiles of 128 output pixels) at a time; the fp32 image
+// of T stays in shared memory and every output element gathers its <= ceil(k/stride)^2 taps from it -- the 42 MB
+// col2im workspace round trip through HBM is gone.
+struct ImgDgradParams {
+  ImgConvGeom g;                      // geometry of the forward conv: x [N,H,W,Cin], dy [N,Ho,Wo,Cout]
+  CUtensorMap tmA;                    // dy as [M, Cout]: box 64 x 128, SWIZZLE_128B
+  CUtensorMap tmA_tail;               // same, box 16 x 128, SWIZZLE_32B (Cout % 64 == 16)
+  int cout, kfull, ktail;             // Cout = 64 * kfull + ktail, ktail in {0, 16}
+  const __nv_bfloat16* w;             // [k*k*Cin][ldw]
+  int ldw;
+  int tiles_per_image;                // Ho*Wo / 128: 1 or 2
+  ImgDiv div_w;                       // reciprocal of W
+  const float* bias;                  // [Cin] or null
+  int act;
+  float leak;
+  const __nv_bfloat16* mask_src;      // same shape as the output; result *= act'(mask_src)
+  int mask_kind;
+  void* out;
+  int out_f32;
+  int stages;
+};
+bool img_dgrad_supported(const ImgConvGeom& g, int cout);
+void launch_img_dgrad(const ImgDgradParams& p, cudaStream_t stream);
+
 // 1 when the fused kernel takes this call (else the caller uses the im2col + GEMM route)
 bool img_fprop_supported(const ImgConvGeom& g, int ncols, int has_bias);
 size_t img_fprop_smem(const ImgFpropParams& p);

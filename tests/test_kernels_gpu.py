@@ -120,6 +120,44 @@ def test_image_side_fused(case):
         assert P.rel_err(z.torch().float(), z_ref) < 6e-3
 
 
+IMG_DGRAD_CASES = [
+    # N, H, W, Cin, Cout, k, stride            fused image-side dgrad: GEMM per image + col2im gather from shared memory
+    (8, 32, 32, 3, 208, 5, 2),                 # IWGAN c1 input gradient / last deconv forward: 2 tiles per image, K tail 16
+    (150, 32, 32, 3, 208, 5, 2),               # more images than SMs: TMEM buffers and the ring wrap
+    (4, 16, 32, 3, 64, 5, 2),                  # 8x16 output pixels: 1 tile per image, no K tail
+    (6, 16, 16, 3, 80, 4, 1),                  # stride 1, even filter
+    (3, 32, 32, 1, 128, 5, 2),                 # Cin 1
+    (5, 16, 16, 2, 144, 3, 1),                 # k3 s1, Cin 2, K = 2 chunks + tail
+]
+
+
+@pytest.mark.parametrize("case", IMG_DGRAD_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_image_side_fused_dgrad(case):
+    """conv^T as GEMM + in-kernel col2im vs autograd of the oracle's conv: plain bf16, fp32 output (the gradient
+    penalty's dx), bias + tanh (generator output layer), and a fused tanh' value mask (critic -> generator path)."""
+    from oracle import tf_ops as OT
+    N, H, W, Cin, Cout, k, s = case
+    E.begin()
+    g = torch.Generator().manual_seed(13)
+    geom = E.conv_geom(N, H, W, Cin, Cout, k, s)
+    Wt = P.bf16_round(torch.randn(k, k, Cin, Cout, generator=g) / (k * (Cout ** 0.5)))
+    dy = P.bf16_round(torch.randn(N, geom.Ho, geom.Wo, Cout, generator=g))
+    b = torch.randn(Cin, generator=g) * 0.3
+    Wp, bp = P.make_param(Wt, "w"), P.make_param(b, "b")
+    xr = torch.zeros(N, H, W, Cin, requires_grad=True)
+    (gx_ref,) = torch.autograd.grad(OT.conv2d_same(xr, Wt, s), [xr], dy)
+    gx = E.conv_like("dgrad", P.dev(dy), Wp, geom)
+    gx32 = E.conv_like("dgrad", P.dev(dy), Wp, geom, out_f32=True)
+    gt = E.conv_like("dgrad", P.dev(dy), Wp, geom, bias=bp, act=K.ACT_TANH)
+    a_prev = P.bf16_round(torch.tanh(torch.randn(N, H, W, Cin, generator=g)))
+    gm = E.conv_like("dgrad", P.dev(dy), Wp, geom, out_mask=(P.dev(a_prev), K.ACT_TANH, 0.0))
+    torch.cuda.synchronize()
+    assert P.rel_err(gx.torch().float(), gx_ref) < 6e-3
+    assert P.rel_err(gx32.torch().float(), gx_ref) < 2e-3
+    assert P.rel_err(gt.torch().float(), torch.tanh(gx_ref + b)) < 6e-3
+    assert P.rel_err(gm.torch().float(), gx_ref * (1 - a_prev * a_prev)) < 6e-3
+
+
 def test_conv_dgrad_fused_mask():
     res = P.conv_case(4, 16, 16, 200, 400, 5, 2, with_mask=True)
     assert res["dgrad"] < TOL["dgrad"], res
