@@ -463,7 +463,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
         q.bits_pitch = e ? e->bits_pitch : 0;
         q.bits_stage = (q.bits_out && M % kTileM == 0 && (q.bits_pitch * kTileM * 2) % 16 == 0) ? 1 : 0;
         q.act = e ? e->act : 0; q.leak = e ? e->leak : 0.f; q.mask_kind = e ? e->mask_kind : 0;
-        q.im2col_out = A16;
+        q.im2col_out = nullptr;                       // (the filter gradient gathers for itself: img_wgrad_kernel)
         launch_img_fprop(q, st);
         return check_launch("conv2d_fprop(fused gather)");
       }
@@ -728,9 +728,24 @@ extern "C" int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, 
       // rows gathered in the row-group layout (left by the fprop of the same input, or gathered here) x dy on the
       // tensor cores into a k*16 x Cout fp32 image, then folded into the TF layout; the ones column of the gather
       // makes row 15 the column sum of dy = the bias gradient
+      if (img_wgrad_supported(img_geom(g), g->Cout) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
+                                                        reinterpret_cast<uintptr_t>(dw)) & 15) == 0 &&
+          (!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0) && !getenv("B200GAN_NO_IMGWGRAD")) {
+        // fused: the rows are gathered in shared memory inside the kernel (no im2col in HBM at all)
+        ImgWgradParams q;
+        memset(&q, 0, sizeof q);
+        q.f.g = img_geom(g); q.f.x = (const __nv_bfloat16*)x;
+        long long dimsD[2] = {g->Cout, M}, strD[2] = {1, g->Cout};
+        int boxD[2] = {64, kTileM}, es[2] = {1, 1};
+        if (make_tmap(&q.tmDy, dy, 2, dimsD, strD, boxD, es)) return -1;
+        q.cout = g->Cout; q.dw = dw; q.ldo = g->Cout; q.dbias = dbias; q.alpha = alpha;
+        launch_img_wgrad(q, st);
+        return check_launch("conv2d_wgrad(fused gather)");
+      }
       const int K16 = g->k * 16;
       __nv_bfloat16* A16 = (__nv_bfloat16*)workspace;
       float* T = (float*)((char*)workspace + img_ws_a(g) + img_ws_w(g));
+      workspace_holds_im2col = 0;                      // (the fused fprop no longer leaves the gathered rows behind)
       if (!workspace_holds_im2col)
         launch_img_im2col16((const __nv_bfloat16*)x, (long long)g->N * g->H * g->W * g->Cin / 2, img_geom(g), A16, 1, st);
       if (cudaMemsetAsync(T, 0, (size_t)K16 * g->Cout * 4, st) != cudaSuccess) return check_launch("conv2d_wgrad(memset)");

@@ -274,6 +274,63 @@ __device__ __forceinline__ void prefetch_window(const ImgFpropParams& p, const T
     asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
 }
 
+// One A row (output pixel r of `tile`): its kK filter rows are read from the window as aligned words, shifted into
+// place and written as 16-slot groups into the swizzled operand tile(s): groups 0..3 -> the SWIZZLE_128B tile at a0,
+// group 4 -> the SWIZZLE_32B tail tile at a1, or (kTail128) the first 32 bytes of the rows of a second SWIZZLE_128B
+// tile at a1.  Slot 15 of groups 0 / 1 = 1.0 (bias pair of the fprop; column sum of dy in the filter gradient).
+template <int kK, bool kTail128>
+__device__ __forceinline__ void gather_row(const ImgFpropParams& p, const TileSpan& ts, uint32_t win, int tile, int r,
+                                           uint32_t a0, uint32_t a1, const uint32_t* wm, bool full14) {
+  const uint32_t ones = 0x3F800000u;
+  const int hw = p.g.Ho * p.g.Wo;
+  const int off0 = p.win_off - p.g.pad_l * p.g.Cin;
+  const long long pix = (long long)tile * kTileM + r;
+  const bool ok = pix < p.M;
+  const int pi = ok ? (int)pix : 0;
+  const int n = fdiv(pi, p.div_hw);
+  const int rem = pi - n * hw;
+  const int oy = fdiv(rem, p.div_wo);
+  const int ox = rem - oy * p.g.Wo;
+  const int e = (n * p.win_hp + oy * p.g.stride - ts.g_first) * p.win_pitch + off0 + ox * p.g.stride * p.g.Cin;
+  const uint32_t src = win + (uint32_t)(e >> 1) * 4;
+  const uint32_t sh = (uint32_t)(e & 1) * 16u;
+  const uint32_t row_pitch = (uint32_t)p.win_pitch * 2;
+#pragma unroll
+  for (int kh = 0; kh < kK; ++kh) {
+    uint32_t wd[9], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(src + kh * row_pitch + i * 4));
+    wd[8] = 0u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
+      if (i == 7 || !full14) o[i] &= wm[i];         // k*Cin >= 14: only the last word holds empty slots
+      if (!ok) o[i] = 0u;
+    }
+    if (kh < 2) o[7] |= ones;
+    if (kh < 4) {
+      const uint32_t base = a0 + r * 128;
+      st_shared_v4(base + (((2 * kh) ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+      st_shared_v4(base + (((2 * kh + 1) ^ (r & 7)) << 4), o[4], o[5], o[6], o[7]);
+    } else if (kTail128) {
+      const uint32_t base = a1 + r * 128;
+      st_shared_v4(base + ((0 ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
+      st_shared_v4(base + ((1 ^ (r & 7)) << 4), o[4], o[5], o[6], o[7]);
+    } else {
+      const uint32_t base = a1 + r * 32;
+      const uint32_t sw = (r >> 2) & 1;
+      st_shared_v4(base + (sw << 4), o[0], o[1], o[2], o[3]);
+      st_shared_v4(base + ((sw ^ 1) << 4), o[4], o[5], o[6], o[7]);
+    }
+    if (p.im2col_out && ok) {
+      uint4* dst = reinterpret_cast<uint4*>(p.im2col_out + (size_t)pix * (kK * 16) + kh * 16);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
 template <int kK>
 __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_constant__ ImgFpropParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -325,7 +382,6 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
   if (warp < kImgFirstEpiWarp) {
     // ------------------------------------------------------------------ producers: window staging, gather, MMA issue
     const int r = threadIdx.x;                              // the A row (output pixel of the tile) of this thread
-    const uint32_t ones = 0x3F800000u;                     // bf16 1.0 in slot 15 of groups 0 / 1 (bias pair; wgrad: colsum)
     uint32_t wm[8];                                        // slots >= k*Cin are zero
 #pragma unroll
     for (int i = 0; i < 8; ++i) wm[i] = (2 * i < kcin ? 0xffffu : 0u) | (2 * i + 1 < kcin ? 0xffff0000u : 0u);
@@ -342,8 +398,6 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
     const uint32_t idesc = make_idesc_bf16(kTileM, p.ncols, 0, 0);
     const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b0), 16, 1024);
     const uint64_t bdesct = make_smem_desc(smem_u32(smem_bt), 16, 256, 6);
-    const int hw = p.g.Ho * p.g.Wo;
-    const int off0 = p.win_off - p.g.pad_l * p.g.Cin;
     int s = 0, it = 0, acc = 0;
     uint32_t par = 0, accpar = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -363,49 +417,7 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
       mbar_wait(smem_u32(&ps->a_empty[s]), par ^ 1);
       if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[0][it] = clock64();
       const uint32_t a_addr = smem_u32(smem_a) + (uint32_t)s * kASlot;
-      {
-        const long long pix = (long long)tile * kTileM + r;
-        const bool ok = pix < p.M;
-        const int pi = ok ? (int)pix : 0;
-        const int n = fdiv(pi, p.div_hw);
-        const int rem = pi - n * hw;
-        const int oy = fdiv(rem, p.div_wo);
-        const int ox = rem - oy * p.g.Wo;
-        const int e = (n * p.win_hp + oy * p.g.stride - ts.g_first) * p.win_pitch + off0 + ox * p.g.stride * p.g.Cin;
-        const uint32_t src = win + (uint32_t)(e >> 1) * 4;
-        const uint32_t sh = (uint32_t)(e & 1) * 16u;
-        const uint32_t row_pitch = (uint32_t)p.win_pitch * 2;
-#pragma unroll
-        for (int kh = 0; kh < kK; ++kh) {
-          uint32_t wd[9], o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(src + kh * row_pitch + i * 4));
-          wd[8] = 0u;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            o[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
-            if (i == 7 || !full14) o[i] &= wm[i];         // k*Cin >= 14: only the last word holds empty slots
-            if (!ok) o[i] = 0u;
-          }
-          if (kh < 2) o[7] |= ones;
-          if (kh < 4) {
-            const uint32_t base = a_addr + r * 128;
-            st_shared_v4(base + (((2 * kh) ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
-            st_shared_v4(base + (((2 * kh + 1) ^ (r & 7)) << 4), o[4], o[5], o[6], o[7]);
-          } else {
-            const uint32_t base = a_addr + kAChunk0 + r * 32;
-            const uint32_t sw = (r >> 2) & 1;
-            st_shared_v4(base + (sw << 4), o[0], o[1], o[2], o[3]);
-            st_shared_v4(base + ((sw ^ 1) << 4), o[4], o[5], o[6], o[7]);
-          }
-          if (p.im2col_out && ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.im2col_out + (size_t)pix * (kK * 16) + kh * 16);
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-        }
-      }
+      gather_row<kK, false>(p, ts, win, tile, r, a_addr, a_addr + kAChunk0, wm, full14);
       if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[8][it] = clock64();
       fence_proxy_async_smem();                            // A rows (generic proxy) -> visible to the tensor core
       if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((it + 1) & 1) * win_bytes, threadIdx.x, wr);
@@ -540,6 +552,144 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
     printf("end %lld\n", clock64() - t0);
   }
   if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem);
+}
+
+// =============================================================================================
+// Fused image-side wgrad (see ImgWgradParams)
+// =============================================================================================
+constexpr int kWgThreads = kImgProducers + 128;          // warps 0-3 producers (thread 0: TMA + MMA issue), 4-7 epilogue
+struct WgSmem {
+  uint64_t full[4], empty[4];
+  uint64_t acc_full;
+  uint32_t tmem_base;
+};
+
+template <int kK>
+__global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_constant__ ImgWgradParams pw) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const ImgFpropParams& p = pw.f;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kcin = p.g.k * p.g.Cin;
+  const int a_bytes = 2 * kAChunk0;                       // two 64-slot blocks: filter rows 0..3 | row 4 (+ zeros)
+  const int b_bytes = pw.nblocks * kAChunk0;              // dy: 64-channel boxes of 128 pixels
+  const int stage_bytes = a_bytes + b_bytes;
+  const int win_bytes = align_up(p.win_rows * p.win_pitch * 2, 128);
+  uint8_t* smem_win = smem + (size_t)pw.stages * stage_bytes;
+  WgSmem* ps = reinterpret_cast<WgSmem*>(smem_win + 2 * win_bytes);
+
+  TileSpan ts_next = tile_span(p, blockIdx.x);
+  WinRegs wr;
+  if (warp < kImgFirstEpiWarp) {
+    stage_load(p, ts_next, threadIdx.x, wr);
+    for (int i = threadIdx.x * 16; i < 2 * win_bytes; i += kImgProducers * 16) st_shared_v4(smem_u32(smem_win) + i, 0u, 0u, 0u, 0u);
+    // the second A block only ever receives filter row 4 (its first 32 bytes per row): the rest stays zero
+    for (int s = 0; s < pw.stages; ++s)
+      for (int i = threadIdx.x * 16; i < kAChunk0; i += kImgProducers * 16)
+        st_shared_v4(smem_u32(smem) + s * stage_bytes + kAChunk0 + i, 0u, 0u, 0u, 0u);
+  }
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&pw.tmDy);
+    for (int s = 0; s < pw.stages; ++s) {
+      mbar_init(smem_u32(&ps->full[s]), 1);
+      mbar_init(smem_u32(&ps->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ps->acc_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = ps->tmem_base;
+
+  if (warp < kImgFirstEpiWarp) {
+    const int r = threadIdx.x;
+    uint32_t wm[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wm[i] = (2 * i < kcin ? 0xffffu : 0u) | (2 * i + 1 < kcin ? 0xffff0000u : 0u);
+    const bool full14 = kcin >= 14;
+    const uint32_t win0 = smem_u32(smem_win);
+    TileSpan ts_next2 = ts_next;
+    if ((int)(blockIdx.x + gridDim.x) < p.num_tiles) {
+      ts_next2 = tile_span(p, blockIdx.x + gridDim.x);
+      if (warp == 3) prefetch_window(p, ts_next2, lane);
+    }
+    stage_store(p, ts_next, win0, threadIdx.x, wr);
+    fence_proxy_async_smem();                              // (the zeroed A blocks, for the tensor core)
+    named_barrier(2, kImgProducers);
+
+    // MN-major operands: 64-element blocks kAChunk0 apart (LBO), 8-pixel groups 1024 B apart (SBO), 16 pixels per MMA
+    const uint32_t idesc = make_idesc_bf16(kTileM, pw.cout, 1, 1);
+    int s = 0, it = 0;
+    uint32_t par = 0, accum = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t win = win0 + (it & 1) * win_bytes;
+      const TileSpan ts = ts_next;
+      const int next = tile + gridDim.x;
+      if (next < p.num_tiles) {
+        ts_next = ts_next2;
+        stage_load(p, ts_next, threadIdx.x, wr);
+        if (next + (int)gridDim.x < p.num_tiles) {
+          ts_next2 = tile_span(p, next + gridDim.x);
+          if (warp == 3) prefetch_window(p, ts_next2, lane);
+        }
+      }
+      mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
+      const uint32_t a_addr = smem_u32(smem) + (uint32_t)s * stage_bytes;
+      if (threadIdx.x == 0) {
+        const uint32_t full = smem_u32(&ps->full[s]);
+        mbar_arrive_expect_tx(full, b_bytes);
+        for (int b = 0; b < pw.nblocks; ++b) tma_load_2d(a_addr + a_bytes + b * kAChunk0, &pw.tmDy, full, b * 64, tile * kTileM);
+      }
+      gather_row<kK, true>(p, ts, win, tile, r, a_addr, a_addr + kAChunk0, wm, full14);
+      fence_proxy_async_smem();
+      if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((it + 1) & 1) * win_bytes, threadIdx.x, wr);
+      named_barrier(2, kImgProducers);
+      if (threadIdx.x == 0) {
+        mbar_wait(smem_u32(&ps->full[s]), par);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc_sw128(a_addr, kAChunk0, 1024);
+        const uint64_t bdesc = make_smem_desc_sw128(a_addr + a_bytes, kAChunk0, 1024);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, accum); accum = 1; }
+        umma_commit(smem_u32(&ps->empty[s]));
+      }
+      __syncwarp();
+      if (++s == pw.stages) { s = 0; par ^= 1; }
+    }
+    if (threadIdx.x == 0) umma_commit(smem_u32(&ps->acc_full));
+  } else {
+    // ------------------------------------------------------------------ one reduction at the end: rows = filter slots
+    const int q = warp & 3;
+    const int kk = q * 32 + lane;
+    mbar_wait(smem_u32(&ps->acc_full), 0);
+    tc_fence_after();
+    const int kh = kk >> 4, j = kk & 15;
+    float* dst = nullptr;
+    if (kk < kK * 16) {
+      if (j < kcin) dst = pw.dw + (size_t)(kh * kcin + j) * pw.ldo;
+      else if (kk == 15) dst = pw.dbias;
+    }
+    if ((int)blockIdx.x < p.num_tiles)
+      for (int c = 0; c < pw.cout; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, v);
+        tmem_ld_wait16(v);
+        if (dst) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + i),
+                         "f"(__uint_as_float(v[i]) * pw.alpha), "f"(__uint_as_float(v[i + 1]) * pw.alpha),
+                         "f"(__uint_as_float(v[i + 2]) * pw.alpha), "f"(__uint_as_float(v[i + 3]) * pw.alpha) : "memory");
+        }
+      }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
 }
 
 // =============================================================================================
@@ -904,6 +1054,50 @@ void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
   if (p.g.k == 5) img_fprop_kernel<5><<<grid, kImgThreads, smem, stream>>>(p);
   else if (p.g.k == 4) img_fprop_kernel<4><<<grid, kImgThreads, smem, stream>>>(p);
   else img_fprop_kernel<3><<<grid, kImgThreads, smem, stream>>>(p);
+}
+
+static size_t img_wgrad_smem(const ImgFpropParams& f, int cout, int stages) {
+  const int nblocks = (cout + 63) / 64;
+  return (size_t)stages * (2 + nblocks) * kAChunk0 + 2 * (size_t)align_up(f.win_rows * f.win_pitch * 2, 128) +
+         sizeof(WgSmem) + 1024;
+}
+
+bool img_wgrad_supported(const ImgConvGeom& g, int cout) {
+  if (!img_fprop_supported(g, cout, 1)) return false;
+  ImgFpropParams q;
+  memset(&q, 0, sizeof q);
+  q.g = g;
+  img_window(g, &q.win_pitch, &q.win_off, &q.win_hp, &q.win_rows);
+  return img_wgrad_smem(q, cout, 2) <= 227 * 1024;
+}
+
+void launch_img_wgrad(const ImgWgradParams& p0, cudaStream_t stream) {
+  ImgWgradParams p = p0;
+  ImgFpropParams& f = p.f;
+  f.M = (long long)f.g.N * f.g.Ho * f.g.Wo;
+  f.num_tiles = (int)((f.M + kTileM - 1) / kTileM);
+  f.x_words = (long long)f.g.N * f.g.H * f.g.W * f.g.Cin / 2;
+  f.im2col_out = nullptr;
+  img_window(f.g, &f.win_pitch, &f.win_off, &f.win_hp, &f.win_rows);
+  f.div_hw = make_div(f.g.Ho * f.g.Wo); f.div_wo = make_div(f.g.Wo); f.div_hp = make_div(f.win_hp);
+  f.win_vec16 = ((f.g.W * f.g.Cin * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(f.x) & 15) == 0) ? 1 : 0;
+  f.win_ppr = f.g.W * f.g.Cin * 2 / (f.win_vec16 ? 16 : 4);
+  f.div_ppr = make_div(f.win_ppr);
+  p.nblocks = (p.cout + 63) / 64;
+  p.stages = 4;
+  while (p.stages > 2 && img_wgrad_smem(f, p.cout, p.stages) > 227 * 1024) --p.stages;
+  const size_t smem = img_wgrad_smem(f, p.cout, p.stages);
+  static bool configured[kMaxDev] = {false};
+  if (first_use(configured)) {
+    cudaFuncSetAttribute(img_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(img_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(img_wgrad_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
+  const int sms = dev_sms();
+  const int grid = f.num_tiles < sms ? f.num_tiles : sms;
+  if (f.g.k == 5) img_wgrad_kernel<5><<<grid, kWgThreads, smem, stream>>>(p);
+  else if (f.g.k == 4) img_wgrad_kernel<4><<<grid, kWgThreads, smem, stream>>>(p);
+  else img_wgrad_kernel<3><<<grid, kWgThreads, smem, stream>>>(p);
 }
 
 static size_t img_dgrad_smem(const ImgConvGeom& g, int cout, int stages) {

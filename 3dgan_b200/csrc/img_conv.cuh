@@ -71,6 +71,23 @@ struct ImgDgradParams {
 bool img_dgrad_supported(const ImgConvGeom& g, int cout);
 void launch_img_dgrad(const ImgDgradParams& p, cudaStream_t stream);
 
+// Fused filter (and bias) gradient of an image-side conv: dw[kh,kw,c,cout] += alpha * sum_pixels x_window * dy, and
+// dbias[cout] += alpha * sum_pixels dy (the ones slot of the gather).  The gathered rows are built in shared memory by
+// the same producer code as the fprop and used as the MN-major A operand (M = filter slots, K = pixels); dy tiles come
+// by TMA as the MN-major B operand; every CTA accumulates its pixel tiles in TMEM and reduces once at the end.
+struct ImgWgradParams {
+  ImgFpropParams f;                   // gather side: g, x, M, num_tiles, window and reciprocals (set by the launcher)
+  CUtensorMap tmDy;                   // dy as [M, Cout]: box 64 x 128, SWIZZLE_128B
+  int cout, nblocks;                  // Cout (multiple of 16, <= 256), 64-channel boxes per tile
+  int stages;
+  float* dw;                          // [k*k*Cin][ldo] fp32, accumulated into
+  int ldo;
+  float* dbias;                       // [cout] or null
+  float alpha;
+};
+bool img_wgrad_supported(const ImgConvGeom& g, int cout);
+void launch_img_wgrad(const ImgWgradParams& p, cudaStream_t stream);
+
 // 1 when the fused kernel takes this call (else the caller uses the im2col + GEMM route)
 bool img_fprop_supported(const ImgConvGeom& g, int ncols, int has_bias);
 size_t img_fprop_smem(const ImgFpropParams& p);
