@@ -15,15 +15,18 @@
 
 namespace b200 {
 
-namespace {
+namespace imgconv {
 
-// 20 warps (5 per scheduler: 96 registers each): warps 0-3 producers (window staging, gather of one A row = output
-// pixel per thread, thread 0 issues the MMAs), warps 4-19 epilogue (they also build the weight tile at kernel start)
+// 20 warps (5 per scheduler: 96 registers each): two producer groups of 4 warps (window staging, gather of one A row =
+// output pixel per thread, thread 0 of a group issues its MMAs) taking alternate tiles, and 12 epilogue warps (they
+// also build the weight tile at kernel start).  kImgProducers is the size of ONE group.
 constexpr int kImgProducers = 128;
-constexpr int kImgEpiWarps = 16;
+constexpr int kImgGroups = 2;
+constexpr int kImgEpiWarps = 12;
+constexpr int kImgCgs = kImgEpiWarps / 4;                // column groups: epilogue warps per TMEM lane quarter
 constexpr int kImgEpiThreads = kImgEpiWarps * 32;
-constexpr int kImgFirstEpiWarp = kImgProducers / 32;
-constexpr int kImgThreads = kImgProducers + kImgEpiThreads;
+constexpr int kImgFirstEpiWarp = kImgGroups * kImgProducers / 32;
+constexpr int kImgThreads = kImgGroups * kImgProducers + kImgEpiThreads;
 constexpr int kAChunk0 = kTileM * 128;                   // K 0..63  (filter rows 0..3): 128 rows x 128 B, SWIZZLE_128B
 constexpr int kATail = kTileM * 32;                      // K 64..79 (filter row 4):     128 rows x 32 B,  SWIZZLE_32B
 constexpr int kASlot = kAChunk0 + kATail;
@@ -35,7 +38,6 @@ struct ImgSmem {
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  long long trace[10][8];   // B200GAN_IMG_DBG & 16: clock stamps of CTA 0's first tiles
 };
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -156,19 +158,20 @@ __device__ __forceinline__ uint32_t img_chunk(const uint32_t* acc, float slope, 
 template <bool kMask, bool kAct, int kBits>
 __device__ __forceinline__ void img_row(uint32_t trow, int my_n, uint32_t srow, uint32_t sbits, const uint16_t* mrow,
                                         uint16_t* brow, bool row_ok, float slope, float neg) {
-  // One accumulator buffer, no lookahead: the 4 epilogue warps of a scheduler cover each other's TMEM-load latency,
+  // One accumulator buffer, no lookahead: the epilogue warps of a scheduler cover each other's TMEM-load latency,
   // and a second buffer in ping-pong made ptxas spill one of them in several of the option combinations
   // (a spilled buffer costs more than all the latency it could hide: local memory is an L2 round trip here).
+  // All bases are for this warp's first chunk; its next chunk is kImgCgs chunks further.
 #pragma unroll 1
   for (int i = 0; i < my_n; ++i) {
     uint32_t v[16];
-    tmem_ld16(trow + 64 * i, v);
+    tmem_ld16(trow + 16 * kImgCgs * i, v);
     uint32_t m = 0;
-    if (kMask) m = row_ok ? (uint32_t)__ldg(mrow + 4 * i) : 0u;
+    if (kMask) m = row_ok ? (uint32_t)__ldg(mrow + kImgCgs * i) : 0u;
     tmem_ld_wait16(v);
-    const uint32_t sw = img_chunk<kMask, kAct, kBits != 0>(v, slope, neg, m, srow + 128 * i);
-    if (kBits == 1) st_shared_u16(sbits + 8 * i, (uint16_t)sw);
-    if (kBits == 2) { if (row_ok) brow[4 * i] = (uint16_t)sw; }
+    const uint32_t sw = img_chunk<kMask, kAct, kBits != 0>(v, slope, neg, m, srow + 32 * kImgCgs * i);
+    if (kBits == 1) st_shared_u16(sbits + 2 * kImgCgs * i, (uint16_t)sw);
+    if (kBits == 2) { if (row_ok) brow[kImgCgs * i] = (uint16_t)sw; }
   }
 }
 
@@ -337,7 +340,8 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long t_start = clock64();
+  const int grp = warp >> 2;                              // 0 / 1: producer groups (alternate tiles), >= 2: epilogue
+  const int gtid = threadIdx.x & (kImgProducers - 1);
   constexpr int kSteps0 = kK < 4 ? kK : 4;              // 16-wide MMA K steps in the SWIZZLE_128B chunk
   constexpr bool kTail = kK == 5;
   const int kcin = p.g.k * p.g.Cin;
@@ -353,15 +357,21 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
   uint8_t* smem_out = smem_a + (size_t)p.slots * kASlot;
   uint8_t* smem_bits = smem_out + 2 * out_bytes;
   uint8_t* smem_win = smem_bits + 2 * bits_bytes;
-  ImgSmem* ps = reinterpret_cast<ImgSmem*>(smem_win + 2 * win_bytes);
+  ImgSmem* ps = reinterpret_cast<ImgSmem*>(smem_win + 2 * kImgGroups * win_bytes);
+  const int gstep = kImgGroups * gridDim.x;               // tile stride of one producer group
+  const int tile0 = blockIdx.x + grp * gridDim.x;         // (producer groups) first tile
 
   // producers: the first window's global loads go out before any setup (DRAM latency under the prologue)
-  TileSpan ts_next = tile_span(p, blockIdx.x);
+  TileSpan ts_next = {0, 0};
   WinRegs wr;
-  if (warp < kImgFirstEpiWarp) {
-    stage_load(p, ts_next, threadIdx.x, wr);
-    // both windows start out zero: the padding columns are never written again
-    for (int i = threadIdx.x * 16; i < 2 * win_bytes; i += kImgProducers * 16) st_shared_v4(smem_u32(smem_win) + i, 0u, 0u, 0u, 0u);
+  if (grp < kImgGroups) {
+    if (tile0 < p.num_tiles) {
+      ts_next = tile_span(p, tile0);
+      stage_load(p, ts_next, gtid, wr);
+    }
+    // all windows start out zero: the padding columns are never written again
+    for (int i = threadIdx.x * 16; i < 2 * kImgGroups * win_bytes; i += kImgGroups * kImgProducers * 16)
+      st_shared_v4(smem_u32(smem_win) + i, 0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmOut);
@@ -379,72 +389,71 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem = ps->tmem_base;
 
-  if (warp < kImgFirstEpiWarp) {
-    // ------------------------------------------------------------------ producers: window staging, gather, MMA issue
-    const int r = threadIdx.x;                              // the A row (output pixel of the tile) of this thread
+  if (grp < kImgGroups) {
+    // ------------------------------------------------------------------ producers: window staging, gather, MMA issue.
+    // Group g takes tiles g, g+2, ... of this CTA: its own window pair, A slots and accumulator (acc = g), so the two
+    // groups only meet at the tensor pipe.  One group alone is a ~4000-cycle dependent chain per tile.
+    const int r = gtid;                                    // the A row (output pixel of the tile) of this thread
     uint32_t wm[8];                                        // slots >= k*Cin are zero
 #pragma unroll
     for (int i = 0; i < 8; ++i) wm[i] = (2 * i < kcin ? 0xffffu : 0u) | (2 * i + 1 < kcin ? 0xffff0000u : 0u);
     const bool full14 = kcin >= 14;
-    const uint32_t win0 = smem_u32(smem_win);
+    const uint32_t win0 = smem_u32(smem_win) + grp * 2 * win_bytes;
+    const int bar = 2 + grp;
+    const int spg = p.slots / kImgGroups;                  // A slots per group
     // tile spans run two tiles ahead: ts_next (staged into registers now) and ts_next2 (its lines pulled into L2)
     TileSpan ts_next2 = ts_next;
-    if ((int)(blockIdx.x + gridDim.x) < p.num_tiles) {
-      ts_next2 = tile_span(p, blockIdx.x + gridDim.x);
-      if (warp == 3) prefetch_window(p, ts_next2, lane);
+    if (tile0 < p.num_tiles) {
+      if (tile0 + gstep < p.num_tiles) {
+        ts_next2 = tile_span(p, tile0 + gstep);
+        if ((warp & 3) == 3) prefetch_window(p, ts_next2, lane);
+      }
+      stage_store(p, ts_next, win0, gtid, wr);            // (zeroed before the CTA barrier above)
     }
-    stage_store(p, ts_next, win0, threadIdx.x, wr);       // (zeroed before the CTA barrier above)
-    named_barrier(2, kImgProducers);
+    named_barrier(bar, kImgProducers);
+
     const uint32_t idesc = make_idesc_bf16(kTileM, p.ncols, 0, 0);
     const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(smem_b0), 16, 1024);
     const uint64_t bdesct = make_smem_desc(smem_u32(smem_bt), 16, 256, 6);
-    int s = 0, it = 0, acc = 0;
-    uint32_t par = 0, accpar = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t win = win0 + (it & 1) * win_bytes;
+    const uint32_t dacc = tmem + grp * kTmemCols;          // this group's accumulator
+    int sl = 0, j = 0;
+    uint32_t par = 0;
+    for (int tile = tile0; tile < p.num_tiles; tile += gstep, ++j) {
+      const uint32_t win = win0 + (j & 1) * win_bytes;
       const TileSpan ts = ts_next;
-      const int next = tile + gridDim.x;
-      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[6][it] = clock64();
+      const int next = tile + gstep;
       if (next < p.num_tiles) {
         ts_next = ts_next2;
-        stage_load(p, ts_next, threadIdx.x, wr);
-        if (next + (int)gridDim.x < p.num_tiles) {
-          ts_next2 = tile_span(p, next + gridDim.x);
-          if (warp == 3) prefetch_window(p, ts_next2, lane);
+        stage_load(p, ts_next, gtid, wr);
+        if (next + gstep < p.num_tiles) {
+          ts_next2 = tile_span(p, next + gstep);
+          if ((warp & 3) == 3) prefetch_window(p, ts_next2, lane);
         }
       }
-      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[7][it] = clock64();
+      const int s = grp * spg + sl;
       mbar_wait(smem_u32(&ps->a_empty[s]), par ^ 1);
-      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[0][it] = clock64();
       const uint32_t a_addr = smem_u32(smem_a) + (uint32_t)s * kASlot;
       gather_row<kK, false>(p, ts, win, tile, r, a_addr, a_addr + kAChunk0, wm, full14);
-      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[8][it] = clock64();
       fence_proxy_async_smem();                            // A rows (generic proxy) -> visible to the tensor core
-      if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((it + 1) & 1) * win_bytes, threadIdx.x, wr);
-      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[9][it] = clock64();
-      named_barrier(2, kImgProducers);
-      if ((p.dbg & 16) && blockIdx.x == 0 && r == 0 && it < 8) ps->trace[1][it] = clock64();
-      if (threadIdx.x == 0) {
-        if (it == 0) mbar_wait(smem_u32(&ps->b_ready), 0);
-        mbar_wait(smem_u32(&ps->acc_empty[acc]), accpar ^ 1);
+      if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((j + 1) & 1) * win_bytes, gtid, wr);
+      named_barrier(bar, kImgProducers);
+      if (gtid == 0) {
+        if (j == 0) mbar_wait(smem_u32(&ps->b_ready), 0);
+        mbar_wait(smem_u32(&ps->acc_empty[grp]), (uint32_t)(j & 1) ^ 1);   // the epilogue has drained this accumulator
         tc_fence_after();
-        if ((p.dbg & 16) && blockIdx.x == 0 && it < 8) ps->trace[2][it] = clock64();
         const uint64_t adesc = make_smem_desc_sw128(a_addr, 16, 1024);
-        const uint32_t d = tmem + acc * kTmemCols;
 #pragma unroll
-        for (int ks = 0; ks < kSteps0; ++ks) umma_bf16(d, adesc + 2 * ks, bdesc0 + 2 * ks, idesc, ks ? 1u : 0u);
-        if (kTail) umma_bf16(d, make_smem_desc(a_addr + kAChunk0, 16, 256, 6), bdesct, idesc, 1u);
+        for (int ks = 0; ks < kSteps0; ++ks) umma_bf16(dacc, adesc + 2 * ks, bdesc0 + 2 * ks, idesc, ks ? 1u : 0u);
+        if (kTail) umma_bf16(dacc, make_smem_desc(a_addr + kAChunk0, 16, 256, 6), bdesct, idesc, 1u);
         umma_commit(smem_u32(&ps->a_empty[s]));
-        umma_commit(smem_u32(&ps->acc_full[acc]));
+        umma_commit(smem_u32(&ps->acc_full[grp]));
       }
       __syncwarp();
-      if (++s == p.slots) { s = 0; par ^= 1; }
-      acc ^= 1;
-      if (acc == 0) accpar ^= 1;
+      if (++sl == spg) { sl = 0; par ^= 1; }
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int et = threadIdx.x - kImgProducers;
+    const int et = threadIdx.x - kImgGroups * kImgProducers;
     // first the weights: B[n][kh*16 + j] = w[(kh*kcin + j)][n]  (K-major, swizzled like a TMA load would leave it);
     // slot 15 of groups 0 / 1 = bias split into a bf16 high and low part (their A column is 1.0)
     {
@@ -485,22 +494,21 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
       mbar_arrive(smem_u32(&ps->b_ready));
     }
     const int q = warp & 3;                                // TMEM lane quarter this warp may read
-    const int cg = (warp - kImgFirstEpiWarp) >> 2;
+    const int cg = (warp - kImgFirstEpiWarp) >> 2;         // 0 .. kImgCgs-1: takes chunks cg, cg + kImgCgs, ...
     const int r = q * 32 + lane;
     const int nchunks = p.ncols >> 4;
     const bool issuer = et == 0;
-    const int my_n = cg < nchunks ? (nchunks - cg + 3) >> 2 : 0;
+    const int my_n = cg < nchunks ? (nchunks - cg + kImgCgs - 1) / kImgCgs : 0;
     const int bits_mode = p.bits_out ? (p.bits_stage ? 1 : 2) : 0;
     const float slope = p.act == ACT_NONE ? 1.f : (p.act == ACT_RELU ? 0.f : p.leak);
     const float neg = p.mask_kind == ACT_LRELU ? p.leak : 0.f;
-    int acc = 0, so = 0, ti = 0;
+    int acc = 0, so = 0;
     uint32_t accpar = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long row = (long long)tile * kTileM + r;
       const bool row_ok = row < p.M;
       mbar_wait(smem_u32(&ps->acc_full[acc]), accpar);
       tc_fence_after();
-      if ((p.dbg & 16) && blockIdx.x == 0 && issuer && ti < 8) ps->trace[3][ti] = clock64();
       if (issuer) bulk_wait_read1();                       // the store that last used this stage has read it
       named_barrier(1, kImgEpiThreads);
       // bases of this warp's first chunk (cg): TMEM column, staged row, staged / global sign words, mask words
@@ -510,8 +518,7 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
       const uint16_t* mrow = p.mask_bits ? p.mask_bits + (row_ok ? row : 0) * p.bits_pitch + cg : nullptr;
       uint16_t* brow = p.bits_out ? p.bits_out + (row_ok ? row : 0) * p.bits_pitch + cg : nullptr;
 #define IMG_ROW(M_, A_, B_) img_row<M_, A_, B_>(trow, my_n, srow, sbits, mrow, brow, row_ok, slope, neg)
-      if (p.dbg & 8) {
-      } else if (p.mask_bits) {
+      if (p.mask_bits) {
         if (bits_mode == 0) IMG_ROW(true, true, 0); else if (bits_mode == 1) IMG_ROW(true, true, 1); else IMG_ROW(true, true, 2);
       } else if (p.act != ACT_NONE) {
         if (bits_mode == 0) IMG_ROW(false, true, 0); else if (bits_mode == 1) IMG_ROW(false, true, 1); else IMG_ROW(false, true, 2);
@@ -522,17 +529,15 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ps->acc_empty[acc]));
-      if ((p.dbg & 16) && blockIdx.x == 0 && issuer && ti < 8) ps->trace[4][ti] = clock64();
       fence_proxy_async_smem();                            // staged rows (generic proxy) -> visible to the bulk copy engine
       named_barrier(1, kImgEpiThreads);
-      if (issuer && !(p.dbg & 4)) {
+      if (issuer) {
         tma_store_2d(&p.tmOut, smem_u32(smem_out) + so * out_bytes, 0, tile * kTileM);
         if (p.bits_stage)
           bulk_store_1d(p.bits_out + (size_t)tile * kTileM * p.bits_pitch, smem_u32(smem_bits) + so * bits_bytes,
                         (uint32_t)(kTileM * p.bits_pitch * 2));
         bulk_commit();
       }
-      if ((p.dbg & 16) && blockIdx.x == 0 && issuer && ti < 8) ps->trace[5][ti] = clock64();
       so ^= 1;
       acc ^= 1;
       if (acc == 0) accpar ^= 1;
@@ -542,22 +547,17 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
-  if ((p.dbg & 16) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const long long t0 = ps->trace[0][0];
-    printf("kernel start->first gather %lld\n", t0 - t_start);
-    for (int i = 0; i < 7; ++i)
-      printf("tile %d: stage %lld..%lld gather %lld..%lld fence+cpwait ..%lld barrier ..%lld  mma %lld  epi %lld..%lld store_issued %lld\n", i,
-             ps->trace[6][i] - t0, ps->trace[7][i] - t0, ps->trace[0][i] - t0, ps->trace[8][i] - t0, ps->trace[9][i] - t0,
-             ps->trace[1][i] - t0, ps->trace[2][i] - t0, ps->trace[3][i] - t0, ps->trace[4][i] - t0, ps->trace[5][i] - t0);
-    printf("end %lld\n", clock64() - t0);
-  }
   if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem);
 }
 
 // =============================================================================================
 // Fused image-side wgrad (see ImgWgradParams)
 // =============================================================================================
-constexpr int kWgThreads = kImgProducers + 128;          // warps 0-3 producers (thread 0: TMA + MMA issue), 4-7 epilogue
+// Two producer groups of 4 warps take alternate tiles (a single group's gather is a ~4000-cycle dependent instruction
+// chain per tile, longer than the dy traffic of the tile): warps 0-3 / 4-7 producers (thread 0 of each group issues its
+// TMA loads and MMAs, into the group's own accumulator), warps 8-11 the final reduction.
+constexpr int kWgGroups = 2;
+constexpr int kWgThreads = kWgGroups * kImgProducers + 128;
 struct WgSmem {
   uint64_t full[4], empty[4];
   uint64_t acc_full;
@@ -571,22 +571,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
   const ImgFpropParams& p = pw.f;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int grp = warp >> 2;                              // 0 / 1: producer groups, 2: reduction warps
+  const int gtid = threadIdx.x & (kImgProducers - 1);
   const int kcin = p.g.k * p.g.Cin;
   const int a_bytes = 2 * kAChunk0;                       // two 64-slot blocks: filter rows 0..3 | row 4 (+ zeros)
   const int b_bytes = pw.nblocks * kAChunk0;              // dy: 64-channel boxes of 128 pixels
   const int stage_bytes = a_bytes + b_bytes;
+  const int spg = pw.stages / kWgGroups;                  // stages per group
   const int win_bytes = align_up(p.win_rows * p.win_pitch * 2, 128);
   uint8_t* smem_win = smem + (size_t)pw.stages * stage_bytes;
-  WgSmem* ps = reinterpret_cast<WgSmem*>(smem_win + 2 * win_bytes);
+  WgSmem* ps = reinterpret_cast<WgSmem*>(smem_win + 2 * kWgGroups * win_bytes);
+  const int gstep = kWgGroups * gridDim.x;                // tile stride of one group
+  const int tile0 = blockIdx.x + grp * gridDim.x;         // (producer groups) first tile
 
-  TileSpan ts_next = tile_span(p, blockIdx.x);
+  TileSpan ts_next = {0, 0};
   WinRegs wr;
-  if (warp < kImgFirstEpiWarp) {
-    stage_load(p, ts_next, threadIdx.x, wr);
-    for (int i = threadIdx.x * 16; i < 2 * win_bytes; i += kImgProducers * 16) st_shared_v4(smem_u32(smem_win) + i, 0u, 0u, 0u, 0u);
+  if (grp < kWgGroups) {
+    if (tile0 < p.num_tiles) {
+      ts_next = tile_span(p, tile0);
+      stage_load(p, ts_next, gtid, wr);
+    }
+    for (int i = threadIdx.x * 16; i < 2 * kWgGroups * win_bytes; i += kWgGroups * kImgProducers * 16)
+      st_shared_v4(smem_u32(smem_win) + i, 0u, 0u, 0u, 0u);
     // the second A block only ever receives filter row 4 (its first 32 bytes per row): the rest stays zero
     for (int s = 0; s < pw.stages; ++s)
-      for (int i = threadIdx.x * 16; i < kAChunk0; i += kImgProducers * 16)
+      for (int i = threadIdx.x * 16; i < kAChunk0; i += kWgGroups * kImgProducers * 16)
         st_shared_v4(smem_u32(smem) + s * stage_bytes + kAChunk0 + i, 0u, 0u, 0u, 0u);
   }
   if (threadIdx.x == 0) {
@@ -595,101 +604,115 @@ __global__ void __launch_bounds__(kWgThreads, 1) img_wgrad_kernel(const __grid_c
       mbar_init(smem_u32(&ps->full[s]), 1);
       mbar_init(smem_u32(&ps->empty[s]), 1);
     }
-    mbar_init(smem_u32(&ps->acc_full), 1);
+    mbar_init(smem_u32(&ps->acc_full), kWgGroups);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<kTmemCols>(smem_u32(&ps->tmem_base));
+  if (warp == 0) tmem_alloc<2 * kTmemCols>(smem_u32(&ps->tmem_base));
+  fence_proxy_async_smem();                                // (the zeroed A blocks, for the tensor core)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = ps->tmem_base;
 
-  if (warp < kImgFirstEpiWarp) {
-    const int r = threadIdx.x;
+  if (grp < kWgGroups) {
+    const int r = gtid;
     uint32_t wm[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) wm[i] = (2 * i < kcin ? 0xffffu : 0u) | (2 * i + 1 < kcin ? 0xffff0000u : 0u);
     const bool full14 = kcin >= 14;
-    const uint32_t win0 = smem_u32(smem_win);
+    const uint32_t win0 = smem_u32(smem_win) + grp * 2 * win_bytes;
+    const int bar = 2 + grp;
     TileSpan ts_next2 = ts_next;
-    if ((int)(blockIdx.x + gridDim.x) < p.num_tiles) {
-      ts_next2 = tile_span(p, blockIdx.x + gridDim.x);
-      if (warp == 3) prefetch_window(p, ts_next2, lane);
+    if (tile0 < p.num_tiles) {
+      if (tile0 + gstep < p.num_tiles) {
+        ts_next2 = tile_span(p, tile0 + gstep);
+        if ((warp & 3) == 3) prefetch_window(p, ts_next2, lane);
+      }
+      stage_store(p, ts_next, win0, gtid, wr);
     }
-    stage_store(p, ts_next, win0, threadIdx.x, wr);
-    fence_proxy_async_smem();                              // (the zeroed A blocks, for the tensor core)
-    named_barrier(2, kImgProducers);
+    named_barrier(bar, kImgProducers);
 
     // MN-major operands: 64-element blocks kAChunk0 apart (LBO), 8-pixel groups 1024 B apart (SBO), 16 pixels per MMA
     const uint32_t idesc = make_idesc_bf16(kTileM, pw.cout, 1, 1);
-    int s = 0, it = 0;
+    const uint32_t dacc = tmem + grp * kTmemCols;          // this group's accumulator
+    int sl = 0, j = 0;
     uint32_t par = 0, accum = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t win = win0 + (it & 1) * win_bytes;
+    for (int tile = tile0; tile < p.num_tiles; tile += gstep, ++j) {
+      const uint32_t win = win0 + (j & 1) * win_bytes;
       const TileSpan ts = ts_next;
-      const int next = tile + gridDim.x;
+      const int next = tile + gstep;
       if (next < p.num_tiles) {
         ts_next = ts_next2;
-        stage_load(p, ts_next, threadIdx.x, wr);
-        if (next + (int)gridDim.x < p.num_tiles) {
-          ts_next2 = tile_span(p, next + gridDim.x);
-          if (warp == 3) prefetch_window(p, ts_next2, lane);
+        stage_load(p, ts_next, gtid, wr);
+        if (next + gstep < p.num_tiles) {
+          ts_next2 = tile_span(p, next + gstep);
+          if ((warp & 3) == 3) prefetch_window(p, ts_next2, lane);
         }
       }
+      const int s = grp * spg + sl;
       mbar_wait(smem_u32(&ps->empty[s]), par ^ 1);
       const uint32_t a_addr = smem_u32(smem) + (uint32_t)s * stage_bytes;
-      if (threadIdx.x == 0) {
+      if (gtid == 0) {
         const uint32_t full = smem_u32(&ps->full[s]);
         mbar_arrive_expect_tx(full, b_bytes);
         for (int b = 0; b < pw.nblocks; ++b) tma_load_2d(a_addr + a_bytes + b * kAChunk0, &pw.tmDy, full, b * 64, tile * kTileM);
       }
       gather_row<kK, true>(p, ts, win, tile, r, a_addr, a_addr + kAChunk0, wm, full14);
       fence_proxy_async_smem();
-      if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((it + 1) & 1) * win_bytes, threadIdx.x, wr);
-      named_barrier(2, kImgProducers);
-      if (threadIdx.x == 0) {
+      if (next < p.num_tiles) stage_store(p, ts_next, win0 + ((j + 1) & 1) * win_bytes, gtid, wr);
+      named_barrier(bar, kImgProducers);
+      if (gtid == 0) {
         mbar_wait(smem_u32(&ps->full[s]), par);
         tc_fence_after();
         const uint64_t adesc = make_smem_desc_sw128(a_addr, kAChunk0, 1024);
         const uint64_t bdesc = make_smem_desc_sw128(a_addr + a_bytes, kAChunk0, 1024);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { umma_bf16(tmem, adesc + 128 * k, bdesc + 128 * k, idesc, accum); accum = 1; }
+        for (int k = 0; k < 8; ++k) { umma_bf16(dacc, adesc + 128 * k, bdesc + 128 * k, idesc, accum); accum = 1; }
         umma_commit(smem_u32(&ps->empty[s]));
       }
       __syncwarp();
-      if (++s == pw.stages) { s = 0; par ^= 1; }
+      if (++sl == spg) { sl = 0; par ^= 1; }
     }
-    if (threadIdx.x == 0) umma_commit(smem_u32(&ps->acc_full));
+    if (gtid == 0) {
+      if (tile0 < p.num_tiles) umma_commit(smem_u32(&ps->acc_full));
+      else mbar_arrive(smem_u32(&ps->acc_full));
+    }
   } else {
     // ------------------------------------------------------------------ one reduction at the end: rows = filter slots
     const int q = warp & 3;
     const int kk = q * 32 + lane;
     mbar_wait(smem_u32(&ps->acc_full), 0);
     tc_fence_after();
-    const int kh = kk >> 4, j = kk & 15;
+    const int kh = kk >> 4, jj = kk & 15;
     float* dst = nullptr;
     if (kk < kK * 16) {
-      if (j < kcin) dst = pw.dw + (size_t)(kh * kcin + j) * pw.ldo;
+      if (jj < kcin) dst = pw.dw + (size_t)(kh * kcin + jj) * pw.ldo;
       else if (kk == 15) dst = pw.dbias;
     }
-    if ((int)blockIdx.x < p.num_tiles)
-      for (int c = 0; c < pw.cout; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, v);
-        tmem_ld_wait16(v);
-        if (dst) {
+    const bool two = (int)(blockIdx.x + gridDim.x) < p.num_tiles;      // the second group had tiles too
+    for (int c = 0; c < pw.cout; c += 16) {
+      uint32_t v[16], u[16];
+      tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c, v);
+      if (two) tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + kTmemCols + c, u);
+      tmem_ld_wait16(v);
+      if (two) {
+        tmem_ld_wait16(u);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + i),
-                         "f"(__uint_as_float(v[i]) * pw.alpha), "f"(__uint_as_float(v[i + 1]) * pw.alpha),
-                         "f"(__uint_as_float(v[i + 2]) * pw.alpha), "f"(__uint_as_float(v[i + 3]) * pw.alpha) : "memory");
-        }
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
       }
+      if (dst) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + i),
+                       "f"(__uint_as_float(v[i]) * pw.alpha), "f"(__uint_as_float(v[i + 1]) * pw.alpha),
+                       "f"(__uint_as_float(v[i + 2]) * pw.alpha), "f"(__uint_as_float(v[i + 3]) * pw.alpha) : "memory");
+      }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<kTmemCols>(tmem);
+  if (warp == 0) tmem_dealloc<2 * kTmemCols>(tmem);
 }
 
 // =============================================================================================
@@ -705,6 +728,54 @@ struct DgSmem {
   uint64_t b_ready;
   uint32_t tmem_base;
 };
+
+// col2im gather of one image from T (see img_dgrad_kernel): one input pixel (all its channels) per thread and step.
+// Tap kh = kh0 + jh*stride with kh0 = (iy + pad_t) mod stride reads output row oy0 - jh (same along x): uniform loop
+// bounds (ceil(k/stride) each way) and predicated loads instead of a divergent walk over all k*k taps.
+// kS / kC: stride and Cin at compile time (0 = read them from the geometry): the hot shapes get fully unrolled code.
+template <int kS, int kC>
+__device__ __forceinline__ void dg_gather(const ImgDgradParams& p, const float* __restrict__ T, size_t obase, int et) {
+  const int st = kS ? kS : p.g.stride;
+  const int cin = kC ? kC : p.g.Cin;
+  const int nj = (p.g.k + st - 1) / st;
+  for (int pix = et; pix < p.g.H * p.g.W; pix += kDgEpiThreads) {
+    const int iy = fdiv(pix, p.div_w);
+    const int ix = pix - iy * p.g.W;
+    const int ty = iy + p.g.pad_t, tx = ix + p.g.pad_l;
+    int kh0, kw0, oy0, ox0;
+    if (st == 2) { kh0 = ty & 1; kw0 = tx & 1; oy0 = ty >> 1; ox0 = tx >> 1; }
+    else if (st == 1) { kh0 = 0; kw0 = 0; oy0 = ty; ox0 = tx; }
+    else { oy0 = ty / st; kh0 = ty - oy0 * st; ox0 = tx / st; kw0 = tx - ox0 * st; }
+    const int base = (oy0 * p.g.Wo + ox0) * kTPitch + kh0 * 16 + kw0 * cin;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int jh = 0; jh < 5; ++jh) {
+      if (jh >= nj) break;
+      const bool vh = kh0 + jh * st < p.g.k && oy0 - jh >= 0 && oy0 - jh < p.g.Ho;
+      const int offh = jh * (st * 16 - p.g.Wo * kTPitch);
+#pragma unroll
+      for (int jw = 0; jw < 5; ++jw) {
+        if (jw >= nj) break;
+        const bool vv = vh && kw0 + jw * st < p.g.k && ox0 - jw >= 0 && ox0 - jw < p.g.Wo;
+        const float* tp = T + (vv ? base + offh + jw * (st * cin - kTPitch) : 0);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < cin) acc[c] += vv ? tp[c] : 0.f;
+      }
+    }
+    const size_t o = obase + (size_t)pix * cin;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c >= cin) break;
+      float v = acc[c];
+      if (p.bias) v += __ldg(p.bias + c);
+      v = act_fwd(v, p.act, p.leak);
+      if (p.mask_src) v *= act_grad_from_out(__bfloat162float(p.mask_src[o + c]), p.mask_kind, p.leak);
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[o + c] = v;
+      else reinterpret_cast<__nv_bfloat16*>(p.out)[o + c] = __float2bfloat16(v);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kDgThreads, 1) img_dgrad_kernel(const __grid_constant__ ImgDgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -854,41 +925,10 @@ __global__ void __launch_bounds__(kDgThreads, 1) img_dgrad_kernel(const __grid_c
       // warp walks <= 9 (stride 2) combinations instead of diverging over all k*k
       const float* T = reinterpret_cast<const float*>(smem_t);
       const size_t obase = (size_t)img * hwc;
-      const int st = p.g.stride, nj = (p.g.k + st - 1) / st;
-      const int cin = p.g.Cin;
-      for (int pix = et; pix < p.g.H * p.g.W; pix += kDgEpiThreads) {     // one input pixel (all its channels) per thread
-        const int iy = fdiv(pix, p.div_w);
-        const int ix = pix - iy * p.g.W;
-        const int ty = iy + p.g.pad_t, tx = ix + p.g.pad_l;
-        int kh0, kw0, oy0, ox0;
-        if (st == 2) { kh0 = ty & 1; kw0 = tx & 1; oy0 = ty >> 1; ox0 = tx >> 1; }
-        else if (st == 1) { kh0 = 0; kw0 = 0; oy0 = ty; ox0 = tx; }
-        else { oy0 = ty / st; kh0 = ty - oy0 * st; ox0 = tx / st; kw0 = tx - ox0 * st; }
-        const int base = (oy0 * p.g.Wo + ox0) * kTPitch + kh0 * 16 + kw0 * cin;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int jh = 0; jh < nj; ++jh) {
-          const bool vh = kh0 + jh * st < p.g.k && oy0 - jh >= 0 && oy0 - jh < p.g.Ho;
-          const int offh = jh * (st * 16 - p.g.Wo * kTPitch);
-          for (int jw = 0; jw < nj; ++jw) {
-            const bool vv = vh && kw0 + jw * st < p.g.k && ox0 - jw >= 0 && ox0 - jw < p.g.Wo;
-            const float* tp = T + (vv ? base + offh + jw * (st * cin - kTPitch) : 0);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c < cin) acc[c] += vv ? tp[c] : 0.f;
-          }
-        }
-        const size_t o = obase + (size_t)pix * cin;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c >= cin) break;
-          float v = acc[c];
-          if (p.bias) v += __ldg(p.bias + c);
-          v = act_fwd(v, p.act, p.leak);
-          if (p.mask_src) v *= act_grad_from_out(__bfloat162float(p.mask_src[o + c]), p.mask_kind, p.leak);
-          if (p.out_f32) reinterpret_cast<float*>(p.out)[o + c] = v;
-          else reinterpret_cast<__nv_bfloat16*>(p.out)[o + c] = __float2bfloat16(v);
-        }
-      }
+      if (p.g.stride == 2 && p.g.Cin == 3) dg_gather<2, 3>(p, T, obase, et);
+      else if (p.g.stride == 2 && p.g.Cin == 1) dg_gather<2, 1>(p, T, obase, et);
+      else if (p.g.stride == 1 && p.g.Cin == 3) dg_gather<1, 3>(p, T, obase, et);
+      else dg_gather<0, 0>(p, T, obase, et);
       named_barrier(1, kDgEpiThreads);                     // T is free for the next image
       ab ^= 1;
       if (ab == 0) abpar ^= 1;
@@ -966,13 +1006,14 @@ int dev_sms() {
   return sms[dev];
 }
 
-}  // namespace
+}  // namespace imgconv
+using namespace imgconv;
 
 size_t img_fprop_smem(const ImgFpropParams& p) {
   const int bt = p.g.k == 5 ? align_up(p.ncols * 32, 1024) : 0;
   return (size_t)p.ncols * 128 + bt + (size_t)p.slots * kASlot + 2 * (size_t)align_up(kTileM * p.stage_pitch, 1024) +
          2 * (size_t)(p.bits_stage ? align_up(kTileM * p.bits_pitch * 2, 128) : 0) +
-         2 * (size_t)align_up(p.win_rows * p.win_pitch * 2, 128) + sizeof(ImgSmem) + 1024;
+         2 * kImgGroups * (size_t)align_up(p.win_rows * p.win_pitch * 2, 128) + sizeof(ImgSmem) + 1024;
 }
 
 static ImgDiv make_div(int d) {
@@ -1036,8 +1077,8 @@ void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
   p.win_vec16 = ((p.g.W * p.g.Cin * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0) ? 1 : 0;
   p.win_ppr = p.g.W * p.g.Cin * 2 / (p.win_vec16 ? 16 : 4);
   p.div_ppr = make_div(p.win_ppr);
-  p.slots = kMaxSlots;
-  while (p.slots > 2 && img_fprop_smem(p) > 227 * 1024) --p.slots;
+  p.slots = kMaxSlots;                                      // per producer group: 2 or 1
+  if (img_fprop_smem(p) > 227 * 1024) p.slots = 2;
   const size_t smem = img_fprop_smem(p);
   static bool configured[kMaxDev] = {false};
   if (first_use(configured)) {
@@ -1047,10 +1088,6 @@ void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
   }
   const int sms = dev_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("B200GAN_IMG_DBG"); dbg = e ? atoi(e) : 0; }
-  p.dbg = dbg;
-  if (dbg & 1) p.im2col_out = nullptr;
   if (p.g.k == 5) img_fprop_kernel<5><<<grid, kImgThreads, smem, stream>>>(p);
   else if (p.g.k == 4) img_fprop_kernel<4><<<grid, kImgThreads, smem, stream>>>(p);
   else img_fprop_kernel<3><<<grid, kImgThreads, smem, stream>>>(p);
@@ -1058,7 +1095,7 @@ void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
 
 static size_t img_wgrad_smem(const ImgFpropParams& f, int cout, int stages) {
   const int nblocks = (cout + 63) / 64;
-  return (size_t)stages * (2 + nblocks) * kAChunk0 + 2 * (size_t)align_up(f.win_rows * f.win_pitch * 2, 128) +
+  return (size_t)stages * (2 + nblocks) * kAChunk0 + 2 * kWgGroups * (size_t)align_up(f.win_rows * f.win_pitch * 2, 128) +
          sizeof(WgSmem) + 1024;
 }
 
@@ -1084,8 +1121,7 @@ void launch_img_wgrad(const ImgWgradParams& p0, cudaStream_t stream) {
   f.win_ppr = f.g.W * f.g.Cin * 2 / (f.win_vec16 ? 16 : 4);
   f.div_ppr = make_div(f.win_ppr);
   p.nblocks = (p.cout + 63) / 64;
-  p.stages = 4;
-  while (p.stages > 2 && img_wgrad_smem(f, p.cout, p.stages) > 227 * 1024) --p.stages;
+  p.stages = img_wgrad_smem(f, p.cout, 4) <= 227 * 1024 ? 4 : 2;      // per producer group: 2 or 1
   const size_t smem = img_wgrad_smem(f, p.cout, p.stages);
   static bool configured[kMaxDev] = {false};
   if (first_use(configured)) {

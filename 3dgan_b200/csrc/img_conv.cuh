@@ -41,7 +41,6 @@ struct ImgFpropParams {
   int act;
   float leak;
   int mask_kind;
-  int dbg;                            // B200GAN_IMG_DBG bit mask (timing experiments: 2 no gather loads, 4 no stores, 8 no epilogue math)
   __nv_bfloat16* im2col_out;          // optional [M][k*16] copy of the gathered rows (for the later filter gradient)
 };
 

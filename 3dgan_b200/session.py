@@ -4,6 +4,7 @@ the data-parallel exchange (one process per GPU; NCCL all-reduce of the flat gra
 place of util.py:118-147's CPU averaging).
 """
 import contextlib
+import gc
 import os
 
 import torch
@@ -253,12 +254,22 @@ class Session:
             self.graphs[key] = {"state": "warm"}
             return out
         if ent["state"] == "warm":
+            # Python's cyclic collector must not run inside the capture: if it finalises a CUDA graph or tensors of
+            # an earlier Session there, the allocator's cudaFree invalidates the capture ("operation failed due to
+            # a previous error during capture", seen intermittently when several Sessions live in one process)
+            gc.collect()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             launches0 = E.S.launches
-            with torch.cuda.graph(g):
-                self.begin_step()
-                out = fn()
+            gc_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    self.begin_step()
+                    out = fn()
+            finally:
+                if gc_on:
+                    gc.enable()
             ent.update(state="graph", graph=g, out=out, launches=E.S.launches - launches0)
             # the engine was bound to the capture stream: rebind it to the current stream so that eager launches
             # after this point (store.load -> refresh_transposed, tests) stay ordered with torch ops

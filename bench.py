@@ -402,6 +402,20 @@ def roofline(sess, job, pools, a, step_ms):
         r["tflops"] = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else None
     if a.profile_out:
         json.dump(rows, open(a.profile_out, "w"), indent=1)
+    # image-side (<= 4 channel) layers: HBM-bound, reported against the measured copy bandwidth.  Algorithmic bytes of
+    # one launch = the big tensor (N*Ho*Wo*Cout bf16) + the image tensor (N*H*W*Cin bf16), logical channels
+    import re
+    hbm = float(pk.get("hbm_gbs", 6547.2)) if os.path.exists(peaks_path) else 6547.2
+    image_side = []
+    for t_, r in sorted(rows.items()):
+        m = re.match(r"smallc-gemm:(\w+) N(\d+) (\d+)x(\d+)x(\d+)->(\d+)x(\d+)x(\d+) ", t_)
+        if not m or r["ms"] <= 0:
+            continue
+        n_, h_, w_, ci, ho, wo, co = (int(v) for v in m.groups()[1:])
+        by = 2.0 * n_ * (h_ * w_ * ci + ho * wo * co)
+        gbs = by * r["launches"] / (r["ms"] * 1e-3) / 1e9
+        image_side.append({"op": t_, "launches": r["launches"], "us_per_launch": 1e3 * r["ms"] / r["launches"],
+                           "algorithmic_bytes_per_launch": by, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / hbm})
     n_tc = sum(r["launches"] for t_, r in rows.items() if t_.startswith("tc:"))
     achieved = tot_f / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     traffic, traffic_src = ncu_traffic_bytes()
@@ -410,6 +424,7 @@ def roofline(sess, job, pools, a, step_ms):
            "kernel": "tapgemm2sm_kernel+wgrad2sm_kernel (tcgen05 cta_group::2 implicit GEMM: conv fprop/dgrad/wgrad, dense)",
            "launches": n_tc, "flops_per_launch_avg": tot_f / max(n_tc, 1), "ms_per_launch_avg": tot_ms / max(n_tc, 1),
            "step_share": tot_ms / step_ms if step_ms > 0 else None,
+           "image_side_hbm": image_side,
            "note": "achieved = sum(2*N*Ho*Wo*k*k*Cin*Cout, logical channels, over the launches) / sum(CUDA-event "
                    "durations), one eager iteration; step_share = those durations / the graph-replayed ms_per_step"}
     if sustained:
