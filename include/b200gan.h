@@ -75,8 +75,10 @@ int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, float* dbia
                            void* workspace, long long workspace_bytes, int workspace_holds_im2col, b200_stream s);
 int b200_conv2d_wgrad_folds_bias(const b200_conv_geom* g, int has_workspace);
 /* scratch the call needs (0 for the direct tensor-core route).  Small-channel (image-side, Cin <= 4) layers
- * run as im2col / col2im + the same tcgen05 GEMM when a workspace of this size is passed; with
- * workspace == NULL they fall back to the coalesced SIMT kernels. */
+ * run on the tensor cores when a workspace of this size is passed: fused kernels that gather the filter window
+ * (fprop, wgrad) or scatter-gather the col2im (dgrad) inside the kernel (csrc/img_conv.cu) where the geometry
+ * allows, else im2col / col2im through the workspace + the same tcgen05 GEMM; with workspace == NULL they fall
+ * back to the coalesced SIMT kernels. */
 long long b200_conv2d_workspace_bytes(const b200_conv_geom* g, int op /*0 fprop,1 dgrad,2 wgrad*/);
 /* which kernel family a geometry maps to: 1 tensor core, 2 small-channel input (image side), 3 small-channel
  * output backward (<= 4 output channels, SIMT), negative = unsupported */
