@@ -458,6 +458,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
   const int iters = ntaps * kloops;
   const int tail_row_bytes = p.tail_mode == 1 ? 32 : 64;      // bytes per row of a narrow (not merged) tail box
 
+  const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (tr && threadIdx.x == 0) ps->trace[0] = clock64();
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
@@ -551,6 +553,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full0 + 8 * s, par);
         tc_fence_after();
+        if (tr && it == 0) ps->trace[1] = clock64();
         const uint64_t adesc = adesc0 + (uint64_t)(desc_step * s);
         const uint64_t bdesc = bdesc0 + (uint64_t)(desc_step * s);
         if (!p.merge_tail && p.tail_mode != 0 && kc == p.kchunks - 1) {
@@ -597,6 +600,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
         if (++kc == kloops) kc = 0;
         if (++s == p.stages) { s = 0; par ^= 1; }
       }
+      if (tr) ps->trace[2] = clock64();
       umma_commit_2sm(smem_u32(&ps->tmem_full), (uint16_t)0x3);   // accumulators final in both CTAs
     }
     __syncwarp();
@@ -650,6 +654,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
     }
     mbar_wait(smem_u32(&ps->tmem_full), 0);
     tc_fence_after();
+    if (tr && threadIdx.x == 64) ps->trace[3] = clock64();
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + i * kTmemCols;
@@ -659,6 +664,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
       }
       epilogue_row<kSimple>(ea, trow, off[i], row_ok[i], n0, cg * 16, ncg * 16, min(p.bn_tile, p.ncols - n0));
     }
+    if (tr && threadIdx.x == 64) ps->trace[4] = clock64();
     if (p.tma_store) {
       fence_proxy_async_smem();
       named_barrier(1, (int)blockDim.x - 64);
@@ -675,6 +681,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) tapgemm2sm_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
+  if (tr && threadIdx.x == 0) {
+    const long long t0 = ps->trace[0];
+    printf("tapgemm2sm grid (%d,%d,%d) iters %d: first_mma %lld  last_mma_issued %lld  epi_start %lld  epi_rows_done %lld  end %lld\n",
+           gridDim.x, gridDim.y, gridDim.z, iters, ps->trace[1] - t0, ps->trace[2] - t0, ps->trace[3] - t0,
+           ps->trace[4] - t0, (long long)clock64() - t0);
+  }
   cluster_sync_all();       // the pair's MMAs / barrier traffic are finished in both CTAs
   if (warp == 1) tmem_dealloc_2sm<2 * kTmemCols>(tmem);
 }
@@ -1251,10 +1263,14 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     const int tiles2 = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2;
     const int ny = (p.ncols + p.bn_tile - 1) / p.bn_tile;
     dim3 grid((tiles2 + 1) / 2 * 2, ny, p.nphases);
+    TapGemmParams q2 = p;
+    static int trace2 = -1;
+    if (trace2 < 0) trace2 = env_int("B200GAN_GEMM_TRACE", 0);
+    q2.trace = trace2;
     if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
-      launch_clustered(tapgemm2sm_kernel<true>, p, grid, smem2, 2, stream);
+      launch_clustered(tapgemm2sm_kernel<true>, q2, grid, smem2, 2, stream);
     else
-      launch_clustered(tapgemm2sm_kernel<false>, p, grid, smem2, 2, stream);
+      launch_clustered(tapgemm2sm_kernel<false>, q2, grid, smem2, 2, stream);
     return;
   }
   const int stage_bytes = tapgemm_stage_bytes(p.dual, p.bn_tile, p.merge_tail);
