@@ -234,6 +234,33 @@ __device__ __forceinline__ void tma_load_nd_2sm(int rank, uint32_t dst, const vo
     default: tma_load_5d_2sm(dst, tmap, bar, c[0], c[1], c[2], c[3], c[4]); break;
   }
 }
+// 2-CTA loads that are also multicast: the box lands at the same offset in every CTA of `mask` and completes bytes on
+// the barrier at this offset in the LEADER of each destination CTA's pair (cute::SM100_TMA_2SM_LOAD_MULTICAST)
+__device__ __forceinline__ void tma_load_nd_2sm_mc(int rank, uint32_t dst, const void* tmap, uint32_t bar, const int* c,
+                                                   uint16_t mask) {
+  const uint32_t b = bar & kPeerBitMask;
+  switch (rank) {
+    case 2:
+      asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                   " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "h"(mask) : "memory");
+      break;
+    case 3:
+      asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                   " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]), "h"(mask)
+                   : "memory");
+      break;
+    case 4:
+      asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                   " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]),
+                   "r"(c[3]), "h"(mask) : "memory");
+      break;
+    default:
+      asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                   " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::"r"(dst), "l"(tmap), "r"(b), "r"(c[0]), "r"(c[1]), "r"(c[2]),
+                   "r"(c[3]), "r"(c[4]), "h"(mask) : "memory");
+      break;
+  }
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");

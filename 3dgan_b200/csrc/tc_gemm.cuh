@@ -53,6 +53,7 @@ struct TapGemmParams {
   int b_rows_total;
   int b_prefetch;                     // 1: CTAs of the first pixel tile pull their N tile's weight rows into L2 at kernel start
   int trace;                          // debug: CTA (0,0,0) prints clock stamps of its phases
+  int quad;                           // 2-CTA kernel: 1 = cluster (2,2,1), the two pairs multicast their shared A tiles
   int cta2;                           // 1: 2-CTA kernel (cta_group::2): B split across the pair, M = 256 per MMA
   CUtensorMap tmOut[kMaxPhases];      // per phase: output viewed as [ext_n, ext_h, ext_w, ncols], box = the tile (tma_store)
   int tma_store;                      // 1: the epilogue stages its tiles in the (idle) pipeline smem and bulk-stores them
