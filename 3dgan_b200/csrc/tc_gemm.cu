@@ -1290,7 +1290,37 @@ void launch_tapgemm(const TapGemmParams& p, cudaStream_t stream) {
     if (trace2 < 0) trace2 = env_int("B200GAN_GEMM_TRACE", 0);
     if (quad_env < 0) quad_env = env_int("B200GAN_QUAD", 1);
     q2.trace = trace2;
-    q2.quad = (quad_env && ny % 2 == 0) ? 1 : 0;
+    // Quad clusters only when they do not cost a wave: four-CTA clusters pack worse into the GPCs (33 of them = 132 SMs
+    // are co-resident, against 74 pairs = 148 SMs), and the shared A tiles make one wave only ~7 % faster
+    q2.quad = 0;
+    if (quad_env && ny % 2 == 0) {
+      static int max_pairs[kMaxDevices] = {0}, max_quads[kMaxDevices] = {0};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < kMaxDevices) {
+        if (!max_pairs[dev]) {
+          auto kern = tapgemm2sm_kernel<true>;
+          cudaLaunchConfig_t cfg;
+          memset(&cfg, 0, sizeof cfg);
+          cfg.gridDim = dim3(8, 2, 1); cfg.blockDim = dim3(gemm_threads()); cfg.dynamicSmemBytes = smem2;
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+          cfg.attrs = at; cfg.numAttrs = 1;
+          int n = 0;
+          if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = device_sms() / 2; }
+          max_pairs[dev] = n;
+          at[0].val.clusterDim.y = 2;
+          n = 0;
+          if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = device_sms() / 5; }
+          max_quads[dev] = n;
+        }
+        const long long pairs_n = (long long)grid.x / 2 * grid.y * grid.z, quads_n = pairs_n / 2;
+        const long long waves_p = (pairs_n + max_pairs[dev] - 1) / max_pairs[dev];
+        const long long waves_q = (quads_n + max_quads[dev] - 1) / max_quads[dev];
+        q2.quad = (waves_q * 93 <= waves_p * 100) ? 1 : 0;
+      }
+    }
     if (epilogue_is_simple(p.act, p.mask_src, p.mask_bits, p.out_f32, p.accumulate))
       launch_clustered(tapgemm2sm_kernel<true>, q2, grid, smem2, 2, stream, q2.quad ? 2 : 1);
     else
