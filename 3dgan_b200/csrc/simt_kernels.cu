@@ -1021,7 +1021,9 @@ static void colsum_launch(const bf16* x, const float* wrow, float* out, float* o
                           cudaStream_t st) {
   const bool vec = (C & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   const int gx = vec ? (C + 255) / 256 : (C + 63) / 64;
-  long long want = ((long long)num_sms() * 8 + gx - 1) / gx;
+  static int per_sm = -1;       // row blocks per SM: fewer blocks = fewer same-address atomics at the end (B200GAN_COLSUM_BLOCKS)
+  if (per_sm < 0) { const char* e = getenv("B200GAN_COLSUM_BLOCKS"); per_sm = e ? atoi(e) : 4; if (per_sm < 1) per_sm = 1; }
+  long long want = ((long long)num_sms() * per_sm + gx - 1) / gx;
   if (want > (R + 31) / 32) want = (R + 31) / 32;
   if (want < 1) want = 1;
   const int rpb = (int)((R + want - 1) / want);
