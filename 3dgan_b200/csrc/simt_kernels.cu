@@ -293,20 +293,21 @@ __global__ void col2im_small_kernel(const float* __restrict__ T, ConvGeom g, int
     const int y = (int)((p / g.W) % g.H);
     const int n = (int)(p / ((long long)g.W * g.H));
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = 0; r < g.k; ++r) {
-      const int th = y + g.pad_t - r;
-      if (th < 0 || th % g.stride) continue;
-      const int oh = th / g.stride;
-      if (oh >= g.Ho) continue;
-      for (int s = 0; s < g.k; ++s) {
-        const int tw = x + g.pad_l - s;
-        if (tw < 0 || tw % g.stride) continue;
-        const int ow = tw / g.stride;
-        if (ow >= g.Wo) continue;
-        const float* t = T + (((long long)n * g.Ho + oh) * g.Wo + ow) * Kp + (r * g.k + s) * g.Cs;
+    // taps r = r0 + jr*stride with r0 = (y + pad_t) mod stride read output row oh0 - jr (same along x): uniform loop
+    // bounds and predicated loads instead of a divergent walk over all k*k taps (as in img_dgrad_kernel)
+    const int st = g.stride, nj = (g.k + st - 1) / st;
+    const int ty = y + g.pad_t, tx = x + g.pad_l;
+    const int oh0 = ty / st, r0 = ty - oh0 * st, ow0 = tx / st, s0 = tx - ow0 * st;
+    for (int jr = 0; jr < nj; ++jr) {
+      const int r = r0 + jr * st, oh = oh0 - jr;
+      const bool vr = r < g.k && oh >= 0 && oh < g.Ho;
+      for (int js = 0; js < nj; ++js) {
+        const int sx = s0 + js * st, ow = ow0 - js;
+        const bool v = vr && sx < g.k && ow >= 0 && ow < g.Wo;
+        const float* t = T + (v ? (((long long)n * g.Ho + oh) * g.Wo + ow) * Kp + (r * g.k + sx) * g.Cs : 0);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-          if (c < g.Cs) acc[c] += t[c];
+          if (c < g.Cs) acc[c] += v ? t[c] : 0.f;
       }
     }
 #pragma unroll
