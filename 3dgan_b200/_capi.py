@@ -37,6 +37,7 @@ _GP, _EP = C.POINTER(ConvGeom), C.POINTER(Epilogue)
 
 # name -> argtypes; mirrors include/b200gan.h one to one (tests/test_abi.py checks the export list)
 SIGNATURES = {
+    "b200_set_tuning": [C.c_char_p, _I],
     "b200_conv2d_fprop": [_P, _P, _P, _P, _GP, _EP, _P, _LL, _P],
     "b200_conv2d_dgrad": [_P, _P, _P, _GP, _EP, _P, _LL, _P],
     "b200_conv2d_wgrad": [_P, _P, _P, _GP, _F, _P, _LL, _I, _P],
@@ -130,6 +131,12 @@ def nccl_library_path():
 
 def workspace_bytes(geom, op):
     return int(lib().b200_conv2d_workspace_bytes(C.byref(geom), op))
+
+
+def set_tuning(key, value):
+    """b200_set_tuning: run-time override of a launch-planner knob (include/b200gan.h)."""
+    if lib().b200_set_tuning(key.encode(), int(value)) != 0:
+        raise B200Error(lib().b200_last_error().decode())
 
 
 def epilogue_bits(geom, op, has_workspace):

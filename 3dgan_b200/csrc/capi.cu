@@ -124,8 +124,9 @@ static int tc_tap_splits(const b200_conv_geom* g, int op) {
     const int tiles = cdiv(g->Wo, bw) * cdiv(g->Ho, bh) * cdiv(g->N, bn);
     const int kch = cdiv(g->Cin, kBlockK);
     iters = kk * kch;
-    const int dual = tapgemm_dual(tiles, iters);
-    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * cdiv(g->Cout, pick_bn_tile(g->Cout));
+    const int ny = cdiv(g->Cout, pick_bn_tile(g->Cout));
+    const int dual = tapgemm_dual(tiles, iters, (long long)cdiv(tiles, 4) * ny);
+    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * ny;
   } else {
     const int ew = cdiv(g->W, st), eh = cdiv(g->H, st);
     pick_pixel_tile(ew, eh, kTileM, &bw, &bh, &bn);
@@ -134,8 +135,9 @@ static int tc_tap_splits(const b200_conv_geom* g, int op) {
     const int phases = st * st;
     const int min_taps = std::max(1, (g->k / st) * (g->k / st));   // taps of the lightest output parity
     iters = std::max(1, kk / phases) * kch;                      // per phase
-    const int dual = tapgemm_dual(tiles, min_taps * kch);
-    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * cdiv(g->Cin, pick_bn_tile(g->Cin)) * phases;
+    const int ny = cdiv(g->Cin, pick_bn_tile(g->Cin));
+    const int dual = tapgemm_dual(tiles, min_taps * kch, (long long)cdiv(tiles, 4) * ny * phases);
+    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * ny * phases;
   }
   if (ctas >= 64 || iters < 16) return 1;
   int s = (int)(160 / ctas);
@@ -547,7 +549,8 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.phase_ext_w[0] = g->Wo; p.phase_ext_h[0] = g->Ho; p.ext_n = g->N;
   p.phase_o_off[0] = 0;
   p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
-  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks * g->k * g->k);
+  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks * g->k * g->k,
+                        (long long)cdiv(p.tiles_w * p.tiles_h * p.tiles_n, 4) * cdiv(p.ncols, p.bn_tile));
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
   p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
   p.stages = std::min(pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
@@ -691,7 +694,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.ext_n = g->N;
   p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
   // two pixel tiles per CTA (and with them the 2-CTA kernels) whenever the lightest phase still has a real K loop
-  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, phs[np - 1].nt * p.kchunks);
+  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, phs[np - 1].nt * p.kchunks,
+                        (long long)cdiv(p.tiles_w * p.tiles_h * p.tiles_n, 4) * cdiv(p.ncols, p.bn_tile) * np);
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
   p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
   p.stages = pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
@@ -831,6 +835,11 @@ extern "C" int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, 
 // thin wrappers
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
+
+extern "C" int b200_set_tuning(const char* key, int value) {
+  if (key && !strcmp(key, "dual_min_pct")) { set_dual_min_pct(value); return 0; }
+  return fail("set_tuning: unknown key");
+}
 extern "C" int b200_abi_version(void) { return 4; }
 extern "C" int b200_device_check(void) {
   int n = 0;

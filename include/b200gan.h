@@ -52,6 +52,11 @@ const char* b200_last_error(void);
 int b200_abi_version(void);
 /* 0 if the current CUDA device can run the library (compute capability 10.x), negative otherwise. */
 int b200_device_check(void);
+/* Launch-planner knobs a host may override at run time (the B200GAN_* environment variables of DESIGN.md 5.2 are
+ * read once per process).  Keys: "dual_min_pct" - the tap GEMMs use two pixel tiles per CTA (and the 2-CTA
+ * kernels) only when that layout's work items cover at least this percentage of the SMs (default 65; 0 = always,
+ * which is how the tests reach the 2-CTA kernels at small batch).  Unknown key: negative return. */
+int b200_set_tuning(const char* key, int value);
 
 /* ---- convolution family (tcgen05 implicit GEMM; small-channel image-side layers use coalesced SIMT kernels)
  * fprop : y  = epi(conv_SAME(x, W))            replaces tf.nn.conv2d            ops/layers.py:101, hem/ops/layers.py:118

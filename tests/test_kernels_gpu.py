@@ -52,6 +52,20 @@ def test_conv_family(case):
         assert err < TOL[op], (case, res)
 
 
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] > 4 and c[0] <= 256],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_conv_family_two_cta_layout_forced(case):
+    """The planner gives layers whose 2-CTA work items cover < 65 % of the SMs single-tile CTAs (tapgemm_dual);
+    with the threshold at 0 the same small cases run the two-tile / 2-CTA / persistent kernels the big layers use."""
+    K.set_tuning("dual_min_pct", 0)
+    try:
+        res = P.conv_case(*case)
+    finally:
+        K.set_tuning("dual_min_pct", 65)
+    for op, err in res.items():
+        assert err < TOL[op], (case, res)
+
+
 @pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] <= 4], ids=lambda c: "x".join(map(str, c)))
 def test_small_channel_simt_fallback(case):
     """The image-side layers without a workspace: coalesced SIMT kernels instead of im2col + GEMM."""

@@ -56,6 +56,10 @@ if os.environ.get("WAVE_CASES") == "ab":
     CASES = [(512, 16, 208, 400, 5), (592, 16, 208, 400, 5), (512, 8, 400, 800, 5), (592, 8, 400, 800, 5)]
 if os.environ.get("WAVE_CASES") == "cin":
     CASES = [(296, 16, c, 400, 5) for c in (192, 200, 208, 224, 256, 264, 320, 328, 336)]
+if os.environ.get("WAVE_CASES") == "p2p":
+    # pix2pix encoder / decoder geometries at the BASELINE batch (hem/models/pix2pix.py:187-227), k4 s2
+    CASES = [(16, 128, 64, 128, 4), (16, 64, 128, 256, 4), (16, 32, 256, 512, 4), (16, 16, 512, 512, 4),
+             (16, 8, 512, 512, 4), (16, 32, 256, 1024, 4), (16, 16, 512, 1024, 4)]
 for (N, H, Cin, Cout, k) in CASES:
     g = torch.Generator().manual_seed(0)
     geom = E.conv_geom(N, H, H, Cin, Cout, k, 2)
