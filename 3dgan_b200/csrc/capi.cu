@@ -88,6 +88,9 @@ static int pick_bn_tile(int cols) {
   const int nt = cdiv(cols, 256);
   return std::max(16, cdiv(cdiv(cols, nt), 16) * 16);
 }
+// Run-time planner overrides (b200_set_tuning): N-tile cap (0 = the planner's own choice) and forced split-K factor
+// (-1 = the planner's own choice); tools/tune_layers.py sweeps them per geometry.
+static int g_bn_cap = 0, g_force_splits = -1;
 static int pick_stages(int stage_bytes) {
   static int cap = -1;          // B200GAN_STAGES: cap the pipeline depth (2 leaves room for two CTAs per SM)
   if (cap < 0) { const char* e = getenv("B200GAN_STAGES"); cap = e ? atoi(e) : 8; }
@@ -108,42 +111,54 @@ static int weight_prefetch() {
 
 static bool is_small(int c) { return c <= 4; }
 
-// Split-K for tensor-core layers with few output tiles and long reductions (pix2pix's inner U-Net layers: 16..1024
-// output pixels, K = 16 taps x 512..1024 channels): without it a handful of CTAs stream the whole weight tensor.
-// Returns the number of K slices (1 = off) for the fprop (op 0) / dgrad (op 1) launch of this geometry.
-static int tc_tap_splits(const b200_conv_geom* g, int op) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("B200GAN_TAPSPLIT"); enabled = e ? atoi(e) : 1; }
-  if (!enabled) return 1;
+// Launch plan of a tensor-core conv tap GEMM (fprop: op 0, dgrad: op 1): pixel-tile layout, N tile and split-K
+// factor.  Fitted to tools/tune_layers.py (every fprop / dgrad geometry of pix2pix, VAE and the cnn autoencoder under
+// all combinations; gpurun_out/tune_layers.json): the fastest plan is the one that puts ~128 CTAs on the 148 SMs --
+//   * two pixel tiles per CTA in CTA pairs (shared B tile, tcgen05 cta_group::2) whenever there are >= 4 pixel tiles;
+//   * the widest N tile (<= 256 columns: one A tile feeds the most MACs) that still yields >= 96 CTAs, down to 64;
+//   * and only then split-K over the taps (fp32 partial image + finalize pass; pix2pix's inner U-Net layers have
+//     16..1024 output pixels and K = 16 taps x 512..1024 channels: a handful of CTAs would stream the whole weight
+//     tensor), at most 8 slices of >= 4 pipeline iterations.
+// Layers that fill the machine anyway (the IWGAN c2 / c3 shapes: 128 .. 256 CTAs at N tile 208) are unaffected.
+struct ConvPlan { int dual, bn_tile, splits, tiles, phases; };
+static ConvPlan conv_plan(const b200_conv_geom* g, int op) {
+  static int split_enabled = -1;
+  if (split_enabled < 0) { const char* e = getenv("B200GAN_TAPSPLIT"); split_enabled = e ? atoi(e) : 1; }
   const int st = g->stride, kk = g->k * g->k;
   int bw, bh, bn;
-  long long ctas;
-  int iters;
+  ConvPlan pl;
+  int cols, iters, iters_min;
   if (op == 0) {
     pick_pixel_tile(g->Wo, g->Ho, kTileM, &bw, &bh, &bn);
-    const int tiles = cdiv(g->Wo, bw) * cdiv(g->Ho, bh) * cdiv(g->N, bn);
-    const int kch = cdiv(g->Cin, kBlockK);
-    iters = kk * kch;
-    const int ny = cdiv(g->Cout, pick_bn_tile(g->Cout));
-    const int dual = tapgemm_dual(tiles, iters, (long long)cdiv(tiles, 4) * ny);
-    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * ny;
+    pl.tiles = cdiv(g->Wo, bw) * cdiv(g->Ho, bh) * cdiv(g->N, bn);
+    pl.phases = 1;
+    cols = g->Cout;
+    iters = iters_min = kk * cdiv(g->Cin, kBlockK);
   } else {
     const int ew = cdiv(g->W, st), eh = cdiv(g->H, st);
     pick_pixel_tile(ew, eh, kTileM, &bw, &bh, &bn);
-    const int tiles = cdiv(ew, bw) * cdiv(eh, bh) * cdiv(g->N, bn);
+    pl.tiles = cdiv(ew, bw) * cdiv(eh, bh) * cdiv(g->N, bn);
+    pl.phases = st * st;
+    cols = g->Cin;
     const int kch = cdiv(g->Cout, kBlockK);
-    const int phases = st * st;
-    const int min_taps = std::max(1, (g->k / st) * (g->k / st));   // taps of the lightest output parity
-    iters = std::max(1, kk / phases) * kch;                      // per phase
-    const int ny = cdiv(g->Cin, pick_bn_tile(g->Cin));
-    const int dual = tapgemm_dual(tiles, min_taps * kch, (long long)cdiv(tiles, 4) * ny * phases);
-    ctas = (long long)((cdiv(tiles, dual) + 1) / 2 * 2) * ny * phases;
+    iters = std::max(1, kk / pl.phases) * kch;                                  // per output parity
+    iters_min = std::max(1, (g->k / st) * (g->k / st)) * kch;                   // lightest output parity
   }
-  if (ctas >= 64 || iters < 16) return 1;
-  int s = (int)(160 / ctas);
-  s = std::min(s, iters / 4);
-  return std::max(s, 1);
+  pl.dual = tapgemm_dual(pl.tiles, iters_min);
+  const long long rows = (pl.dual == 2 ? 2LL * cdiv(pl.tiles, 4) : (long long)pl.tiles) * pl.phases;   // CTAs per N tile
+  int cap = g_bn_cap > 0 ? g_bn_cap : 256;
+  auto bn_of = [&](int cp) { const int nt = cdiv(cols, cp); return std::max(16, cdiv(cdiv(cols, nt), 16) * 16); };
+  if (g_bn_cap <= 0)
+    while (cap > 64 && rows * cdiv(cols, bn_of(cap)) < 96) cap /= 2;
+  pl.bn_tile = bn_of(cap);
+  const long long ctas = rows * cdiv(cols, pl.bn_tile);
+  pl.splits = 1;
+  if (g_force_splits >= 1) pl.splits = std::min(g_force_splits, std::max(1, iters / 2));
+  else if (split_enabled && ctas < 96 && iters >= 16)
+    while (pl.splits < 8 && ctas * pl.splits < 96 && iters / (2 * pl.splits) >= 4) pl.splits *= 2;   // 2, 4 or 8 (the measured factors)
+  return pl;
 }
+static int tc_tap_splits(const b200_conv_geom* g, int op) { return conv_plan(g, op).splits; }
 static long long tc_out_elems(const b200_conv_geom* g, int op) {
   return op == 0 ? (long long)g->N * g->Ho * g->Wo * g->Cout : (long long)g->N * g->H * g->W * g->Cin;
 }
@@ -510,7 +525,8 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   }
   p.a_rank = 4;
   p.ncols = g->Cout;
-  p.bn_tile = pick_bn_tile(g->Cout);
+  const ConvPlan plan = conv_plan(g, 0);
+  p.bn_tile = plan.bn_tile;
   p.cluster = tapgemm_cluster_size(p);
   {
     long long dims[2] = {g->Cin, (long long)g->k * g->k * g->Cout};
@@ -549,8 +565,7 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
   p.phase_ext_w[0] = g->Wo; p.phase_ext_h[0] = g->Ho; p.ext_n = g->N;
   p.phase_o_off[0] = 0;
   p.o_sw = g->Cout; p.o_sh = (long long)g->Wo * g->Cout; p.o_sn = (long long)g->Ho * g->Wo * g->Cout;
-  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, p.kchunks * g->k * g->k,
-                        (long long)cdiv(p.tiles_w * p.tiles_h * p.tiles_n, 4) * cdiv(p.ncols, p.bn_tile));
+  p.dual = plan.dual;
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
   p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
   p.stages = std::min(pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
@@ -633,7 +648,8 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   }
   p.a_rank = 4;
   p.ncols = g->Cin;
-  p.bn_tile = pick_bn_tile(g->Cin);
+  const ConvPlan plan = conv_plan(g, 1);
+  p.bn_tile = plan.bn_tile;
   p.cluster = tapgemm_cluster_size(p);
   {
     long long dims[2] = {g->Cout, (long long)g->k * g->k * g->Cin};
@@ -694,8 +710,7 @@ extern "C" int b200_conv2d_dgrad(const void* dy, const void* w, void* dx, const 
   p.ext_n = g->N;
   p.o_sw = (long long)st_ * g->Cin; p.o_sh = (long long)st_ * g->W * g->Cin; p.o_sn = (long long)g->H * g->W * g->Cin;
   // two pixel tiles per CTA (and with them the 2-CTA kernels) whenever the lightest phase still has a real K loop
-  p.dual = tapgemm_dual(p.tiles_w * p.tiles_h * p.tiles_n, phs[np - 1].nt * p.kchunks,
-                        (long long)cdiv(p.tiles_w * p.tiles_h * p.tiles_n, 4) * cdiv(p.ncols, p.bn_tile) * np);
+  p.dual = plan.dual;
   p.merge_tail = (p.tail_mode == 1 && p.kchunks >= 2 && !getenv("B200GAN_NO_MERGE_TAIL")) ? 1 : 0;
   p.cta2 = tapgemm_2sm(p.cluster, p.dual, p.tail_mode, p.merge_tail, p.bn_tile);
   p.stages = pick_stages(p.cta2 ? tapgemm_stage_bytes_2sm(p.bn_tile, p.merge_tail)
@@ -838,6 +853,8 @@ extern "C" const char* b200_last_error(void) { return g_err.c_str(); }
 
 extern "C" int b200_set_tuning(const char* key, int value) {
   if (key && !strcmp(key, "dual_min_pct")) { set_dual_min_pct(value); return 0; }
+  if (key && !strcmp(key, "bn_tile_cap")) { g_bn_cap = value < 0 ? 0 : value; return 0; }
+  if (key && !strcmp(key, "tap_splits")) { g_force_splits = value; return 0; }
   return fail("set_tuning: unknown key");
 }
 extern "C" int b200_abi_version(void) { return 4; }

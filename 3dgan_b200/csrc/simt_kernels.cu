@@ -1148,6 +1148,57 @@ __global__ void bn_bwd_sums_kernel(const bf16* __restrict__ g, const bf16* __res
   atomicAdd(bsum + c, s1);
   atomicAdd(bsum + C + c, s2);
 }
+// vector form (C % 8 == 0, 16-byte aligned): block = 32 column-octets x 8 row lanes as in colsum_vec_kernel, one
+// 16-byte load of g and of z per thread and row; row lanes combined through shared memory, one atomic per column
+__global__ void bn_bwd_sums_vec_kernel(const bf16* __restrict__ g, const bf16* __restrict__ z,
+                                       const float* __restrict__ stats, float* bsum, long long R, int C, float eps,
+                                       int rows_per_block) {
+  __shared__ float red[2][8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 8;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > R) r1 = R;
+  float s[8], q[8], mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; mean[j] = 0.f; rstd[j] = 0.f; }
+  if (c < C) {
+    const float invR = 1.f / (float)R;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = stats[c + j] * invR;
+      rstd[j] = rsqrtf(fmaxf(stats[C + c + j] * invR - mean[j] * mean[j], 0.f) + eps);
+    }
+#pragma unroll 2
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const uint4 gr = *reinterpret_cast<const uint4*>(g + r * C + c);
+      const uint4 zr = *reinterpret_cast<const uint4*>(z + r * C + c);
+      const uint32_t g4[4] = {gr.x, gr.y, gr.z, gr.w}, z4[4] = {zr.x, zr.y, zr.z, zr.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g0 = __uint_as_float(g4[j] << 16), g1 = __uint_as_float(g4[j] & 0xffff0000u);
+        const float z0 = __uint_as_float(z4[j] << 16), z1 = __uint_as_float(z4[j] & 0xffff0000u);
+        s[2 * j] += g0; s[2 * j + 1] += g1;
+        q[2 * j] = fmaf(g0, z0 - mean[2 * j], q[2 * j]);
+        q[2 * j + 1] = fmaf(g1, z1 - mean[2 * j + 1], q[2 * j + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][ty][tx * 8 + j] = s[j];
+    red[1][ty][tx * 8 + j] = q[j] * rstd[j];           // sum g * (z - mean) * rstd
+  }
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < C) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a += red[0][j][threadIdx.x]; b += red[1][j][threadIdx.x]; }
+    atomicAdd(bsum + cc, a);
+    atomicAdd(bsum + C + cc, b);
+  }
+}
 // dz = rstd * (g - s1/R - xhat*s2/R)
 __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ z, const float* __restrict__ stats,
                                     const float* __restrict__ bsum, bf16* dz, long long R, int C, float eps) {
@@ -1214,8 +1265,18 @@ int bn_bwd(const void* g, const void* z, const float* stats, float* bsum, void* 
   if (want < 1) want = 1;
   const int rpb = (int)((R + want - 1) / want);
   const int gy = (int)((R + rpb - 1) / rpb);
-  bn_bwd_sums_kernel<<<dim3(gx, gy), threads, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, R, C, eps, rpb);
   const uintptr_t al = reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz);
+  if ((C & 7) == 0 && (al & 15) == 0) {
+    const int vx = (C + 255) / 256;
+    long long wv = ((long long)num_sms() * 4 + vx - 1) / vx;
+    if (wv > (R + 31) / 32) wv = (R + 31) / 32;
+    if (wv < 1) wv = 1;
+    const int rpbv = (int)((R + wv - 1) / wv);
+    const int vy = (int)((R + rpbv - 1) / rpbv);
+    bn_bwd_sums_vec_kernel<<<dim3(vx, vy), 256, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, R, C, eps, rpbv);
+  } else {
+    bn_bwd_sums_kernel<<<dim3(gx, gy), threads, 0, st>>>((const bf16*)g, (const bf16*)z, stats, bsum, R, C, eps, rpb);
+  }
   if ((C & 7) == 0 && (al & 15) == 0) {
     const int sx = (C + kBnSlab - 1) / kBnSlab;
     long long w2 = ((long long)num_sms() * 8 + sx - 1) / sx;

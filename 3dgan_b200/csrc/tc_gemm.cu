@@ -1114,20 +1114,18 @@ int l2_prefetch_distance() {
 
 static int g_dual_min_pct = -1;      // B200GAN_DUAL_MIN_PCT / b200_set_tuning("dual_min_pct", v)
 void set_dual_min_pct(int v) { g_dual_min_pct = v < 0 ? 0 : v; }
-int tapgemm_dual(int m_tiles, int iters, long long pair_items) {
-  // two pixel tiles per CTA when there is enough work to still fill the machine
+int tapgemm_dual(int m_tiles, int iters) {
+  // two pixel tiles per CTA (and with them the 2-CTA kernels: a CTA pair works on 4 pixel tiles) when there are at
+  // least 4 pixel tiles; below that single-tile CTAs leave fewer SMs idle (tools/tune_layers.py).
+  // dual_min_pct 0: whenever possible (the tests reach the 2-CTA kernels at small batch); > 100: never.
   static int v = -1;
   if (v < 0) v = env_int("B200GAN_DUAL", 2);
   if (g_dual_min_pct < 0) g_dual_min_pct = env_int("B200GAN_DUAL_MIN_PCT", 65);
-  const int min_pct = g_dual_min_pct;
   // short K loops (image-side GEMMs) gain more from two co-resident CTAs per SM than from sharing B
   if (!(v == 2 && m_tiles >= 2 && iters > 4)) return 1;
-  // pair_items = work items of the 2-CTA layout (groups of 4 pixel tiles x N tiles x output phases), one per CTA
-  // pair.  When they cover less than ~2/3 of the SMs, single-tile CTAs (2-4x as many) finish sooner although
-  // each loads its own B tile: pix2pix's inner layers at batch 16, 16..32 items (tools/gpu_p2p_sweep.sh: fprop
-  // 32x32x256->512 56 -> 42 us, dgrad 16x16x512->512 49 -> 27 us); the headline's c3 (64 items) stays dual.
-  if (pair_items >= 0 && 2 * pair_items * 100 < (long long)min_pct * device_sms()) return 1;
-  return 2;
+  if (g_dual_min_pct == 0) return 2;
+  if (g_dual_min_pct > 100) return 1;
+  return m_tiles >= 4 ? 2 : 1;
 }
 
 static int env_cluster() {

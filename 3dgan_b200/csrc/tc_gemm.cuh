@@ -113,7 +113,7 @@ struct WgradParams {
 };
 
 int tapgemm_cluster_size(const TapGemmParams& p);
-int tapgemm_dual(int m_tiles, int iters, long long pair_items = -1);
+int tapgemm_dual(int m_tiles, int iters);
 void set_dual_min_pct(int v);
 int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail);
 int tapgemm_2sm(int cluster, int dual, int tail_mode, int merge_tail, int bn_tile);

@@ -53,9 +53,11 @@ int b200_abi_version(void);
 /* 0 if the current CUDA device can run the library (compute capability 10.x), negative otherwise. */
 int b200_device_check(void);
 /* Launch-planner knobs a host may override at run time (the B200GAN_* environment variables of DESIGN.md 5.2 are
- * read once per process).  Keys: "dual_min_pct" - the tap GEMMs use two pixel tiles per CTA (and the 2-CTA
- * kernels) only when that layout's work items cover at least this percentage of the SMs (default 65; 0 = always,
- * which is how the tests reach the 2-CTA kernels at small batch).  Unknown key: negative return. */
+ * read once per process).  Keys: "dual_min_pct" - 0: the tap GEMMs use two pixel tiles per CTA (and the 2-CTA
+ * kernels) whenever the geometry allows, which is how the tests reach those kernels at small batch; > 100: never;
+ * anything else (default 65): the planner's rule (>= 4 pixel tiles).  "bn_tile_cap" - widest N tile of the conv tap
+ * GEMMs (0 = planner's choice, else e.g. 64 / 128 / 256); "tap_splits" - split-K factor of the conv tap GEMMs
+ * (-1 = planner's choice).  The last two exist for tools/tune_layers.py.  Unknown key: negative return. */
 int b200_set_tuning(const char* key, int value);
 
 /* ---- convolution family (tcgen05 implicit GEMM; small-channel image-side layers use coalesced SIMT kernels)
