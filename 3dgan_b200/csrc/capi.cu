@@ -115,10 +115,11 @@ static bool is_small(int c) { return c <= 4; }
 // factor.  Fitted to tools/tune_layers.py (every fprop / dgrad geometry of pix2pix, VAE and the cnn autoencoder under
 // all combinations; gpurun_out/tune_layers.json): the fastest plan is the one that puts ~128 CTAs on the 148 SMs --
 //   * two pixel tiles per CTA in CTA pairs (shared B tile, tcgen05 cta_group::2) whenever there are >= 4 pixel tiles;
-//   * the widest N tile (<= 256 columns: one A tile feeds the most MACs) that still yields >= 96 CTAs, down to 64;
+//   * the widest N tile (<= 256 columns: one A tile feeds the most MACs) that still yields >= 96 CTAs: 128, or 64
+//     when 64 alone gets there;
 //   * and only then split-K over the taps (fp32 partial image + finalize pass; pix2pix's inner U-Net layers have
 //     16..1024 output pixels and K = 16 taps x 512..1024 channels: a handful of CTAs would stream the whole weight
-//     tensor), at most 8 slices of >= 4 pipeline iterations.
+//     tensor), at most 8 (dgrad: 4) slices of >= 6 pipeline iterations.
 // Layers that fill the machine anyway (the IWGAN c2 / c3 shapes: 128 .. 256 CTAs at N tile 208) are unaffected.
 struct ConvPlan { int dual, bn_tile, splits, tiles, phases; };
 static ConvPlan conv_plan(const b200_conv_geom* g, int op) {
@@ -148,14 +149,24 @@ static ConvPlan conv_plan(const b200_conv_geom* g, int op) {
   const long long rows = (pl.dual == 2 ? 2LL * cdiv(pl.tiles, 4) : (long long)pl.tiles) * pl.phases;   // CTAs per N tile
   int cap = g_bn_cap > 0 ? g_bn_cap : 256;
   auto bn_of = [&](int cp) { const int nt = cdiv(cols, cp); return std::max(16, cdiv(cdiv(cols, nt), 16) * 16); };
-  if (g_bn_cap <= 0)
-    while (cap > 64 && rows * cdiv(cols, bn_of(cap)) < 96) cap /= 2;
+  // (a single pixel tile -- <= 128 output pixels per parity -- is better served by 128 columns and one more split:
+  //  4x4x512->1024 fprop 29.5 -> 19.9 us, dgrad 28.4 -> 18.4 us)
+  //  64 columns only when that alone reaches 96 CTAs: otherwise 128 columns and split-K (16x16x512->1024 fprop:
+  //  64 columns x 2 slices 41 us, 128 columns x 4 slices 35 us)
+  //  -- for deep reductions (k*k*C >= 8192: pix2pix's inner layers); the shallower VAE / cnn layers (k*k*C <= 6400)
+  //  are faster with 64 columns and fewer slices (cnn 7x7x128->256 fprop 16.5 vs 18.9 us)
+  const bool deep = (long long)kk * (op == 0 ? g->Cin : g->Cout) >= 8192;
+  if (g_bn_cap <= 0) {
+    if (rows * cdiv(cols, bn_of(cap)) < 96) cap = 128;
+    if (pl.tiles > 1 && rows * cdiv(cols, bn_of(128)) < 96 && (!deep || rows * cdiv(cols, bn_of(64)) >= 96)) cap = 64;
+  }
   pl.bn_tile = bn_of(cap);
   const long long ctas = rows * cdiv(cols, pl.bn_tile);
   pl.splits = 1;
   if (g_force_splits >= 1) pl.splits = std::min(g_force_splits, std::max(1, iters / 2));
   else if (split_enabled && ctas < 96 && iters >= 16)
-    while (pl.splits < 8 && ctas * pl.splits < 96 && iters / (2 * pl.splits) >= 4) pl.splits *= 2;   // 2, 4 or 8 (the measured factors)
+    while (pl.splits < (op == 1 ? 4 : 8) && ctas * pl.splits < 96 && iters / (2 * pl.splits) >= 6)
+      pl.splits *= 2;       // 2, 4 or 8 (the measured factors); dgrad's output parities already multiply its CTAs
   return pl;
 }
 static int tc_tap_splits(const b200_conv_geom* g, int op) { return conv_plan(g, op).splits; }
