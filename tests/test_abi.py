@@ -59,6 +59,28 @@ def test_route_is_host_only_logic():
         pass
 
 
+def test_launch_planner_is_host_only_logic_and_tunable():
+    """conv_plan (csrc/capi.cu): the headline's layers fill the machine and never split; pix2pix's inner layers ask
+    for the fp32 partial image of a split-K launch; b200_set_tuning overrides the choice and rejects unknown keys."""
+    c2 = _capi.ConvGeom(N=512, H=16, W=16, Cin=208, Ho=8, Wo=8, Cout=416, k=5, stride=2, pad_t=1, pad_l=1)
+    c3 = _capi.ConvGeom(N=512, H=8, W=8, Cin=416, Ho=4, Wo=4, Cout=832, k=5, stride=2, pad_t=1, pad_l=1)
+    e5 = _capi.ConvGeom(N=16, H=16, W=16, Cin=512, Ho=8, Wo=8, Cout=512, k=4, stride=2, pad_t=1, pad_l=1)
+    for g in (c2, c3):
+        assert _capi.workspace_bytes(g, 0) == 0 and _capi.workspace_bytes(g, 1) == 0
+    assert _capi.workspace_bytes(e5, 0) >= 16 * 8 * 8 * 512 * 4
+    _capi.set_tuning("tap_splits", 1)
+    try:
+        assert _capi.workspace_bytes(e5, 0) == 0
+    finally:
+        _capi.set_tuning("tap_splits", -1)
+    assert _capi.workspace_bytes(e5, 0) > 0
+    try:
+        _capi.set_tuning("no_such_knob", 1)
+        assert False
+    except _capi.B200Error:
+        pass
+
+
 def test_ctypes_structs_match_the_c_header(tmp_path):
     """Compile a probe against include/b200gan.h with the host C compiler and compare struct sizes and field
     offsets with the ctypes mirrors in _capi.py (a silent layout mismatch would corrupt every call)."""
