@@ -2067,7 +2067,10 @@ static void launch_wgrad_2sm(const WgradParams& p0, cudaStream_t stream) {
   const long long total = (long long)p.units * p.total_chunks;
   long long pairs = total / 4;
   const int sms = device_sms();
-  if (pairs > sms / 2) pairs = sms / 2;
+  static int pairs_env = -1;        // B200GAN_WGRAD_PAIRS: CTA pairs of the stream-K partition (default: all SMs)
+  if (pairs_env < 0) pairs_env = env_int("B200GAN_WGRAD_PAIRS", 0);
+  const int max_pairs = (pairs_env > 0 && pairs_env < sms / 2) ? pairs_env : sms / 2;
+  if (pairs > max_pairs) pairs = max_pairs;
   if (pairs < 1) pairs = 1;
   p.chunks_per_cta = (int)((total + pairs - 1) / pairs);
   const int npairs = (int)((total + p.chunks_per_cta - 1) / p.chunks_per_cta);
