@@ -146,6 +146,14 @@ static ConvPlan conv_plan(const b200_conv_geom* g, int op) {
     iters_min = std::max(1, (g->k / st) * (g->k / st)) * kch;                   // lightest output parity
   }
   pl.dual = tapgemm_dual(pl.tiles, iters_min);
+  // short-K layers stay single-tile (two co-resident CTAs per SM hide each other's latency) unless that grid needs a
+  // second wave which two-tile CTAs avoid: the generator's fc1 as a 1x1 conv, 4 pixel tiles x 50 N tiles = 200 CTAs
+  {
+    const long long per_tile = (long long)pl.phases * cdiv(cols, 256);
+    if (pl.dual == 1 && iters_min <= 4 && pl.tiles >= 4 && tapgemm_dual(pl.tiles, 5) == 2 &&
+        pl.tiles * per_tile > 148 && 2LL * cdiv(pl.tiles, 4) * per_tile <= 148)
+      pl.dual = 2;
+  }
   const long long rows = (pl.dual == 2 ? 2LL * cdiv(pl.tiles, 4) : (long long)pl.tiles) * pl.phases;   // CTAs per N tile
   int cap = g_bn_cap > 0 ? g_bn_cap : 256;
   auto bn_of = [&](int cp) { const int nt = cdiv(cols, cp); return std::max(16, cdiv(cdiv(cols, nt), 16) * 16); };
@@ -343,6 +351,11 @@ static int dense_gemm(const void* A, long long M, int K, int lda, const void* B,
   p.phase_ext_w[0] = (int)M; p.phase_ext_h[0] = 1; p.ext_n = 1;
   p.o_sw = ldo;
   p.dual = tapgemm_dual(p.tiles_w, p.kchunks);
+  // short-K dense layers whose single-tile grid needs a second wave (the generator's fc1: 4 row tiles x 50 column
+  // tiles = 200 CTAs on 148 SMs) take two row tiles per CTA instead
+  if (p.dual == 1 && p.tiles_w >= 2 && (long long)p.tiles_w * cdiv(ncols, p.bn_tile) > 148 &&
+      (long long)cdiv(p.tiles_w, 2) * cdiv(ncols, p.bn_tile) <= 148)
+    p.dual = 2;
   p.stages = std::min(pick_stages(p.dual * kTileM * kBlockK * 2 + p.bn_tile * kBlockK * 2), std::max(2, p.kchunks));
   p.out = out;
   launch_tapgemm(p, st);
