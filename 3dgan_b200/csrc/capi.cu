@@ -200,6 +200,7 @@ extern "C" int b200_conv2d_route(const b200_conv_geom* g, int op) {
 // the SIMT small-channel / small-output epilogues do not)
 extern "C" int b200_conv2d_epilogue_bits(const b200_conv_geom* g, int op, int has_workspace) {
   const int r = b200_conv2d_route(g, op);
+  if (r == 1 && op == 0 && g->Cout == 1) return 0;      // one output channel: the SIMT dot-product kernel (smallout_fprop)
   if (r == 1) return (op == 0 || op == 1) && !(has_workspace && tc_tap_splits(g, op) > 1);
   if (r == 2) return op == 0 && has_workspace && (g->Cout % 8 == 0);
   return 0;
@@ -531,6 +532,13 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     if (e && e->accumulate) return fail("small-channel fprop: accumulate unsupported");
     if (smallc_fprop(x, w, a, st)) return fail("smallc_fprop: unsupported shape");
     return check_launch("smallc_fprop");
+  }
+  if (g->Cout == 1 && !(e && (e->accumulate || e->mask_bits || e->bits_out))) {
+    // one output channel (pix2pix PatchGAN head, hem/models/pix2pix.py:256): 1024 dot products, not a GEMM
+    SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
+                    e ? e->bias : nullptr, e ? e->act : 0, e ? e->leak : 0.f, e ? e->mask_src : nullptr,
+                    e ? e->mask_kind : 0, y, e ? e->out_f32 : 0};
+    if (smallout_fprop(x, w, a, st) == 0) return check_launch("smallout_fprop");
   }
   if (!w_t) return fail("conv2d_fprop: tensor-core path needs w_t");
   TapGemmParams p;

@@ -400,11 +400,169 @@ __global__ void smallout_wgrad_kernel(const bf16* __restrict__ x, const bf16* __
       if (co < g.Cb) atomicAdd(dw + ((long long)tap * g.Cs + ci) * g.Cb + co, acc[co] * alpha);
   }
 }
+// ---- one output channel (the PatchGAN head itself): the whole filter [k*k, Cin] sits in shared memory, a warp owns an
+// input pixel at a time, gathers its <= ceil(k/stride)^2 (tap, dy) pairs and every lane produces 8 channels per step
+// with 16-byte accesses (the generic kernel above walked all k*k taps per element with 2-byte loads: 68 us for the
+// 4 MB gradient of pix2pix's m5 at batch 16)
+__global__ void smallout1_dgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ w, ConvGeom g,
+                                       EpilogueArgs e, int npix) {
+  extern __shared__ uint4 sw4[];                       // [k*k][Cs] bf16
+  const int C = g.Cs, kk = g.k * g.k;
+  for (int i = threadIdx.x; i < kk * C / 8; i += blockDim.x) sw4[i] = reinterpret_cast<const uint4*>(w)[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int st = g.stride, nj = (g.k + st - 1) / st;
+  for (int p = blockIdx.x * nw + wid; p < npix; p += gridDim.x * nw) {
+    const int x = p % g.W, y = (p / g.W) % g.H, n = p / (g.W * g.H);
+    const int ty = y + g.pad_t, tx = x + g.pad_l;
+    const int oh0 = ty / st, r0 = ty - oh0 * st, ow0 = tx / st, s0 = tx - ow0 * st;
+    for (int c0 = lane * 8; c0 < C; c0 += 256) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int jr = 0; jr < nj; ++jr) {
+        const int r = r0 + jr * st, oh = oh0 - jr;
+        if (r >= g.k || oh < 0 || oh >= g.Ho) continue;
+        for (int js = 0; js < nj; ++js) {
+          const int sx = s0 + js * st, ow = ow0 - js;
+          if (sx >= g.k || ow < 0 || ow >= g.Wo) continue;
+          const float d = __bfloat162float(dy[(n * g.Ho + oh) * g.Wo + ow]);
+          const uint4 wv = sw4[((r * g.k + sx) * C + c0) >> 3];
+          const uint32_t w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[2 * j] = fmaf(d, __uint_as_float(w4[j] << 16), acc[2 * j]);
+            acc[2 * j + 1] = fmaf(d, __uint_as_float(w4[j] & 0xffff0000u), acc[2 * j + 1]);
+          }
+        }
+      }
+      const long long o = (long long)p * C + c0;
+      uint4 mv = make_uint4(0, 0, 0, 0);
+      if (e.mask_src) mv = *reinterpret_cast<const uint4*>(e.mask_src + o);
+      const uint32_t m4[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = acc[j] * e.alpha;
+        if (e.bias) v += e.bias[c0 + j];
+        v = act_fwd(v, e.act, e.leak);
+        if (e.mask_src) {
+          const float mval = (j & 1) ? __uint_as_float(m4[j >> 1] & 0xffff0000u) : __uint_as_float(m4[j >> 1] << 16);
+          v *= act_grad_from_out(mval, e.mask_kind, e.leak);
+        }
+        acc[j] = v;
+      }
+      if (e.out_f32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + o);
+        op[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        op[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      } else {
+        uint32_t o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+          o4[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out) + o) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+}
+// dw[tap, ci] += alpha * sum_p x[n, oh*st+r-pt, ow*st+s-pl, ci] * dy[p]: block = (8 output pixels, tap), a thread owns
+// a channel pair; the 8 x-loads of a thread are independent (the generic kernel's were one dependent chain per pixel)
+__global__ void smallout1_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* dw, ConvGeom g,
+                                       float alpha, int npix) {
+  constexpr int kPix = 8;
+  const int tap = blockIdx.y, r = tap / g.k, s = tap % g.k;
+  const int p0 = blockIdx.x * kPix;
+  __shared__ float sd[kPix];
+  __shared__ int soff[kPix];                            // element offset of the tap's input pixel, -1 = padding
+  if (threadIdx.x < kPix) {
+    const int p = p0 + threadIdx.x;
+    int off = -1;
+    float d = 0.f;
+    if (p < npix) {
+      const int ow = p % g.Wo, oh = (p / g.Wo) % g.Ho, n = p / (g.Wo * g.Ho);
+      const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
+      if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) { off = ((n * g.H + ih) * g.W + iw) * g.Cs; d = __bfloat162float(dy[p]); }
+    }
+    soff[threadIdx.x] = off; sd[threadIdx.x] = d;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 2; c < g.Cs; c += blockDim.x * 2) {
+    uint32_t v[kPix];
+#pragma unroll
+    for (int i = 0; i < kPix; ++i) v[i] = soff[i] >= 0 ? *reinterpret_cast<const uint32_t*>(x + soff[i] + c) : 0u;
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPix; ++i) {
+      a0 = fmaf(__uint_as_float(v[i] << 16), sd[i], a0);
+      a1 = fmaf(__uint_as_float(v[i] & 0xffff0000u), sd[i], a1);
+    }
+    atomicAdd(dw + (long long)tap * g.Cs + c, a0 * alpha);
+    atomicAdd(dw + (long long)tap * g.Cs + c + 1, a1 * alpha);
+  }
+}
+// y[p] = epi( sum_{r,s in bounds} x[n, oh*st+r-pt, ow*st+s-pl, :] . w[r,s,:] ): one block of 128 threads per output pixel,
+// 16-byte loads of the x rows (the tcgen05 route pads the single column to an N tile of 16 and needs split-K: 20 us
+// for 1024 dot products of 8192 elements)
+__global__ void smallout1_fprop_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, ConvGeom g,
+                                       EpilogueArgs e) {
+  __shared__ float part[4];
+  const int p = blockIdx.x;
+  const int ow = p % g.Wo, oh = (p / g.Wo) % g.Ho, n = p / (g.Wo * g.Ho);
+  const int C8 = g.Cs >> 3, kk = g.k * g.k;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < kk * C8; i += blockDim.x) {
+    const int tap = i / C8, c0 = (i - tap * C8) << 3;
+    const int r = tap / g.k, s = tap - r * g.k;
+    const int ih = oh * g.stride + r - g.pad_t, iw = ow * g.stride + s - g.pad_l;
+    if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + ((long long)(n * g.H + ih) * g.W + iw) * g.Cs + c0);
+    const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w + (long long)tap * g.Cs + c0));
+    const uint32_t x4[4] = {xv.x, xv.y, xv.z, xv.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc = fmaf(__uint_as_float(x4[j] << 16), __uint_as_float(w4[j] << 16), acc);
+      acc = fmaf(__uint_as_float(x4[j] & 0xffff0000u), __uint_as_float(w4[j] & 0xffff0000u), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = (part[0] + part[1] + part[2] + part[3]) * e.alpha;
+    if (e.bias) v += e.bias[0];
+    v = act_fwd(v, e.act, e.leak);
+    if (e.mask_src) v *= act_grad_from_out(__bfloat162float(e.mask_src[p]), e.mask_kind, e.leak);
+    if (e.out_f32) reinterpret_cast<float*>(e.out)[p] = v;
+    else reinterpret_cast<bf16*>(e.out)[p] = __float2bfloat16(v);
+  }
+}
+// a.Cs = Cin, a.Cb = Cout (== 1); returns -1 when the shape is not taken
+int smallout_fprop(const void* x, const void* w, const SmallConvArgs& a, cudaStream_t st) {
+  const long long npix = (long long)a.N * a.Ho * a.Wo;
+  if (a.Cb != 1 || a.Cs % 8 || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) ||
+      npix >= (1 << 30) || (long long)a.N * a.H * a.W >= (1 << 30))
+    return -1;
+  ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
+  EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, 1, 0};
+  smallout1_fprop_kernel<<<(unsigned)npix, 128, 0, st>>>((const bf16*)x, (const bf16*)w, g, e);
+  return 0;
+}
 int smallout_dgrad(const void* dy, const void* w, const SmallConvArgs& a, cudaStream_t st) {
   // a.Cs = Cin (many channels, the conv input), a.Cb = Cout (<= 4)
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
   EpilogueArgs e{a.bias, a.act, a.leak, (const bf16*)a.mask_src, a.mask_kind, 1.f, a.out, a.out_f32, 0, a.Cs, 0};
   const long long total = (long long)a.N * a.H * a.W * a.Cs;
+  const size_t wbytes = (size_t)a.k * a.k * a.Cs * 2;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.mask_src);
+  if (a.Cb == 1 && a.Cs % 8 == 0 && wbytes <= 48 * 1024 && (al & 15) == 0 && total < (1ll << 31)) {
+    const int npix = a.N * a.H * a.W;
+    int blocks = (npix + 7) / 8;
+    if (blocks > num_sms() * 4) blocks = num_sms() * 4;
+    smallout1_dgrad_kernel<<<blocks, 256, wbytes, st>>>((const bf16*)dy, (const bf16*)w, g, e, npix);
+    return 0;
+  }
   smallout_dgrad_kernel<<<stride_grid(total, 256, 2), 256, 0, st>>>((const bf16*)dy, (const bf16*)w, g, e, total);
   return 0;
 }
@@ -412,6 +570,12 @@ int smallout_wgrad(const void* x, const void* dy, float* dw, const SmallConvArgs
   if (a.Cb > 4) return -1;
   ConvGeom g{a.N, a.H, a.W, a.Cs, a.Ho, a.Wo, a.Cb, a.k, a.stride, a.pad_t, a.pad_l};
   const long long npix = (long long)a.N * a.Ho * a.Wo;
+  if (a.Cb == 1 && a.Cs % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0 &&
+      (long long)a.N * a.H * a.W * a.Cs < (1ll << 31) && npix < (1 << 30)) {
+    smallout1_wgrad_kernel<<<dim3((unsigned)((npix + 7) / 8), a.k * a.k), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, g,
+                                                                                       alpha, (int)npix);
+    return 0;
+  }
   int blocks = num_sms() * 2 / (a.k * a.k) + 1;
   int ppb = (int)((npix + blocks - 1) / blocks);
   if (ppb < 1) ppb = 1;

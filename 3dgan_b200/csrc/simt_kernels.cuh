@@ -25,6 +25,7 @@ int im2col_small(const void* xs, void* A, const SmallConvArgs& a, int Kp, cudaSt
 int wpad_transpose(const void* w, void* wt, int kk, int Cb, int Kp, cudaStream_t st);
 int col2im_small(const float* T, const SmallConvArgs& a, int Kp, cudaStream_t st);
 
+int smallout_fprop(const void* x, const void* w, const SmallConvArgs& a, cudaStream_t st);
 int smallout_dgrad(const void* dy, const void* w, const SmallConvArgs& a, cudaStream_t st);
 int smallout_wgrad(const void* x, const void* dy, float* dw, const SmallConvArgs& a, float alpha, cudaStream_t st);
 

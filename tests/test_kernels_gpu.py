@@ -42,6 +42,9 @@ CONV_CASES = [
     (512, 16, 16, 208, 400, 5, 2),           # bench.py's c2 exactly (B=512, padded 200 -> 208): 2-CTA schedules, stream-K
     (512, 8, 8, 400, 800, 5, 2),             # bench.py's c3 exactly
     (512, 32, 32, 3, 208, 5, 2),             # bench.py's c1 / last deconv exactly
+    (16, 16, 16, 512, 1, 4, 2),              # pix2pix PatchGAN head m5 (one output channel): smallout1_* backward kernels
+    (3, 9, 7, 64, 1, 5, 2),                  # the same kernels on odd sizes / k5 (borders, partial pixel blocks)
+    (2, 8, 8, 24, 2, 4, 2),                  # two output channels: generic small-output backward kernels
 ]
 
 
@@ -180,6 +183,8 @@ def test_conv_dgrad_fused_mask():
     res = P.conv_case(128, 16, 16, 208, 400, 5, 2, with_mask=True)       # stream-K finisher applies the fused mask
     assert res["dgrad"] < TOL["dgrad"], res
     res = P.conv_case(4, 32, 32, 3, 200, 5, 2, with_mask=True)
+    assert res["dgrad"] < TOL["dgrad"], res
+    res = P.conv_case(16, 16, 16, 512, 1, 4, 2, with_mask=True)          # one-output-channel dgrad with the value mask
     assert res["dgrad"] < TOL["dgrad"], res
 
 

@@ -20,7 +20,7 @@ SETS = {
     "cnn": [(64, 14, 64, 128, 5), (64, 7, 128, 256, 5), (64, 4, 256, 256, 5)],
     "iwgan": [(512, 16, 208, 416, 5), (512, 8, 416, 832, 5)],
 }
-which = os.environ.get("TUNE_SETS", "p2p,vae,cnn").split(",")
+which = [w for w in os.environ.get("TUNE_SETS", "p2p,vae,cnn").split(",") if w]
 
 
 def timed(fn, inner=10, reps=5):
