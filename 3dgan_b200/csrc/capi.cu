@@ -478,7 +478,10 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
     // im2col (bf16 [M,Kp]) + padded transposed filter [Cout,Kp] -> tcgen05 GEMM with the fused epilogue
     if (workspace_bytes < b200_conv2d_workspace_bytes(g, 0)) return fail("conv2d_fprop: workspace too small");
     const long long M = (long long)g->N * g->Ho * g->Wo;
-    if (img_layout(g)) {
+    // k = 4, Cin = 4 (pix2pix's discriminator input): the fused fprop in its virtual-fifth-row form; everything else
+    // of that layer keeps the im2col route below
+    const bool virt = !img_layout(g) && img_fprop_virtual_supported(img_geom(g), g->Cout);
+    if (img_layout(g) || virt) {
       // fused gather + GEMM + epilogue (img_conv.cu); general epilogues (fp32 out, value masks, tanh / sigmoid,
       // accumulate) keep the GEMM route, fed in the same row-group layout so that the workspace always holds
       // what the filter gradient of this layer expects
@@ -506,9 +509,16 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
         q.bits_stage = (q.bits_out && M % kTileM == 0 && (q.bits_pitch * kTileM * 2) % 16 == 0) ? 1 : 0;
         q.act = e ? e->act : 0; q.leak = e ? e->leak : 0.f; q.mask_kind = e ? e->mask_kind : 0;
         q.im2col_out = nullptr;                       // (the filter gradient gathers for itself: img_wgrad_kernel)
+        q.virt = virt ? 1 : 0;
         launch_img_fprop(q, st);
         return check_launch("conv2d_fprop(fused gather)");
       }
+    }
+    if (img_layout(g)) {
+      const ImgConvGeom ig = img_geom(g);
+      const int K16 = g->k * 16;
+      __nv_bfloat16* A16 = (__nv_bfloat16*)workspace;
+      const long long x_words = (long long)g->N * g->H * g->W * g->Cin / 2;
       __nv_bfloat16* Wt16 = (__nv_bfloat16*)((char*)workspace + img_ws_a(g));
       launch_img_im2col16((const __nv_bfloat16*)x, x_words, ig, A16, 1, st);
       launch_img_wpad16((const __nv_bfloat16*)w, g->Cout, g->Cout, g->k, g->k * g->Cin, Wt16, st);
@@ -810,6 +820,8 @@ extern "C" int b200_conv2d_wgrad_bias(const void* x, const void* dy, float* dw, 
     SmallConvArgs a{g->N, g->H, g->W, g->Cin, g->Ho, g->Wo, g->Cout, g->k, g->stride, g->pad_t, g->pad_l,
                     nullptr, 0, 0.f, nullptr, 0, nullptr, 0};
     // the fprop of the same input leaves im2col(x) at the start of its workspace: reuse it when told so
+    // (not for the geometry whose fprop runs fused in the virtual-row form: it gathers in shared memory only)
+    if (img_fprop_virtual_supported(img_geom(g), g->Cout)) workspace_holds_im2col = 0;
     if (!workspace_holds_im2col && im2col_small(x, workspace, a, Kp, st)) return fail("im2col: k*k*Cin too large");
     if (dense_wgrad(workspace, kk, Kp, dy, g->Cout, M, dw, g->Cout, alpha, st)) return -1;
     return check_launch("conv2d_wgrad(im2col)");

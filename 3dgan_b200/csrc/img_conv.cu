@@ -301,17 +301,23 @@ __device__ __forceinline__ void gather_row(const ImgFpropParams& p, const TileSp
 #pragma unroll
   for (int kh = 0; kh < kK; ++kh) {
     uint32_t wd[9], o[8];
+    if (kK == 5 && kh == 4 && p.virt) {             // virtual fifth row (k = 4, k*Cin = 16): zeros + the ones pair
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(src + kh * row_pitch + i * 4));
-    wd[8] = 0u;
+      for (int i = 0; i < 7; ++i) o[i] = 0u;
+      o[7] = 0x3F803F80u;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
-      if (i == 7 || !full14) o[i] &= wm[i];         // k*Cin >= 14: only the last word holds empty slots
-      if (!ok) o[i] = 0u;
+      for (int i = 0; i < 8; ++i)
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wd[i]) : "r"(src + kh * row_pitch + i * 4));
+      wd[8] = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i] = __funnelshift_r(wd[i], wd[i + 1], sh);
+        if (i == 7 || !full14) o[i] &= wm[i];         // k*Cin >= 14: only the last word holds empty slots
+        if (!ok) o[i] = 0u;
+      }
+      if (kh < 2 && !p.virt) o[7] |= ones;
     }
-    if (kh < 2) o[7] |= ones;
     if (kh < 4) {
       const uint32_t base = a0 + r * 128;
       st_shared_v4(base + (((2 * kh) ^ (r & 7)) << 4), o[0], o[1], o[2], o[3]);
@@ -463,10 +469,13 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
         const int kk = item % K16, n8 = item / K16;
         const int kh = kk >> 4, j = kk & 15;
         uint32_t v[4] = {0u, 0u, 0u, 0u};
-        if (j < kcin) {
+        const bool vrow = p.virt && kh >= 4;                 // the virtual row group: bias pair in slots 14 / 15 only
+        const bool bias_hi = p.virt ? (vrow && j == 14) : (j == 15 && kh == 0);
+        const bool bias_lo = p.virt ? (vrow && j == 15) : (j == 15 && kh == 1);
+        if (j < kcin && !vrow) {
           const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t)(kh * kcin + j) * p.ldw + n8 * 8));
           v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-        } else if (j == 15 && p.bias && kh < 2) {
+        } else if (p.bias && (bias_hi || bias_lo)) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t h2[2];
@@ -474,7 +483,7 @@ __global__ void __launch_bounds__(kImgThreads, 1) img_fprop_kernel(const __grid_
             for (int h = 0; h < 2; ++h) {
               const float bv = __ldg(p.bias + n8 * 8 + 2 * i + h);
               const __nv_bfloat16 hi = __float2bfloat16(bv);
-              const __nv_bfloat16 val = kh == 0 ? hi : __float2bfloat16(bv - __bfloat162float(hi));
+              const __nv_bfloat16 val = bias_hi ? hi : __float2bfloat16(bv - __bfloat162float(hi));
               h2[h] = (uint32_t)__bfloat16_as_ushort(val);
             }
             v[i] = h2[0] | (h2[1] << 16);
@@ -1010,7 +1019,7 @@ int dev_sms() {
 using namespace imgconv;
 
 size_t img_fprop_smem(const ImgFpropParams& p) {
-  const int bt = p.g.k == 5 ? align_up(p.ncols * 32, 1024) : 0;
+  const int bt = (p.g.k == 5 || p.virt) ? align_up(p.ncols * 32, 1024) : 0;
   return (size_t)p.ncols * 128 + bt + (size_t)p.slots * kASlot + 2 * (size_t)align_up(kTileM * p.stage_pitch, 1024) +
          2 * (size_t)(p.bits_stage ? align_up(kTileM * p.bits_pitch * 2, 128) : 0) +
          2 * kImgGroups * (size_t)align_up(p.win_rows * p.win_pitch * 2, 128) + sizeof(ImgSmem) + 1024;
@@ -1070,6 +1079,27 @@ bool img_fprop_supported(const ImgConvGeom& g, int ncols, int has_bias) {
   return img_fprop_smem(q) <= 227 * 1024;
 }
 
+// k = 4 with k*Cin = 16 (pix2pix's discriminator input: rgb + depth): every slot of the four filter rows holds data, so
+// the bias pair moves into a fifth, otherwise empty row group (the kernel's k = 5 form; ImgFpropParams.virt).  Only the
+// fused fprop takes this form: the layer's filter / input gradients keep the im2col route.
+bool img_fprop_virtual_supported(const ImgConvGeom& g, int ncols) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("B200GAN_NO_IMGFUSE"); off = e ? atoi(e) : 0; }
+  if (off) return false;
+  if (g.k != 4 || g.k * g.Cin != 16) return false;          // (Cin = 4: every window starts on an even element)
+  if (ncols % 16 || ncols < 16 || ncols > 256) return false;
+  const long long numel = (long long)g.N * g.H * g.W * g.Cin;
+  if (numel >= (1ll << 31) || (long long)g.N * g.Ho * g.Wo >= (1ll << 31) - 256) return false;
+  ImgFpropParams q;
+  memset(&q, 0, sizeof q);
+  q.g = g; q.ncols = ncols; q.slots = 2; q.stage_pitch = ncols * 2 + 16; q.bits_stage = 1; q.bits_pitch = ncols / 16;
+  q.virt = 1;
+  img_window(g, &q.win_pitch, &q.win_off, &q.win_hp, &q.win_rows);
+  const int rb = g.W * g.Cin * 2;
+  if (q.win_rows * (rb / (rb % 16 == 0 ? 16 : 4)) > kImgProducers * kWinRegs * (rb % 16 == 0 ? 1 : 4)) return false;
+  return img_fprop_smem(q) <= 227 * 1024;
+}
+
 void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
   ImgFpropParams p = p0;
   img_window(p.g, &p.win_pitch, &p.win_off, &p.win_hp, &p.win_rows);
@@ -1088,7 +1118,7 @@ void launch_img_fprop(const ImgFpropParams& p0, cudaStream_t stream) {
   }
   const int sms = dev_sms();
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-  if (p.g.k == 5) img_fprop_kernel<5><<<grid, kImgThreads, smem, stream>>>(p);
+  if (p.g.k == 5 || p.virt) img_fprop_kernel<5><<<grid, kImgThreads, smem, stream>>>(p);
   else if (p.g.k == 4) img_fprop_kernel<4><<<grid, kImgThreads, smem, stream>>>(p);
   else img_fprop_kernel<3><<<grid, kImgThreads, smem, stream>>>(p);
 }

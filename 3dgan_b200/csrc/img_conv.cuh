@@ -42,6 +42,8 @@ struct ImgFpropParams {
   float leak;
   int mask_kind;
   __nv_bfloat16* im2col_out;          // optional [M][k*16] copy of the gathered rows (for the later filter gradient)
+  int virt;                           // 1: k == 4 and k*Cin == 16 (no free slot in any filter row): the kernel runs as
+                                      // its k = 5 form whose fifth row group holds only the ones / bias pair (slots 14, 15)
 };
 
 // Fused input gradient / transposed-conv forward of an image-side layer: dx[N,H,W,Cin] = epi(conv^T(dy, W)).
@@ -89,6 +91,7 @@ void launch_img_wgrad(const ImgWgradParams& p, cudaStream_t stream);
 
 // 1 when the fused kernel takes this call (else the caller uses the im2col + GEMM route)
 bool img_fprop_supported(const ImgConvGeom& g, int ncols, int has_bias);
+bool img_fprop_virtual_supported(const ImgConvGeom& g, int ncols);
 size_t img_fprop_smem(const ImgFpropParams& p);
 void launch_img_fprop(const ImgFpropParams& p, cudaStream_t stream);
 

@@ -28,6 +28,7 @@ CONV_CASES = [
     (8, 32, 32, 3, 200, 5, 2),               # small-channel path (IWGAN c1 / dc-last)
     (4, 28, 28, 1, 64, 5, 2),                # MNIST-shaped first conv
     (2, 16, 16, 4, 64, 4, 2),                # pix2pix PatchGAN first conv (rgb+depth)
+    (4, 64, 64, 4, 64, 4, 2),                # same, several tiles per image: fused fprop in its virtual-fifth-row form (k*Cin = 16)
     (16, 2, 2, 512, 512, 4, 2),              # pix2pix e8 / d1: 16 output pixels, K = 16 x 512 -> split-K over taps
     (16, 4, 4, 512, 512, 4, 2),              # pix2pix e7 / d2
     (16, 16, 16, 512, 512, 4, 2),            # pix2pix e5: 1024 output pixels, split-K
