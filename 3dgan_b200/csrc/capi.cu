@@ -899,6 +899,7 @@ extern "C" int b200_set_tuning(const char* key, int value) {
   if (key && !strcmp(key, "dual_min_pct")) { set_dual_min_pct(value); return 0; }
   if (key && !strcmp(key, "bn_tile_cap")) { g_bn_cap = value < 0 ? 0 : value; return 0; }
   if (key && !strcmp(key, "tap_splits")) { g_force_splits = value; return 0; }
+  if (key && !strcmp(key, "wgrad_min_chunks")) { set_wgrad_min_chunks(value); return 0; }
   return fail("set_tuning: unknown key");
 }
 extern "C" int b200_abi_version(void) { return 4; }

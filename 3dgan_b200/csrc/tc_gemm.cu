@@ -2043,10 +2043,45 @@ __global__ void __launch_bounds__(kMaxThreads, 1) wgrad2sm_kernel(const __grid_c
   if (warp == 1) tmem_dealloc_2sm<2 * kTmemCols>(tmem);
 }
 
+static int g_wgrad_min_chunks = 0;    // b200_set_tuning("wgrad_min_chunks", v): fewest 64-pixel chunks a CTA of the stream-K cut takes
+void set_wgrad_min_chunks(int v) { g_wgrad_min_chunks = v; }
+static int wgrad_min_chunks() { return g_wgrad_min_chunks > 0 ? g_wgrad_min_chunks : 4; }
 int wgrad_dual(int m_tiles) {
   static int v = -1;
   if (v < 0) v = env_int("B200GAN_DUAL", 2);
   return (v == 2 && m_tiles >= 2) ? 2 : 1;
+}
+
+// Chunks per CTA (pair) of the stream-K cut over `units` x `total_chunks` 64-pixel chunks on at most `max_ctas` CTAs.
+// A range that crosses a unit boundary costs one more epilogue (a whole fp32 tile of red.global.add: ~7.7 us for
+// 2 x 128 x 256, against ~0.6 us per chunk of main loop -- tools/tune_wgrad.py), so besides the plain equal cut
+// (every SM busy; right for the long reductions of the IWGAN layers) the cut aligned to the units is costed: every
+// unit split into s equal parts (s | total_chunks, units * s CTAs), or whole units per CTA when there are more units
+// than CTAs.  pix2pix 4x4x512->1024: 35 -> 12 us, 16x16x512->512: 24 -> 17 us, 32x32x256->512: 28.5 -> 22 us.
+static int wgrad_chunks_per_cta(long long units, long long total_chunks, int max_ctas) {
+  const long long total = units * total_chunks;
+  const double t_chunk = 0.6, t_epi = 7.7;
+  long long ctas = total / wgrad_min_chunks();
+  if (ctas > max_ctas) ctas = max_ctas;
+  if (ctas < 1) ctas = 1;
+  const long long cpc_a = (total + ctas - 1) / ctas;
+  if (g_wgrad_min_chunks > 0) return (int)cpc_a;                        // forced by the tuning tool
+  const bool aligned_a = (cpc_a <= total_chunks) ? (total_chunks % cpc_a == 0) : (cpc_a % total_chunks == 0);
+  const long long segs_a = aligned_a ? std::max(1LL, cpc_a / total_chunks) : cpc_a / total_chunks + 2;
+  double best = cpc_a * t_chunk + (segs_a - 1) * t_epi;
+  long long cpc = cpc_a;
+  if (units > max_ctas) {
+    const long long upc = (units + max_ctas - 1) / max_ctas;
+    const double c = upc * total_chunks * t_chunk + (upc - 1) * t_epi;
+    if (c < best) { best = c; cpc = upc * total_chunks; }
+  } else {
+    for (long long s = 1; s <= total_chunks && units * s <= max_ctas; ++s) {
+      if (total_chunks % s) continue;
+      const double c = (double)(total_chunks / s) * t_chunk;
+      if (c < best) { best = c; cpc = total_chunks / s; }
+    }
+  }
+  return (int)cpc;
 }
 
 static void launch_wgrad_2sm(const WgradParams& p0, cudaStream_t stream) {
@@ -2065,14 +2100,11 @@ static void launch_wgrad_2sm(const WgradParams& p0, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * stage_bytes + sizeof(PipeSmem) + 1024;
   p.units = ((p.Cb + 511) / 512) * p.n_tiles * p.ntaps;
   const long long total = (long long)p.units * p.total_chunks;
-  long long pairs = total / 4;
   const int sms = device_sms();
   static int pairs_env = -1;        // B200GAN_WGRAD_PAIRS: CTA pairs of the stream-K partition (default: all SMs)
   if (pairs_env < 0) pairs_env = env_int("B200GAN_WGRAD_PAIRS", 0);
   const int max_pairs = (pairs_env > 0 && pairs_env < sms / 2) ? pairs_env : sms / 2;
-  if (pairs > max_pairs) pairs = max_pairs;
-  if (pairs < 1) pairs = 1;
-  p.chunks_per_cta = (int)((total + pairs - 1) / pairs);
+  p.chunks_per_cta = wgrad_chunks_per_cta(p.units, p.total_chunks, max_pairs);
   const int npairs = (int)((total + p.chunks_per_cta - 1) / p.chunks_per_cta);
   launch_clustered(wgrad2sm_kernel, p, dim3(2 * npairs), smem, 2, stream);
 }
@@ -2095,11 +2127,7 @@ void launch_wgrad(const WgradParams& p0, int /*splits_hint*/, cudaStream_t strea
   // equal share of the (unit, chunk) space per CTA, one CTA per SM; a CTA gets at least 4 chunks
   p.units = ((p.m_tiles + p.dual - 1) / p.dual) * p.n_tiles * p.ntaps;
   const long long total = (long long)p.units * p.total_chunks;
-  long long ctas = total / 4;
-  const int sms = device_sms();
-  if (ctas > sms) ctas = sms;
-  if (ctas < 1) ctas = 1;
-  p.chunks_per_cta = (int)((total + ctas - 1) / ctas);
+  p.chunks_per_cta = wgrad_chunks_per_cta(p.units, p.total_chunks, device_sms());
   static int trace_env = -1;
   if (trace_env < 0) trace_env = env_int("B200GAN_GEMM_TRACE", 0);
   p.trace = trace_env;

@@ -115,6 +115,7 @@ struct WgradParams {
 int tapgemm_cluster_size(const TapGemmParams& p);
 int tapgemm_dual(int m_tiles, int iters);
 void set_dual_min_pct(int v);
+void set_wgrad_min_chunks(int v);
 int tapgemm_stage_bytes(int dual, int bn_tile, int merge_tail);
 int tapgemm_2sm(int cluster, int dual, int tail_mode, int merge_tail, int bn_tile);
 int tapgemm_stage_bytes_2sm(int bn_tile, int merge_tail);

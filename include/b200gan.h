@@ -57,7 +57,9 @@ int b200_device_check(void);
  * kernels) whenever the geometry allows, which is how the tests reach those kernels at small batch; > 100: never;
  * anything else (default 65): the planner's rule (>= 4 pixel tiles).  "bn_tile_cap" - widest N tile of the conv tap
  * GEMMs (0 = planner's choice, else e.g. 64 / 128 / 256); "tap_splits" - split-K factor of the conv tap GEMMs
- * (-1 = planner's choice).  The last two exist for tools/tune_layers.py.  Unknown key: negative return. */
+ * (-1 = planner's choice); "wgrad_min_chunks" - fewest 64-pixel chunks per CTA of the filter gradient's plain
+ * stream-K cut (0 = the launcher's own cost model).  The last three exist for tools/tune_layers.py / tune_wgrad.py.
+ * Unknown key: negative return. */
 int b200_set_tuning(const char* key, int value);
 
 /* ---- convolution family (tcgen05 implicit GEMM; small-channel image-side layers use coalesced SIMT kernels)
