@@ -486,8 +486,6 @@ extern "C" int b200_conv2d_fprop(const void* x, const void* w, const void* w_t, 
       // accumulate) keep the GEMM route, fed in the same row-group layout so that the workspace always holds
       // what the filter gradient of this layer expects
       const ImgConvGeom ig = img_geom(g);
-      const int K16 = g->k * 16;
-      __nv_bfloat16* A16 = (__nv_bfloat16*)workspace;
       const long long x_words = (long long)g->N * g->H * g->W * g->Cin / 2;
       const bool epi_ok = !e || (!e->out_f32 && !e->accumulate && e->act <= ACT_LRELU && (!e->mask_src || e->mask_bits));
       const uintptr_t al = reinterpret_cast<uintptr_t>(y) | (e ? reinterpret_cast<uintptr_t>(e->bits_out) : 0);
