@@ -44,6 +44,33 @@ def test_conv_transpose_is_exact_adjoint(h, k, hout):
     assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs))
 
 
+@pytest.mark.parametrize("h,w,k,s", [(7, 5, 5, 2), (8, 8, 4, 2), (6, 6, 3, 1), (4, 4, 5, 2), (5, 9, 1, 1)])
+def test_conv_same_matches_a_direct_loop_of_the_tf_definition(h, w, k, s):
+    """tf.nn.conv2d's documented definition, written as plain loops with no torch conv involved:
+    out[b,i,j,o] = sum_{di,dj,q} in[b, s*i + di - pad_top, s*j + dj - pad_left, q] * filter[di,dj,q,o], SAME padding
+    = ceil(size/s) outputs with the smaller half of the padding first (ops/layers.py:101 calls exactly this op).
+    conv2d_transpose is then pinned by the adjointness test above."""
+    import numpy as np
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, h, w, 3, generator=g, dtype=torch.float64)
+    K = torch.randn(k, k, 3, 2, generator=g, dtype=torch.float64)
+    got = OT.conv2d_same(x, K, s).numpy()
+    ho, wo = -(-h // s), -(-w // s)
+    pt = max((ho - 1) * s + k - h, 0) // 2
+    pl = max((wo - 1) * s + k - w, 0) // 2
+    xn, Kn = x.numpy(), K.numpy()
+    want = np.zeros((2, ho, wo, 2))
+    for i in range(ho):
+        for j in range(wo):
+            for di in range(k):
+                for dj in range(k):
+                    y, z = s * i + di - pt, s * j + dj - pl
+                    if 0 <= y < h and 0 <= z < w:
+                        want[:, i, j, :] += xn[:, y, z, :] @ Kn[di, dj]
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-10
+
+
 def test_lrelu_gradient_at_zero_is_leak():
     x = torch.tensor([-1.0, 0.0, 2.0], requires_grad=True)
     OT.lrelu(x, 0.2).sum().backward()
