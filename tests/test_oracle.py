@@ -71,6 +71,20 @@ def test_conv_same_matches_a_direct_loop_of_the_tf_definition(h, w, k, s):
     assert np.abs(got - want).max() < 1e-10
 
 
+def test_sigmoid_ce_is_the_bernoulli_negative_log_likelihood():
+    """tf.nn.sigmoid_cross_entropy_with_logits' stable form (hem/models/pix2pix.py:283-299) against the definition
+    -z log s(x) - (1-z) log(1 - s(x)) in float64, including saturated logits where the naive form loses digits."""
+    x = torch.tensor([-30.0, -4.0, -0.5, 0.0, 0.3, 5.0, 30.0], dtype=torch.float64)
+    for z in (0.0, 1.0, 0.25):
+        zz = torch.full_like(x, z)
+        s = torch.sigmoid(x)
+        want = -(zz * torch.log(s) + (1 - zz) * torch.log1p(-s))
+        ok = torch.isfinite(want) & (x.abs() < 20)
+        got = OT.sigmoid_ce(x, zz)
+        assert float((got[ok] - want[ok]).abs().max()) < 1e-12
+        assert torch.isfinite(got).all() and float(got.min()) >= 0.0
+
+
 def test_lrelu_gradient_at_zero_is_leak():
     x = torch.tensor([-1.0, 0.0, 2.0], requires_grad=True)
     OT.lrelu(x, 0.2).sum().backward()
